@@ -1,0 +1,141 @@
+/* taub200.h -- C ABI of libtaub200.so, the B200 (sm_100a) kernels behind the TauFactor
+ * steady-state diffusion solve.
+ *
+ * The reference (tldr-group/taufactor v1.2.1) has NO FFI of its own: its hot path is a chain of
+ * eager PyTorch tensor expressions inside taufactor/taufactor.py.  Each entry point below
+ * replaces the reference lines cited next to it; the Python classes in taufactor_b200/solvers.py
+ * keep the reference's surface (Solver / PeriodicSolver / MultiPhaseSolver /
+ * PeriodicMultiPhaseSolver, .solve(), .tau, .D_eff ...) and call these through ctypes.
+ *
+ * Conventions: extern "C"; plain pointers and sizes only (no torch types); every function
+ * returns 0 on success and a negative taub_status otherwise, with a message retrievable from
+ * taub_last_error(); nothing throws, nothing calls back into Python.  The library never
+ * allocates fields: the caller (PyTorch) owns all device memory and passes raw device pointers
+ * plus a cudaStream_t (as void*).  All launches are asynchronous on that stream.
+ *
+ * Storage layout ("slab storage"): per image
+ *     field[planes][rows][pitch]   fp32,  planes = Nx + 2G, rows = Ny + 2G, G = 2
+ * voxel (i, j, k) of the local slab lives at plane i+G, row j+G, column k+4 (so interior rows
+ * start 16-byte aligned; columns 2,3 and Nz+4,Nz+5 are the z ghosts).  The reference's padded
+ * tensor field[bs, Nx+2, Ny+2, Nz+2] is the strided window starting at (plane 1, row 1, col 3).
+ * x is the flux direction (reference dim 1): planes are the slab-partition and march axis.
+ */
+#ifndef TAUB200_H
+#define TAUB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TAUB_ABI_VERSION 1
+#define TAUB_GHOST 2            /* ghost width in x (planes), y (rows) and z (columns) */
+#define TAUB_COL0 4             /* column of interior voxel k = 0 */
+#define TAUB_MAX_LABELS 64      /* dense phase indices 0..L-1, L <= 64; index L = "outside" */
+
+typedef enum taub_status {
+    TAUB_OK = 0,
+    TAUB_ERR_ARG = -1,          /* bad argument / unsupported shape */
+    TAUB_ERR_CUDA = -2,         /* a CUDA call failed (message has the cudaError string) */
+    TAUB_ERR_UNSUPPORTED = -3   /* path not available for this problem (e.g. fused sweep) */
+} taub_status;
+
+typedef enum taub_kind { TAUB_BINARY = 0, TAUB_MULTIPHASE = 1 } taub_kind;
+
+/* Geometry of one rank's slab.  Filled by taub_geom_init. */
+typedef struct taub_geom {
+    int32_t bs;                 /* images in the batch */
+    int32_t Nx, Ny, Nz;         /* LOCAL voxel extents (Nx = planes owned by this rank) */
+    int32_t Nx_global;          /* x extent of the whole volume */
+    int32_t i_offset;           /* global x index of local plane 0 */
+    int32_t periodic;           /* 1: y/z periodic (PeriodicSolver family) */
+    int32_t planes, rows, pitch;/* storage extents: Nx+2G, Ny+2G, round_up(Nz+6, 8) */
+    int64_t plane_stride;       /* rows * pitch   (elements) */
+    int64_t image_stride;       /* planes * plane_stride */
+} taub_geom;
+
+/* Everything a sweep needs.  Mirrors the state SORSolver.__init__ builds (taufactor.py:24-67):
+ * field (two ping-pong copies), the per-voxel prefactor in compressed form (4-bit neighbour
+ * count per voxel for the binary solvers instead of the fp32 `factor` tensor; 1-byte dense
+ * phase index + an (L+1)x(L+1) harmonic-mean table for the multi-phase solvers instead of
+ * D_x, D_y, D_z, factor), and omega.  No chequerboard tensors: parity is computed on the fly. */
+typedef struct taub_problem {
+    taub_geom g;
+    int32_t kind;               /* taub_kind */
+    int32_t L;                  /* multi-phase: number of dense phase indices */
+    float *field[2];            /* ping-pong buffers, bs * image_stride floats each */
+    uint16_t *codes;            /* binary: bs * planes * rows * pitch/4 nibble-quads */
+    uint8_t *labels;            /* multi-phase: bs * image_stride bytes */
+    float *lut;                 /* multi-phase: (L+1)*(L+1) fp32 harmonic means, device */
+    float omega;                /* over-relaxation factor rounded once to fp32 (taufactor.py:224) */
+    int32_t cur;                /* index of the buffer that holds the current field */
+} taub_problem;
+
+/* -- library ------------------------------------------------------------------------------ */
+int taub_abi_version(void);
+const char *taub_last_error(void);
+/* Device / toolchain facts for logs: SM count, compute capability, runtime version. */
+int taub_device_info(int *sm_count, int *cc_major, int *cc_minor, int *runtime_version);
+/* Number of kernels this library has launched since it was loaded (all threads). */
+unsigned long long taub_launch_count(void);
+/* Select the CUDA device for the calling thread (the library links its own static CUDA runtime,
+ * whose current device is independent of PyTorch's).  Call before any other entry point. */
+int taub_set_device(int ordinal);
+
+/* -- geometry ----------------------------------------------------------------------------- */
+int taub_geom_init(taub_geom *g, int bs, int Nx_local, int Ny, int Nz, int Nx_global,
+                   int i_offset, int periodic);
+size_t taub_field_elems(const taub_geom *g);   /* floats per ping-pong buffer */
+size_t taub_codes_elems(const taub_geom *g);   /* uint16 elements */
+size_t taub_sums_ws_bytes(const taub_geom *g); /* workspace for taub_plane_means */
+
+/* -- construction (replaces taufactor.py:40-59: mask, vol_x, init_field :282-291,
+ *    init_conductive_neighbours :402-410 / :493-499 / :585-604 / :626-650, _init_chequerboard) -- */
+/* img: device uint8 [bs][img_n][Ny][Nz] holding global planes [img_i0, img_i0+img_n), which must
+ * cover [i_offset-3, i_offset+Nx+3) clipped to the volume.  vec: device fp32 [Nx_global], the
+ * reference's torch.linspace profile.  Fills both field buffers and the neighbour codes. */
+int taub_init_binary(const taub_problem *p, const uint8_t *img, int img_i0, int img_n,
+                     const float *vec, void *stream);
+/* map256: device uint8[256] raw label -> dense index; cond: device fp32 [L+1], 1.0 where the
+ * phase conducts (D > 0); p->lut must already hold the harmonic-mean table. */
+int taub_init_multiphase(const taub_problem *p, const uint8_t *img, int img_i0, int img_n,
+                         const uint8_t *map256, const float *cond, const float *vec, void *stream);
+/* counts[b][i] (int64, device) = voxels of local plane i whose raw label has sel256[label] != 0
+ * (numerator of vol_x, taufactor.py:42); hist[b][256] (int64, device, may be NULL) = label
+ * histogram (numerators of VF, taufactor.py:564-567). */
+int taub_plane_counts(const taub_geom *g, const uint8_t *img, int img_i0, int img_n,
+                      const uint8_t *sel256, int64_t *counts, int64_t *hist, void *stream);
+
+/* -- the hot loop (replaces taufactor.py:174-182) ------------------------------------------ */
+/* apply_boundary_conditions (taufactor.py:501-505, :652-656) on storage planes [p_lo, p_hi) of
+ * one buffer: y/z ghost frame (width G, corners included) := periodic image of the interior. */
+int taub_refresh_ghosts(const taub_geom *g, float *field, int p_lo, int p_hi, void *stream);
+/* ONE reference iteration (one colour) field[cur] -> field[cur^1] on local planes
+ * [i_lo, i_hi); iter = the reference's self.iter before the increment (selects the colour).
+ * Generic path: any shape, both kinds.  Does not flip p->cur. */
+int taub_half_sweep(const taub_problem *p, int64_t iter, int i_lo, int i_hi, void *stream);
+/* TWO consecutive reference iterations (iter, iter+1) fused in one pass over HBM: temporally
+ * blocked, TMA-bulk staged shared-memory tiles, register-rotating plane march.  Binary kind.
+ * Returns TAUB_ERR_UNSUPPORTED when the problem does not qualify (see taub_can_fuse). */
+int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, void *stream);
+int taub_can_fuse(const taub_problem *p);
+/* n iterations starting at iter on the whole local slab (single-rank use): refreshes periodic
+ * ghosts, picks fused pairs where possible, flips p->cur.  flags bit0: force the generic path. */
+int taub_iterate(taub_problem *p, int64_t iter, int n, int flags, void *stream);
+
+/* -- the check (replaces vertical_flux :412-419 / :615-620 and the two torch.mean reductions in
+ *    compute_metrics :296, :307) --------------------------------------------------------------- */
+/* flux_mean[b][i], i in [0, Nx-1+has_next): mean over (y,z) of the (masked / weighted) flux
+ * through the face between local planes i and i+1 (the last entry uses the upper ghost plane
+ * and exists only when this slab is not the last: Nx_out = Nx-1 + (i_offset+Nx < Nx_global));
+ * field_mean[b][i], i in [0, Nx): mean of the field over plane i.  fp64 accumulation in a fixed
+ * order (deterministic), results rounded to fp32.  Outputs are device pointers. */
+int taub_plane_means(const taub_problem *p, void *workspace, float *flux_mean, float *field_mean,
+                     void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAUB200_H */

@@ -1,0 +1,272 @@
+// taub_init.cu -- construction kernels: slab storage, neighbour codes / phase indices, counts.
+//
+// Replaces the state build of SORSolver.__init__ (taufactor.py:40-59): initial field
+// (init_field :282-291), conductive-neighbour prefactor (:402-410, :493-499, :585-604, :626-650)
+// and the per-slice volume-fraction numerators (:42).  One pass over the uint8 label image; no
+// fp32 image copy, no meshgrid, no chequerboard tensors.
+#include "taub_common.cuh"
+
+namespace taub {
+
+struct ImgView {
+    const uint8_t *img;  // [bs][img_n][Ny][Nz], global planes [i0, i0 + n)
+    int i0, n, Ny, Nz, Nx_global, periodic;
+    int64_t image_stride;  // n * Ny * Nz
+};
+
+// Raw label of voxel (b, i, j, k) in GLOBAL x index; j/k must already be inside [0,Ny)x[0,Nz).
+__device__ __forceinline__ int raw_label(const ImgView &v, int b, int i, int j, int k)
+{
+    return v.img[(int64_t)b * v.image_stride + ((int64_t)(i - v.i0) * v.Ny + j) * v.Nz + k];
+}
+
+// Weight a neighbour contributes to the binary neighbour count (taufactor.py:404-405, :494-495):
+// the two Dirichlet ghost planes count 2, y/z outside counts 0 or wraps, inside = the mask.
+__device__ __forceinline__ int nn_weight(const ImgView &v, int b, int i, int j, int k)
+{
+    if (i < 0 || i >= v.Nx_global) return 2;
+    if (j < 0 || j >= v.Ny || k < 0 || k >= v.Nz) {
+        if (!v.periodic) return 0;
+        j = wrap(j, v.Ny);
+        k = wrap(k, v.Nz);
+    }
+    return raw_label(v, b, i, j, k) == 1;
+}
+
+// One thread per float4 group of the slab storage.
+__global__ void __launch_bounds__(256)
+init_binary_kernel(taub_geom g, ImgView v, const float *__restrict__ vec, float *__restrict__ f0,
+                   float *__restrict__ f1, uint16_t *__restrict__ codes)
+{
+    const int ngroups = g.pitch >> 2;
+    const int64_t total = (int64_t)g.bs * g.planes * g.rows * ngroups;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int grp = (int)(t % ngroups);
+        int64_t r = t / ngroups;
+        const int jr = (int)(r % g.rows);
+        r /= g.rows;
+        const int ip = (int)(r % g.planes);
+        const int b = (int)(r / g.planes);
+        const int i = ip - G + g.i_offset;  // global x
+        const int j = jr - G;
+        float val[4];
+        unsigned code = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int k = grp * 4 + q - COL0;
+            int jj = j;
+            bool present = (k >= -G && k < g.Nz + G);  // interior or ghost frame (not row padding)
+            const bool inside = (jj >= 0 && jj < g.Ny && k >= 0 && k < g.Nz);
+            if (present && !inside) {
+                if (g.periodic) {
+                    jj = wrap(jj, g.Ny);
+                    k = wrap(k, g.Nz);
+                } else {
+                    present = false;
+                }
+            }
+            float x = 0.0f;
+            unsigned c = 0;
+            if (present) {
+                if (i < 0) {
+                    x = -1.0f;  // 2 * top_bc, taufactor.py:279, :291
+                } else if (i >= g.Nx_global) {
+                    x = 1.0f;   // 2 * bot_bc
+                } else {
+                    const int m = raw_label(v, b, i, jj, k) == 1;
+                    x = __fmul_rn(m ? 1.0f : 0.0f, vec[i]);  // mask * linspace (keeps -0.0)
+                    if (m) {
+                        c = nn_weight(v, b, i + 1, jj, k) + nn_weight(v, b, i - 1, jj, k) +
+                            nn_weight(v, b, i, jj + 1, k) + nn_weight(v, b, i, jj - 1, k) +
+                            nn_weight(v, b, i, jj, k + 1) + nn_weight(v, b, i, jj, k - 1);
+                    }
+                }
+            }
+            val[q] = x;
+            code |= c << (4 * q);
+        }
+        const float4 out = make_float4(val[0], val[1], val[2], val[3]);
+        reinterpret_cast<float4 *>(f0)[t] = out;
+        reinterpret_cast<float4 *>(f1)[t] = out;
+        codes[t] = (uint16_t)code;
+    }
+}
+
+// Multi-phase: dense phase index per storage voxel.  Ghost frame: wrapped (periodic) or the
+// isolating pseudo-phase L; the two Dirichlet ghost planes copy the adjacent plane
+// (taufactor.py:590-592, :631-638).  One thread per storage voxel quad.
+__global__ void __launch_bounds__(256)
+init_multi_kernel(taub_geom g, ImgView v, int L, const uint8_t *__restrict__ map256,
+                  const float *__restrict__ cond, const float *__restrict__ vec,
+                  float *__restrict__ f0, float *__restrict__ f1, uint8_t *__restrict__ labels)
+{
+    const int ngroups = g.pitch >> 2;
+    const int64_t total = (int64_t)g.bs * g.planes * g.rows * ngroups;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int grp = (int)(t % ngroups);
+        int64_t r = t / ngroups;
+        const int jr = (int)(r % g.rows);
+        r /= g.rows;
+        const int ip = (int)(r % g.planes);
+        const int b = (int)(r / g.planes);
+        const int i = ip - G + g.i_offset;
+        const int j = jr - G;
+        float val[4];
+        unsigned packed = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int k = grp * 4 + q - COL0;
+            int jj = j;
+            bool present = (k >= -G && k < g.Nz + G);
+            const bool inside = (jj >= 0 && jj < g.Ny && k >= 0 && k < g.Nz);
+            if (present && !inside) {
+                if (g.periodic) {
+                    jj = wrap(jj, g.Ny);
+                    k = wrap(k, g.Nz);
+                } else {
+                    present = false;
+                }
+            }
+            float x = 0.0f;
+            unsigned lab = (unsigned)L;
+            if (present) {
+                const int ic = min(max(i, 0), g.Nx_global - 1);  // Dirichlet ghosts copy the edge plane
+                lab = map256[raw_label(v, b, ic, jj, k)];
+                if (i < 0)
+                    x = -1.0f;
+                else if (i >= g.Nx_global)
+                    x = 1.0f;
+                else
+                    x = __fmul_rn(cond[lab], vec[i]);
+            }
+            val[q] = x;
+            packed |= lab << (8 * q);
+        }
+        const float4 out = make_float4(val[0], val[1], val[2], val[3]);
+        reinterpret_cast<float4 *>(f0)[t] = out;
+        reinterpret_cast<float4 *>(f1)[t] = out;
+        reinterpret_cast<uint32_t *>(labels)[t] = packed;
+    }
+}
+
+// counts[b][i] = voxels of local plane i whose raw label is selected; hist[b][256] optional.
+__global__ void __launch_bounds__(256)
+plane_counts_kernel(taub_geom g, ImgView v, const uint8_t *__restrict__ sel256,
+                    unsigned long long *__restrict__ counts, unsigned long long *__restrict__ hist)
+{
+    __shared__ unsigned s_hist[256];
+    __shared__ uint8_t s_sel[256];
+    __shared__ unsigned s_cnt;
+    const int b = blockIdx.y, il = blockIdx.x;
+    const int i = il + g.i_offset;
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) {
+        s_hist[t] = 0;
+        s_sel[t] = sel256[t];
+    }
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const int64_t n = (int64_t)g.Ny * g.Nz;
+    const uint8_t *plane = v.img + (int64_t)b * v.image_stride + (int64_t)(i - v.i0) * n;
+    unsigned local = 0;
+    for (int64_t t = threadIdx.x; t < n; t += blockDim.x) {
+        const int lab = plane[t];
+        local += s_sel[lab] != 0;
+        if (hist) atomicAdd(&s_hist[lab], 1u);
+    }
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt, local);
+    __syncthreads();
+    if (threadIdx.x == 0) counts[(int64_t)b * g.Nx + il] = s_cnt;
+    if (hist)
+        for (int t = threadIdx.x; t < 256; t += blockDim.x)
+            if (s_hist[t]) atomicAdd(&hist[(int64_t)b * 256 + t], (unsigned long long)s_hist[t]);
+}
+
+static int check_img_cover(const taub_geom &g, int img_i0, int img_n, int halo)
+{
+    const int lo = max(0, g.i_offset - halo), hi = min(g.Nx_global, g.i_offset + g.Nx + halo);
+    TAUB_REQUIRE(img_i0 <= lo && img_i0 + img_n >= hi,
+                 "image planes [%d, %d) do not cover the required [%d, %d)", img_i0, img_i0 + img_n, lo, hi);
+    TAUB_REQUIRE(img_i0 >= 0 && img_i0 + img_n <= g.Nx_global, "image planes outside the volume");
+    return TAUB_OK;
+}
+
+static ImgView make_view(const taub_geom &g, const uint8_t *img, int img_i0, int img_n)
+{
+    ImgView v;
+    v.img = img;
+    v.i0 = img_i0;
+    v.n = img_n;
+    v.Ny = g.Ny;
+    v.Nz = g.Nz;
+    v.Nx_global = g.Nx_global;
+    v.periodic = g.periodic;
+    v.image_stride = (int64_t)img_n * g.Ny * g.Nz;
+    return v;
+}
+
+static int grid_for(int64_t items, int block)
+{
+    int64_t blocks = ceil_div64(items, block);
+    const int64_t cap = 148 * 64;  // grid-stride loop beyond this
+    return (int)(blocks < cap ? blocks : cap);
+}
+
+}  // namespace taub
+
+using namespace taub;
+
+extern "C" {
+
+int taub_init_binary(const taub_problem *p, const uint8_t *img, int img_i0, int img_n,
+                     const float *vec, void *stream)
+{
+    TAUB_REQUIRE(p && img && vec, "taub_init_binary: null pointer");
+    TAUB_REQUIRE(p->kind == TAUB_BINARY && p->field[0] && p->field[1] && p->codes,
+                 "taub_init_binary: problem is not a bound binary problem");
+    const taub_geom &g = p->g;
+    if (int rc = check_img_cover(g, img_i0, img_n, G + 1)) return rc;
+    const int64_t total = (int64_t)taub_codes_elems(&g);
+    init_binary_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        g, make_view(g, img, img_i0, img_n), vec, p->field[0], p->field[1], p->codes);
+    TAUB_CUDA(cudaGetLastError());
+    count_launch();
+    return TAUB_OK;
+}
+
+int taub_init_multiphase(const taub_problem *p, const uint8_t *img, int img_i0, int img_n,
+                         const uint8_t *map256, const float *cond, const float *vec, void *stream)
+{
+    TAUB_REQUIRE(p && img && vec && map256 && cond, "taub_init_multiphase: null pointer");
+    TAUB_REQUIRE(p->kind == TAUB_MULTIPHASE && p->field[0] && p->field[1] && p->labels && p->lut,
+                 "taub_init_multiphase: problem is not a bound multi-phase problem");
+    TAUB_REQUIRE(p->L >= 1 && p->L <= TAUB_MAX_LABELS, "taub_init_multiphase: L=%d outside [1, %d]",
+                 p->L, TAUB_MAX_LABELS);
+    const taub_geom &g = p->g;
+    if (int rc = check_img_cover(g, img_i0, img_n, G)) return rc;
+    const int64_t total = (int64_t)taub_codes_elems(&g);
+    init_multi_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        g, make_view(g, img, img_i0, img_n), p->L, map256, cond, vec, p->field[0], p->field[1], p->labels);
+    TAUB_CUDA(cudaGetLastError());
+    count_launch();
+    return TAUB_OK;
+}
+
+int taub_plane_counts(const taub_geom *g, const uint8_t *img, int img_i0, int img_n,
+                      const uint8_t *sel256, int64_t *counts, int64_t *hist, void *stream)
+{
+    TAUB_REQUIRE(g && img && sel256 && counts, "taub_plane_counts: null pointer");
+    if (int rc = check_img_cover(*g, img_i0, img_n, 0)) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (hist) TAUB_CUDA(cudaMemsetAsync(hist, 0, sizeof(int64_t) * 256 * g->bs, s));
+    dim3 grid(g->Nx, g->bs);
+    plane_counts_kernel<<<grid, 256, 0, s>>>(*g, make_view(*g, img, img_i0, img_n), sel256,
+                                             (unsigned long long *)counts, (unsigned long long *)hist);
+    TAUB_CUDA(cudaGetLastError());
+    count_launch();
+    return TAUB_OK;
+}
+
+}  // extern "C"

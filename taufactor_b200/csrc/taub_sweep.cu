@@ -1,0 +1,201 @@
+// taub_sweep.cu -- generic one-colour sweep (any shape, both solver kinds), periodic ghost
+// refresh, and the iteration driver.
+//
+// Replaces the body of the reference's hot loop, taufactor.py:174-182: nine to nineteen eager
+// elementwise launches and 108-180 B/voxel of HBM traffic become ONE launch that reads the field
+// once (4 B), the compressed prefactor (0.5 B nibble codes / 1 B phase index) and writes the
+// field once (4 B) into the other ping-pong buffer.  Ping-pong makes the sweep a pure function
+// of the source buffer, which is exactly the reference's snapshot semantics for periodic ghosts
+// (taufactor.py:501-505 run BEFORE the update), including odd Ny/Nz where the wrap joins two
+// voxels of the same colour.
+#include "taub_common.cuh"
+
+namespace taub {
+
+// ------------------------------------------------------------------------------------------
+// Periodic ghost frame: rows [0,G) u [G+Ny, rows) over columns [2, Nz+6), and columns
+// {2,3,Nz+4,Nz+5} of the interior rows, := image of the wrapped interior voxel.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+refresh_ghosts_kernel(taub_geom g, float *__restrict__ f, int p_lo)
+{
+    const int W = g.Nz + 2 * G;
+    const int n_rows_part = 2 * G * W;
+    const int total = n_rows_part + g.Ny * 2 * G;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    int jr, c;
+    if (t < n_rows_part) {
+        const int r = t / W;
+        jr = r < G ? r : g.Ny + r;  // r in [G, 2G) -> rows [G+Ny, 2G+Ny)
+        c = COL0 - G + (t - r * W);
+    } else {
+        const int u = t - n_rows_part;
+        const int r = u / (2 * G), q = u - r * (2 * G);
+        jr = G + r;
+        c = q < G ? COL0 - G + q : COL0 + g.Nz + (q - G);
+    }
+    float *plane = f + (int64_t)blockIdx.z * g.image_stride + (int64_t)(p_lo + blockIdx.y) * g.plane_stride;
+    const int js = G + wrap(jr - G, g.Ny), cs = COL0 + wrap(c - COL0, g.Nz);
+    plane[(int64_t)jr * g.pitch + c] = plane[(int64_t)js * g.pitch + cs];
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic half-sweep: one thread per interior float4 group (4 consecutive z voxels), all four
+// results computed branch-free and the active colour selected.  blockDim = (32, 8):
+// x -> groups along z (coalesced 512 B per warp), y -> rows; grid.z -> (image, plane).
+// ------------------------------------------------------------------------------------------
+template <bool MULTI>
+__global__ void __launch_bounds__(256)
+half_sweep_kernel(taub_geom g, const float *__restrict__ src, float *__restrict__ dst,
+                  const uint16_t *__restrict__ codes, const uint8_t *__restrict__ labels,
+                  const float *__restrict__ lut, int L, float omega, int colour, int i_lo, int n_planes)
+{
+    __shared__ float2 s_div[16];
+    extern __shared__ float s_lut[];  // MULTI: (L+1)^2
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if (!MULTI) {
+        if (tid < 16) s_div[tid] = div_entry(tid);
+    } else {
+        for (int t = tid; t < (L + 1) * (L + 1); t += blockDim.x * blockDim.y) s_lut[t] = lut[t];
+    }
+    __syncthreads();
+
+    const int ng = interior_groups(g.Nz);
+    const int grp = blockIdx.x * blockDim.x + threadIdx.x;  // 0-based interior group
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (grp >= ng || j >= g.Ny) return;
+    const int64_t ps = g.plane_stride;
+    const int pitch = g.pitch;
+
+    for (int z = blockIdx.z; z < g.bs * n_planes; z += gridDim.z) {
+        const int b = z / n_planes;
+        const int il = i_lo + (z - b * n_planes);  // local plane
+        const int ig = il + g.i_offset;            // global plane
+        const int64_t o = (int64_t)b * g.image_stride + (int64_t)(il + G) * ps +
+                          (int64_t)(j + G) * pitch + COL0 + 4 * grp;
+        const float4 c4 = *reinterpret_cast<const float4 *>(src + o);
+        const float4 xp4 = *reinterpret_cast<const float4 *>(src + o + ps);
+        const float4 xm4 = *reinterpret_cast<const float4 *>(src + o - ps);
+        const float4 yp4 = *reinterpret_cast<const float4 *>(src + o + pitch);
+        const float4 ym4 = *reinterpret_cast<const float4 *>(src + o - pitch);
+        const float zl = src[o - 1], zr = src[o + 4];
+        const float c[4] = {c4.x, c4.y, c4.z, c4.w};
+        const float xp[4] = {xp4.x, xp4.y, xp4.z, xp4.w}, xm[4] = {xm4.x, xm4.y, xm4.z, xm4.w};
+        const float yp[4] = {yp4.x, yp4.y, yp4.z, yp4.w}, ym[4] = {ym4.x, ym4.y, ym4.z, ym4.w};
+        const float zp[4] = {c4.y, c4.z, c4.w, zr}, zm[4] = {zl, c4.x, c4.y, c4.z};
+        // voxel q is active when (i + j + k) % 2 == colour; k = 4*grp + q so only q matters
+        const int par0 = (ig + j + colour) & 1;  // 0: q = 0,2 active, 1: q = 1,3 active
+        float out[4];
+        if (!MULTI) {
+            const unsigned code = codes[o >> 2];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float nv = sor_binary(c[q], xp[q], xm[q], yp[q], ym[q], zp[q], zm[q],
+                                            s_div[(code >> (4 * q)) & 15u], omega);
+                out[q] = ((q & 1) == par0) ? nv : c[q];
+            }
+        } else {
+            const uint32_t lc = *reinterpret_cast<const uint32_t *>(labels + o);
+            const uint32_t lxp = *reinterpret_cast<const uint32_t *>(labels + o + ps);
+            const uint32_t lxm = *reinterpret_cast<const uint32_t *>(labels + o - ps);
+            const uint32_t lyp = *reinterpret_cast<const uint32_t *>(labels + o + pitch);
+            const uint32_t lym = *reinterpret_cast<const uint32_t *>(labels + o - pitch);
+            const uint32_t lzl = labels[o - 1], lzr = labels[o + 4];
+            const uint64_t lrow = ((uint64_t)lzr << 40) | ((uint64_t)lc << 8) | lzl;  // k-1 .. k+4
+            const bool first = (ig == 0), last = (ig == g.Nx_global - 1);
+            const int L1 = L + 1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float *row = s_lut + ((lc >> (8 * q)) & 255u) * L1;
+                const float nv = sor_multi(
+                    c[q], xp[q], xm[q], yp[q], ym[q], zp[q], zm[q], row[(lxp >> (8 * q)) & 255u],
+                    row[(lxm >> (8 * q)) & 255u], row[(lyp >> (8 * q)) & 255u],
+                    row[(lym >> (8 * q)) & 255u], row[(lrow >> (8 * (q + 2))) & 255u],
+                    row[(lrow >> (8 * q)) & 255u], first, last, omega);
+                out[q] = ((q & 1) == par0) ? nv : c[q];
+            }
+        }
+        *reinterpret_cast<float4 *>(dst + o) = make_float4(out[0], out[1], out[2], out[3]);
+    }
+}
+
+}  // namespace taub
+
+using namespace taub;
+
+extern "C" {
+
+int taub_refresh_ghosts(const taub_geom *g, float *field, int p_lo, int p_hi, void *stream)
+{
+    TAUB_REQUIRE(g && field, "taub_refresh_ghosts: null pointer");
+    TAUB_REQUIRE(p_lo >= 0 && p_hi <= g->planes && p_lo < p_hi, "taub_refresh_ghosts: planes [%d, %d) invalid", p_lo, p_hi);
+    const int total = 2 * G * (g->Nz + 2 * G) + g->Ny * 2 * G;
+    for (int b0 = 0; b0 < g->bs; b0 += 65535) {
+        dim3 grid(ceil_div(total, 256), p_hi - p_lo, min(g->bs - b0, 65535));
+        refresh_ghosts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+            *g, field + (int64_t)b0 * g->image_stride, p_lo);
+    }
+    TAUB_CUDA(cudaGetLastError());
+    count_launch();
+    return TAUB_OK;
+}
+
+int taub_half_sweep(const taub_problem *p, int64_t iter, int i_lo, int i_hi, void *stream)
+{
+    TAUB_REQUIRE(p && p->field[0] && p->field[1], "taub_half_sweep: unbound problem");
+    const taub_geom &g = p->g;
+    TAUB_REQUIRE(i_lo >= -(G - 1) && i_hi <= g.Nx + (G - 1) && i_lo < i_hi,
+                 "taub_half_sweep: planes [%d, %d) outside the slab", i_lo, i_hi);
+    TAUB_REQUIRE(i_lo + g.i_offset >= 0 && i_hi + g.i_offset <= g.Nx_global,
+                 "taub_half_sweep: planes [%d, %d) touch a Dirichlet plane", i_lo, i_hi);
+    const float *src = p->field[p->cur];
+    float *dst = p->field[p->cur ^ 1];
+    const int colour = (int)(iter & 1);
+    const int n_planes = i_hi - i_lo;
+    dim3 block(32, 8);
+    dim3 grid(ceil_div(interior_groups(g.Nz), 32), ceil_div(g.Ny, 8),
+              (unsigned)min((int64_t)g.bs * n_planes, (int64_t)65535));
+    TAUB_REQUIRE(grid.y <= 65535, "taub_half_sweep: Ny too large");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (p->kind == TAUB_BINARY) {
+        TAUB_REQUIRE(p->codes, "taub_half_sweep: binary problem without codes");
+        half_sweep_kernel<false><<<grid, block, 0, s>>>(g, src, dst, p->codes, nullptr, nullptr, 0,
+                                                        p->omega, colour, i_lo, n_planes);
+    } else {
+        TAUB_REQUIRE(p->labels && p->lut && p->L >= 1 && p->L <= TAUB_MAX_LABELS,
+                     "taub_half_sweep: multi-phase problem without labels / table");
+        const size_t smem = sizeof(float) * (p->L + 1) * (p->L + 1);
+        half_sweep_kernel<true><<<grid, block, smem, s>>>(g, src, dst, nullptr, p->labels, p->lut,
+                                                          p->L, p->omega, colour, i_lo, n_planes);
+    }
+    TAUB_CUDA(cudaGetLastError());
+    count_launch();
+    return TAUB_OK;
+}
+
+int taub_iterate(taub_problem *p, int64_t iter, int n, int flags, void *stream)
+{
+    TAUB_REQUIRE(p && n >= 0, "taub_iterate: bad arguments");
+    const taub_geom &g = p->g;
+    TAUB_REQUIRE(g.i_offset == 0 && g.Nx == g.Nx_global,
+                 "taub_iterate drives a whole volume; slabs interleave halo exchange in the caller");
+    const bool fuse_ok = !(flags & 1) && taub_can_fuse(p) == 1;
+    int done = 0;
+    while (done < n) {
+        if (g.periodic) {
+            if (int rc = taub_refresh_ghosts(&g, p->field[p->cur], 0, g.planes, stream)) return rc;
+        }
+        if (fuse_ok && n - done >= 2) {
+            if (int rc = taub_fused_sweep2(p, iter + done, 0, g.Nx, stream)) return rc;
+            done += 2;
+        } else {
+            if (int rc = taub_half_sweep(p, iter + done, 0, g.Nx, stream)) return rc;
+            done += 1;
+        }
+        p->cur ^= 1;
+    }
+    return TAUB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,453 @@
+"""Drop-in solver classes for TauFactor's steady-state diffusion solve on B200.
+
+Same surface as the reference (``/root/reference/taufactor/taufactor.py``): ``Solver``,
+``PeriodicSolver``, ``MultiPhaseSolver``, ``PeriodicMultiPhaseSolver``; constructor keywords,
+``solve(iter_limit, verbose, conv_crit, plot_interval)``, the result attributes (``tau``,
+``D_eff``, ``D_mean``, ``tau_x``, ``c_x``, ``flux_1d``, ``vol_x``, ``iter``, ``converged``,
+``walltime``, ``field`` ...), the error types and the printed report are kept.  Underneath, the
+state build, the checkerboard SOR loop (ref:174-182) and the flux reduction (ref:293-307) run as
+hand-written sm_100a kernels behind the C ABI of ``include/taub200.h``.  There is no CPU or
+PyTorch-eager fallback: without a CUDA device or without ``libtaub200.so`` construction raises.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+from timeit import default_timer as timer
+
+import numpy as np
+
+try:
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+from . import _lib
+from ._lib import Geom, Problem, check
+
+TOP_BC, BOT_BC = -0.5, 0.5   # ref:279
+
+
+def _expand_to_4d(img):
+    """ref:195-204."""
+    if not isinstance(img, np.ndarray):
+        raise TypeError("Error: input image must be a NumPy array!")
+    if img.ndim == 2:
+        img = img[..., None]
+    if img.ndim == 3:
+        img = img[None, ...]
+    if img.ndim != 4:
+        raise ValueError("expected [B, X, Y, Z]")
+    return img
+
+
+def _as_uint8_labels(img4):
+    """uint8 view/copy of an integer-valued label image, or None if it does not fit 0..255."""
+    if img4.dtype == np.uint8:
+        return np.ascontiguousarray(img4)
+    if img4.dtype == np.bool_:
+        return np.ascontiguousarray(img4).view(np.uint8)
+    lo, hi = img4.min(), img4.max()
+    if not (np.isfinite(lo) and np.isfinite(hi)) or lo < 0 or hi > 255:
+        return None
+    u8 = img4.astype(np.uint8)
+    if not np.array_equal(u8, img4):
+        return None
+    return u8
+
+
+def _through_fraction_is_zero(mask3):
+    """True when no 6-connected cluster of ``mask3`` touches both x faces -- the condition the
+    reference derives from metrics.extract_through_feature(mask, 1, 'x') (ref:320-322)."""
+    from scipy.ndimage import label
+    if not mask3.any():
+        return True
+    lab, _ = label(mask3)
+    first = np.unique(lab[0])
+    last = np.unique(lab[-1])
+    return len(np.intersect1d(first[first != 0], last[last != 0])) == 0
+
+
+class SORSolver:
+    """Shared machinery: device state, the iteration loop and the stop rule (ref:15-269)."""
+
+    _kind = _lib.BINARY
+    _periodic = False
+
+    # ------------------------------------------------------------------ construction
+    def _setup(self, img4, omega, device, label_u8, prepare, extra_init):
+        if torch is None:
+            raise ImportError("PyTorch is required to use TauFactor solvers.")
+        self._lib = _lib.load()
+        self.cpu_img = img4
+        self.batch_size, self.Nx, self.Ny, self.Nz = img4.shape
+        self.device = self._init_device(device)
+        self.precision = torch.float
+        if omega is None:
+            omega = 2 - math.pi / (1.5 * self.Nx)     # ref:36-37
+        self.omega = omega
+        dev = self.device
+        self._dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+        self._call(self._lib.taub_set_device(self._dev_index), "taub_set_device")
+
+        g = Geom()
+        self._call(self._lib.taub_geom_init(g, self.batch_size, self.Nx, self.Ny, self.Nz, self.Nx, 0,
+                                            int(self._periodic)), "taub_geom_init")
+        self._geom = g
+        n = self._lib.taub_field_elems(g)
+        with torch.cuda.device(dev):
+            self._bufs = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(2)]
+            img_dev = torch.from_numpy(label_u8).to(dev, non_blocking=False)
+            # ref:284-286 -- the linear start profile, computed by torch on the host like the oracle
+            sh = 1 / (2 * self.Nx)
+            vec = torch.linspace(TOP_BC + sh, BOT_BC - sh, self.Nx, dtype=torch.float32).to(dev)
+            p = Problem()
+            p.g = g
+            p.kind = self._kind
+            p.field[0], p.field[1] = self._bufs[0].data_ptr(), self._bufs[1].data_ptr()
+            p.omega = float(np.float32(omega))          # rounded once to fp32, ref:224
+            p.cur = 0
+            self._prob = p
+            # label histogram (ref:564-567) -> which phases exist; then the per-slice volume
+            # fraction numerators of the conductive phases (ref:42)
+            counts = torch.zeros(self.batch_size * self.Nx, dtype=torch.int64, device=dev)
+            hist = torch.zeros(self.batch_size * 256, dtype=torch.int64, device=dev)
+            sel = torch.zeros(256, dtype=torch.uint8, device=dev)
+            self._call(self._lib.taub_plane_counts(g, img_dev.data_ptr(), 0, self.Nx, sel.data_ptr(),
+                                                   counts.data_ptr(), hist.data_ptr(), self._stream()),
+                       "taub_plane_counts")
+            self._hist = hist.cpu().numpy().reshape(self.batch_size, 256)
+            sel = torch.from_numpy(prepare(self._hist)).to(dev)
+            self._call(self._lib.taub_plane_counts(g, img_dev.data_ptr(), 0, self.Nx, sel.data_ptr(),
+                                                   counts.data_ptr(), None, self._stream()),
+                       "taub_plane_counts")
+            self._keep = extra_init(p, img_dev, vec)    # kind-specific tensors + init kernel
+            ws = self._lib.taub_sums_ws_bytes(g)
+            self._ws = torch.empty(max(ws, 16), dtype=torch.uint8, device=dev)
+            self._flux_dev = torch.zeros(self.batch_size * max(self.Nx - 1, 1), dtype=torch.float32, device=dev)
+            self._mean_dev = torch.zeros(self.batch_size * self.Nx, dtype=torch.float32, device=dev)
+            counts = counts.cpu().numpy().reshape(self.batch_size, self.Nx)
+            del img_dev
+        self.vol_x = (counts.astype(np.float32) / np.float32(self.Ny * self.Nz)).astype(np.float32)
+        # ref:62-67
+        self.converged = False
+        self.old_tau = 0
+        self.iter = 0
+        self.tau = None
+        self.tau_x = None
+        self.D_eff = None
+        self.force_generic = False   # True: never use the fused two-colour kernel
+
+    @staticmethod
+    def _init_device(device):
+        """ref:207-216 keeps a silent CPU fallback; this build has none and says so."""
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError(
+                f"taufactor_b200 runs on CUDA devices only (got device={device}); "
+                "use the reference package for CPU runs")
+        if not torch.cuda.is_available():
+            raise RuntimeError("taufactor_b200 needs a CUDA device (B200, sm_100a); none is available "
+                               "and there is no CPU fallback")
+        return device
+
+    def _call(self, rc, what):
+        check(rc, what)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ------------------------------------------------------------------ views
+    @property
+    def field(self):
+        """The reference's padded tensor [bs, Nx+2, Ny+2, Nz+2] as a zero-copy strided window of
+        the current ping-pong buffer (periodic ghosts refreshed first)."""
+        g, p = self._geom, self._prob
+        buf = self._bufs[p.cur]
+        if self._periodic:
+            self._lib.taub_set_device(self._dev_index)
+            self._call(self._lib.taub_refresh_ghosts(g, buf.data_ptr(), 0, g.planes, self._stream()),
+                       "taub_refresh_ghosts")
+        G = _lib.GHOST
+        off = (G - 1) * g.plane_stride + (G - 1) * g.pitch + _lib.COL0 - 1
+        return buf.as_strided((g.bs, g.Nx + 2, g.Ny + 2, g.Nz + 2),
+                              (g.image_stride, g.plane_stride, g.pitch, 1), off)
+
+    # ------------------------------------------------------------------ the check (ref:109-153)
+    def check_convergence(self, verbose, conv_crit, plot_interval):
+        self.tau, relative_error = self.compute_metrics()
+        if verbose == 'per_iter' or verbose == 'debug':
+            i = np.argmax(relative_error)
+            print(f'Iter: {self.iter}, conv error: {abs(relative_error[i]):.3E}, '
+                  f'tau: {self.tau[i]:.5f} (batch element {i})')
+        if not np.all(relative_error < conv_crit):
+            self.old_tau = self.tau
+            return False
+        tau_error = np.max(np.abs(self.tau - self.old_tau))
+        if not tau_error < 2e-3:
+            self.old_tau = self.tau
+            return False
+        self.tau[self.tau == 0] = np.inf
+        return True
+
+    def _plane_means(self):
+        """flux_1d (bs, Nx-1) and mean field per slice (bs, Nx) from the fused reduction kernel."""
+        self._call(self._lib.taub_plane_means(self._prob, self._ws.data_ptr(), self._flux_dev.data_ptr(),
+                                              self._mean_dev.data_ptr(), self._stream()), "taub_plane_means")
+        bs, Nx = self.batch_size, self.Nx
+        flux = self._flux_dev[: bs * (Nx - 1)].cpu().numpy().reshape(bs, Nx - 1)
+        mean = self._mean_dev.cpu().numpy().reshape(bs, Nx)
+        return flux, mean
+
+    def compute_metrics(self):
+        """ref:293-331 -- identical host post-processing of the two per-slice profiles."""
+        self.flux_1d, c_mean = self._plane_means()
+        fl = self.flux_1d
+        with np.errstate(invalid="ignore", divide="ignore"):
+            fl_max, fl_min, mean_fl = fl.max(axis=1), fl.min(axis=1), fl.mean(axis=1)
+            relative_error = np.divide(fl_max - fl_min, fl_max, out=np.full_like(fl_max, np.nan),
+                                       where=fl_max != 0)
+            D_rel = mean_fl * self.Nx / abs(self.top_bc - self.bot_bc)
+            tau = np.divide(self.D_mean, D_rel, out=np.full_like(D_rel, np.nan), where=D_rel != 0)
+            c_x = np.divide(c_mean, self.vol_x, out=np.zeros_like(self.vol_x), where=self.vol_x != 0)
+            self.c_x = c_x
+            dc = c_x[:, 1:] - c_x[:, :-1]
+            dc[self.vol_x[:, 1:] == 0] = 0
+            dc[self.vol_x[:, :-1] == 0] = 0
+            eps = 0.5 * (self.vol_x[:, :-1] + self.vol_x[:, 1:])
+            self.tau_x = np.divide(eps * dc, fl, out=np.full_like(dc, np.nan), where=fl != 0)
+        for b in range(self.batch_size):
+            if fl_min[b] == 0 or fl_max[b] == 0 or mean_fl[b] == 0:
+                conductive = np.isin(self.cpu_img[b], self.conductive_labels)
+                if _through_fraction_is_zero(conductive):
+                    print(f"Warning: batch element {b} has no percolating path!")
+                    relative_error[b] = 0
+                    D_rel[b] = 0
+                    tau[b] = 0
+                    self.tau_x[b, :] = 0
+        relative_error[np.isnan(mean_fl)] = 0   # NaN counts as converged, ref:328-329
+        self.D_eff = self.D_0 * D_rel
+        return tau, relative_error
+
+    # ------------------------------------------------------------------ the loop (ref:156-191)
+    def solve(self, iter_limit=10000, verbose=True, conv_crit=1e-2, plot_interval=10):
+        """Iterate the checkerboard SOR scheme until the reference's stop rule fires.
+
+        :param iter_limit: max iterations before aborting
+        :param verbose: True, 'per_iter' (text per check) or False/None
+        :param conv_crit: relative spread of the per-slice flux that counts as converged
+        :return: tau_x (local tortuosity profile) like the reference
+        """
+        if verbose in ('plot', 'debug'):
+            warnings.warn("verbose='plot'/'debug' need matplotlib/IPython; printing per-check text instead")
+            verbose = 'per_iter'
+        if verbose:
+            torch.cuda.reset_peak_memory_stats(device=self.device)
+        start = timer()
+        while not self.converged and self.iter < iter_limit:
+            self._advance(min(100 - self.iter % 100, iter_limit - self.iter))
+            if self.iter % 100 == 0:
+                self.converged = self.check_convergence(verbose, conv_crit, plot_interval)
+        torch.cuda.synchronize(self.device)
+        self.walltime = timer() - start
+        self._end_simulation(self.iter, verbose)
+        if self.tau_x is None:
+            return self.tau
+        return self.tau_x
+
+    def _advance(self, n):
+        """n reference iterations on the device, no check, no host sync (ref:175-182 x n)."""
+        self._lib.taub_set_device(self._dev_index)
+        flags = 1 if self.force_generic else 0
+        self._call(self._lib.taub_iterate(self._prob, self.iter, int(n), flags, self._stream()), "taub_iterate")
+        self.iter += int(n)
+
+    def _check_only(self):
+        """The reduction + device->host read of one convergence check, without the stop rule."""
+        return self._plane_means()
+
+    def sweep_kernel_name(self):
+        fused = (not self.force_generic) and self._lib.taub_can_fuse(self._prob) == 1
+        return "fused_sweep2_kernel" if fused else "half_sweep_kernel"
+
+    def _end_simulation(self, iterations, verbose):
+        """ref:255-269 -- same text (taufactor/benchmark.py:170-178 parses the GPU-RAM line)."""
+        if self.converged:
+            msg = "converged to"
+        else:
+            print("Warning: not converged")
+            msg = "unconverged value of tau"
+        if verbose:
+            print(f"{msg}: {self.tau} after: {iterations} iterations in: "
+                  f"{np.around(self.walltime, 4)} s "
+                  f"({np.around(self.walltime / max(iterations, 1), 4)} s/iter)")
+            print(f"GPU-RAM currently {torch.cuda.memory_allocated(device=self.device) / 1e6:.2f} MB "
+                  f"(max allocated {torch.cuda.max_memory_allocated(device=self.device) / 1e6:.2f} MB; "
+                  f"{torch.cuda.max_memory_reserved(device=self.device) / 1e6:.2f} MB reserved)")
+
+
+class ThroughTransportSolver(SORSolver):
+    """Dirichlet -0.5 / +0.5 in x, flux-based tau (ref:272-331)."""
+    top_bc, bot_bc = TOP_BC, BOT_BC
+
+
+class Solver(ThroughTransportSolver):
+    """Two-phase (binary) through-transport solver, ref:355-419.
+
+    Args:
+        img: binary image, labels in {0, 1} (1 = conductive); [X,Y], [X,Y,Z] or [B,X,Y,Z].
+        omega: over-relaxation factor (default 2 - pi / (1.5 Nx)).
+        D_0: reference diffusivity.
+        device: CUDA device.
+    """
+    _kind = _lib.BINARY
+
+    def __init__(self, img, omega=None, D_0=1, device='cuda'):
+        self._check_binary_labels(img)
+        self.conductive_labels = [1]
+        img4 = _expand_to_4d(img)
+        u8 = _as_uint8_labels(img4)
+
+        def prepare(hist):
+            sel = np.zeros(256, np.uint8)
+            sel[1] = 1
+            return sel
+
+        self._setup(img4, omega, device, u8, prepare, self._init_binary)
+        self.D_0 = D_0
+        self.D_mean = np.mean(self.vol_x, axis=1)     # ref:385
+
+    @staticmethod
+    def _check_binary_labels(img):
+        """ref:387-397 -- every voxel must be exactly 0 or 1."""
+        a = np.asarray(img)
+        if a.size and not np.logical_or(a == 0, a == 1).all():
+            raise ValueError(
+                "Input image must only contain 0s and 1s. "
+                "Your image must be segmented to use this tool. "
+                "If your image has been segmented, ensure your labels are "
+                "0 for non-conductive and 1 for conductive phase. "
+                f"Your image has the following labels: {np.unique(a)}. "
+                "If you have more than one conductive phase, use the multi-phase solver.")
+
+    def _init_binary(self, p, img_dev, vec):
+        codes = torch.empty(self._lib.taub_codes_elems(p.g), dtype=torch.int16, device=self.device)
+        p.codes = codes.data_ptr()
+        self._call(self._lib.taub_init_binary(p, img_dev.data_ptr(), 0, self.Nx, vec.data_ptr(),
+                                              self._stream()), "taub_init_binary")
+        return (codes, vec)
+
+    @property
+    def factor(self):
+        """The reference's prefactor tensor [bs,Nx,Ny,Nz] (ref:402-410), rebuilt on demand from
+        the 4-bit neighbour codes (values 1..8, inf where non-conductive or isolated)."""
+        g = self._geom
+        G = _lib.GHOST
+        codes = self._keep[0].view(g.bs, g.planes, g.rows, g.pitch // 4)[:, G:G + g.Nx, G:G + g.Ny]
+        c = codes.to(torch.int32) & 0xFFFF
+        nib = torch.stack([(c >> (4 * q)) & 15 for q in range(4)], dim=-1).reshape(g.bs, g.Nx, g.Ny, -1)
+        nib = nib[..., _lib.COL0:_lib.COL0 + g.Nz].to(torch.float32)
+        nib[nib == 0] = torch.inf
+        return nib
+
+
+class PeriodicSolver(Solver):
+    """Binary solver with periodic y/z boundaries, ref:481-505."""
+    _periodic = True
+
+
+class MultiPhaseSolver(ThroughTransportSolver):
+    """Multi-phase solver with per-phase diffusivities and harmonic-mean face conductances,
+    ref:508-620.
+
+    Args:
+        img: labelled image.
+        diffusivities: dict label -> diffusivity (>= 0); labels left out are isolating (warns).
+        D_scaling: reference diffusivity D_0.
+    """
+    _kind = _lib.MULTIPHASE
+
+    def __init__(self, img, diffusivities=None, D_scaling=1, omega=None, device='cuda'):
+        if diffusivities is None:
+            diffusivities = {0: 0, 1: 1}
+        if not isinstance(diffusivities, dict):
+            raise TypeError("diffusivities must be a dictionary mapping phase labels to diffusivities")
+        for phase, D_p in diffusivities.items():
+            if not isinstance(phase, (int, np.integer)):
+                raise TypeError(f"Phase label must be integer, got {type(phase).__name__}")
+            D_p = float(D_p)
+            if (not np.isfinite(D_p)) or (D_p < 0):
+                raise ValueError(f"Diffusivity for label {phase} must be finite and >= 0, got {D_p}")
+        self.Ds = diffusivities
+        img4 = _expand_to_4d(img)
+        u8 = _as_uint8_labels(img4)
+        if u8 is None:
+            # labels outside 0..255: remap to dense indices on the host
+            present, inv = np.unique(img4, return_inverse=True)
+            if len(present) > 255:
+                raise ValueError("more than 255 distinct phase labels")
+            u8 = inv.reshape(img4.shape).astype(np.uint8)
+            raw_of_u8 = list(present)
+        else:
+            raw_of_u8 = None
+        to_raw = (lambda v: raw_of_u8[v]) if raw_of_u8 is not None else (lambda v: v)
+
+        def prepare(hist):
+            present_u8 = np.flatnonzero(hist.sum(axis=0))
+            present_raw = [to_raw(int(v)) for v in present_u8]
+            missing = sorted(int(l) for l in present_raw if l not in self.Ds)   # ref:550-558
+            if missing:
+                warnings.warn("No diffusivity provided for phase label(s) "
+                              f"{missing}; assuming these phases are isolating.", UserWarning)
+                for lbl in missing:
+                    self.Ds[lbl] = 0.0
+            self.conductive_labels = [lbl for lbl, D_p in self.Ds.items() if D_p > 0]   # ref:560
+            L = len(present_u8)
+            if L > _lib.MAX_LABELS:
+                raise ValueError(f"at most {_lib.MAX_LABELS} distinct phases are supported, got {L}")
+            # dense phase tables: D per dense index (+ the isolating pseudo-phase L), ref:586-588
+            D = np.zeros(L + 1, np.float32)
+            map256 = np.full(256, L, np.uint8)
+            sel = np.zeros(256, np.uint8)
+            for d, v in enumerate(present_u8):
+                D[d] = np.float32(self.Ds[to_raw(int(v))])
+                map256[v] = d
+                sel[v] = 1 if D[d] > 0 else 0
+            self._dense_D, self._map256, self._L = D, map256, L
+            self._present = (present_u8, present_raw)
+            return sel
+
+        self._setup(img4, omega, device, u8, prepare, self._init_multi)
+        present_u8, present_raw = self._present
+        N = float(self.Nx) * self.Ny * self.Nz
+        self.VF = {int(r): self._hist[:, int(v)].astype(np.float64) / N for v, r in zip(present_u8, present_raw)}
+        self.D_0 = D_scaling
+        self.D_mean = np.sum([self.VF[z] * self.Ds.get(z, 0.0) for z in self.VF], axis=0)   # ref:569
+
+    @staticmethod
+    def harmonic_table(D):
+        """ref:577-583 -- ((2 a) b) / (a + b) in fp32, 0 where a + b == 0; symmetric table."""
+        a = D[:, None].astype(np.float32)
+        b = D[None, :].astype(np.float32)
+        denom = (a + b).astype(np.float32)
+        num = ((np.float32(2) * a).astype(np.float32) * b).astype(np.float32)
+        out = np.zeros_like(denom)
+        np.divide(num, denom, out=out, where=denom > 0)
+        return out.astype(np.float32)
+
+    def _init_multi(self, p, img_dev, vec):
+        dev = self.device
+        labels = torch.empty(self._lib.taub_field_elems(p.g), dtype=torch.uint8, device=dev)
+        lut = torch.from_numpy(self.harmonic_table(self._dense_D)).contiguous().to(dev)
+        cond = torch.from_numpy((self._dense_D > 0).astype(np.float32)).to(dev)
+        m256 = torch.from_numpy(self._map256).to(dev)
+        p.labels, p.lut, p.L = labels.data_ptr(), lut.data_ptr(), self._L
+        self._call(self._lib.taub_init_multiphase(p, img_dev.data_ptr(), 0, self.Nx, m256.data_ptr(),
+                                                  cond.data_ptr(), vec.data_ptr(), self._stream()),
+                   "taub_init_multiphase")
+        return (labels, lut, cond, m256, vec)
+
+
+class PeriodicMultiPhaseSolver(MultiPhaseSolver):
+    """Multi-phase solver with periodic y/z boundaries, ref:623-656."""
+    _periodic = True

@@ -1,0 +1,103 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads, exports every symbol the header
+declares, computes the storage geometry, and the Python surface raises the reference's errors."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from taufactor_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    from taufactor_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "taub200.h")).read()
+    declared = set(re.findall(r"\b(taub_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in taub200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes prototype"
+    assert lib.taub_abi_version() == 1
+
+
+def test_struct_layout_matches_header(lib):
+    import ctypes
+    from taufactor_b200 import _lib
+    assert ctypes.sizeof(_lib.Geom) == 10 * 4 + 2 * 8
+    assert _lib.Problem.field.offset == ctypes.sizeof(_lib.Geom) + 8
+    assert ctypes.sizeof(_lib.Problem) == ctypes.sizeof(_lib.Geom) + 8 + 5 * 8 + 8
+
+
+@pytest.mark.parametrize("shape", [(1, 512, 512, 512), (3, 11, 13, 9), (2, 30, 28, 1), (1, 8, 8, 2049)])
+def test_geometry(lib, shape):
+    from taufactor_b200 import _lib
+    g = _lib.Geom()
+    bs, Nx, Ny, Nz = shape
+    assert lib.taub_geom_init(g, bs, Nx, Ny, Nz, Nx, 0, 1) == 0
+    assert (g.planes, g.rows) == (Nx + 4, Ny + 4)
+    assert g.pitch % 8 == 0 and g.pitch >= Nz + 8 and g.pitch < Nz + 16
+    assert g.plane_stride == g.rows * g.pitch and g.image_stride == g.planes * g.plane_stride
+    assert lib.taub_field_elems(g) == bs * g.image_stride
+    assert lib.taub_codes_elems(g) * 4 == lib.taub_field_elems(g)
+    assert lib.taub_sums_ws_bytes(g) >= 16 * bs * Nx
+
+
+def test_geometry_rejects_bad_slab(lib):
+    from taufactor_b200 import _lib
+    g = _lib.Geom()
+    assert lib.taub_geom_init(g, 1, 10, 4, 4, 8, 0, 0) == _lib.ERR_ARG
+    assert b"slab" in lib.taub_last_error()
+    assert lib.taub_geom_init(g, 0, 10, 4, 4, 10, 0, 0) == _lib.ERR_ARG
+
+
+def test_reference_error_conventions():
+    """ref: taufactor.py:196-203 (TypeError / ValueError on the image), :391-397 (binary labels),
+    :539-546 (diffusivities); raised before any device work, like the reference."""
+    import taufactor_b200 as tau
+    with pytest.raises(TypeError):
+        tau.Solver([[0, 1], [1, 0]])
+    with pytest.raises(ValueError):
+        tau.Solver(np.ones((2, 2, 2, 2, 2)))
+    with pytest.raises(ValueError, match="only contain 0s and 1s"):
+        tau.Solver(np.full((4, 4, 4), 2))
+    with pytest.raises(ValueError):
+        tau.MultiPhaseSolver(np.zeros([6, 6, 6]), {0: 1.0, 1: -0.1})
+    with pytest.raises(TypeError):
+        tau.MultiPhaseSolver(np.zeros([6, 6, 6]), [1.0])
+    with pytest.raises(TypeError):
+        tau.MultiPhaseSolver(np.zeros([6, 6, 6]), {"a": 1.0})
+
+
+def test_no_cpu_fallback():
+    import torch
+    import taufactor_b200 as tau
+    with pytest.raises(RuntimeError, match="CUDA"):
+        tau.Solver(np.ones((4, 4, 4)), device="cpu")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            tau.Solver(np.ones((4, 4, 4)))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "taufactor_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_harmonic_table_matches_oracle():
+    from taufactor_b200.solvers import MultiPhaseSolver
+    from oracle import sor_numpy as orc
+    D = np.array([0.0, 1.0, 0.3, 2.0, 0.5, 1e-3, 0.0], np.float32)
+    t = MultiPhaseSolver.harmonic_table(D)
+    ref = orc.harmonic_mean(np.repeat(D[:, None], len(D), 1), np.repeat(D[None, :], len(D), 0))
+    assert np.array_equal(t, ref) and np.array_equal(t, t.T)

@@ -1,0 +1,224 @@
+"""Parity of the CUDA path (through the Python surface -> C ABI -> sm_100a kernels) against the
+oracle and the committed golden vectors of the reference.  Runs on the B200 box (-m gpu)."""
+import json
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SOLVE = json.load(open(os.path.join(HERE, "golden", "solve.json")))
+FIELDS = np.load(os.path.join(HERE, "golden", "fields.npz"))
+
+# tolerance north_star states: tau and D_eff within 1e-4 relative in fp32, same stop rule
+RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def tau():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import taufactor_b200
+    return taufactor_b200
+
+
+def make(tau, name, **over):
+    cls, build, ckw, skw, _ = cases.CASES[name]
+    ckw = {k: (dict(v) if isinstance(v, dict) else v) for k, v in ckw.items()}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        S = getattr(tau, cls)(build(), device="cuda", **ckw)
+    for k, v in over.items():
+        setattr(S, k, v)
+    return S, skw
+
+
+def oracle_state(name):
+    from oracle import sor_numpy as orc
+    cls, build, ckw, skw, _ = cases.CASES[name]
+    periodic = cls.startswith("Periodic")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if "MultiPhase" in cls:
+            d = ckw.get("diffusivities")
+            return orc.build_multiphase(build(), dict(d) if d else None, periodic=periodic, omega=ckw.get("omega"))
+        return orc.build_binary(build(), periodic=periodic, omega=ckw.get("omega"))
+
+
+def used_part(f):
+    """Everything a 7-point stencil can read: interior + the six ghost faces (no edges/corners)."""
+    m = np.zeros(f.shape[1:], bool)
+    m[1:-1, 1:-1, :] = True
+    m[1:-1, :, 1:-1] = True
+    m[:, 1:-1, 1:-1] = True
+    return f[:, m]
+
+
+# ------------------------------------------------------------------ bit-exact trajectories
+@pytest.mark.parametrize("name", cases.SNAPSHOT_CASES)
+@pytest.mark.parametrize("generic", [True, False])
+def test_field_bitwise_vs_reference_goldens(tau, name, generic):
+    S, _ = make(tau, name, force_generic=generic)
+    f0 = S.field.cpu().numpy()
+    assert np.array_equal(f0[:, 1:-1, 1:-1, 1:-1], FIELDS[f"{name}@0"][:, 1:-1, 1:-1, 1:-1])
+    if hasattr(S, "factor"):
+        assert np.array_equal(S.factor.cpu().numpy(), FIELDS[f"{name}@factor"])
+    for k in cases.SNAPSHOT_ITERS:
+        S.solve(iter_limit=k, verbose=False)
+        assert S.iter == k
+        got = S.field.cpu().numpy()
+        ref = FIELDS[f"{name}@{k}"]
+        assert np.array_equal(got[:, 1:-1, 1:-1, 1:-1], ref[:, 1:-1, 1:-1, 1:-1]), (name, k)
+        if not type(S).__name__.startswith("Periodic"):
+            assert np.array_equal(used_part(got), used_part(ref)), (name, k)
+
+
+@pytest.mark.parametrize("name", ["rand40", "blobs64_per", "blobs3_48_mp", "blobs3_48_pmp", "batch3_blobs48",
+                                  "flat2d_per_batch", "omega_custom"])
+@pytest.mark.parametrize("generic", [True, False])
+def test_field_bitwise_vs_oracle_after_57_iterations(tau, name, generic):
+    from oracle import sor_c
+    S, _ = make(tau, name, force_generic=generic)
+    st = oracle_state(name)
+    S.solve(iter_limit=57, verbose=False)
+    sor_c.sweep(st, 57)
+    got = S.field.cpu().numpy()
+    assert np.array_equal(got[:, 1:-1, 1:-1, 1:-1], st["field"][:, 1:-1, 1:-1, 1:-1])
+    assert np.array_equal(S.vol_x, st["vol_x"])
+    assert np.allclose(np.atleast_1d(S.D_mean), np.atleast_1d(st["D_mean"]), rtol=1e-7)
+
+
+# ------------------------------------------------------------------ end-to-end solves
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_solve_matches_reference(tau, name):
+    S, skw = make(tau, name)
+    S.solve(verbose=False, **skw)
+    g = SOLVE[name]
+    assert S.iter == g["iter"], "stop rule fired at a different check"
+    assert bool(S.converged) == g["converged"]
+    gt, gd = np.array(g["tau"], np.float64), np.array(g["D_eff"], np.float64)
+    t, d = np.asarray(S.tau, np.float64), np.asarray(S.D_eff, np.float64)
+    assert t.shape == gt.shape
+    fin = np.isfinite(gt)
+    assert np.array_equal(np.isfinite(t), fin)
+    if abs(gt[fin]).max(initial=0) < 1e-6:      # diverged (odd periodic dims): reference blows up too
+        return
+    assert np.allclose(t[fin], gt[fin], rtol=RTOL, atol=0)
+    assert np.allclose(d[fin], gd[fin], rtol=RTOL, atol=1e-9)
+    exp = cases.CASES[name][4]
+    if exp is not None:                        # the reference's own assertions, tests/test_taufactor.py
+        kind, val = exp
+        if kind == "inf":
+            assert np.all(np.isinf(S.tau))
+        else:
+            assert np.around(S.tau, decimals=int(kind[3:]))[0] == val
+    assert S.tau.dtype == np.float32 and S.tau.shape == (S.batch_size,)
+    assert S.tau_x.shape == (S.batch_size, S.Nx - 1) and S.c_x.shape == (S.batch_size, S.Nx)
+
+
+def test_deadend_reference_assertions(tau):
+    """ref tests/test_taufactor.py:68-76."""
+    S, _ = make(tau, "ref_deadend")
+    S.solve(verbose=False)
+    assert np.around(S.D_eff, decimals=5) == 0
+    assert S.tau == np.inf
+
+
+def test_missing_diffusivities_warn(tau):
+    """ref tests/test_taufactor.py:170-178."""
+    N = 10
+    img = np.zeros([N, N, N])
+    img[:, :, : N // 2] = 1
+    img[:, :, N // 2:] = 2
+    with pytest.warns(UserWarning, match="assuming these phases are isolating."):
+        s = tau.MultiPhaseSolver(img, {1: 1.0}, device="cuda")
+    assert s.Ds[2] == 0.0
+
+
+def test_cross_solver_equivalences(tau):
+    """ref tests/test_taufactor.py:195-247: MultiPhase == Solver on binary input; batched ==
+    per-sample; PeriodicMultiPhase == PeriodicSolver on odd periodic dims."""
+    img = cases.slanted_strip()
+    a = tau.Solver(img, device="cuda"); a.solve(iter_limit=1000, verbose=False)
+    b = tau.MultiPhaseSolver(img, device="cuda"); b.solve(iter_limit=1000, verbose=False)
+    assert np.isclose(float(a.tau[0]), float(b.tau[0]), atol=1e-3)
+    imgs = cases.batched_mp()
+    Ds = {0: 0.0, 1: 1.0, 2: 0.5}
+    sb = tau.MultiPhaseSolver(imgs, dict(Ds), device="cuda"); sb.solve(iter_limit=1000, verbose=False)
+    s0 = tau.MultiPhaseSolver(imgs[0], dict(Ds), device="cuda"); s0.solve(iter_limit=1000, verbose=False)
+    s1 = tau.MultiPhaseSolver(imgs[1], dict(Ds), device="cuda"); s1.solve(iter_limit=1000, verbose=False)
+    assert np.allclose(np.asarray(sb.tau), np.array([s0.tau[0], s1.tau[0]]), atol=1e-3)
+
+
+def test_solve_resumes_and_reports(tau, capsys):
+    """iter / field persist across solve() calls (ref:62-67, :174); the printed report keeps the
+    reference's format (ref:255-269; benchmark.py:170-178 parses the GPU-RAM line)."""
+    S, _ = make(tau, "rand40")
+    assert S.solve(iter_limit=50, verbose=False) is None and S.tau is None   # N5: < 100 iterations
+    S.solve(iter_limit=150, verbose=False)
+    assert S.iter == 150 and S.tau is not None
+    S.solve(verbose='per_iter')
+    out = capsys.readouterr().out
+    assert S.iter == SOLVE["rand40"]["iter"]
+    assert "converged to:" in out and "GPU-RAM currently" in out and "max allocated" in out
+    assert "Iter: 200, conv error:" in out
+
+
+# ------------------------------------------------------------------ larger volumes vs the C oracle
+@pytest.mark.parametrize("cls,periodic", [("Solver", False), ("PeriodicSolver", True)])
+def test_blobs128_solve_vs_oracle(tau, cls, periodic):
+    from oracle import sor_c, sor_numpy as orc
+    img = cases.blobs(128, 0.5, seed=128)
+    S = getattr(tau, cls)(img, device="cuda")
+    S.solve(verbose=False)
+    st = orc.build_binary(img, periodic=periodic)
+    orc.solve(st, sweep=lambda s, n: sor_c.sweep_threaded(s, n, os.cpu_count() or 1))
+    assert S.iter == st["iter"]
+    assert np.allclose(S.tau, st["tau"], rtol=RTOL) and np.allclose(S.D_eff, st["D_eff"], rtol=RTOL)
+    assert np.array_equal(S.field.cpu().numpy()[:, 1:-1, 1:-1, 1:-1], st["field"][:, 1:-1, 1:-1, 1:-1])
+    if not periodic:
+        assert abs(float(S.tau[0]) - 1.9421792) < 2e-4       # SURVEY.md 8c probe golden (reference, CPU)
+
+
+def test_three_phase_96_goldens(tau):
+    """SURVEY.md 8c probe goldens produced by the reference: 1.7569389 / 1.7266513 @ 300."""
+    img = cases.blobs3(96, seed=768)
+    Ds = {0: 0.0, 1: 1.0, 2: 0.3}
+    a = tau.MultiPhaseSolver(img, dict(Ds), device="cuda"); a.solve(verbose=False)
+    b = tau.PeriodicMultiPhaseSolver(img, dict(Ds), device="cuda"); b.solve(verbose=False)
+    assert a.iter == 300 and b.iter == 300
+    assert abs(float(a.tau[0]) / 1.7569389 - 1) < RTOL and abs(float(b.tau[0]) / 1.7266513 - 1) < RTOL
+    assert abs(float(a.D_eff[0]) / 0.2418978 - 1) < RTOL and abs(float(b.D_eff[0]) / 0.2461410 - 1) < RTOL
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_size_properties_384(tau):
+    """At a size the oracle cannot sweep in seconds: (i) the fused and the generic kernels give
+    the same bits, (ii) the discrete maximum principle holds (field within the Dirichlet values),
+    (iii) non-conductive voxels stay exactly 0, (iv) flux profile flattens monotonically."""
+    import torch
+    img = cases.random_img(384, 0.65, seed=3)
+    A = tau.Solver(img, device="cuda")
+    B = tau.Solver(img, device="cuda")
+    B.force_generic = True
+    A.solve(iter_limit=200, verbose=False)
+    B.solve(iter_limit=200, verbose=False)
+    fa, fb = A.field[:, 1:-1, 1:-1, 1:-1], B.field[:, 1:-1, 1:-1, 1:-1]
+    assert torch.equal(fa, fb)
+    assert float(fa.max()) <= 1.0 and float(fa.min()) >= -1.0
+    solid = torch.from_numpy(img == 0).to(fa.device)[None]
+    assert float(fa[solid].abs().max()) == 0.0
+    assert np.array_equal(A.flux_1d, B.flux_1d)
+    assert np.array_equal(A.tau, B.tau)
+
+
+def test_uniform_block_analytic_256(tau):
+    """Analytic known answer at size: an all-conductive block has tau = 1 (ref tests :12-37)."""
+    S = tau.Solver(np.ones((256, 256, 256), np.uint8), device="cuda")
+    S.solve(verbose=False)
+    assert abs(float(S.tau[0]) - 1.0) < 1e-5

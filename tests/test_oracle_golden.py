@@ -94,3 +94,17 @@ def test_numpy_and_c_sweeps_agree_on_cfg1_prefix():
         orc.half_sweep(st1)
     sor_c.sweep(st2, 7)
     assert np.array_equal(st1["field"], st2["field"])
+
+
+@pytest.mark.parametrize("name", ["odd_11_13_9_per", "odd3_pmp", "rand40"])
+def test_torch_eager_port_is_bitwise_the_same(name):
+    from oracle import sor_torch
+    st, _ = build_state(name)
+    t = sor_torch.from_state(st)
+    for _ in range(9):
+        orc.half_sweep(st)
+        sor_torch.half_sweep(t)
+    assert np.array_equal(t["field"].numpy(), st["field"])
+    fl, cm = sor_torch.flux_check(t)
+    fl2, cm2 = orc.plane_means(st)
+    assert np.allclose(fl, fl2, rtol=1e-5, atol=1e-9) and np.allclose(cm, cm2, rtol=1e-5, atol=1e-9)
