@@ -1,19 +1,319 @@
-// taub_fused.cu -- temporally blocked two-colour sweep (placeholder until the kernel lands).
+// taub_fused.cu -- temporally blocked two-colour sweep: TWO reference iterations per HBM pass.
+//
+// One pass reads the field once and writes it once while applying iteration t (colour A) and
+// iteration t+1 (colour B) of taufactor.py:174-182, i.e. 4 B + 0.25 B of traffic per voxel per
+// iteration instead of 8.5 (generic kernel) or 108 (reference eager path).
+//
+// Structure (per CTA): a (rows x z-groups) tile marched along x (the flux / slab axis).
+//   * plane staging: every needed x-plane of the tile (output tile + 2 halo rows, + 1 halo float4
+//     group each side) is brought into a 6-deep shared-memory ring by the TMA bulk-copy engine
+//     (cp.async.bulk, one row per copy, completion on an mbarrier) three planes ahead of use;
+//   * register rotation: each thread owns NI float4 columns and keeps a[p-2], a[p-1], raw[p],
+//     raw[p+1] of its columns in registers, so x-neighbours never touch shared memory;
+//   * wavefront: at step p colour A is applied to plane p (in place in shared memory -- legal
+//     because a colour-A voxel only reads colour-B neighbours) and colour B to plane p-1, whose
+//     result goes straight from registers to the destination buffer with 128-bit stores.
+// y/z halos are recomputed by the neighbouring tile (overlapped tiling); the source buffer is
+// read-only during the pass (ping-pong), so there is no inter-CTA hazard.  The arithmetic per
+// voxel is the same correctly rounded sequence as the generic kernel: results are bit-identical.
 #include "taub_common.cuh"
+
+namespace taub {
+
+constexpr int F_NT = 256;  // threads per CTA
+constexpr int F_NB = 6;    // ring depth (planes in shared memory)
+
+struct FusedParams {
+    taub_geom g;
+    const float *src;
+    float *dst;
+    const uint16_t *codes;
+    float omega;
+    int colourA;
+    int i_lo, i_hi;    // output planes (local)
+    int a_lo, a_hi;    // planes that receive the colour-A update (output planes +-1, clipped to real planes)
+    int LR, LG, LGp;   // loaded rows, loaded float4 groups, groups rounded up to 16 (thread map)
+    int OR_, OG;       // output rows / groups per tile
+    int tiles_k;
+    int chunk_len;     // output planes per CTA
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// Colour update of two voxels of a float4 (x,z when par == 0, y,w when par == 1).
+// c: centre group, xp/xm: x neighbours (registers), up/dn: y+1 / y-1 groups, zl: z-1 of .x (par 0)
+// or z+1 of .w (par 1) -- the one scalar that lives in the adjacent group.
+__device__ __forceinline__ float4 colour_update(float4 c, const float4 &xp, const float4 &xm, const float4 &up,
+                                                const float4 &dn, float zs, int par, unsigned code,
+                                                const float2 *s_div, float omega)
+{
+    if (par == 0) {
+        c.x = sor_binary(c.x, xp.x, xm.x, up.x, dn.x, c.y, zs, s_div[code & 15u], omega);
+        c.z = sor_binary(c.z, xp.z, xm.z, up.z, dn.z, c.w, c.y, s_div[(code >> 8) & 15u], omega);
+    } else {
+        c.y = sor_binary(c.y, xp.y, xm.y, up.y, dn.y, c.z, c.x, s_div[(code >> 4) & 15u], omega);
+        c.w = sor_binary(c.w, xp.w, xm.w, up.w, dn.w, zs, c.z, s_div[(code >> 12) & 15u], omega);
+    }
+    return c;
+}
+
+template <int NI>
+__global__ void __launch_bounds__(F_NT, 2) fused_sweep2_kernel(const FusedParams P)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const taub_geom &g = P.g;
+    const int LR = P.LR, LG = P.LG;
+    const int plane_f4 = LR * LG;
+    float4 *planes = reinterpret_cast<float4 *>(smem_raw);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)F_NB * plane_f4 * 16);
+    float2 *s_div = reinterpret_cast<float2 *>(mbar + F_NB);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tk = blockIdx.x % P.tiles_k, tj = blockIdx.x / P.tiles_k;
+    const int b = blockIdx.z;
+    const int c0 = P.i_lo + blockIdx.y * P.chunk_len;
+    const int c1 = min(c0 + P.chunk_len, P.i_hi);
+    const int R0 = tj * P.OR_, G0 = tk * P.OG;   // storage row / group of loaded (0, 0)
+    const int PG = g.pitch >> 2;
+    const int nrows_valid = min(LR, g.rows - R0);
+    const int rowbytes = min(LG, PG - G0) * 16;
+    const int total_rel = c1 - c0 + 4;           // planes c0-2 .. c1+1
+    const int64_t ps = g.plane_stride;
+
+    for (int i = tid; i < F_NB * plane_f4; i += F_NT) planes[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < 16) s_div[tid] = div_entry(tid);
+    if (tid == 0) {
+        for (int n = 0; n < F_NB; ++n) mbar_init(smem_u32(&mbar[n]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const float *src_tile = P.src + (int64_t)b * g.image_stride + (int64_t)R0 * g.pitch + 4 * G0;
+    // warp 0 stages plane rel (local plane c0-2+rel) into ring slot rel % NB, one bulk copy per row
+    auto issue = [&](int rel) {
+        const int slot = rel % F_NB;
+        const uint32_t bar = smem_u32(&mbar[slot]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (lane == 0) mbar_expect_tx(bar, (uint32_t)(nrows_valid * rowbytes));
+        __syncwarp();
+        const float *sp = src_tile + (int64_t)(c0 - 2 + rel + G) * ps;
+        const uint32_t dp = smem_u32(planes + (size_t)slot * plane_f4);
+        for (int lr = lane; lr < nrows_valid; lr += 32)
+            bulk_g2s(dp + (uint32_t)(lr * LG * 16), sp + (int64_t)lr * g.pitch, (uint32_t)rowbytes, bar);
+    };
+    if (warp == 0)
+        for (int rel = 0; rel < min(F_NB - 1, total_rel); ++rel) issue(rel);
+
+    // ---- per-thread items: fixed (row, group) columns, rows permuted so that a warp sees one parity
+    const int NR = LR - 2, n_even = (NR + 1) >> 1;
+    int idx[NI];          // float4 index inside a plane buffer
+    int64_t goff[NI];     // element offset of the group in local plane 0 (storage plane G)
+    int jpar[NI];
+    bool doit[NI], canB[NI];
+#pragma unroll
+    for (int n = 0; n < NI; ++n) {
+        const int u = tid + n * F_NT;
+        const int rr = u / P.LGp, gg = u - rr * P.LGp;
+        const int lr = 1 + (rr < n_even ? 2 * rr : 2 * (rr - n_even) + 1);
+        const int R = R0 + lr, Gs = G0 + gg;
+        doit[n] = (rr < NR) && (gg < LG) && (R < g.rows - 1) && (Gs < PG);
+        canB[n] = doit[n] && lr >= 2 && lr < LR - 2 && gg >= 1 && gg < LG - 1 && R >= G && R < G + g.Ny &&
+                  Gs >= 1 && Gs < 1 + interior_groups(g.Nz);
+        idx[n] = lr * LG + gg;
+        goff[n] = (int64_t)b * g.image_stride + (int64_t)G * ps + (int64_t)R * g.pitch + 4 * Gs;
+        jpar[n] = (R - G + g.i_offset + P.colourA) & 1;
+    }
+
+    // ---- prologue: a[c0-2] (only ever read as an x-neighbour) and raw[c0-1]
+    mbar_wait(smem_u32(&mbar[0]), 0);
+    mbar_wait(smem_u32(&mbar[1 % F_NB]), 0);
+    float4 am2[NI], am1[NI], r0[NI];
+    unsigned codeA[NI], codeB[NI];
+#pragma unroll
+    for (int n = 0; n < NI; ++n) {
+        am2[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+        am1[n] = r0[n] = am2[n];
+        codeA[n] = codeB[n] = 0;
+        if (doit[n]) {
+            am1[n] = planes[idx[n]];
+            r0[n] = planes[plane_f4 + idx[n]];
+            codeA[n] = P.codes[(goff[n] + (int64_t)(c0 - 1) * ps) >> 2];
+        }
+    }
+
+    const int n_steps = c1 - c0 + 2;
+    for (int s = 0; s < n_steps; ++s) {
+        const int p = c0 - 1 + s;   // plane receiving colour A; colour B goes to plane p-1
+        __syncthreads();            // ring slot of plane p-2 is free; a[p-1] is visible in its slot
+        if (warp == 0 && s - 1 + F_NB < total_rel) issue(s - 1 + F_NB);
+        mbar_wait(smem_u32(&mbar[(s + 2) % F_NB]), (uint32_t)(((s + 2) / F_NB) & 1));
+        const float4 *bufM1 = planes + (size_t)(s % F_NB) * plane_f4;
+        float4 *bufP = planes + (size_t)((s + 1) % F_NB) * plane_f4;
+        const float4 *bufP1 = planes + (size_t)((s + 2) % F_NB) * plane_f4;
+        const bool doA = (p >= P.a_lo) && (p < P.a_hi);
+        const bool keepA = (p >= c0) && (p < c1);   // a[p] is read by colour B of plane p next step
+        const bool doB = (s >= 2);
+#pragma unroll
+        for (int n = 0; n < NI; ++n) {
+            if (!doit[n]) continue;
+            const int i4 = idx[n];
+            const float4 rp1 = bufP1[i4];
+            unsigned codeN = 0;
+            if (s + 1 < n_steps) codeN = P.codes[(goff[n] + (int64_t)(p + 1) * ps) >> 2];
+            const int par = (jpar[n] + p) & 1;
+            const int zoff = par ? 4 * i4 + 4 : 4 * i4 - 1;   // z+1 of .w / z-1 of .x
+            float4 a0 = r0[n];
+            if (doA) {
+                const float4 up = bufP[i4 + LG], dn = bufP[i4 - LG];
+                const float zs = reinterpret_cast<const float *>(bufP)[zoff];
+                a0 = colour_update(a0, rp1, am1[n], up, dn, zs, par, codeA[n], s_div, P.omega);
+                if (keepA) bufP[i4] = a0;
+            }
+            if (doB && canB[n]) {
+                const float4 up = bufM1[i4 + LG], dn = bufM1[i4 - LG];
+                const float zs = reinterpret_cast<const float *>(bufM1)[zoff];
+                const float4 out = colour_update(am1[n], a0, am2[n], up, dn, zs, par, codeB[n], s_div, P.omega);
+                *reinterpret_cast<float4 *>(P.dst + goff[n] + (int64_t)(p - 1) * ps) = out;
+            }
+            am2[n] = am1[n];
+            am1[n] = a0;
+            r0[n] = rp1;
+            codeB[n] = codeA[n];
+            codeA[n] = codeN;
+        }
+    }
+}
+
+struct TileChoice {
+    int NI, LR, LG, LGp, OR_, OG, tiles_j, tiles_k;
+    double eff;
+};
+
+// Pick the tile shape that wastes the fewest thread-items: items = NI*256 per tile, rows are
+// split into NR = items / LGp rows of LGp (multiple of 16) group slots.
+static TileChoice choose_tile(const taub_geom &g)
+{
+    const int ng = interior_groups(g.Nz);
+    TileChoice best{};
+    best.eff = -1.0;
+    for (int NI = 2; NI <= 3; ++NI) {
+        for (int LGp = 16; LGp <= 256; LGp += 16) {
+            const int NR = (NI * F_NT) / LGp;
+            if (NR < 4) break;
+            int LG = LGp;
+            if (LG > ng + 2) LG = ng + 2;            // never wider than the row needs
+            if (LG <= LGp - 16) continue;            // a smaller LGp covers it
+            const int OR_ = NR - 2, OG = LG - 2;
+            const int LR = NR + 2;
+            if (OR_ < 1 || OG < 1) continue;
+            const size_t smem = (size_t)F_NB * LR * LG * 16 + 256;
+            if (smem > 110 * 1024) continue;         // two CTAs per SM
+            const int tj = ceil_div(g.Ny, OR_), tk = ceil_div(ng, OG);
+            double eff = ((double)g.Ny * ng) / ((double)tj * tk * NI * F_NT);
+            if (NI == 4) eff *= 0.97;                // register pressure tie-break
+            if (eff > best.eff) best = TileChoice{NI, LR, LG, LGp, OR_, OG, tj, tk, eff};
+        }
+    }
+    return best;
+}
+
+}  // namespace taub
+
+using namespace taub;
 
 extern "C" {
 
 int taub_can_fuse(const taub_problem *p)
 {
-    (void)p;
-    return 0;
+    if (!p || p->kind != TAUB_BINARY || !p->codes || !p->field[0] || !p->field[1]) return 0;
+    const taub_geom &g = p->g;
+    // periodic wrap with odd Ny/Nz couples two voxels of the SAME colour (reference reads a ghost
+    // snapshot); the in-place shared-memory colour update cannot express that -> generic path.
+    if (g.periodic && ((g.Ny & 1) || (g.Nz & 1))) return 0;
+    if (g.bs > 65535) return 0;
+    return choose_tile(g).eff > 0.0 ? 1 : 0;
 }
 
 int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, void *stream)
 {
-    (void)p; (void)iter; (void)i_lo; (void)i_hi; (void)stream;
-    taub::set_error("taub_fused_sweep2: not available for this problem");
-    return TAUB_ERR_UNSUPPORTED;
+    if (taub_can_fuse(p) != 1) {
+        set_error("taub_fused_sweep2: problem does not qualify for the fused path");
+        return TAUB_ERR_UNSUPPORTED;
+    }
+    const taub_geom &g = p->g;
+    TAUB_REQUIRE(i_lo >= 0 && i_hi <= g.Nx && i_lo < i_hi, "taub_fused_sweep2: planes [%d, %d) outside the slab", i_lo, i_hi);
+    const TileChoice t = choose_tile(g);
+    FusedParams P;
+    P.g = g;
+    P.src = p->field[p->cur];
+    P.dst = p->field[p->cur ^ 1];
+    P.codes = p->codes;
+    P.omega = p->omega;
+    P.colourA = (int)(iter & 1);
+    P.i_lo = i_lo;
+    P.i_hi = i_hi;
+    P.a_lo = max(i_lo - 1, -g.i_offset);
+    P.a_hi = min(i_hi + 1, g.Nx_global - g.i_offset);
+    P.LR = t.LR; P.LG = t.LG; P.LGp = t.LGp; P.OR_ = t.OR_; P.OG = t.OG;
+    P.tiles_k = t.tiles_k;
+    // planes per CTA: ~3 waves of CTAs on 148 SMs x 2, but at least 16 planes to amortise the
+    // 4-plane prologue
+    const int n_planes = i_hi - i_lo;
+    const int64_t tiles = (int64_t)t.tiles_j * t.tiles_k * g.bs;
+    int chunks = (int)ceil_div64(3 * 148 * 2, tiles);
+    if (chunks < 1) chunks = 1;
+    int chunk_len = ceil_div(n_planes, chunks);
+    if (chunk_len < 16) chunk_len = min(16, n_planes);
+    chunks = ceil_div(n_planes, chunk_len);
+    P.chunk_len = chunk_len;
+    TAUB_REQUIRE(chunks <= 65535, "taub_fused_sweep2: too many plane chunks");
+    const size_t smem = (size_t)F_NB * t.LR * t.LG * 16 + F_NB * 8 + 16 * 8;
+    dim3 grid(t.tiles_j * t.tiles_k, chunks, g.bs);
+    cudaStream_t s = (cudaStream_t)stream;
+#define TAUB_LAUNCH_FUSED(NI_)                                                                               \
+    do {                                                                                                     \
+        TAUB_CUDA(cudaFuncSetAttribute(fused_sweep2_kernel<NI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)smem));                                                          \
+        fused_sweep2_kernel<NI_><<<grid, F_NT, smem, s>>>(P);                                                \
+    } while (0)
+    if (t.NI == 2)
+        TAUB_LAUNCH_FUSED(2);
+    else if (t.NI == 3)
+        TAUB_LAUNCH_FUSED(3);
+    else
+        TAUB_LAUNCH_FUSED(4);
+#undef TAUB_LAUNCH_FUSED
+    TAUB_CUDA(cudaGetLastError());
+    count_launch();
+    return TAUB_OK;
 }
 
 }  // extern "C"
