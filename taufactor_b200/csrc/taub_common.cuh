@@ -49,7 +49,7 @@ static inline __host__ __device__ int interior_groups(int Nz) { return (Nz + 3) 
 // (taufactor.py:177).  For a divisor c with correctly rounded reciprocal r = RN(1/c) the
 // Markstein sequence  q0 = RN(s*r); rem = s - q0*c (exact, one FMA); q = RN(q0 + rem*r)
 // returns the correctly rounded quotient for every normal s (checked exhaustively over all 2^23
-// mantissas for c = 1..8).  Tiny |s| (< 2^-100, where the remainder could go subnormal), inf and
+// mantissas for c = 1..8).  Tiny non-zero |s| (< 2^-100, where the remainder could go subnormal), inf and
 // NaN take the __fdiv_rn path, so the result is bit-identical to IEEE division everywhere.
 // Table entry for code 0 ("factor = inf": non-conductive voxel or no conductive neighbour) is
 // (c, r) = (0, 0), which yields q = 0 = s / inf without a special case.
@@ -66,8 +66,10 @@ __device__ __forceinline__ float div_small(float s, float2 cr)
     float q0 = __fmul_rn(s, cr.y);
     float rem = __fmaf_rn(-q0, cr.x, s);
     float q = __fmaf_rn(rem, cr.y, q0);
-    const unsigned e = __float_as_uint(s) & 0x7f800000u;
-    if ((e - (27u << 23)) >= ((255u - 27u) << 23)) {  // exponent < 27 (|s| < 2^-100) or inf/NaN
+    // rare path: 0 < |s| < 2^-100, inf or NaN.  s == 0 (every voxel inside the solid phase) must
+    // stay on the fast path: the sequence above already returns the exact 0.
+    const unsigned a = __float_as_uint(s) & 0x7fffffffu;
+    if ((a - (27u << 23)) >= ((255u - 27u) << 23) && a != 0u) {
         q = (cr.x > 0.0f) ? __fdiv_rn(s, cr.x) : __fdiv_rn(s, __int_as_float(0x7f800000));
     }
     return q;

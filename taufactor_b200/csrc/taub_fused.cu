@@ -6,8 +6,9 @@
 //
 // Structure (per CTA): a (rows x z-groups) tile marched along x (the flux / slab axis).
 //   * plane staging: every needed x-plane of the tile (output tile + 2 halo rows, + 1 halo float4
-//     group each side) is brought into a 6-deep shared-memory ring by the TMA bulk-copy engine
-//     (cp.async.bulk, one row per copy, completion on an mbarrier) three planes ahead of use;
+//     group each side) is brought into a 6-deep shared-memory ring by TMA: ONE
+//     cp.async.bulk.tensor.3d box (rows x columns x 1 plane, out-of-bounds zero filled) per plane,
+//     completion on an mbarrier, issued three planes ahead of use;
 //   * register rotation: each thread owns NI float4 columns and keeps a[p-2], a[p-1], raw[p],
 //     raw[p+1] of its columns in registers, so x-neighbours never touch shared memory;
 //   * wavefront: at step p colour A is applied to plane p (in place in shared memory -- legal
@@ -16,6 +17,8 @@
 // y/z halos are recomputed by the neighbouring tile (overlapped tiling); the source buffer is
 // read-only during the pass (ping-pong), so there is no inter-CTA hazard.  The arithmetic per
 // voxel is the same correctly rounded sequence as the generic kernel: results are bit-identical.
+#include <cuda.h>   // CUtensorMap types only; the encoder is fetched through the runtime (no -lcuda)
+
 #include "taub_common.cuh"
 
 namespace taub {
@@ -36,6 +39,7 @@ struct FusedParams {
     int OR_, OG;       // output rows / groups per tile
     int tiles_k;
     int chunk_len;     // output planes per CTA
+    int slot_f4;       // float4 per ring slot
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -61,11 +65,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
             : "memory");
     } while (!ok);
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+// One TMA box: tensor coordinates (column, row, plane) in elements -> shared memory, signalling bar.
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
 }
 
 // Colour update of two voxels of a float4 (x,z when par == 0, y,w when par == 1).
@@ -86,25 +92,26 @@ __device__ __forceinline__ float4 colour_update(float4 c, const float4 &xp, cons
 }
 
 template <int NI>
-__global__ void __launch_bounds__(F_NT, 2) fused_sweep2_kernel(const FusedParams P)
+__global__ void __launch_bounds__(F_NT, 2)
+fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tmap)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ unsigned char smem_dyn[];
+    // TMA destinations need 128-byte alignment: align the base, slots are multiples of 128 B
+    unsigned char *smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
     const taub_geom &g = P.g;
     const int LR = P.LR, LG = P.LG;
-    const int plane_f4 = LR * LG;
+    const int plane_f4 = P.slot_f4;              // ring slot size in float4 (>= LR*LG, multiple of 8)
     float4 *planes = reinterpret_cast<float4 *>(smem_raw);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)F_NB * plane_f4 * 16);
     float2 *s_div = reinterpret_cast<float2 *>(mbar + F_NB);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int tk = blockIdx.x % P.tiles_k, tj = blockIdx.x / P.tiles_k;
     const int b = blockIdx.z;
     const int c0 = P.i_lo + blockIdx.y * P.chunk_len;
     const int c1 = min(c0 + P.chunk_len, P.i_hi);
     const int R0 = tj * P.OR_, G0 = tk * P.OG;   // storage row / group of loaded (0, 0)
     const int PG = g.pitch >> 2;
-    const int nrows_valid = min(LR, g.rows - R0);
-    const int rowbytes = min(LG, PG - G0) * 16;
     const int total_rel = c1 - c0 + 4;           // planes c0-2 .. c1+1
     const int64_t ps = g.plane_stride;
 
@@ -116,20 +123,16 @@ __global__ void __launch_bounds__(F_NT, 2) fused_sweep2_kernel(const FusedParams
     }
     __syncthreads();
 
-    const float *src_tile = P.src + (int64_t)b * g.image_stride + (int64_t)R0 * g.pitch + 4 * G0;
-    // warp 0 stages plane rel (local plane c0-2+rel) into ring slot rel % NB, one bulk copy per row
+    // one thread stages plane rel (local plane c0-2+rel) into ring slot rel % NB with one TMA box
+    // (columns 4*G0.., rows R0.., one plane); the part of the box outside the tensor reads as 0
     auto issue = [&](int rel) {
         const int slot = rel % F_NB;
         const uint32_t bar = smem_u32(&mbar[slot]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (lane == 0) mbar_expect_tx(bar, (uint32_t)(nrows_valid * rowbytes));
-        __syncwarp();
-        const float *sp = src_tile + (int64_t)(c0 - 2 + rel + G) * ps;
-        const uint32_t dp = smem_u32(planes + (size_t)slot * plane_f4);
-        for (int lr = lane; lr < nrows_valid; lr += 32)
-            bulk_g2s(dp + (uint32_t)(lr * LG * 16), sp + (int64_t)lr * g.pitch, (uint32_t)rowbytes, bar);
+        mbar_expect_tx(bar, (uint32_t)(LR * LG * 16));
+        tma_load_3d(smem_u32(planes + (size_t)slot * plane_f4), &tmap, 4 * G0, R0, b * g.planes + (c0 - 2 + rel + G), bar);
     };
-    if (warp == 0)
+    if (tid == 0)
         for (int rel = 0; rel < min(F_NB - 1, total_rel); ++rel) issue(rel);
 
     // ---- per-thread items: fixed (row, group) columns, rows permuted so that a warp sees one parity
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(F_NT, 2) fused_sweep2_kernel(const FusedParams
     for (int s = 0; s < n_steps; ++s) {
         const int p = c0 - 1 + s;   // plane receiving colour A; colour B goes to plane p-1
         __syncthreads();            // ring slot of plane p-2 is free; a[p-1] is visible in its slot
-        if (warp == 0 && s - 1 + F_NB < total_rel) issue(s - 1 + F_NB);
+        if (tid == 0 && s - 1 + F_NB < total_rel) issue(s - 1 + F_NB);
         mbar_wait(smem_u32(&mbar[(s + 2) % F_NB]), (uint32_t)(((s + 2) / F_NB) & 1));
         const float4 *bufM1 = planes + (size_t)(s % F_NB) * plane_f4;
         float4 *bufP = planes + (size_t)((s + 1) % F_NB) * plane_f4;
@@ -225,7 +228,7 @@ static TileChoice choose_tile(const taub_geom &g)
     TileChoice best{};
     best.eff = -1.0;
     for (int NI = 2; NI <= 3; ++NI) {
-        for (int LGp = 16; LGp <= 256; LGp += 16) {
+        for (int LGp = 16; LGp <= 64; LGp += 16) {   // TMA box: at most 256 elements wide
             const int NR = (NI * F_NT) / LGp;
             if (NR < 4) break;
             int LG = LGp;
@@ -234,7 +237,7 @@ static TileChoice choose_tile(const taub_geom &g)
             const int OR_ = NR - 2, OG = LG - 2;
             const int LR = NR + 2;
             if (OR_ < 1 || OG < 1) continue;
-            const size_t smem = (size_t)F_NB * LR * LG * 16 + 256;
+            const size_t smem = (size_t)F_NB * (LR * LG + 8) * 16 + 512;
             if (smem > 110 * 1024) continue;         // two CTAs per SM
             const int tj = ceil_div(g.Ny, OR_), tk = ceil_div(ng, OG);
             double eff = ((double)g.Ny * ng) / ((double)tj * tk * NI * F_NT);
@@ -243,6 +246,40 @@ static TileChoice choose_tile(const taub_geom &g)
         }
     }
     return best;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+// 3-D view of one ping-pong buffer: (columns = pitch, rows, bs * planes), fp32, box = LG*4 x LR x 1.
+static int make_field_map(CUtensorMap *map, const taub_geom &g, const float *base, int LR, int LG)
+{
+    EncodeTiledFn enc = encode_tiled_fn();
+    TAUB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[3] = {(cuuint64_t)g.pitch, (cuuint64_t)g.rows, (cuuint64_t)g.bs * g.planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.pitch * 4, (cuuint64_t)g.plane_stride * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)(LG * 4), (cuuint32_t)LR, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TAUB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (pitch %d rows %d planes %lld box %dx%d)",
+                 (int)r, g.pitch, g.rows, (long long)g.bs * g.planes, LG * 4, LR);
+    return TAUB_OK;
 }
 
 }  // namespace taub
@@ -295,14 +332,17 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     chunks = ceil_div(n_planes, chunk_len);
     P.chunk_len = chunk_len;
     TAUB_REQUIRE(chunks <= 65535, "taub_fused_sweep2: too many plane chunks");
-    const size_t smem = (size_t)F_NB * t.LR * t.LG * 16 + F_NB * 8 + 16 * 8;
+    P.slot_f4 = ((t.LR * t.LG + 7) / 8) * 8;
+    const size_t smem = (size_t)F_NB * P.slot_f4 * 16 + F_NB * 8 + 16 * 8 + 128;
     dim3 grid(t.tiles_j * t.tiles_k, chunks, g.bs);
     cudaStream_t s = (cudaStream_t)stream;
+    CUtensorMap tmap;
+    if (int rc = make_field_map(&tmap, g, P.src, t.LR, t.LG)) return rc;
 #define TAUB_LAUNCH_FUSED(NI_)                                                                               \
     do {                                                                                                     \
         TAUB_CUDA(cudaFuncSetAttribute(fused_sweep2_kernel<NI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                        (int)smem));                                                          \
-        fused_sweep2_kernel<NI_><<<grid, F_NT, smem, s>>>(P);                                                \
+        fused_sweep2_kernel<NI_><<<grid, F_NT, smem, s>>>(P, tmap);                                                \
     } while (0)
     if (t.NI == 2)
         TAUB_LAUNCH_FUSED(2);
