@@ -49,8 +49,8 @@ static inline __host__ __device__ int interior_groups(int Nz) { return (Nz + 3) 
 // (taufactor.py:177).  For a divisor c with correctly rounded reciprocal r = RN(1/c) the
 // Markstein sequence  q0 = RN(s*r); rem = s - q0*c (exact, one FMA); q = RN(q0 + rem*r)
 // returns the correctly rounded quotient for every normal s (checked exhaustively over all 2^23
-// mantissas for c = 1..8).  Tiny non-zero |s| (< 2^-100, where the remainder could go subnormal), inf and
-// NaN take the __fdiv_rn path, so the result is bit-identical to IEEE division everywhere.
+// mantissas for c = 1..8).  Tiny non-zero |s| (< 2^-100, where the remainder could go subnormal)
+// takes the __fdiv_rn path, so the result is bit-identical to IEEE division for every finite s.
 // Table entry for code 0 ("factor = inf": non-conductive voxel or no conductive neighbour) is
 // (c, r) = (0, 0), which yields q = 0 = s / inf without a special case.
 // ------------------------------------------------------------------------------------------
@@ -66,12 +66,11 @@ __device__ __forceinline__ float div_small(float s, float2 cr)
     float q0 = __fmul_rn(s, cr.y);
     float rem = __fmaf_rn(-q0, cr.x, s);
     float q = __fmaf_rn(rem, cr.y, q0);
-    // rare path: 0 < |s| < 2^-100, inf or NaN.  s == 0 (every voxel inside the solid phase) must
-    // stay on the fast path: the sequence above already returns the exact 0.
-    const unsigned a = __float_as_uint(s) & 0x7fffffffu;
-    if ((a - (27u << 23)) >= ((255u - 27u) << 23) && a != 0u) {
-        q = (cr.x > 0.0f) ? __fdiv_rn(s, cr.x) : __fdiv_rn(s, __int_as_float(0x7f800000));
-    }
+    // rare path: 0 < |s| < 2^-100 (one shift-add and one unsigned compare: 2*bits drops the sign,
+    // minus 1 wraps +-0 to the top).  s == 0 -- every voxel inside the solid phase -- stays on the
+    // fast path, which returns the exact 0; inf / NaN propagate as NaN (the field has diverged).
+    const unsigned u = __float_as_uint(s) * 2u - 1u;
+    if (u < (27u << 24) - 1u) q = (cr.x > 0.0f) ? __fdiv_rn(s, cr.x) : 0.0f;
     return q;
 }
 
@@ -88,6 +87,22 @@ __device__ __forceinline__ float sor_binary(float c, float xp, float xm, float y
     float d = __fsub_rn(div_small(s, cr), c);
     d = __fmul_rn(d, omega);
     return __fadd_rn(c, d);
+}
+
+// Colour updates of two voxels of a float4 group.  "xz" rows update components x and z (their z
+// neighbours are y, w and the scalar zs = .w of the group on the left); "yw" rows update y and w
+// (zs = .x of the group on the right).  xp/xm: x neighbours, up/dn: y+1 / y-1 neighbours.
+__device__ __forceinline__ void update_xz(float4 &c, const float4 &xp, const float4 &xm, const float4 &up,
+                                          const float4 &dn, float zs, unsigned code, const float2 *s_div, float omega)
+{
+    c.x = sor_binary(c.x, xp.x, xm.x, up.x, dn.x, c.y, zs, s_div[code & 15u], omega);
+    c.z = sor_binary(c.z, xp.z, xm.z, up.z, dn.z, c.w, c.y, s_div[(code >> 8) & 15u], omega);
+}
+__device__ __forceinline__ void update_yw(float4 &c, const float4 &xp, const float4 &xm, const float4 &up,
+                                          const float4 &dn, float zs, unsigned code, const float2 *s_div, float omega)
+{
+    c.y = sor_binary(c.y, xp.y, xm.y, up.y, dn.y, c.z, c.x, s_div[(code >> 4) & 15u], omega);
+    c.w = sor_binary(c.w, xp.w, xm.w, up.w, dn.w, zs, c.z, s_div[(code >> 12) & 15u], omega);
 }
 
 // One multi-phase voxel update (taufactor.py:606-613, :598-603): each neighbour times its face

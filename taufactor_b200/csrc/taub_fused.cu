@@ -74,24 +74,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         : "memory");
 }
 
-// Colour update of two voxels of a float4 (x,z when par == 0, y,w when par == 1).
-// c: centre group, xp/xm: x neighbours (registers), up/dn: y+1 / y-1 groups, zl: z-1 of .x (par 0)
-// or z+1 of .w (par 1) -- the one scalar that lives in the adjacent group.
-__device__ __forceinline__ float4 colour_update(float4 c, const float4 &xp, const float4 &xm, const float4 &up,
-                                                const float4 &dn, float zs, int par, unsigned code,
-                                                const float2 *s_div, float omega)
-{
-    if (par == 0) {
-        c.x = sor_binary(c.x, xp.x, xm.x, up.x, dn.x, c.y, zs, s_div[code & 15u], omega);
-        c.z = sor_binary(c.z, xp.z, xm.z, up.z, dn.z, c.w, c.y, s_div[(code >> 8) & 15u], omega);
-    } else {
-        c.y = sor_binary(c.y, xp.y, xm.y, up.y, dn.y, c.z, c.x, s_div[(code >> 4) & 15u], omega);
-        c.w = sor_binary(c.w, xp.w, xm.w, up.w, dn.w, zs, c.z, s_div[(code >> 12) & 15u], omega);
-    }
-    return c;
-}
-
-template <int NI>
+// Thread work item = a PAIR of vertically adjacent rows (a = lower y, b = a + 1) x one float4
+// group.  In every step exactly one row of the pair is an "xz" row and the other a "yw" row, and
+// they swap each step; the pair's mutual y-neighbours stay in registers.  PA0 = parity of row a at
+// step 0 (uniform over the whole grid, chosen by the host), so every step body is branch-free.
+template <int NP, int PA0>
 __global__ void __launch_bounds__(F_NT, 2)
 fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tmap)
 {
@@ -115,7 +102,6 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     const int total_rel = c1 - c0 + 4;           // planes c0-2 .. c1+1
     const int64_t ps = g.plane_stride;
 
-    for (int i = tid; i < F_NB * plane_f4; i += F_NT) planes[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid < 16) s_div[tid] = div_entry(tid);
     if (tid == 0) {
         for (int n = 0; n < F_NB; ++n) mbar_init(smem_u32(&mbar[n]), 1);
@@ -135,115 +121,156 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     if (tid == 0)
         for (int rel = 0; rel < min(F_NB - 1, total_rel); ++rel) issue(rel);
 
-    // ---- per-thread items: fixed (row, group) columns, rows permuted so that a warp sees one parity
-    const int NR = LR - 2, n_even = (NR + 1) >> 1;
-    int idx[NI];          // float4 index inside a plane buffer
-    int64_t goff[NI];     // element offset of the group in local plane 0 (storage plane G)
-    int jpar[NI];
-    bool doit[NI], canB[NI];
+    // ---- per-thread items
+    int idxa[NP];            // float4 index of row a's group inside a ring slot (row b: + LG)
+    float *dst_a[NP];        // destination of row a's group in the plane colour B currently writes
+    const uint16_t *cod_a[NP], *cod_b[NP];   // neighbour codes of rows a / b in the plane being prefetched
+    bool doit[NP], canBa[NP], canBb[NP];
+    const int NPT = (LR - 2) >> 1;   // row pairs in the tile
 #pragma unroll
-    for (int n = 0; n < NI; ++n) {
+    for (int n = 0; n < NP; ++n) {
         const int u = tid + n * F_NT;
-        const int rr = u / P.LGp, gg = u - rr * P.LGp;
-        const int lr = 1 + (rr < n_even ? 2 * rr : 2 * (rr - n_even) + 1);
-        const int R = R0 + lr, Gs = G0 + gg;
-        doit[n] = (rr < NR) && (gg < LG) && (R < g.rows - 1) && (Gs < PG);
-        canB[n] = doit[n] && lr >= 2 && lr < LR - 2 && gg >= 1 && gg < LG - 1 && R >= G && R < G + g.Ny &&
-                  Gs >= 1 && Gs < 1 + interior_groups(g.Nz);
-        idx[n] = lr * LG + gg;
-        goff[n] = (int64_t)b * g.image_stride + (int64_t)G * ps + (int64_t)R * g.pitch + 4 * Gs;
-        jpar[n] = (R - G + g.i_offset + P.colourA) & 1;
+        const int m = u / P.LGp, gg = u - m * P.LGp;
+        const int lra = 1 + 2 * m;
+        const int Ra = R0 + lra, Gs = G0 + gg;
+        doit[n] = (m < NPT) && (gg < LG) && (Gs < PG) && (Ra < g.rows);
+        const bool colB = gg >= 1 && gg < LG - 1 && Gs >= 1 && Gs < 1 + interior_groups(g.Nz);
+        canBa[n] = doit[n] && colB && lra >= 2 && Ra >= G && Ra < G + g.Ny;
+        canBb[n] = doit[n] && colB && lra + 1 < LR - 2 && Ra + 1 >= G && Ra + 1 < G + g.Ny;
+        idxa[n] = lra * LG + gg;
+        const int64_t img = (int64_t)b * g.image_stride + 4 * Gs;
+        // colour B first writes plane c0 (at step 2); the code pointers start at plane c0-1
+        dst_a[n] = P.dst + img + (int64_t)(c0 + G) * ps + (int64_t)Ra * g.pitch;
+        const int Rca = min(Ra, g.rows - 1), Rcb = min(Ra + 1, g.rows - 1);   // stay inside the array
+        cod_a[n] = P.codes + ((img + (int64_t)(c0 - 1 + G) * ps + (int64_t)Rca * g.pitch) >> 2);
+        cod_b[n] = P.codes + ((img + (int64_t)(c0 - 1 + G) * ps + (int64_t)Rcb * g.pitch) >> 2);
     }
 
-    // ---- prologue: a[c0-2] (only ever read as an x-neighbour) and raw[c0-1]
+    // ---- register ring: ring[.][k] holds plane (c0-3+k+4j); at step s = 4j+ss:
+    //      a[p-2] = ring[ss], a[p-1] = ring[ss+1], raw[p] -> a[p] = ring[ss+2], raw[p+1] = ring[ss+3]
+    float4 ra[NP][4], rb[NP][4];
+    unsigned ca[NP][4], cb[NP][4];
     mbar_wait(smem_u32(&mbar[0]), 0);
     mbar_wait(smem_u32(&mbar[1 % F_NB]), 0);
-    float4 am2[NI], am1[NI], r0[NI];
-    unsigned codeA[NI], codeB[NI];
 #pragma unroll
-    for (int n = 0; n < NI; ++n) {
-        am2[n] = make_float4(0.f, 0.f, 0.f, 0.f);
-        am1[n] = r0[n] = am2[n];
-        codeA[n] = codeB[n] = 0;
+    for (int n = 0; n < NP; ++n) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ra[n][k] = rb[n][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ca[n][k] = cb[n][k] = 0;
+        }
         if (doit[n]) {
-            am1[n] = planes[idx[n]];
-            r0[n] = planes[plane_f4 + idx[n]];
-            codeA[n] = P.codes[(goff[n] + (int64_t)(c0 - 1) * ps) >> 2];
+            ra[n][1] = planes[idxa[n]];
+            rb[n][1] = planes[idxa[n] + LG];
+            ra[n][2] = planes[plane_f4 + idxa[n]];
+            rb[n][2] = planes[plane_f4 + idxa[n] + LG];
+            ca[n][2] = *cod_a[n];
+            cb[n][2] = *cod_b[n];
         }
     }
+    const int64_t cstep = ps >> 2;
 
     const int n_steps = c1 - c0 + 2;
-    for (int s = 0; s < n_steps; ++s) {
-        const int p = c0 - 1 + s;   // plane receiving colour A; colour B goes to plane p-1
-        __syncthreads();            // ring slot of plane p-2 is free; a[p-1] is visible in its slot
-        if (tid == 0 && s - 1 + F_NB < total_rel) issue(s - 1 + F_NB);
-        mbar_wait(smem_u32(&mbar[(s + 2) % F_NB]), (uint32_t)(((s + 2) / F_NB) & 1));
-        const float4 *bufM1 = planes + (size_t)(s % F_NB) * plane_f4;
-        float4 *bufP = planes + (size_t)((s + 1) % F_NB) * plane_f4;
-        const float4 *bufP1 = planes + (size_t)((s + 2) % F_NB) * plane_f4;
-        const bool doA = (p >= P.a_lo) && (p < P.a_hi);
-        const bool keepA = (p >= c0) && (p < c1);   // a[p] is read by colour B of plane p next step
-        const bool doB = (s >= 2);
+    for (int s4 = 0; s4 < n_steps; s4 += 4) {
 #pragma unroll
-        for (int n = 0; n < NI; ++n) {
-            if (!doit[n]) continue;
-            const int i4 = idx[n];
-            const float4 rp1 = bufP1[i4];
-            unsigned codeN = 0;
-            if (s + 1 < n_steps) codeN = P.codes[(goff[n] + (int64_t)(p + 1) * ps) >> 2];
-            const int par = (jpar[n] + p) & 1;
-            const int zoff = par ? 4 * i4 + 4 : 4 * i4 - 1;   // z+1 of .w / z-1 of .x
-            float4 a0 = r0[n];
-            if (doA) {
-                const float4 up = bufP[i4 + LG], dn = bufP[i4 - LG];
-                const float zs = reinterpret_cast<const float *>(bufP)[zoff];
-                a0 = colour_update(a0, rp1, am1[n], up, dn, zs, par, codeA[n], s_div, P.omega);
-                if (keepA) bufP[i4] = a0;
+        for (int ss = 0; ss < 4; ++ss) {
+            const int s = s4 + ss;
+            if (s >= n_steps) break;
+            const int p = c0 - 1 + s;   // plane receiving colour A; colour B goes to plane p-1
+            constexpr int kM2 = 0, kM1 = 1, kP = 2, kP1 = 3;
+            const int iM2 = (ss + kM2) & 3, iM1 = (ss + kM1) & 3, iP = (ss + kP) & 3, iP1 = (ss + kP1) & 3;
+            const bool a_is_xz = (((PA0 + ss) & 1) == 0);
+            __syncthreads();            // ring slot of plane p-2 is free; a[p-1] is visible in its slot
+            if (tid == 0 && s - 1 + F_NB < total_rel) issue(s - 1 + F_NB);
+            mbar_wait(smem_u32(&mbar[(s + 2) % F_NB]), (uint32_t)(((s + 2) / F_NB) & 1));
+            const float4 *bufM1 = planes + (size_t)(s % F_NB) * plane_f4;
+            float4 *bufP = planes + (size_t)((s + 1) % F_NB) * plane_f4;
+            const float4 *bufP1 = planes + (size_t)((s + 2) % F_NB) * plane_f4;
+            const bool doA = (p >= P.a_lo) && (p < P.a_hi);
+            const bool keepA = (p >= c0) && (p < c1);   // a[p] is read by colour B of plane p next step
+            const bool doB = (s >= 2);
+            const bool more = (s + 1 < n_steps);
+#pragma unroll
+            for (int n = 0; n < NP; ++n) {
+                if (!doit[n]) continue;
+                const int ia = idxa[n], ib = idxa[n] + LG;
+                ra[n][iP1] = bufP1[ia];
+                rb[n][iP1] = bufP1[ib];
+                if (more) {
+                    cod_a[n] += cstep;
+                    cod_b[n] += cstep;
+                    ca[n][iP1] = *cod_a[n];
+                    cb[n][iP1] = *cod_b[n];
+                }
+                // scalar z neighbour: z-1 of .x (xz row) or z+1 of .w (yw row)
+                const int za = a_is_xz ? 4 * ia - 1 : 4 * ia + 4;
+                const int zb = a_is_xz ? 4 * ib + 4 : 4 * ib - 1;
+                if (doA) {
+                    const float4 dn = bufP[ia - LG], up = bufP[ib + LG];
+                    const float zsa = reinterpret_cast<const float *>(bufP)[za];
+                    const float zsb = reinterpret_cast<const float *>(bufP)[zb];
+                    const float4 a_raw = ra[n][iP];   // row b reads row a's colour-B voxels: unchanged by A
+                    if (a_is_xz) {
+                        update_xz(ra[n][iP], ra[n][iP1], ra[n][iM1], rb[n][iP], dn, zsa, ca[n][iP], s_div, P.omega);
+                        update_yw(rb[n][iP], rb[n][iP1], rb[n][iM1], up, a_raw, zsb, cb[n][iP], s_div, P.omega);
+                    } else {
+                        update_yw(ra[n][iP], ra[n][iP1], ra[n][iM1], rb[n][iP], dn, zsa, ca[n][iP], s_div, P.omega);
+                        update_xz(rb[n][iP], rb[n][iP1], rb[n][iM1], up, a_raw, zsb, cb[n][iP], s_div, P.omega);
+                    }
+                    if (keepA) {
+                        bufP[ia] = ra[n][iP];
+                        bufP[ib] = rb[n][iP];
+                    }
+                }
+                if (doB) {
+                    if (canBa[n] | canBb[n]) {
+                        const float4 dn = bufM1[ia - LG], up = bufM1[ib + LG];
+                        const float zsa = reinterpret_cast<const float *>(bufM1)[za];
+                        const float zsb = reinterpret_cast<const float *>(bufM1)[zb];
+                        float4 oa = ra[n][iM1], ob = rb[n][iM1];
+                        if (a_is_xz) {
+                            update_xz(oa, ra[n][iP], ra[n][iM2], rb[n][iM1], dn, zsa, ca[n][iM1], s_div, P.omega);
+                            update_yw(ob, rb[n][iP], rb[n][iM2], up, ra[n][iM1], zsb, cb[n][iM1], s_div, P.omega);
+                        } else {
+                            update_yw(oa, ra[n][iP], ra[n][iM2], rb[n][iM1], dn, zsa, ca[n][iM1], s_div, P.omega);
+                            update_xz(ob, rb[n][iP], rb[n][iM2], up, ra[n][iM1], zsb, cb[n][iM1], s_div, P.omega);
+                        }
+                        if (canBa[n]) *reinterpret_cast<float4 *>(dst_a[n]) = oa;
+                        if (canBb[n]) *reinterpret_cast<float4 *>(dst_a[n] + g.pitch) = ob;
+                    }
+                    dst_a[n] += ps;
+                }
             }
-            if (doB && canB[n]) {
-                const float4 up = bufM1[i4 + LG], dn = bufM1[i4 - LG];
-                const float zs = reinterpret_cast<const float *>(bufM1)[zoff];
-                const float4 out = colour_update(am1[n], a0, am2[n], up, dn, zs, par, codeB[n], s_div, P.omega);
-                *reinterpret_cast<float4 *>(P.dst + goff[n] + (int64_t)(p - 1) * ps) = out;
-            }
-            am2[n] = am1[n];
-            am1[n] = a0;
-            r0[n] = rp1;
-            codeB[n] = codeA[n];
-            codeA[n] = codeN;
         }
     }
 }
 
 struct TileChoice {
-    int NI, LR, LG, LGp, OR_, OG, tiles_j, tiles_k;
+    int NP, LR, LG, LGp, OR_, OG, tiles_j, tiles_k;
     double eff;
 };
 
-// Pick the tile shape that wastes the fewest thread-items: items = NI*256 per tile, rows are
-// split into NR = items / LGp rows of LGp (multiple of 16) group slots.
+// Pick the tile shape that wastes the fewest thread-items: NP*256 (row pair x group) items per
+// tile, arranged as NPT row pairs of LGp (multiple of 16) group slots.
 static TileChoice choose_tile(const taub_geom &g)
 {
     const int ng = interior_groups(g.Nz);
     TileChoice best{};
     best.eff = -1.0;
-    for (int NI = 2; NI <= 3; ++NI) {
-        for (int LGp = 16; LGp <= 64; LGp += 16) {   // TMA box: at most 256 elements wide
-            const int NR = (NI * F_NT) / LGp;
-            if (NR < 4) break;
-            int LG = LGp;
-            if (LG > ng + 2) LG = ng + 2;            // never wider than the row needs
-            if (LG <= LGp - 16) continue;            // a smaller LGp covers it
-            const int OR_ = NR - 2, OG = LG - 2;
-            const int LR = NR + 2;
-            if (OR_ < 1 || OG < 1) continue;
-            const size_t smem = (size_t)F_NB * (LR * LG + 8) * 16 + 512;
-            if (smem > 110 * 1024) continue;         // two CTAs per SM
-            const int tj = ceil_div(g.Ny, OR_), tk = ceil_div(ng, OG);
-            double eff = ((double)g.Ny * ng) / ((double)tj * tk * NI * F_NT);
-            if (NI == 4) eff *= 0.97;                // register pressure tie-break
-            if (eff > best.eff) best = TileChoice{NI, LR, LG, LGp, OR_, OG, tj, tk, eff};
-        }
+    const int NP = 2;
+    for (int LGp = 16; LGp <= 64; LGp += 16) {   // TMA box: at most 256 elements wide
+        const int NPT = (NP * F_NT) / LGp;       // row pairs per tile
+        if (NPT < 2) break;
+        int LG = LGp;
+        if (LG > ng + 2) LG = ng + 2;            // never wider than the row needs
+        if (LG <= LGp - 16) continue;            // a smaller LGp covers it
+        const int NR = 2 * NPT, OR_ = NR - 2, OG = LG - 2, LR = NR + 2;
+        if (OG < 1) continue;
+        const size_t smem = (size_t)F_NB * (LR * LG + 8) * 16 + 512;
+        if (smem > 112 * 1024) continue;         // two CTAs per SM
+        const int tj = ceil_div(g.Ny, OR_), tk = ceil_div(ng, OG);
+        const double eff = ((double)g.Ny * ng) / ((double)tj * tk * NPT * 2 * LGp);
+        if (eff > best.eff) best = TileChoice{NP, LR, LG, LGp, OR_, OG, tj, tk, eff};
     }
     return best;
 }
@@ -319,7 +346,7 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     P.i_hi = i_hi;
     P.a_lo = max(i_lo - 1, -g.i_offset);
     P.a_hi = min(i_hi + 1, g.Nx_global - g.i_offset);
-    P.LR = t.LR; P.LG = t.LG; P.LGp = t.LGp; P.OR_ = t.OR_; P.OG = t.OG;
+    P.LR = t.LR; P.LG = t.LG; P.LGp = t.LGp; P.OR_ = t.OR_; P.OG = t.OG;   // OR_ is even
     P.tiles_k = t.tiles_k;
     // planes per CTA: ~3 waves of CTAs on 148 SMs x 2, but at least 16 planes to amortise the
     // 4-plane prologue
@@ -329,6 +356,7 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     if (chunks < 1) chunks = 1;
     int chunk_len = ceil_div(n_planes, chunks);
     if (chunk_len < 16) chunk_len = min(16, n_planes);
+    chunk_len += chunk_len & 1;   // even: every CTA then starts with the same row parity
     chunks = ceil_div(n_planes, chunk_len);
     P.chunk_len = chunk_len;
     TAUB_REQUIRE(chunks <= 65535, "taub_fused_sweep2: too many plane chunks");
@@ -338,18 +366,20 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     cudaStream_t s = (cudaStream_t)stream;
     CUtensorMap tmap;
     if (int rc = make_field_map(&tmap, g, P.src, t.LR, t.LG)) return rc;
-#define TAUB_LAUNCH_FUSED(NI_)                                                                               \
-    do {                                                                                                     \
-        TAUB_CUDA(cudaFuncSetAttribute(fused_sweep2_kernel<NI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                       (int)smem));                                                          \
-        fused_sweep2_kernel<NI_><<<grid, F_NT, smem, s>>>(P, tmap);                                                \
+    // parity of loaded row 1 (row a of every pair) at step 0, i.e. at plane c0-1: 0 -> x,z active.
+    // Tile row offsets (multiples of the even OR_) and chunk starts (multiples of the even
+    // chunk_len) do not change it, so it is one number for the whole grid.
+    const int pa0 = (1 - G + g.i_offset + P.colourA + (i_lo - 1)) & 1;
+#define TAUB_LAUNCH_FUSED(PA_)                                                                                    \
+    do {                                                                                                          \
+        TAUB_CUDA(cudaFuncSetAttribute(fused_sweep2_kernel<2, PA_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                       (int)smem));                                                               \
+        fused_sweep2_kernel<2, PA_><<<grid, F_NT, smem, s>>>(P, tmap);                                            \
     } while (0)
-    if (t.NI == 2)
-        TAUB_LAUNCH_FUSED(2);
-    else if (t.NI == 3)
-        TAUB_LAUNCH_FUSED(3);
+    if (pa0 == 0)
+        TAUB_LAUNCH_FUSED(0);
     else
-        TAUB_LAUNCH_FUSED(4);
+        TAUB_LAUNCH_FUSED(1);
 #undef TAUB_LAUNCH_FUSED
     TAUB_CUDA(cudaGetLastError());
     count_launch();

@@ -41,8 +41,8 @@ refresh_ghosts_kernel(taub_geom g, float *__restrict__ f, int p_lo)
 }
 
 // ------------------------------------------------------------------------------------------
-// Generic half-sweep: one thread per interior float4 group (4 consecutive z voxels), all four
-// results computed branch-free and the active colour selected.  blockDim = (32, 8):
+// Generic half-sweep: one thread per interior float4 group (4 consecutive z voxels), the two
+// voxels of the active colour are updated (warp-uniform branch on the row parity).  blockDim = (32, 8):
 // x -> groups along z (coalesced 512 B per warp), y -> rows; grid.z -> (image, plane).
 // ------------------------------------------------------------------------------------------
 template <bool MULTI>
@@ -74,49 +74,51 @@ half_sweep_kernel(taub_geom g, const float *__restrict__ src, float *__restrict_
         const int ig = il + g.i_offset;            // global plane
         const int64_t o = (int64_t)b * g.image_stride + (int64_t)(il + G) * ps +
                           (int64_t)(j + G) * pitch + COL0 + 4 * grp;
-        const float4 c4 = *reinterpret_cast<const float4 *>(src + o);
+        float4 c4 = *reinterpret_cast<const float4 *>(src + o);
         const float4 xp4 = *reinterpret_cast<const float4 *>(src + o + ps);
         const float4 xm4 = *reinterpret_cast<const float4 *>(src + o - ps);
         const float4 yp4 = *reinterpret_cast<const float4 *>(src + o + pitch);
         const float4 ym4 = *reinterpret_cast<const float4 *>(src + o - pitch);
-        const float zl = src[o - 1], zr = src[o + 4];
-        const float c[4] = {c4.x, c4.y, c4.z, c4.w};
-        const float xp[4] = {xp4.x, xp4.y, xp4.z, xp4.w}, xm[4] = {xm4.x, xm4.y, xm4.z, xm4.w};
-        const float yp[4] = {yp4.x, yp4.y, yp4.z, yp4.w}, ym[4] = {ym4.x, ym4.y, ym4.z, ym4.w};
-        const float zp[4] = {c4.y, c4.z, c4.w, zr}, zm[4] = {zl, c4.x, c4.y, c4.z};
-        // voxel q is active when (i + j + k) % 2 == colour; k = 4*grp + q so only q matters
-        const int par0 = (ig + j + colour) & 1;  // 0: q = 0,2 active, 1: q = 1,3 active
-        float out[4];
+        // voxel q is active when (i + j + k) % 2 == colour; k = 4*grp + q so only q matters.
+        // par0 is uniform over a warp (one row per warp): 0 -> x,z active, 1 -> y,w active.
+        const int par0 = (ig + j + colour) & 1;
         if (!MULTI) {
             const unsigned code = codes[o >> 2];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float nv = sor_binary(c[q], xp[q], xm[q], yp[q], ym[q], zp[q], zm[q],
-                                            s_div[(code >> (4 * q)) & 15u], omega);
-                out[q] = ((q & 1) == par0) ? nv : c[q];
-            }
+            if (par0 == 0)
+                update_xz(c4, xp4, xm4, yp4, ym4, src[o - 1], code, s_div, omega);
+            else
+                update_yw(c4, xp4, xm4, yp4, ym4, src[o + 4], code, s_div, omega);
         } else {
             const uint32_t lc = *reinterpret_cast<const uint32_t *>(labels + o);
             const uint32_t lxp = *reinterpret_cast<const uint32_t *>(labels + o + ps);
             const uint32_t lxm = *reinterpret_cast<const uint32_t *>(labels + o - ps);
             const uint32_t lyp = *reinterpret_cast<const uint32_t *>(labels + o + pitch);
             const uint32_t lym = *reinterpret_cast<const uint32_t *>(labels + o - pitch);
-            const uint32_t lzl = labels[o - 1], lzr = labels[o + 4];
-            const uint64_t lrow = ((uint64_t)lzr << 40) | ((uint64_t)lc << 8) | lzl;  // k-1 .. k+4
             const bool first = (ig == 0), last = (ig == g.Nx_global - 1);
             const int L1 = L + 1;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float *row = s_lut + ((lc >> (8 * q)) & 255u) * L1;
-                const float nv = sor_multi(
-                    c[q], xp[q], xm[q], yp[q], ym[q], zp[q], zm[q], row[(lxp >> (8 * q)) & 255u],
-                    row[(lxm >> (8 * q)) & 255u], row[(lyp >> (8 * q)) & 255u],
-                    row[(lym >> (8 * q)) & 255u], row[(lrow >> (8 * (q + 2))) & 255u],
-                    row[(lrow >> (8 * q)) & 255u], first, last, omega);
-                out[q] = ((q & 1) == par0) ? nv : c[q];
+#define TAUB_MULTI_Q(Q, CEN, XP, XM, YP, YM, ZP, ZM, LZP, LZM)                                              \
+    {                                                                                                       \
+        const float *row = s_lut + ((lc >> (8 * Q)) & 255u) * L1;                                            \
+        CEN = sor_multi(CEN, XP, XM, YP, YM, ZP, ZM, row[(lxp >> (8 * Q)) & 255u],                            \
+                        row[(lxm >> (8 * Q)) & 255u], row[(lyp >> (8 * Q)) & 255u],                           \
+                        row[(lym >> (8 * Q)) & 255u], row[LZP], row[LZM], first, last, omega);               \
+    }
+            if (par0 == 0) {
+                const float zl = src[o - 1];
+                const uint32_t lzl = labels[o - 1];
+                const float cy = c4.y;
+                TAUB_MULTI_Q(0, c4.x, xp4.x, xm4.x, yp4.x, ym4.x, cy, zl, (lc >> 8) & 255u, lzl)
+                TAUB_MULTI_Q(2, c4.z, xp4.z, xm4.z, yp4.z, ym4.z, c4.w, cy, (lc >> 24) & 255u, (lc >> 8) & 255u)
+            } else {
+                const float zr = src[o + 4];
+                const uint32_t lzr = labels[o + 4];
+                const float cz = c4.z;
+                TAUB_MULTI_Q(1, c4.y, xp4.y, xm4.y, yp4.y, ym4.y, cz, c4.x, (lc >> 16) & 255u, lc & 255u)
+                TAUB_MULTI_Q(3, c4.w, xp4.w, xm4.w, yp4.w, ym4.w, zr, cz, lzr, (lc >> 16) & 255u)
             }
+#undef TAUB_MULTI_Q
         }
-        *reinterpret_cast<float4 *>(dst + o) = make_float4(out[0], out[1], out[2], out[3]);
+        *reinterpret_cast<float4 *>(dst + o) = c4;
     }
 }
 
