@@ -51,7 +51,7 @@ typedef struct taub_geom {
     int32_t Nx_global;          /* x extent of the whole volume */
     int32_t i_offset;           /* global x index of local plane 0 */
     int32_t periodic;           /* 1: y/z periodic (PeriodicSolver family) */
-    int32_t planes, rows, pitch;/* storage extents: Nx+2G, Ny+2G, round_up(Nz+6, 8) */
+    int32_t planes, rows, pitch;/* storage extents: Nx+2G, Ny+2G, round_up(Nz+8, 32) */
     int64_t plane_stride;       /* rows * pitch   (elements) */
     int64_t image_stride;       /* planes * plane_stride */
 } taub_geom;

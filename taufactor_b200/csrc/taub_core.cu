@@ -67,8 +67,9 @@ int taub_geom_init(taub_geom *g, int bs, int Nx_local, int Ny, int Nz, int Nx_gl
     g->planes = Nx_local + 2 * TAUB_GHOST;
     g->rows = Ny + 2 * TAUB_GHOST;
     // interior at column 4 (16-byte aligned), z ghosts either side, then room for the float4
-    // group that holds the last interior voxel plus its right-hand neighbour; 32-byte rows.
-    g->pitch = ((Nz + 8 + 7) / 8) * 8;
+    // group that holds the last interior voxel plus its right-hand neighbour; rows are multiples of
+    // 128 bytes (full cache lines; the uint16 code rows are then multiples of 16 bytes, which TMA needs).
+    g->pitch = ((Nz + 8 + 31) / 32) * 32;
     g->plane_stride = (int64_t)g->rows * g->pitch;
     g->image_stride = (int64_t)g->planes * g->plane_stride;
     return TAUB_OK;

@@ -9,6 +9,7 @@
 //     group each side) is brought into a 6-deep shared-memory ring by TMA: ONE
 //     cp.async.bulk.tensor.3d box (rows x columns x 1 plane, out-of-bounds zero filled) per plane,
 //     completion on an mbarrier, issued three planes ahead of use;
+//     the 4-bit neighbour codes of the same box ride along in a second (uint16) TMA box;
 //   * register rotation: each thread owns NI float4 columns and keeps a[p-2], a[p-1], raw[p],
 //     raw[p+1] of its columns in registers, so x-neighbours never touch shared memory;
 //   * wavefront: at step p colour A is applied to plane p (in place in shared memory -- legal
@@ -39,7 +40,8 @@ struct FusedParams {
     int OR_, OG;       // output rows / groups per tile
     int tiles_k;
     int chunk_len;     // output planes per CTA
-    int slot_f4;       // float4 per ring slot
+    int slot_f4;       // float4 per field ring slot
+    int cslot_h;       // uint16 per code ring slot
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,7 +82,8 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
 // step 0 (uniform over the whole grid, chosen by the host), so every step body is branch-free.
 template <int NP, int PA0>
 __global__ void __launch_bounds__(F_NT, 2)
-fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tmap)
+fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tmap,
+                    const __grid_constant__ CUtensorMap cmap)
 {
     extern __shared__ unsigned char smem_dyn[];
     // TMA destinations need 128-byte alignment: align the base, slots are multiples of 128 B
@@ -88,8 +91,10 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     const taub_geom &g = P.g;
     const int LR = P.LR, LG = P.LG;
     const int plane_f4 = P.slot_f4;              // ring slot size in float4 (>= LR*LG, multiple of 8)
+    const int cslot = P.cslot_h;
     float4 *planes = reinterpret_cast<float4 *>(smem_raw);
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)F_NB * plane_f4 * 16);
+    uint16_t *cplanes = reinterpret_cast<uint16_t *>(smem_raw + (size_t)F_NB * plane_f4 * 16);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(cplanes + (size_t)F_NB * cslot);
     float2 *s_div = reinterpret_cast<float2 *>(mbar + F_NB);
 
     const int tid = threadIdx.x;
@@ -115,8 +120,10 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
         const int slot = rel % F_NB;
         const uint32_t bar = smem_u32(&mbar[slot]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, (uint32_t)(LR * LG * 16));
-        tma_load_3d(smem_u32(planes + (size_t)slot * plane_f4), &tmap, 4 * G0, R0, b * g.planes + (c0 - 2 + rel + G), bar);
+        mbar_expect_tx(bar, (uint32_t)(LR * LG * 18));
+        const int pl = b * g.planes + (c0 - 2 + rel + G);
+        tma_load_3d(smem_u32(planes + (size_t)slot * plane_f4), &tmap, 4 * G0, R0, pl, bar);
+        tma_load_3d(smem_u32(cplanes + (size_t)slot * cslot), &cmap, G0, R0, pl, bar);
     };
     if (tid == 0)
         for (int rel = 0; rel < min(F_NB - 1, total_rel); ++rel) issue(rel);
@@ -124,7 +131,6 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     // ---- per-thread items
     int idxa[NP];            // float4 index of row a's group inside a ring slot (row b: + LG)
     float *dst_a[NP];        // destination of row a's group in the plane colour B currently writes
-    const uint16_t *cod_a[NP], *cod_b[NP];   // neighbour codes of rows a / b in the plane being prefetched
     bool doit[NP], canBa[NP], canBb[NP];
     const int NPT = (LR - 2) >> 1;   // row pairs in the tile
 #pragma unroll
@@ -139,17 +145,13 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
         canBb[n] = doit[n] && colB && lra + 1 < LR - 2 && Ra + 1 >= G && Ra + 1 < G + g.Ny;
         idxa[n] = lra * LG + gg;
         const int64_t img = (int64_t)b * g.image_stride + 4 * Gs;
-        // colour B first writes plane c0 (at step 2); the code pointers start at plane c0-1
+        // colour B first writes plane c0 (at step 2)
         dst_a[n] = P.dst + img + (int64_t)(c0 + G) * ps + (int64_t)Ra * g.pitch;
-        const int Rca = min(Ra, g.rows - 1), Rcb = min(Ra + 1, g.rows - 1);   // stay inside the array
-        cod_a[n] = P.codes + ((img + (int64_t)(c0 - 1 + G) * ps + (int64_t)Rca * g.pitch) >> 2);
-        cod_b[n] = P.codes + ((img + (int64_t)(c0 - 1 + G) * ps + (int64_t)Rcb * g.pitch) >> 2);
     }
 
     // ---- register ring: ring[.][k] holds plane (c0-3+k+4j); at step s = 4j+ss:
     //      a[p-2] = ring[ss], a[p-1] = ring[ss+1], raw[p] -> a[p] = ring[ss+2], raw[p+1] = ring[ss+3]
     float4 ra[NP][4], rb[NP][4];
-    unsigned ca[NP][4], cb[NP][4];
     mbar_wait(smem_u32(&mbar[0]), 0);
     mbar_wait(smem_u32(&mbar[1 % F_NB]), 0);
 #pragma unroll
@@ -157,18 +159,14 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             ra[n][k] = rb[n][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            ca[n][k] = cb[n][k] = 0;
         }
         if (doit[n]) {
             ra[n][1] = planes[idxa[n]];
             rb[n][1] = planes[idxa[n] + LG];
             ra[n][2] = planes[plane_f4 + idxa[n]];
             rb[n][2] = planes[plane_f4 + idxa[n] + LG];
-            ca[n][2] = *cod_a[n];
-            cb[n][2] = *cod_b[n];
         }
     }
-    const int64_t cstep = ps >> 2;
 
     const int n_steps = c1 - c0 + 2;
     for (int s4 = 0; s4 < n_steps; s4 += 4) {
@@ -186,22 +184,17 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
             const float4 *bufM1 = planes + (size_t)(s % F_NB) * plane_f4;
             float4 *bufP = planes + (size_t)((s + 1) % F_NB) * plane_f4;
             const float4 *bufP1 = planes + (size_t)((s + 2) % F_NB) * plane_f4;
+            const uint16_t *codM1 = cplanes + (size_t)(s % F_NB) * cslot;
+            const uint16_t *codP = cplanes + (size_t)((s + 1) % F_NB) * cslot;
             const bool doA = (p >= P.a_lo) && (p < P.a_hi);
             const bool keepA = (p >= c0) && (p < c1);   // a[p] is read by colour B of plane p next step
             const bool doB = (s >= 2);
-            const bool more = (s + 1 < n_steps);
 #pragma unroll
             for (int n = 0; n < NP; ++n) {
                 if (!doit[n]) continue;
                 const int ia = idxa[n], ib = idxa[n] + LG;
                 ra[n][iP1] = bufP1[ia];
                 rb[n][iP1] = bufP1[ib];
-                if (more) {
-                    cod_a[n] += cstep;
-                    cod_b[n] += cstep;
-                    ca[n][iP1] = *cod_a[n];
-                    cb[n][iP1] = *cod_b[n];
-                }
                 // scalar z neighbour: z-1 of .x (xz row) or z+1 of .w (yw row)
                 const int za = a_is_xz ? 4 * ia - 1 : 4 * ia + 4;
                 const int zb = a_is_xz ? 4 * ib + 4 : 4 * ib - 1;
@@ -209,13 +202,14 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                     const float4 dn = bufP[ia - LG], up = bufP[ib + LG];
                     const float zsa = reinterpret_cast<const float *>(bufP)[za];
                     const float zsb = reinterpret_cast<const float *>(bufP)[zb];
-                    const float4 a_raw = ra[n][iP];   // row b reads row a's colour-B voxels: unchanged by A
+                    const unsigned cda = codP[ia], cdb = codP[ib];
+                    // each row only reads the components of the other row that this step leaves unchanged
                     if (a_is_xz) {
-                        update_xz(ra[n][iP], ra[n][iP1], ra[n][iM1], rb[n][iP], dn, zsa, ca[n][iP], s_div, P.omega);
-                        update_yw(rb[n][iP], rb[n][iP1], rb[n][iM1], up, a_raw, zsb, cb[n][iP], s_div, P.omega);
+                        update_xz(ra[n][iP], ra[n][iP1], ra[n][iM1], rb[n][iP], dn, zsa, cda, s_div, P.omega);
+                        update_yw(rb[n][iP], rb[n][iP1], rb[n][iM1], up, ra[n][iP], zsb, cdb, s_div, P.omega);
                     } else {
-                        update_yw(ra[n][iP], ra[n][iP1], ra[n][iM1], rb[n][iP], dn, zsa, ca[n][iP], s_div, P.omega);
-                        update_xz(rb[n][iP], rb[n][iP1], rb[n][iM1], up, a_raw, zsb, cb[n][iP], s_div, P.omega);
+                        update_yw(ra[n][iP], ra[n][iP1], ra[n][iM1], rb[n][iP], dn, zsa, cda, s_div, P.omega);
+                        update_xz(rb[n][iP], rb[n][iP1], rb[n][iM1], up, ra[n][iP], zsb, cdb, s_div, P.omega);
                     }
                     if (keepA) {
                         bufP[ia] = ra[n][iP];
@@ -227,13 +221,14 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                         const float4 dn = bufM1[ia - LG], up = bufM1[ib + LG];
                         const float zsa = reinterpret_cast<const float *>(bufM1)[za];
                         const float zsb = reinterpret_cast<const float *>(bufM1)[zb];
+                        const unsigned cda = codM1[ia], cdb = codM1[ib];
                         float4 oa = ra[n][iM1], ob = rb[n][iM1];
                         if (a_is_xz) {
-                            update_xz(oa, ra[n][iP], ra[n][iM2], rb[n][iM1], dn, zsa, ca[n][iM1], s_div, P.omega);
-                            update_yw(ob, rb[n][iP], rb[n][iM2], up, ra[n][iM1], zsb, cb[n][iM1], s_div, P.omega);
+                            update_xz(oa, ra[n][iP], ra[n][iM2], rb[n][iM1], dn, zsa, cda, s_div, P.omega);
+                            update_yw(ob, rb[n][iP], rb[n][iM2], up, ra[n][iM1], zsb, cdb, s_div, P.omega);
                         } else {
-                            update_yw(oa, ra[n][iP], ra[n][iM2], rb[n][iM1], dn, zsa, ca[n][iM1], s_div, P.omega);
-                            update_xz(ob, rb[n][iP], rb[n][iM2], up, ra[n][iM1], zsb, cb[n][iM1], s_div, P.omega);
+                            update_yw(oa, ra[n][iP], ra[n][iM2], rb[n][iM1], dn, zsa, cda, s_div, P.omega);
+                            update_xz(ob, rb[n][iP], rb[n][iM2], up, ra[n][iM1], zsb, cdb, s_div, P.omega);
                         }
                         if (canBa[n]) *reinterpret_cast<float4 *>(dst_a[n]) = oa;
                         if (canBb[n]) *reinterpret_cast<float4 *>(dst_a[n] + g.pitch) = ob;
@@ -243,6 +238,13 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
             }
         }
     }
+}
+
+static size_t fused_smem_bytes(int LR, int LG)
+{
+    const size_t slot = ((size_t)(LR * LG + 7) / 8) * 8 * 16;        // fp32 box, 128-byte multiple
+    const size_t cslot = ((size_t)(LR * LG * 2 + 127) / 128) * 128;  // uint16 box
+    return F_NB * (slot + cslot) + F_NB * 8 + 16 * 8 + 128;          // + mbarriers, division table, alignment slack
 }
 
 struct TileChoice {
@@ -262,12 +264,11 @@ static TileChoice choose_tile(const taub_geom &g)
         const int NPT = (NP * F_NT) / LGp;       // row pairs per tile
         if (NPT < 2) break;
         int LG = LGp;
-        if (LG > ng + 2) LG = ng + 2;            // never wider than the row needs
-        if (LG <= LGp - 16) continue;            // a smaller LGp covers it
+        if (LG > ng + 2) LG = ((ng + 2 + 7) / 8) * 8;   // never (much) wider than the row needs; the
+        if (LG <= LGp - 16) continue;                   // uint16 code box must be a multiple of 16 bytes
         const int NR = 2 * NPT, OR_ = NR - 2, OG = LG - 2, LR = NR + 2;
         if (OG < 1) continue;
-        const size_t smem = (size_t)F_NB * (LR * LG + 8) * 16 + 512;
-        if (smem > 112 * 1024) continue;         // two CTAs per SM
+        if (fused_smem_bytes(LR, LG) > 115000) continue;   // two CTAs per SM
         const int tj = ceil_div(g.Ny, OR_), tk = ceil_div(ng, OG);
         const double eff = ((double)g.Ny * ng) / ((double)tj * tk * NPT * 2 * LGp);
         if (eff > best.eff) best = TileChoice{NP, LR, LG, LGp, OR_, OG, tj, tk, eff};
@@ -309,6 +310,43 @@ static int make_field_map(CUtensorMap *map, const taub_geom &g, const float *bas
     return TAUB_OK;
 }
 
+// Same view of the neighbour codes: (groups = pitch/4, rows, bs * planes), uint16, box = LG x LR x 1.
+static int make_code_map(CUtensorMap *map, const taub_geom &g, const uint16_t *base, int LR, int LG)
+{
+    EncodeTiledFn enc = encode_tiled_fn();
+    TAUB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t PG = (cuuint64_t)(g.pitch >> 2);
+    const cuuint64_t dims[3] = {PG, (cuuint64_t)g.rows, (cuuint64_t)g.bs * g.planes};
+    const cuuint64_t strides[2] = {PG * 2, (cuuint64_t)g.rows * PG * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)LG, (cuuint32_t)LR, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<uint16_t *>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TAUB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (codes) failed with CUresult %d", (int)r);
+    return TAUB_OK;
+}
+
+// Plane chunks per tile column: fewest "waves x (planes + prologue)" on the resident-CTA capacity.
+static void choose_chunks(int n_planes, int64_t tiles, int capacity, int *chunk_len, int *chunks)
+{
+    double best = 1e30;
+    *chunk_len = n_planes + (n_planes & 1);
+    *chunks = 1;
+    for (int c = 1; c <= 512 && c <= (n_planes + 1) / 2; ++c) {
+        int cl = ceil_div(n_planes, c);
+        cl += cl & 1;   // even: every CTA starts with the same row parity
+        const int ce = ceil_div(n_planes, cl);
+        const int64_t waves = ceil_div64(tiles * ce, capacity);
+        const double cost = (double)waves * (cl + 5);
+        if (cost < best - 1e-9) {
+            best = cost;
+            *chunk_len = cl;
+            *chunks = ce;
+        }
+    }
+}
+
 }  // namespace taub
 
 using namespace taub;
@@ -348,24 +386,26 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     P.a_hi = min(i_hi + 1, g.Nx_global - g.i_offset);
     P.LR = t.LR; P.LG = t.LG; P.LGp = t.LGp; P.OR_ = t.OR_; P.OG = t.OG;   // OR_ is even
     P.tiles_k = t.tiles_k;
-    // planes per CTA: ~3 waves of CTAs on 148 SMs x 2, but at least 16 planes to amortise the
-    // 4-plane prologue
     const int n_planes = i_hi - i_lo;
     const int64_t tiles = (int64_t)t.tiles_j * t.tiles_k * g.bs;
-    int chunks = (int)ceil_div64(3 * 148 * 2, tiles);
-    if (chunks < 1) chunks = 1;
-    int chunk_len = ceil_div(n_planes, chunks);
-    if (chunk_len < 16) chunk_len = min(16, n_planes);
-    chunk_len += chunk_len & 1;   // even: every CTA then starts with the same row parity
-    chunks = ceil_div(n_planes, chunk_len);
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        TAUB_CUDA(cudaGetDevice(&dev));
+        TAUB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    int chunk_len, chunks;
+    choose_chunks(n_planes, tiles, 2 * sm_count, &chunk_len, &chunks);
     P.chunk_len = chunk_len;
     TAUB_REQUIRE(chunks <= 65535, "taub_fused_sweep2: too many plane chunks");
     P.slot_f4 = ((t.LR * t.LG + 7) / 8) * 8;
-    const size_t smem = (size_t)F_NB * P.slot_f4 * 16 + F_NB * 8 + 16 * 8 + 128;
+    P.cslot_h = ((t.LR * t.LG * 2 + 127) / 128) * 64;
+    const size_t smem = fused_smem_bytes(t.LR, t.LG);
     dim3 grid(t.tiles_j * t.tiles_k, chunks, g.bs);
     cudaStream_t s = (cudaStream_t)stream;
-    CUtensorMap tmap;
+    CUtensorMap tmap, cmap;
     if (int rc = make_field_map(&tmap, g, P.src, t.LR, t.LG)) return rc;
+    if (int rc = make_code_map(&cmap, g, P.codes, t.LR, t.LG)) return rc;
     // parity of loaded row 1 (row a of every pair) at step 0, i.e. at plane c0-1: 0 -> x,z active.
     // Tile row offsets (multiples of the even OR_) and chunk starts (multiples of the even
     // chunk_len) do not change it, so it is one number for the whole grid.
@@ -374,7 +414,7 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     do {                                                                                                          \
         TAUB_CUDA(cudaFuncSetAttribute(fused_sweep2_kernel<2, PA_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                        (int)smem));                                                               \
-        fused_sweep2_kernel<2, PA_><<<grid, F_NT, smem, s>>>(P, tmap);                                            \
+        fused_sweep2_kernel<2, PA_><<<grid, F_NT, smem, s>>>(P, tmap, cmap);                                            \
     } while (0)
     if (pa0 == 0)
         TAUB_LAUNCH_FUSED(0);

@@ -42,7 +42,7 @@ def test_geometry(lib, shape):
     bs, Nx, Ny, Nz = shape
     assert lib.taub_geom_init(g, bs, Nx, Ny, Nz, Nx, 0, 1) == 0
     assert (g.planes, g.rows) == (Nx + 4, Ny + 4)
-    assert g.pitch % 8 == 0 and g.pitch >= Nz + 8 and g.pitch < Nz + 16
+    assert g.pitch % 32 == 0 and g.pitch >= Nz + 8 and g.pitch < Nz + 40
     assert g.plane_stride == g.rows * g.pitch and g.image_stride == g.planes * g.plane_stride
     assert lib.taub_field_elems(g) == bs * g.image_stride
     assert lib.taub_codes_elems(g) * 4 == lib.taub_field_elems(g)
