@@ -36,7 +36,7 @@ struct FusedParams {
     int colourA;
     int i_lo, i_hi;    // output planes (local)
     int a_lo, a_hi;    // planes that receive the colour-A update (output planes +-1, clipped to real planes)
-    int LR, LG, LGp;   // loaded rows, loaded float4 groups, groups rounded up to 16 (thread map)
+    int LR, LG, LGc;   // loaded rows, loaded float4 groups, code-box width (LG rounded up to 8)
     int OR_, OG;       // output rows / groups per tile
     int tiles_k;
     int chunk_len;     // output planes per CTA
@@ -120,7 +120,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
         const int slot = rel % F_NB;
         const uint32_t bar = smem_u32(&mbar[slot]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, (uint32_t)(LR * LG * 18));
+        mbar_expect_tx(bar, (uint32_t)(LR * (LG * 16 + P.LGc * 2)));
         const int pl = b * g.planes + (c0 - 2 + rel + G);
         tma_load_3d(smem_u32(planes + (size_t)slot * plane_f4), &tmap, 4 * G0, R0, pl, bar);
         tma_load_3d(smem_u32(cplanes + (size_t)slot * cslot), &cmap, G0, R0, pl, bar);
@@ -130,13 +130,14 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
 
     // ---- per-thread items
     int idxa[NP];            // float4 index of row a's group inside a ring slot (row b: + LG)
+    int idca[NP];            // uint16 index of row a's code inside a code slot (row b: + LGc)
     float *dst_a[NP];        // destination of row a's group in the plane colour B currently writes
     bool doit[NP], canBa[NP], canBb[NP];
     const int NPT = (LR - 2) >> 1;   // row pairs in the tile
 #pragma unroll
     for (int n = 0; n < NP; ++n) {
         const int u = tid + n * F_NT;
-        const int m = u / P.LGp, gg = u - m * P.LGp;
+        const int m = u / LG, gg = u - m * LG;
         const int lra = 1 + 2 * m;
         const int Ra = R0 + lra, Gs = G0 + gg;
         doit[n] = (m < NPT) && (gg < LG) && (Gs < PG) && (Ra < g.rows);
@@ -144,6 +145,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
         canBa[n] = doit[n] && colB && lra >= 2 && Ra >= G && Ra < G + g.Ny;
         canBb[n] = doit[n] && colB && lra + 1 < LR - 2 && Ra + 1 >= G && Ra + 1 < G + g.Ny;
         idxa[n] = lra * LG + gg;
+        idca[n] = lra * P.LGc + gg;
         const int64_t img = (int64_t)b * g.image_stride + 4 * Gs;
         // colour B first writes plane c0 (at step 2)
         dst_a[n] = P.dst + img + (int64_t)(c0 + G) * ps + (int64_t)Ra * g.pitch;
@@ -202,7 +204,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                     const float4 dn = bufP[ia - LG], up = bufP[ib + LG];
                     const float zsa = reinterpret_cast<const float *>(bufP)[za];
                     const float zsb = reinterpret_cast<const float *>(bufP)[zb];
-                    const unsigned cda = codP[ia], cdb = codP[ib];
+                    const unsigned cda = codP[idca[n]], cdb = codP[idca[n] + P.LGc];
                     // each row only reads the components of the other row that this step leaves unchanged
                     if (a_is_xz) {
                         update_xz(ra[n][iP], ra[n][iP1], ra[n][iM1], rb[n][iP], dn, zsa, cda, s_div, P.omega);
@@ -221,7 +223,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                         const float4 dn = bufM1[ia - LG], up = bufM1[ib + LG];
                         const float zsa = reinterpret_cast<const float *>(bufM1)[za];
                         const float zsb = reinterpret_cast<const float *>(bufM1)[zb];
-                        const unsigned cda = codM1[ia], cdb = codM1[ib];
+                        const unsigned cda = codM1[idca[n]], cdb = codM1[idca[n] + P.LGc];
                         float4 oa = ra[n][iM1], ob = rb[n][iM1];
                         if (a_is_xz) {
                             update_xz(oa, ra[n][iP], ra[n][iM2], rb[n][iM1], dn, zsa, cda, s_div, P.omega);
@@ -240,38 +242,39 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     }
 }
 
-static size_t fused_smem_bytes(int LR, int LG)
+static size_t fused_smem_bytes(int LR, int LG, int LGc)
 {
-    const size_t slot = ((size_t)(LR * LG + 7) / 8) * 8 * 16;        // fp32 box, 128-byte multiple
-    const size_t cslot = ((size_t)(LR * LG * 2 + 127) / 128) * 128;  // uint16 box
-    return F_NB * (slot + cslot) + F_NB * 8 + 16 * 8 + 128;          // + mbarriers, division table, alignment slack
+    const size_t slot = ((size_t)(LR * LG + 7) / 8) * 8 * 16;         // fp32 box, 128-byte multiple
+    const size_t cslot = ((size_t)(LR * LGc * 2 + 127) / 128) * 128;  // uint16 box
+    return F_NB * (slot + cslot) + F_NB * 8 + 16 * 8 + 128;           // + mbarriers, division table, alignment slack
 }
 
 struct TileChoice {
-    int NP, LR, LG, LGp, OR_, OG, tiles_j, tiles_k;
+    int NP, LR, LG, LGc, OR_, OG, tiles_j, tiles_k;
     double eff;
 };
 
-// Pick the tile shape that wastes the fewest thread-items: NP*256 (row pair x group) items per
-// tile, arranged as NPT row pairs of LGp (multiple of 16) group slots.
+// Tile = NPT row pairs x LG float4 groups (OG = LG - 2 of them are outputs).  TMA wants every box to
+// start on a 16-byte boundary and to be a multiple of 16 bytes wide; for the uint16 code box that
+// means OG (the tile step) is a multiple of 8 groups and the code box is LG rounded up to 8.  A box
+// is at most 256 elements wide (LG <= 64).  Pick the shape that wastes the fewest thread-items while
+// two CTAs still fit in one SM's shared memory.
 static TileChoice choose_tile(const taub_geom &g)
 {
     const int ng = interior_groups(g.Nz);
     TileChoice best{};
     best.eff = -1.0;
     const int NP = 2;
-    for (int LGp = 16; LGp <= 64; LGp += 16) {   // TMA box: at most 256 elements wide
-        const int NPT = (NP * F_NT) / LGp;       // row pairs per tile
-        if (NPT < 2) break;
-        int LG = LGp;
-        if (LG > ng + 2) LG = ((ng + 2 + 7) / 8) * 8;   // never (much) wider than the row needs; the
-        if (LG <= LGp - 16) continue;                   // uint16 code box must be a multiple of 16 bytes
-        const int NR = 2 * NPT, OR_ = NR - 2, OG = LG - 2, LR = NR + 2;
-        if (OG < 1) continue;
-        if (fused_smem_bytes(LR, LG) > 115000) continue;   // two CTAs per SM
+    for (int OG = 8; OG <= 56; OG += 8) {
+        const int LG = OG + 2, LGc = ((LG + 7) / 8) * 8;
+        int NPT = (NP * F_NT) / LG;   // row pairs the CTA's thread-items can cover
+        while (NPT >= 2 && fused_smem_bytes(2 * NPT + 2, LG, LGc) > 115000) --NPT;
+        if (NPT < 2) continue;
+        const int NR = 2 * NPT, OR_ = NR - 2, LR = NR + 2;
         const int tj = ceil_div(g.Ny, OR_), tk = ceil_div(ng, OG);
-        const double eff = ((double)g.Ny * ng) / ((double)tj * tk * NPT * 2 * LGp);
-        if (eff > best.eff) best = TileChoice{NP, LR, LG, LGp, OR_, OG, tj, tk, eff};
+        const double eff = ((double)g.Ny * ng) / ((double)tj * tk * NP * F_NT * 2);   // 2 rows per item
+        if (eff > best.eff + 1e-12) best = TileChoice{NP, LR, LG, LGc, OR_, OG, tj, tk, eff};
+        if (OG >= ng) break;          // one tile already spans the row
     }
     return best;
 }
@@ -310,15 +313,15 @@ static int make_field_map(CUtensorMap *map, const taub_geom &g, const float *bas
     return TAUB_OK;
 }
 
-// Same view of the neighbour codes: (groups = pitch/4, rows, bs * planes), uint16, box = LG x LR x 1.
-static int make_code_map(CUtensorMap *map, const taub_geom &g, const uint16_t *base, int LR, int LG)
+// Same view of the neighbour codes: (groups = pitch/4, rows, bs * planes), uint16, box = LGc x LR x 1.
+static int make_code_map(CUtensorMap *map, const taub_geom &g, const uint16_t *base, int LR, int LGc)
 {
     EncodeTiledFn enc = encode_tiled_fn();
     TAUB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t PG = (cuuint64_t)(g.pitch >> 2);
     const cuuint64_t dims[3] = {PG, (cuuint64_t)g.rows, (cuuint64_t)g.bs * g.planes};
     const cuuint64_t strides[2] = {PG * 2, (cuuint64_t)g.rows * PG * 2};
-    const cuuint32_t box[3] = {(cuuint32_t)LG, (cuuint32_t)LR, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)LGc, (cuuint32_t)LR, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<uint16_t *>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -384,7 +387,7 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     P.i_hi = i_hi;
     P.a_lo = max(i_lo - 1, -g.i_offset);
     P.a_hi = min(i_hi + 1, g.Nx_global - g.i_offset);
-    P.LR = t.LR; P.LG = t.LG; P.LGp = t.LGp; P.OR_ = t.OR_; P.OG = t.OG;   // OR_ is even
+    P.LR = t.LR; P.LG = t.LG; P.LGc = t.LGc; P.OR_ = t.OR_; P.OG = t.OG;   // OR_ is even, OG % 8 == 0
     P.tiles_k = t.tiles_k;
     const int n_planes = i_hi - i_lo;
     const int64_t tiles = (int64_t)t.tiles_j * t.tiles_k * g.bs;
@@ -399,13 +402,13 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     P.chunk_len = chunk_len;
     TAUB_REQUIRE(chunks <= 65535, "taub_fused_sweep2: too many plane chunks");
     P.slot_f4 = ((t.LR * t.LG + 7) / 8) * 8;
-    P.cslot_h = ((t.LR * t.LG * 2 + 127) / 128) * 64;
-    const size_t smem = fused_smem_bytes(t.LR, t.LG);
+    P.cslot_h = ((t.LR * t.LGc * 2 + 127) / 128) * 64;
+    const size_t smem = fused_smem_bytes(t.LR, t.LG, t.LGc);
     dim3 grid(t.tiles_j * t.tiles_k, chunks, g.bs);
     cudaStream_t s = (cudaStream_t)stream;
     CUtensorMap tmap, cmap;
     if (int rc = make_field_map(&tmap, g, P.src, t.LR, t.LG)) return rc;
-    if (int rc = make_code_map(&cmap, g, P.codes, t.LR, t.LG)) return rc;
+    if (int rc = make_code_map(&cmap, g, P.codes, t.LR, t.LGc)) return rc;
     // parity of loaded row 1 (row a of every pair) at step 0, i.e. at plane c0-1: 0 -> x,z active.
     // Tile row offsets (multiples of the even OR_) and chunk starts (multiples of the even
     // chunk_len) do not change it, so it is one number for the whole grid.
