@@ -121,6 +121,12 @@ int taub_half_sweep(const taub_problem *p, int64_t iter, int i_lo, int i_hi, voi
  * Returns TAUB_ERR_UNSUPPORTED when the problem does not qualify (see taub_can_fuse). */
 int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, void *stream);
 int taub_can_fuse(const taub_problem *p);
+/* The fused kernel divides by the neighbour count with an FMA-corrected reciprocal that equals the
+ * IEEE quotient for s == 0 and every |s| >= 2^-100.  This counts the threads that ever saw a
+ * non-zero sum below 2^-100 (there the result may differ from IEEE division by one subnormal ulp);
+ * 0 -- the only value ever observed -- certifies the fused trajectory bit-identical to the generic
+ * kernel and the reference.  Synchronises the device. */
+unsigned long long taub_inexact_events(void);
 /* n iterations starting at iter on the whole local slab (single-rank use): refreshes periodic
  * ghosts, picks fused pairs where possible, flips p->cur.  flags bit0: force the generic path. */
 int taub_iterate(taub_problem *p, int64_t iter, int n, int flags, void *stream);

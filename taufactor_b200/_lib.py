@@ -47,6 +47,7 @@ SIGNATURES = {
     "taub_refresh_ghosts": (c_int, [ctypes.POINTER(Geom), c_vp, c_int, c_int, c_vp]),
     "taub_half_sweep": (c_int, [ctypes.POINTER(Problem), c_i64, c_int, c_int, c_vp]),
     "taub_fused_sweep2": (c_int, [ctypes.POINTER(Problem), c_i64, c_int, c_int, c_vp]),
+    "taub_inexact_events": (ctypes.c_ulonglong, []),
     "taub_can_fuse": (c_int, [ctypes.POINTER(Problem)]),
     "taub_iterate": (c_int, [ctypes.POINTER(Problem), c_i64, c_int, c_int, c_vp]),
     "taub_plane_means": (c_int, [ctypes.POINTER(Problem), c_vp, c_vp, c_vp, c_vp]),

@@ -52,7 +52,8 @@ static inline __host__ __device__ int interior_groups(int Nz) { return (Nz + 3) 
 // mantissas for c = 1..8).  Tiny non-zero |s| (< 2^-100, where the remainder could go subnormal)
 // takes the __fdiv_rn path, so the result is bit-identical to IEEE division for every finite s.
 // Table entry for code 0 ("factor = inf": non-conductive voxel or no conductive neighbour) is
-// (c, r) = (0, 0), which yields q = 0 = s / inf without a special case.
+// (c, r) = (0, 0), which yields q = 0 = s / inf without a special case.  The guard is evaluated once
+// per group of updates (a branch per update would stop the compiler from interleaving the chains).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float2 div_entry(int code)
 {
@@ -61,48 +62,125 @@ __device__ __forceinline__ float2 div_entry(int code)
     return make_float2(c, r);
 }
 
-__device__ __forceinline__ float div_small(float s, float2 cr)
+// Fast quotient (exact for s == 0 and for every |s| >= 2^-100) plus the guard word of s:
+// u = 2*bits(s) - 1 drops the sign and wraps +-0 to the top, so "0 < |s| < 2^-100" <=> u < GUARD_T.
+constexpr unsigned GUARD_T = (27u << 24) - 1u;
+
+__device__ __forceinline__ float div_fast(float s, float2 cr, unsigned &umin)
 {
-    float q0 = __fmul_rn(s, cr.y);
-    float rem = __fmaf_rn(-q0, cr.x, s);
-    float q = __fmaf_rn(rem, cr.y, q0);
-    // rare path: 0 < |s| < 2^-100 (one shift-add and one unsigned compare: 2*bits drops the sign,
-    // minus 1 wraps +-0 to the top).  s == 0 -- every voxel inside the solid phase -- stays on the
-    // fast path, which returns the exact 0; inf / NaN propagate as NaN (the field has diverged).
-    const unsigned u = __float_as_uint(s) * 2u - 1u;
-    if (u < (27u << 24) - 1u) q = (cr.x > 0.0f) ? __fdiv_rn(s, cr.x) : 0.0f;
-    return q;
+    const float q0 = __fmul_rn(s, cr.y);
+    const float rem = __fmaf_rn(-q0, cr.x, s);
+    umin = min(umin, __float_as_uint(s) * 2u - 1u);
+    return __fmaf_rn(rem, cr.y, q0);
 }
 
-// One binary-solver voxel update, the reference's op order (taufactor.py:97-102, :177-181):
-// s = ((((x+ + x-) + y+) + y-) + z+) + z-;  f += omega * (s / nn - f).  No FMA contraction.
-__device__ __forceinline__ float sor_binary(float c, float xp, float xm, float yp, float ym,
-                                            float zp, float zm, float2 cr, float omega)
+// Neighbour sum in the reference's order (taufactor.py:97-102).
+__device__ __forceinline__ float nbr_sum(float xp, float xm, float yp, float ym, float zp, float zm)
 {
     float s = __fadd_rn(xp, xm);
     s = __fadd_rn(s, yp);
     s = __fadd_rn(s, ym);
     s = __fadd_rn(s, zp);
-    s = __fadd_rn(s, zm);
-    float d = __fsub_rn(div_small(s, cr), c);
-    d = __fmul_rn(d, omega);
-    return __fadd_rn(c, d);
+    return __fadd_rn(s, zm);
+}
+
+// f += omega * (q - f), taufactor.py:177-181, no FMA contraction.
+__device__ __forceinline__ float relax(float c, float q, float omega)
+{
+    return __fadd_rn(c, __fmul_rn(__fsub_rn(q, c), omega));
+}
+
+// One binary-solver voxel update on the fast path; the caller checks umin once per group of updates.
+__device__ __forceinline__ float sor_fast(float c, float xp, float xm, float yp, float ym, float zp, float zm,
+                                          float2 cr, float omega, unsigned &umin)
+{
+    return relax(c, div_fast(nbr_sum(xp, xm, yp, ym, zp, zm), cr, umin), omega);
+}
+
+// The same update with a true IEEE division: taken only when some sum in the group is a non-zero
+// value below 2^-100 (never seen in practice; keeps the result bit-identical for every finite input).
+static __device__ __noinline__ float sor_exact(float c, float xp, float xm, float yp, float ym, float zp, float zm,
+                                        float divisor, float omega)
+{
+    const float s = nbr_sum(xp, xm, yp, ym, zp, zm);
+    const float q = (divisor > 0.0f) ? __fdiv_rn(s, divisor) : __fdiv_rn(s, __int_as_float(0x7f800000));
+    return relax(c, q, omega);
 }
 
 // Colour updates of two voxels of a float4 group.  "xz" rows update components x and z (their z
 // neighbours are y, w and the scalar zs = .w of the group on the left); "yw" rows update y and w
 // (zs = .x of the group on the right).  xp/xm: x neighbours, up/dn: y+1 / y-1 neighbours.
+// The *_fast forms return the new values in n0/n1 and fold the guard into umin; commit_* writes them
+// after the (single, rare) exactness check of the caller.
+__device__ __forceinline__ void xz_fast(const float4 &c, const float4 &xp, const float4 &xm, const float4 &up,
+                                        const float4 &dn, float zs, unsigned code, const float2 *s_div, float omega,
+                                        float &n0, float &n1, unsigned &umin)
+{
+    n0 = sor_fast(c.x, xp.x, xm.x, up.x, dn.x, c.y, zs, s_div[code & 15u], omega, umin);
+    n1 = sor_fast(c.z, xp.z, xm.z, up.z, dn.z, c.w, c.y, s_div[(code >> 8) & 15u], omega, umin);
+}
+__device__ __forceinline__ void yw_fast(const float4 &c, const float4 &xp, const float4 &xm, const float4 &up,
+                                        const float4 &dn, float zs, unsigned code, const float2 *s_div, float omega,
+                                        float &n0, float &n1, unsigned &umin)
+{
+    n0 = sor_fast(c.y, xp.y, xm.y, up.y, dn.y, c.z, c.x, s_div[(code >> 4) & 15u], omega, umin);
+    n1 = sor_fast(c.w, xp.w, xm.w, up.w, dn.w, zs, c.z, s_div[(code >> 12) & 15u], omega, umin);
+}
+__device__ __forceinline__ void xz_exact(const float4 &c, const float4 &xp, const float4 &xm, const float4 &up,
+                                         const float4 &dn, float zs, unsigned code, float omega, float &n0, float &n1)
+{
+    n0 = sor_exact(c.x, xp.x, xm.x, up.x, dn.x, c.y, zs, (float)(code & 15u), omega);
+    n1 = sor_exact(c.z, xp.z, xm.z, up.z, dn.z, c.w, c.y, (float)((code >> 8) & 15u), omega);
+}
+__device__ __forceinline__ void yw_exact(const float4 &c, const float4 &xp, const float4 &xm, const float4 &up,
+                                         const float4 &dn, float zs, unsigned code, float omega, float &n0, float &n1)
+{
+    n0 = sor_exact(c.y, xp.y, xm.y, up.y, dn.y, c.z, c.x, (float)((code >> 4) & 15u), omega);
+    n1 = sor_exact(c.w, xp.w, xm.w, up.w, dn.w, zs, c.z, (float)((code >> 12) & 15u), omega);
+}
+
+// Single-row forms (generic kernel): fast path, one exactness check per row group.
 __device__ __forceinline__ void update_xz(float4 &c, const float4 &xp, const float4 &xm, const float4 &up,
                                           const float4 &dn, float zs, unsigned code, const float2 *s_div, float omega)
 {
-    c.x = sor_binary(c.x, xp.x, xm.x, up.x, dn.x, c.y, zs, s_div[code & 15u], omega);
-    c.z = sor_binary(c.z, xp.z, xm.z, up.z, dn.z, c.w, c.y, s_div[(code >> 8) & 15u], omega);
+    float n0, n1;
+    unsigned umin = 0xffffffffu;
+    xz_fast(c, xp, xm, up, dn, zs, code, s_div, omega, n0, n1, umin);
+    if (umin < GUARD_T) xz_exact(c, xp, xm, up, dn, zs, code, omega, n0, n1);
+    c.x = n0;
+    c.z = n1;
 }
 __device__ __forceinline__ void update_yw(float4 &c, const float4 &xp, const float4 &xm, const float4 &up,
                                           const float4 &dn, float zs, unsigned code, const float2 *s_div, float omega)
 {
-    c.y = sor_binary(c.y, xp.y, xm.y, up.y, dn.y, c.z, c.x, s_div[(code >> 4) & 15u], omega);
-    c.w = sor_binary(c.w, xp.w, xm.w, up.w, dn.w, zs, c.z, s_div[(code >> 12) & 15u], omega);
+    float n0, n1;
+    unsigned umin = 0xffffffffu;
+    yw_fast(c, xp, xm, up, dn, zs, code, s_div, omega, n0, n1, umin);
+    if (umin < GUARD_T) yw_exact(c, xp, xm, up, dn, zs, code, omega, n0, n1);
+    c.y = n0;
+    c.w = n1;
+}
+
+// A row PAIR (a below b) in one step of the fused kernel: the xz row and the yw row on the fast path
+// only.  A_IS_XZ (a constant after unrolling) selects which of the two rows updates x,z; ca/cb are
+// updated in place; umin accumulates the guard word (see taub_inexact_events()).
+__device__ __forceinline__ void update_pair(const bool A_IS_XZ, float4 &ca, float4 &cb, const float4 &axp,
+                                            const float4 &axm, const float4 &bxp, const float4 &bxm, const float4 &a_dn,
+                                            const float4 &b_up, float zsa, float zsb, unsigned cda, unsigned cdb,
+                                            const float2 *s_div, float omega, unsigned &umin)
+{
+    // row a: up neighbour is row b, down neighbour comes from shared memory; row b: the mirror image.
+    // Each row only reads components of the other that this step leaves unchanged.
+    float a0, a1, b0, b1;
+    if (A_IS_XZ) {
+        xz_fast(ca, axp, axm, cb, a_dn, zsa, cda, s_div, omega, a0, a1, umin);
+        yw_fast(cb, bxp, bxm, b_up, ca, zsb, cdb, s_div, omega, b0, b1, umin);
+        ca.x = a0; ca.z = a1; cb.y = b0; cb.w = b1;
+    } else {
+        yw_fast(ca, axp, axm, cb, a_dn, zsa, cda, s_div, omega, a0, a1, umin);
+        xz_fast(cb, bxp, bxm, b_up, ca, zsb, cdb, s_div, omega, b0, b1, umin);
+        ca.y = a0; ca.w = a1; cb.x = b0; cb.z = b1;
+    }
 }
 
 // One multi-phase voxel update (taufactor.py:606-613, :598-603): each neighbour times its face

@@ -67,6 +67,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
             : "memory");
     } while (!ok);
 }
+__device__ unsigned long long g_inexact_events = 0ULL;
+
 // One TMA box: tensor coordinates (column, row, plane) in elements -> shared memory, signalling bar.
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar)
 {
@@ -170,6 +172,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
         }
     }
 
+    unsigned umin = 0xffffffffu;   // guard word of every neighbour sum this thread divides
     const int n_steps = c1 - c0 + 2;
     for (int s4 = 0; s4 < n_steps; s4 += 4) {
 #pragma unroll
@@ -205,14 +208,8 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                     const float zsa = reinterpret_cast<const float *>(bufP)[za];
                     const float zsb = reinterpret_cast<const float *>(bufP)[zb];
                     const unsigned cda = codP[idca[n]], cdb = codP[idca[n] + P.LGc];
-                    // each row only reads the components of the other row that this step leaves unchanged
-                    if (a_is_xz) {
-                        update_xz(ra[n][iP], ra[n][iP1], ra[n][iM1], rb[n][iP], dn, zsa, cda, s_div, P.omega);
-                        update_yw(rb[n][iP], rb[n][iP1], rb[n][iM1], up, ra[n][iP], zsb, cdb, s_div, P.omega);
-                    } else {
-                        update_yw(ra[n][iP], ra[n][iP1], ra[n][iM1], rb[n][iP], dn, zsa, cda, s_div, P.omega);
-                        update_xz(rb[n][iP], rb[n][iP1], rb[n][iM1], up, ra[n][iP], zsb, cdb, s_div, P.omega);
-                    }
+                    update_pair(a_is_xz, ra[n][iP], rb[n][iP], ra[n][iP1], ra[n][iM1], rb[n][iP1], rb[n][iM1], dn, up,
+                                           zsa, zsb, cda, cdb, s_div, P.omega, umin);
                     if (keepA) {
                         bufP[ia] = ra[n][iP];
                         bufP[ib] = rb[n][iP];
@@ -225,13 +222,8 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                         const float zsb = reinterpret_cast<const float *>(bufM1)[zb];
                         const unsigned cda = codM1[idca[n]], cdb = codM1[idca[n] + P.LGc];
                         float4 oa = ra[n][iM1], ob = rb[n][iM1];
-                        if (a_is_xz) {
-                            update_xz(oa, ra[n][iP], ra[n][iM2], rb[n][iM1], dn, zsa, cda, s_div, P.omega);
-                            update_yw(ob, rb[n][iP], rb[n][iM2], up, ra[n][iM1], zsb, cdb, s_div, P.omega);
-                        } else {
-                            update_yw(oa, ra[n][iP], ra[n][iM2], rb[n][iM1], dn, zsa, cda, s_div, P.omega);
-                            update_xz(ob, rb[n][iP], rb[n][iM2], up, ra[n][iM1], zsb, cdb, s_div, P.omega);
-                        }
+                        update_pair(a_is_xz, oa, ob, ra[n][iP], ra[n][iM2], rb[n][iP], rb[n][iM2], dn, up, zsa, zsb, cda,
+                                               cdb, s_div, P.omega, umin);
                         if (canBa[n]) *reinterpret_cast<float4 *>(dst_a[n]) = oa;
                         if (canBb[n]) *reinterpret_cast<float4 *>(dst_a[n] + g.pitch) = ob;
                     }
@@ -240,6 +232,9 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
             }
         }
     }
+    // a non-zero sum below 2^-100 went through the fast division: count it (results stay within one
+    // subnormal ulp of the reference there; never observed -- taub_inexact_events() reports it)
+    if (umin < GUARD_T) atomicAdd(&g_inexact_events, 1ULL);
 }
 
 static size_t fused_smem_bytes(int LR, int LG, int LGc)
@@ -355,6 +350,13 @@ static void choose_chunks(int n_planes, int64_t tiles, int capacity, int *chunk_
 using namespace taub;
 
 extern "C" {
+
+unsigned long long taub_inexact_events(void)
+{
+    unsigned long long v = 0;
+    if (cudaMemcpyFromSymbol(&v, g_inexact_events, sizeof(v)) != cudaSuccess) return ~0ULL;
+    return v;
+}
 
 int taub_can_fuse(const taub_problem *p)
 {

@@ -266,6 +266,13 @@ class SORSolver:
         """The reduction + device->host read of one convergence check, without the stop rule."""
         return self._plane_means()
 
+    @property
+    def inexact_events(self):
+        """Process-wide count of fused-kernel threads that divided a non-zero neighbour sum below
+        2^-100 on the fast path (0 certifies bit-identity with the reference; see taub200.h)."""
+        self._lib.taub_set_device(self._dev_index)
+        return int(self._lib.taub_inexact_events())
+
     def sweep_kernel_name(self):
         fused = (not self.force_generic) and self._lib.taub_can_fuse(self._prob) == 1
         return "fused_sweep2_kernel" if fused else "half_sweep_kernel"

@@ -24,4 +24,5 @@ for shape, cls in [((20, 20, 20), "Solver"), ((11, 13, 9), "Solver"), ((24, 31, 
             break
     else:
         print("  bitwise equal through", A.iter, "iterations", flush=True)
+print("inexact events:", A.inexact_events)
 print("PROBE", "OK" if ok else "FAILED")

@@ -222,3 +222,12 @@ def test_uniform_block_analytic_256(tau):
     S = tau.Solver(np.ones((256, 256, 256), np.uint8), device="cuda")
     S.solve(verbose=False)
     assert abs(float(S.tau[0]) - 1.0) < 1e-5
+
+
+def test_zz_fused_fast_division_was_exact_everywhere(tau):
+    """Runs last: no thread of the fused kernel ever divided a sub-2^-100 sum on the fast path, so
+    every fused trajectory above was bit-identical to IEEE division (taub_inexact_events)."""
+    S, _ = make(tau, "rand40")
+    S.solve(iter_limit=100, verbose=False)
+    assert S.sweep_kernel_name() == "fused_sweep2_kernel"
+    assert S.inexact_events == 0
