@@ -156,6 +156,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     // ---- register ring: ring[.][k] holds plane (c0-3+k+4j); at step s = 4j+ss:
     //      a[p-2] = ring[ss], a[p-1] = ring[ss+1], raw[p] -> a[p] = ring[ss+2], raw[p+1] = ring[ss+3]
     float4 ra[NP][4], rb[NP][4];
+    unsigned cr[NP][4];   // neighbour codes of rows a (low half) and b (high half), same ring positions
     mbar_wait(smem_u32(&mbar[0]), 0);
     mbar_wait(smem_u32(&mbar[1 % F_NB]), 0);
 #pragma unroll
@@ -163,12 +164,14 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             ra[n][k] = rb[n][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            cr[n][k] = 0;
         }
         if (doit[n]) {
             ra[n][1] = planes[idxa[n]];
             rb[n][1] = planes[idxa[n] + LG];
             ra[n][2] = planes[plane_f4 + idxa[n]];
             rb[n][2] = planes[plane_f4 + idxa[n] + LG];
+            cr[n][2] = (unsigned)cplanes[cslot + idca[n]] | ((unsigned)cplanes[cslot + idca[n] + P.LGc] << 16);
         }
     }
 
@@ -189,8 +192,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
             const float4 *bufM1 = planes + (size_t)(s % F_NB) * plane_f4;
             float4 *bufP = planes + (size_t)((s + 1) % F_NB) * plane_f4;
             const float4 *bufP1 = planes + (size_t)((s + 2) % F_NB) * plane_f4;
-            const uint16_t *codM1 = cplanes + (size_t)(s % F_NB) * cslot;
-            const uint16_t *codP = cplanes + (size_t)((s + 1) % F_NB) * cslot;
+            const uint16_t *codP1 = cplanes + (size_t)((s + 2) % F_NB) * cslot;
             const bool doA = (p >= P.a_lo) && (p < P.a_hi);
             const bool keepA = (p >= c0) && (p < c1);   // a[p] is read by colour B of plane p next step
             const bool doB = (s >= 2);
@@ -200,6 +202,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                 const int ia = idxa[n], ib = idxa[n] + LG;
                 ra[n][iP1] = bufP1[ia];
                 rb[n][iP1] = bufP1[ib];
+                cr[n][iP1] = (unsigned)codP1[idca[n]] | ((unsigned)codP1[idca[n] + P.LGc] << 16);
                 // scalar z neighbour: z-1 of .x (xz row) or z+1 of .w (yw row)
                 const int za = a_is_xz ? 4 * ia - 1 : 4 * ia + 4;
                 const int zb = a_is_xz ? 4 * ib + 4 : 4 * ib - 1;
@@ -207,7 +210,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                     const float4 dn = bufP[ia - LG], up = bufP[ib + LG];
                     const float zsa = reinterpret_cast<const float *>(bufP)[za];
                     const float zsb = reinterpret_cast<const float *>(bufP)[zb];
-                    const unsigned cda = codP[idca[n]], cdb = codP[idca[n] + P.LGc];
+                    const unsigned cda = cr[n][iP], cdb = cr[n][iP] >> 16;
                     update_pair(a_is_xz, ra[n][iP], rb[n][iP], ra[n][iP1], ra[n][iM1], rb[n][iP1], rb[n][iM1], dn, up,
                                            zsa, zsb, cda, cdb, s_div, P.omega, umin);
                     if (keepA) {
@@ -220,7 +223,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                         const float4 dn = bufM1[ia - LG], up = bufM1[ib + LG];
                         const float zsa = reinterpret_cast<const float *>(bufM1)[za];
                         const float zsb = reinterpret_cast<const float *>(bufM1)[zb];
-                        const unsigned cda = codM1[idca[n]], cdb = codM1[idca[n] + P.LGc];
+                        const unsigned cda = cr[n][iM1], cdb = cr[n][iM1] >> 16;
                         float4 oa = ra[n][iM1], ob = rb[n][iM1];
                         update_pair(a_is_xz, oa, ob, ra[n][iP], ra[n][iM2], rb[n][iP], rb[n][iM2], dn, up, zsa, zsb, cda,
                                                cdb, s_div, P.omega, umin);

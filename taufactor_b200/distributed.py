@@ -1,0 +1,321 @@
+"""x-slab partitioned solves across the GPUs of one box (one process per GPU, torch.distributed).
+
+The reference has no distributed code; this is the B200-side answer to
+volumes that do not fit -- or should run faster than -- one GPU.  The volume is cut along x (the
+flux direction, the slowest-varying axis): rank r owns planes [lo_r, hi_r) plus TAUB_GHOST = 2
+ghost planes on each side, which hold the neighbour's boundary planes (or the Dirichlet planes on
+the first / last rank).  Ghost planes are whole contiguous storage planes, so one halo message per
+neighbour per pass moves ``2 * plane_stride`` floats; a pass is the fused two-colour kernel (two
+reference iterations), whose colour-A step is recomputed on the first ghost plane, so ONE exchange
+feeds TWO iterations.  Per-slice flux / mean profiles are reduced locally (taub_plane_means; the
+face that straddles two slabs belongs to the lower rank) and all-gathered, after which every rank
+evaluates the reference's stop rule (taufactor.py:109-153) on identical numbers.
+
+The partitioned field is bit-identical to the single-GPU field at every iteration: the update of a
+voxel does not depend on the order in which voxels are visited (tests/test_gpu_slab.py).
+"""
+from __future__ import annotations
+
+import math
+from timeit import default_timer as timer
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import Geom, Problem
+from .solvers import BOT_BC, TOP_BC, SORSolver, Solver, _as_uint8_labels, _expand_to_4d
+
+G = _lib.GHOST
+
+
+# ----------------------------------------------------------------------------- host-side logic
+def slab_bounds(Nx, world):
+    """[lo, hi) of every rank: contiguous, sizes differ by at most one plane."""
+    cuts = [Nx * r // world for r in range(world + 1)]
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def image_window(lo, hi, Nx, halo=G + 1):
+    """Global planes of the label image a rank needs to build its storage (taub_init_binary)."""
+    return max(0, lo - halo), min(Nx, hi + halo)
+
+
+def halo_plan(rank, world, Nx_local, width=G):
+    """(peer, send_plane, recv_plane) triples in storage-plane indices, ``width`` planes each:
+    own first planes -> lower neighbour's upper ghosts, own last planes -> upper neighbour's lower
+    ghosts."""
+    plan = []
+    if rank > 0:
+        plan.append((rank - 1, G, G - width))                       # send first owned, recv into lower ghosts
+    if rank < world - 1:
+        plan.append((rank + 1, G + Nx_local - width, G + Nx_local))  # send last owned, recv into upper ghosts
+    return plan
+
+
+def _staged(flat, group):
+    """gloo cannot move CUDA tensors point-to-point: stage through the host (test configurations
+    that run several ranks on one GPU); NCCL and CPU tensors go direct."""
+    return flat.is_cuda and dist.get_backend(group) == "gloo"
+
+
+def exchange_halos(flat, bs, image_stride, plane_stride, Nx_local, rank, world, group=None, width=G):
+    """Ghost-plane exchange on the flat storage tensor (CPU/gloo or CUDA/NCCL).  Returns the
+    number of bytes this rank sent."""
+    ops, sent, back = [], 0, []
+    n = width * plane_stride
+    staged = _staged(flat, group)
+    for peer, sp, rp in halo_plan(rank, world, Nx_local, width):
+        for b in range(bs):
+            base = b * image_stride
+            s = flat[base + sp * plane_stride: base + sp * plane_stride + n]
+            r = flat[base + rp * plane_stride: base + rp * plane_stride + n]
+            if staged:
+                s, r_host = s.cpu(), torch.empty(n, dtype=flat.dtype)
+                back.append((r, r_host))
+                r = r_host
+            ops.append(dist.P2POp(dist.isend, s, peer, group))
+            ops.append(dist.P2POp(dist.irecv, r, peer, group))
+            sent += n * flat.element_size()
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    for dst, src in back:
+        dst.copy_(src)
+    return sent
+
+
+def all_gather_flat(out, inp, group=None):
+    """all_gather_into_tensor with a host-staged fall-back for gloo."""
+    if dist.get_backend(group) == "gloo":
+        world = dist.get_world_size(group)
+        parts = [torch.empty(inp.numel(), dtype=inp.dtype) for _ in range(world)]
+        dist.all_gather(parts, inp.reshape(-1).cpu(), group=group)
+        out.copy_(torch.cat(parts).to(out.device))
+    else:
+        dist.all_gather_into_tensor(out, inp, group=group)
+
+
+def assemble_profiles(parts, bounds, bs):
+    """parts[r] = (flux (bs, n_r), mean (bs, Nx_r)) of rank r -> global (bs, Nx-1), (bs, Nx)."""
+    flux = np.concatenate([p[0] for p in parts], axis=1)
+    mean = np.concatenate([p[1] for p in parts], axis=1)
+    Nx = bounds[-1][1]
+    assert flux.shape == (bs, Nx - 1) and mean.shape == (bs, Nx), (flux.shape, mean.shape)
+    return flux, mean
+
+
+# ----------------------------------------------------------------------------- the solver
+class DistributedSolver(Solver):
+    """``Solver`` / ``PeriodicSolver`` on an x-slab partition (binary labels).
+
+    Args:
+        img: either the FULL label image on every rank, or -- with ``window=(g_lo, g_hi)`` -- only
+            the global planes [g_lo, g_hi) of it, which must cover ``image_window`` of this rank.
+        shape: global (Nx, Ny, Nz) when ``img`` is a window.
+        periodic: PeriodicSolver semantics (y/z periodic).
+        group: process group (default: the world group).
+    """
+
+    def __init__(self, img, omega=None, D_0=1, device=None, periodic=False, group=None, window=None, shape=None):
+        self._lib = _lib.load()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self._periodic = bool(periodic)
+        self.conductive_labels = [1]
+        img4 = _expand_to_4d(img)
+        self._check_binary_labels(img4)
+        if window is None:
+            window = (0, img4.shape[1])
+            Nx_g, Ny, Nz = img4.shape[1:]
+            self.cpu_img = img4
+        else:
+            Nx_g, Ny, Nz = shape
+            self.cpu_img = None          # no full image on this rank (percolation fallback unavailable)
+        self.batch_size = img4.shape[0]
+        self.Nx, self.Ny, self.Nz = Nx_g, Ny, Nz
+        self.bounds = slab_bounds(Nx_g, self.world)
+        self.lo, self.hi = self.bounds[self.rank]
+        if self.hi - self.lo < G:
+            raise ValueError(f"slab of rank {self.rank} has {self.hi - self.lo} planes; need at least {G}")
+        self.local_shape = (self.batch_size, self.hi - self.lo, Ny, Nz)
+        self.global_voxels = self.batch_size * Nx_g * Ny * Nz
+        need = image_window(self.lo, self.hi, Nx_g)
+        if window[0] > need[0] or window[1] < need[1]:
+            raise ValueError(f"image window {window} does not cover the planes {need} rank {self.rank} needs")
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = self._init_device(device)
+        self.precision = torch.float
+        if omega is None:
+            omega = 2 - math.pi / (1.5 * Nx_g)            # ref:36-37, global Nx
+        self.omega = omega
+        dev = self.device
+        self._dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+        self._call(self._lib.taub_set_device(self._dev_index), "taub_set_device")
+
+        g = Geom()
+        self._call(self._lib.taub_geom_init(g, self.batch_size, self.hi - self.lo, Ny, Nz, Nx_g, self.lo,
+                                            int(self._periodic)), "taub_geom_init")
+        self._geom = g
+        n = self._lib.taub_field_elems(g)
+        with torch.cuda.device(dev):
+            self._bufs = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(2)]
+            # only the planes this rank needs travel to the device
+            sub = np.ascontiguousarray(_as_uint8_labels(img4[:, need[0] - window[0]: need[1] - window[0]]))
+            img_dev = torch.from_numpy(sub).to(dev)
+            sh = 1 / (2 * Nx_g)
+            vec = torch.linspace(TOP_BC + sh, BOT_BC - sh, Nx_g, dtype=torch.float32).to(dev)
+            p = Problem()
+            p.g = g
+            p.kind = _lib.BINARY
+            p.field[0], p.field[1] = self._bufs[0].data_ptr(), self._bufs[1].data_ptr()
+            p.omega = float(np.float32(omega))
+            p.cur = 0
+            codes = torch.empty(self._lib.taub_codes_elems(g), dtype=torch.int16, device=dev)
+            p.codes = codes.data_ptr()
+            self._prob = p
+            self._call(self._lib.taub_init_binary(p, img_dev.data_ptr(), need[0], need[1] - need[0],
+                                                  vec.data_ptr(), self._stream()), "taub_init_binary")
+            sel = torch.zeros(256, dtype=torch.uint8, device=dev)
+            sel[1] = 1
+            counts = torch.zeros(self.batch_size * g.Nx, dtype=torch.int64, device=dev)
+            self._call(self._lib.taub_plane_counts(g, img_dev.data_ptr(), need[0], need[1] - need[0], sel.data_ptr(),
+                                                   counts.data_ptr(), None, self._stream()), "taub_plane_counts")
+            self._keep = (codes, vec)
+            self._ws = torch.empty(max(self._lib.taub_sums_ws_bytes(g), 16), dtype=torch.uint8, device=dev)
+            self._n_flux = g.Nx - 1 + (1 if self.hi < Nx_g else 0)
+            self._max_local = max(h - l for l, h in self.bounds)
+            # one padded record per rank: [flux (bs x max_local) | mean (bs x max_local)]
+            self._rec = torch.zeros(2 * self.batch_size * self._max_local, dtype=torch.float32, device=dev)
+            self._flux_dev = torch.zeros(self.batch_size * max(self._n_flux, 1), dtype=torch.float32, device=dev)
+            self._mean_dev = torch.zeros(self.batch_size * g.Nx, dtype=torch.float32, device=dev)
+            self._gather = torch.zeros(self.world * self._rec.numel(), dtype=torch.float32, device=dev)
+            # global per-slice volume fractions (ref:42): gather the per-plane counts
+            cpad = torch.zeros(self.batch_size * self._max_local, dtype=torch.int64, device=dev)
+            cpad.view(self.batch_size, self._max_local)[:, : g.Nx] = counts.view(self.batch_size, g.Nx)
+            call = torch.zeros(self.world * cpad.numel(), dtype=torch.int64, device=dev)
+            all_gather_flat(call, cpad, group)
+            call = call.cpu().numpy().reshape(self.world, self.batch_size, self._max_local)
+            del img_dev
+        counts_g = np.concatenate([call[r][:, : h - l] for r, (l, h) in enumerate(self.bounds)], axis=1)
+        self.vol_x = (counts_g.astype(np.float32) / np.float32(Ny * Nz)).astype(np.float32)
+        self.converged = False
+        self.old_tau = 0
+        self.iter = 0
+        self.tau = None
+        self.tau_x = None
+        self.D_eff = None
+        self.force_generic = False
+        self.D_0 = D_0
+        self.D_mean = np.mean(self.vol_x, axis=1)
+        self.halo_bytes_sent = 0
+        self._fuse = None
+        self._report = (self.rank == 0)
+
+    # ---- the loop: refresh (periodic) -> halo exchange -> pass, two iterations per pass when fused
+    def _advance(self, n):
+        lib, p, g = self._lib, self._prob, self._geom
+        lib.taub_set_device(self._dev_index)
+        if self._fuse is None:
+            self._fuse = lib.taub_can_fuse(p) == 1
+        done = 0
+        while done < n:
+            cur = self._bufs[p.cur]
+            if self._periodic:
+                self._call(lib.taub_refresh_ghosts(g, cur.data_ptr(), G, G + g.Nx, self._stream()), "taub_refresh_ghosts")
+            if self.world > 1:
+                self.halo_bytes_sent += exchange_halos(cur, g.bs, g.image_stride, g.plane_stride, g.Nx, self.rank,
+                                                       self.world, self.group)
+            if self._fuse and not self.force_generic and n - done >= 2:
+                self._call(lib.taub_fused_sweep2(p, self.iter + done, 0, g.Nx, self._stream()), "taub_fused_sweep2")
+                done += 2
+            else:
+                self._call(lib.taub_half_sweep(p, self.iter + done, 0, g.Nx, self._stream()), "taub_half_sweep")
+                done += 1
+            p.cur ^= 1
+        self.iter += n
+
+    def _plane_means(self):
+        lib, p, g = self._lib, self._prob, self._geom
+        cur = self._bufs[p.cur]
+        if self.world > 1:   # the face to the next slab reads the upper ghost plane: make it current
+            self.halo_bytes_sent += exchange_halos(cur, g.bs, g.image_stride, g.plane_stride, g.Nx, self.rank,
+                                                   self.world, self.group, width=1)
+        self._call(lib.taub_plane_means(p, self._ws.data_ptr(), self._flux_dev.data_ptr(), self._mean_dev.data_ptr(),
+                                        self._stream()), "taub_plane_means")
+        bs, ml = self.batch_size, self._max_local
+        rec = self._rec.view(2, bs, ml)
+        rec.zero_()
+        if self._n_flux:
+            rec[0, :, : self._n_flux] = self._flux_dev[: bs * self._n_flux].view(bs, self._n_flux)
+        rec[1, :, : g.Nx] = self._mean_dev.view(bs, g.Nx)
+        if self.world > 1:
+            all_gather_flat(self._gather, self._rec, self.group)
+            allr = self._gather.cpu().numpy().reshape(self.world, 2, bs, ml)
+        else:
+            allr = self._rec.cpu().numpy().reshape(1, 2, bs, ml)
+        parts = []
+        for r, (l, h) in enumerate(self.bounds):
+            nf = (h - l) - 1 + (1 if h < self.Nx else 0)
+            parts.append((allr[r, 0, :, :nf], allr[r, 1, :, : h - l]))
+        return assemble_profiles(parts, self.bounds, bs)
+
+    def _host_conductive_mask(self, b):
+        if self.cpu_img is None:
+            raise RuntimeError("a slice flux is exactly 0 and the percolation check (ref:318-327) needs the whole "
+                               "image on the host; construct DistributedSolver from the full image")
+        return super()._host_conductive_mask(b)
+
+    @property
+    def field(self):
+        """This rank's slab as the reference-style padded window [bs, Nx_local+2, Ny+2, Nz+2]."""
+        return super().field
+
+    def gather_field(self):
+        """Interior field of the whole volume on every rank (testing / small volumes only)."""
+        loc = self.field[:, 1:-1, 1:-1, 1:-1].contiguous()
+        ml = self._max_local
+        pad = torch.zeros((self.batch_size, ml, self.Ny, self.Nz), dtype=torch.float32, device=self.device)
+        pad[:, : loc.shape[1]] = loc
+        out = torch.zeros((self.world,) + tuple(pad.shape), dtype=torch.float32, device=self.device)
+        if self.world > 1:
+            all_gather_flat(out.view(-1), pad.view(-1), self.group)
+        else:
+            out[0] = pad
+        return torch.cat([out[r][:, : h - l] for r, (l, h) in enumerate(self.bounds)], dim=1)
+
+
+# ----------------------------------------------------------------------------- bench helper
+def make_bench_solver(args, rank, world, dev):
+    """Workloads of ``bench.py --gpus N`` (N > 1)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    import cases
+    if args.workload == "batch":
+        # BASELINE configs[2]: one independent 384^3 image per GPU
+        from . import Solver as Single
+        img = cases.blobs(384, 0.5, seed=384 + rank)
+        host = torch.empty(img.shape, dtype=torch.uint8).pin_memory()
+        host.numpy()[...] = img
+
+        class Batch(Single):
+            global_voxels = img.size * world
+            local_shape = img.shape
+        return (lambda: Batch(host.numpy(), device=dev), f"batched Solver: {world} x 384^3 independent volumes, one per GPU",
+                f"batch sharded, {world} ranks, no data-path collective", host.numpy())
+    # BASELINE configs[4]: the periodic 512^3 blob tiled to side*side*side, x-slab partitioned
+    side = args.size if args.size > 512 else 2048
+    reps = side // 512
+    blob = cases.blobs(512, 0.5, seed=512)
+    lo, hi = slab_bounds(side, world)[rank]
+    w0, w1 = image_window(lo, hi, side)
+    planes = np.arange(w0, w1) % 512
+    window = torch.empty((w1 - w0, side, side), dtype=torch.uint8).pin_memory()
+    window.numpy()[...] = np.tile(blob[planes], (1, reps, reps))
+    host = window.numpy()
+    make = lambda: DistributedSolver(host, device=dev, window=(w0, w1), shape=(side, side, side))
+    return (make, f"tau.Solver on {side}^3 volume (512^3 blob tiled {reps}x{reps}x{reps}), x-slab partitioned",
+            f"{world} x-slabs of {side // world} planes, 2-plane ghost exchange per fused pass (NCCL send/recv)", host)

@@ -176,7 +176,7 @@ class SORSolver:
     # ------------------------------------------------------------------ the check (ref:109-153)
     def check_convergence(self, verbose, conv_crit, plot_interval):
         self.tau, relative_error = self.compute_metrics()
-        if verbose == 'per_iter' or verbose == 'debug':
+        if (verbose == 'per_iter' or verbose == 'debug') and self._report:
             i = np.argmax(relative_error)
             print(f'Iter: {self.iter}, conv error: {abs(relative_error[i]):.3E}, '
                   f'tau: {self.tau[i]:.5f} (batch element {i})')
@@ -218,9 +218,9 @@ class SORSolver:
             self.tau_x = np.divide(eps * dc, fl, out=np.full_like(dc, np.nan), where=fl != 0)
         for b in range(self.batch_size):
             if fl_min[b] == 0 or fl_max[b] == 0 or mean_fl[b] == 0:
-                conductive = np.isin(self.cpu_img[b], self.conductive_labels)
-                if _through_fraction_is_zero(conductive):
-                    print(f"Warning: batch element {b} has no percolating path!")
+                if _through_fraction_is_zero(self._host_conductive_mask(b)):
+                    if self._report:
+                        print(f"Warning: batch element {b} has no percolating path!")
                     relative_error[b] = 0
                     D_rel[b] = 0
                     tau[b] = 0
@@ -228,6 +228,12 @@ class SORSolver:
         relative_error[np.isnan(mean_fl)] = 0   # NaN counts as converged, ref:328-329
         self.D_eff = self.D_0 * D_rel
         return tau, relative_error
+
+    def _host_conductive_mask(self, b):
+        """Boolean conductive mask of image b on the host (only the zero-flux branch needs it)."""
+        return np.isin(self.cpu_img[b], self.conductive_labels)
+
+    _report = True   # False on the non-zero ranks of a distributed solve: no printing
 
     # ------------------------------------------------------------------ the loop (ref:156-191)
     def solve(self, iter_limit=10000, verbose=True, conv_crit=1e-2, plot_interval=10):
@@ -279,6 +285,8 @@ class SORSolver:
 
     def _end_simulation(self, iterations, verbose):
         """ref:255-269 -- same text (taufactor/benchmark.py:170-178 parses the GPU-RAM line)."""
+        if not self._report:
+            return
         if self.converged:
             msg = "converged to"
         else:

@@ -1,0 +1,73 @@
+"""x-slab partition on the GPU: DistributedSolver ranks (sharing cuda:0 here, gloo with host-staged
+halos; on the multi-GPU box the same code runs one rank per GPU over NCCL) must reproduce the
+single-GPU field bit for bit and the same tau / iteration count."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, shape, periodic, mode, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.cuda.set_device(0)
+        from taufactor_b200.distributed import DistributedSolver, image_window, slab_bounds
+        img = cases.random_img(shape, 0.7, seed=sum(shape))
+        if mode == "window":       # each rank only gets the planes it needs
+            lo, hi = slab_bounds(shape[0], world)[rank]
+            w = image_window(lo, hi, shape[0])
+            S = DistributedSolver(img[w[0]:w[1]], device="cuda:0", periodic=periodic, window=w, shape=shape)
+        else:
+            S = DistributedSolver(img, device="cuda:0", periodic=periodic)
+        S._advance(37)
+        f37 = S.gather_field().cpu().numpy()
+        S.iter = 0   # restart the bookkeeping; the field keeps evolving from iteration 37 (odd parity)
+        S2 = DistributedSolver(img, device="cuda:0", periodic=periodic)
+        S2.solve(verbose=False)
+        if rank == 0:
+            np.savez(out, f37=f37, tau=S2.tau, D_eff=S2.D_eff, iters=S2.iter, final=S2.gather_field().cpu().numpy(),
+                     flux=S2.flux_1d, sent=S2.halo_bytes_sent)
+        else:
+            S2.gather_field()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape,periodic,world,mode", [((24, 20, 28), False, 2, "full"), ((30, 22, 16), True, 3, "window"),
+                                                       ((64, 48, 40), False, 2, "window")])
+def test_slabs_equal_single_gpu(tmp_path, shape, periodic, world, mode):
+    import torch.multiprocessing as mp
+    import taufactor_b200 as tau
+    out = str(tmp_path / "slab.npz")
+    mp.get_context("spawn")
+    mp.spawn(_worker, args=(world, _free_port(), shape, periodic, mode, out), nprocs=world, join=True)
+    got = np.load(out)
+    img = cases.random_img(shape, 0.7, seed=sum(shape))
+    cls = tau.PeriodicSolver if periodic else tau.Solver
+    A = cls(img, device="cuda")
+    A._advance(37)
+    assert np.array_equal(A.field[:, 1:-1, 1:-1, 1:-1].cpu().numpy(), got["f37"])
+    B = cls(img, device="cuda")
+    B.solve(verbose=False)
+    assert int(got["iters"]) == B.iter
+    assert np.array_equal(B.field[:, 1:-1, 1:-1, 1:-1].cpu().numpy(), got["final"])
+    assert np.array_equal(B.flux_1d, got["flux"])
+    assert np.array_equal(B.tau, got["tau"]) and np.array_equal(B.D_eff, got["D_eff"])
+    assert int(got["sent"]) > 0
