@@ -63,16 +63,22 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def wait_first(self, timeout=3.0):
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def stop(self, t_begin=None, t_end=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for t, r in self.rows if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end + 0.1)]
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for n, v in zip(names, r[5:9]):
@@ -202,9 +208,13 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step()
     sampler = ClockSampler(local)
-    sync_all()
     if rank == 0:
         sampler.start()
+        sampler.wait_first()
+    for _ in range(3):      # keep the GPU under the same load while the sampler spins up
+        step()
+    sync_all()
+    t_begin = time.perf_counter()
     l0 = lib.taub_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -218,7 +228,7 @@ def run_ours(args):
         tt = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
     value = voxels_total * ITERS_PER_STEP * args.steps / (ms * 1e-3) / 1e9
 
     # ---- roofline of the dominant kernel (the sweep): sweeps only, CUDA events on the same stream
@@ -281,7 +291,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=512)

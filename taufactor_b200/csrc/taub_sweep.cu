@@ -19,25 +19,40 @@ namespace taub {
 __global__ void __launch_bounds__(256)
 refresh_ghosts_kernel(taub_geom g, float *__restrict__ f, int p_lo)
 {
-    const int W = g.Nz + 2 * G;
-    const int n_rows_part = 2 * G * W;
-    const int total = n_rows_part + g.Ny * 2 * G;
+    // items: the 2G ghost rows as float4 groups (pitch/4 each), then for every interior row the left
+    // and the right ghost column pair (one float2 each; columns 2,3 and Nz+4,Nz+5 are 8-byte aligned
+    // when Nz is even, otherwise the pair is moved as two scalars).
+    const int PG = g.pitch >> 2;
+    const int n_row_items = 2 * G * PG;
+    const int total = n_row_items + 2 * g.Ny;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
-    int jr, c;
-    if (t < n_rows_part) {
-        const int r = t / W;
-        jr = r < G ? r : g.Ny + r;  // r in [G, 2G) -> rows [G+Ny, 2G+Ny)
-        c = COL0 - G + (t - r * W);
-    } else {
-        const int u = t - n_rows_part;
-        const int r = u / (2 * G), q = u - r * (2 * G);
-        jr = G + r;
-        c = q < G ? COL0 - G + q : COL0 + g.Nz + (q - G);
-    }
     float *plane = f + (int64_t)blockIdx.z * g.image_stride + (int64_t)(p_lo + blockIdx.y) * g.plane_stride;
-    const int js = G + wrap(jr - G, g.Ny), cs = COL0 + wrap(c - COL0, g.Nz);
-    plane[(int64_t)jr * g.pitch + c] = plane[(int64_t)js * g.pitch + cs];
+    if (t < n_row_items) {
+        const int r = t / PG, grp = t - r * PG;
+        const int jr = r < G ? r : g.Ny + r;          // r in [G, 2G) -> rows [G+Ny, 2G+Ny)
+        const int js = G + wrap(jr - G, g.Ny);
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = 4 * grp + q;
+            const bool frame = (c >= COL0 - G) && (c < COL0 + g.Nz + G);
+            v[q] = frame ? plane[(int64_t)js * g.pitch + COL0 + wrap(c - COL0, g.Nz)] : 0.0f;
+        }
+        *reinterpret_cast<float4 *>(plane + (int64_t)jr * g.pitch + 4 * grp) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+        const int u = t - n_row_items;
+        const int r = u >> 1, side = u & 1;
+        float *row = plane + (int64_t)(G + r) * g.pitch;
+        const int c = side ? COL0 + g.Nz : COL0 - G;   // first of the two ghost columns
+        const float v0 = row[COL0 + wrap(c - COL0, g.Nz)], v1 = row[COL0 + wrap(c + 1 - COL0, g.Nz)];
+        if ((c & 1) == 0)
+            *reinterpret_cast<float2 *>(row + c) = make_float2(v0, v1);
+        else {
+            row[c] = v0;
+            row[c + 1] = v1;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -132,7 +147,7 @@ int taub_refresh_ghosts(const taub_geom *g, float *field, int p_lo, int p_hi, vo
 {
     TAUB_REQUIRE(g && field, "taub_refresh_ghosts: null pointer");
     TAUB_REQUIRE(p_lo >= 0 && p_hi <= g->planes && p_lo < p_hi, "taub_refresh_ghosts: planes [%d, %d) invalid", p_lo, p_hi);
-    const int total = 2 * G * (g->Nz + 2 * G) + g->Ny * 2 * G;
+    const int total = 2 * G * (g->pitch >> 2) + 2 * g->Ny;
     for (int b0 = 0; b0 < g->bs; b0 += 65535) {
         dim3 grid(ceil_div(total, 256), p_hi - p_lo, min(g->bs - b0, 65535));
         refresh_ghosts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(

@@ -116,9 +116,12 @@ class DistributedSolver(Solver):
         shape: global (Nx, Ny, Nz) when ``img`` is a window.
         periodic: PeriodicSolver semantics (y/z periodic).
         group: process group (default: the world group).
+        overlap: run the ghost exchange + boundary planes on a side stream, concurrently with the
+            interior planes (default on; needs slabs of at least 32 planes).
     """
 
-    def __init__(self, img, omega=None, D_0=1, device=None, periodic=False, group=None, window=None, shape=None):
+    def __init__(self, img, omega=None, D_0=1, device=None, periodic=False, group=None, window=None, shape=None,
+                 overlap=True):
         self._lib = _lib.load()
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
@@ -212,28 +215,52 @@ class DistributedSolver(Solver):
         self.D_mean = np.mean(self.vol_x, axis=1)
         self.halo_bytes_sent = 0
         self._fuse = None
+        self.overlap = overlap
         self._report = (self.rank == 0)
 
-    # ---- the loop: refresh (periodic) -> halo exchange -> pass, two iterations per pass when fused
+    # ---- the loop: refresh (periodic) -> halo exchange -> pass, two iterations per pass when fused.
+    # With overlap, the ghost exchange and the BW boundary planes of each side run on a side stream
+    # while the interior planes (which need no ghost data) run on the compute stream.
+    BW = 8   # boundary width in planes
+
+    def _sweep(self, it, fused, lo, hi):
+        lib, p = self._lib, self._prob
+        if fused:
+            self._call(lib.taub_fused_sweep2(p, it, lo, hi, self._stream()), "taub_fused_sweep2")
+        else:
+            self._call(lib.taub_half_sweep(p, it, lo, hi, self._stream()), "taub_half_sweep")
+
     def _advance(self, n):
         lib, p, g = self._lib, self._prob, self._geom
         lib.taub_set_device(self._dev_index)
         if self._fuse is None:
             self._fuse = lib.taub_can_fuse(p) == 1
+            self._overlap = (self.overlap and self.world > 1 and g.Nx >= 4 * self.BW and g.Ny * g.Nz >= 128 * 128)
+            self._side = torch.cuda.Stream(device=self.device) if self._overlap else None
         done = 0
+        main = torch.cuda.current_stream(self.device)
         while done < n:
             cur = self._bufs[p.cur]
+            fused = self._fuse and not self.force_generic and n - done >= 2
+            it = self.iter + done
             if self._periodic:
                 self._call(lib.taub_refresh_ghosts(g, cur.data_ptr(), G, G + g.Nx, self._stream()), "taub_refresh_ghosts")
-            if self.world > 1:
-                self.halo_bytes_sent += exchange_halos(cur, g.bs, g.image_stride, g.plane_stride, g.Nx, self.rank,
-                                                       self.world, self.group)
-            if self._fuse and not self.force_generic and n - done >= 2:
-                self._call(lib.taub_fused_sweep2(p, self.iter + done, 0, g.Nx, self._stream()), "taub_fused_sweep2")
-                done += 2
+            if self._overlap:
+                side = self._side
+                side.wait_stream(main)                      # previous pass (and the refresh) done
+                with torch.cuda.stream(side):
+                    self.halo_bytes_sent += exchange_halos(cur, g.bs, g.image_stride, g.plane_stride, g.Nx,
+                                                           self.rank, self.world, self.group)
+                    self._sweep(it, fused, 0, self.BW)
+                    self._sweep(it, fused, g.Nx - self.BW, g.Nx)
+                self._sweep(it, fused, self.BW, g.Nx - self.BW)   # interior: no ghost dependency
+                main.wait_stream(side)
             else:
-                self._call(lib.taub_half_sweep(p, self.iter + done, 0, g.Nx, self._stream()), "taub_half_sweep")
-                done += 1
+                if self.world > 1:
+                    self.halo_bytes_sent += exchange_halos(cur, g.bs, g.image_stride, g.plane_stride, g.Nx,
+                                                           self.rank, self.world, self.group)
+                self._sweep(it, fused, 0, g.Nx)
+            done += 2 if fused else 1
             p.cur ^= 1
         self.iter += n
 

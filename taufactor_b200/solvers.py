@@ -124,8 +124,12 @@ class SORSolver:
             self._keep = extra_init(p, img_dev, vec)    # kind-specific tensors + init kernel
             ws = self._lib.taub_sums_ws_bytes(g)
             self._ws = torch.empty(max(ws, 16), dtype=torch.uint8, device=dev)
-            self._flux_dev = torch.zeros(self.batch_size * max(self.Nx - 1, 1), dtype=torch.float32, device=dev)
-            self._mean_dev = torch.zeros(self.batch_size * self.Nx, dtype=torch.float32, device=dev)
+            # one device record [flux (bs x (Nx-1)) | mean (bs x Nx)] and its pinned host mirror:
+            # a check costs one small async D2H and one stream sync
+            nf = self.batch_size * max(self.Nx - 1, 1)
+            self._prof_dev = torch.zeros(nf + self.batch_size * self.Nx, dtype=torch.float32, device=dev)
+            self._prof_host = torch.zeros(self._prof_dev.numel(), dtype=torch.float32).pin_memory()
+            self._flux_dev, self._mean_dev = self._prof_dev[:nf], self._prof_dev[nf:]
             counts = counts.cpu().numpy().reshape(self.batch_size, self.Nx)
             del img_dev
         self.vol_x = (counts.astype(np.float32) / np.float32(self.Ny * self.Nz)).astype(np.float32)
@@ -195,8 +199,12 @@ class SORSolver:
         self._call(self._lib.taub_plane_means(self._prob, self._ws.data_ptr(), self._flux_dev.data_ptr(),
                                               self._mean_dev.data_ptr(), self._stream()), "taub_plane_means")
         bs, Nx = self.batch_size, self.Nx
-        flux = self._flux_dev[: bs * (Nx - 1)].cpu().numpy().reshape(bs, Nx - 1)
-        mean = self._mean_dev.cpu().numpy().reshape(bs, Nx)
+        self._prof_host.copy_(self._prof_dev, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        host = self._prof_host.numpy()
+        nf = self._flux_dev.numel()
+        flux = host[: bs * (Nx - 1)].reshape(bs, Nx - 1).copy()
+        mean = host[nf:].reshape(bs, Nx).copy()
         return flux, mean
 
     def compute_metrics(self):
