@@ -78,11 +78,55 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         : "memory");
 }
 
-// Thread work item = a PAIR of vertically adjacent rows (a = lower y, b = a + 1) x one float4
-// group.  In every step exactly one row of the pair is an "xz" row and the other a "yw" row, and
-// they swap each step; the pair's mutual y-neighbours stay in registers.  PA0 = parity of row a at
-// step 0 (uniform over the whole grid, chosen by the host), so every step body is branch-free.
-template <int NP, int PA0>
+// 128-bit shared load that the compiler cannot split into scalar loads (a scalar load of one
+// component of consecutive float4 groups is a 4-way bank conflict: same wavefronts, a quarter of the data).
+__device__ __forceinline__ float4 lds128(const float4 *p)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+    return v;
+}
+
+// One row of a column: "xz" rows update components x and z, "yw" rows y and w.  zs is the one z
+// neighbour that lives in the adjacent group (.w of the left group / .x of the right group).
+__device__ __forceinline__ void row_update(const bool is_xz, float4 &c, const float4 &xp, const float4 &xm,
+                                           const float4 &up, const float4 &dn, float zs, unsigned code,
+                                           const float2 *s_div, float omega, unsigned &umin)
+{
+    float n0, n1;
+    if (is_xz) {
+        xz_fast(c, xp, xm, up, dn, zs, code, s_div, omega, n0, n1, umin);
+        c.x = n0;
+        c.z = n1;
+    } else {
+        yw_fast(c, xp, xm, up, dn, zs, code, s_div, omega, n0, n1, umin);
+        c.y = n0;
+        c.w = n1;
+    }
+}
+
+// The z neighbour from the adjacent lane's registers (one crossbar pass instead of a 4-way conflicted
+// shared load); the two lanes at the warp ends read shared memory.  All 32 lanes must call this.
+__device__ __forceinline__ float z_neighbour(const bool is_xz, const float4 &v, const float4 *buf, int i4, int lane,
+                                             bool valid)
+{
+    float zs;
+    if (is_xz) {
+        zs = __shfl_up_sync(0xffffffffu, v.w, 1);
+        if (lane == 0 && valid) zs = reinterpret_cast<const float *>(buf)[4 * i4 - 1];
+    } else {
+        zs = __shfl_down_sync(0xffffffffu, v.x, 1);
+        if (lane == 31 && valid) zs = reinterpret_cast<const float *>(buf)[4 * i4 + 4];
+    }
+    return zs;
+}
+
+// Thread work item = a COLUMN of NRW vertically adjacent rows x one float4 group.  In every step the
+// rows of a column alternate between "xz" and "yw" rows and swap roles each step; the column's internal
+// y-neighbours stay in registers, only the rows above and below it come from shared memory.  PA0 = parity
+// of the column's first row at step 0 (uniform over the whole grid, chosen by the host), so every step
+// body is branch-free.
+template <int NRW, int PA0>
 __global__ void __launch_bounds__(F_NT, 2)
 fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tmap,
                     const __grid_constant__ CUtensorMap cmap)
@@ -91,7 +135,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     // TMA destinations need 128-byte alignment: align the base, slots are multiples of 128 B
     unsigned char *smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
     const taub_geom &g = P.g;
-    const int LR = P.LR, LG = P.LG;
+    const int LR = P.LR, LG = P.LG, LGc = P.LGc;
     const int plane_f4 = P.slot_f4;              // ring slot size in float4 (>= LR*LG, multiple of 8)
     const int cslot = P.cslot_h;
     float4 *planes = reinterpret_cast<float4 *>(smem_raw);
@@ -99,7 +143,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     uint64_t *mbar = reinterpret_cast<uint64_t *>(cplanes + (size_t)F_NB * cslot);
     float2 *s_div = reinterpret_cast<float2 *>(mbar + F_NB);
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int tk = blockIdx.x % P.tiles_k, tj = blockIdx.x / P.tiles_k;
     const int b = blockIdx.z;
     const int c0 = P.i_lo + blockIdx.y * P.chunk_len;
@@ -117,12 +161,13 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     __syncthreads();
 
     // one thread stages plane rel (local plane c0-2+rel) into ring slot rel % NB with one TMA box
-    // (columns 4*G0.., rows R0.., one plane); the part of the box outside the tensor reads as 0
+    // (columns 4*G0.., rows R0.., one plane) plus the matching box of neighbour codes; the part of a
+    // box outside the tensor reads as 0
     auto issue = [&](int rel) {
         const int slot = rel % F_NB;
         const uint32_t bar = smem_u32(&mbar[slot]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, (uint32_t)(LR * (LG * 16 + P.LGc * 2)));
+        mbar_expect_tx(bar, (uint32_t)(LR * (LG * 16 + LGc * 2)));
         const int pl = b * g.planes + (c0 - 2 + rel + G);
         tma_load_3d(smem_u32(planes + (size_t)slot * plane_f4), &tmap, 4 * G0, R0, pl, bar);
         tma_load_3d(smem_u32(cplanes + (size_t)slot * cslot), &cmap, G0, R0, pl, bar);
@@ -130,49 +175,43 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     if (tid == 0)
         for (int rel = 0; rel < min(F_NB - 1, total_rel); ++rel) issue(rel);
 
-    // ---- per-thread items
-    int idxa[NP];            // float4 index of row a's group inside a ring slot (row b: + LG)
-    int idca[NP];            // uint16 index of row a's code inside a code slot (row b: + LGc)
-    float *dst_a[NP];        // destination of row a's group in the plane colour B currently writes
-    bool doit[NP], canBa[NP], canBb[NP];
-    const int NPT = (LR - 2) >> 1;   // row pairs in the tile
+    // ---- this thread's column: rows lr0 .. lr0+NRW-1 of the tile, group gg
+    const int NCT = (LR - 2) / NRW;          // columns stacked in the tile
+    const int m = tid / LG, gg = tid - m * LG;
+    const int lr0 = 1 + NRW * m;
+    const int Ra = R0 + lr0, Gs = G0 + gg;
+    const bool doit = (m < NCT) && (Gs < PG) && (Ra < g.rows);
+    const bool colB = gg >= 1 && gg < LG - 1 && Gs >= 1 && Gs < 1 + interior_groups(g.Nz);
+    unsigned canB = 0;                       // bit r: row r of the column is an output row
 #pragma unroll
-    for (int n = 0; n < NP; ++n) {
-        const int u = tid + n * F_NT;
-        const int m = u / LG, gg = u - m * LG;
-        const int lra = 1 + 2 * m;
-        const int Ra = R0 + lra, Gs = G0 + gg;
-        doit[n] = (m < NPT) && (gg < LG) && (Gs < PG) && (Ra < g.rows);
-        const bool colB = gg >= 1 && gg < LG - 1 && Gs >= 1 && Gs < 1 + interior_groups(g.Nz);
-        canBa[n] = doit[n] && colB && lra >= 2 && Ra >= G && Ra < G + g.Ny;
-        canBb[n] = doit[n] && colB && lra + 1 < LR - 2 && Ra + 1 >= G && Ra + 1 < G + g.Ny;
-        idxa[n] = lra * LG + gg;
-        idca[n] = lra * P.LGc + gg;
-        const int64_t img = (int64_t)b * g.image_stride + 4 * Gs;
-        // colour B first writes plane c0 (at step 2)
-        dst_a[n] = P.dst + img + (int64_t)(c0 + G) * ps + (int64_t)Ra * g.pitch;
-    }
+    for (int r = 0; r < NRW; ++r)
+        if (doit && colB && lr0 + r >= 2 && lr0 + r < LR - 2 && Ra + r >= G && Ra + r < G + g.Ny) canB |= 1u << r;
+    const int i0 = lr0 * LG + gg;            // float4 index of row 0 inside a ring slot (row r: + r*LG)
+    const int ic0 = lr0 * LGc + gg;          // uint16 index of row 0's code (row r: + r*LGc)
+    // colour B first writes plane c0 (at step 2)
+    float *dst0 = P.dst + (int64_t)b * g.image_stride + 4 * Gs + (int64_t)(c0 + G) * ps + (int64_t)Ra * g.pitch;
 
-    // ---- register ring: ring[.][k] holds plane (c0-3+k+4j); at step s = 4j+ss:
-    //      a[p-2] = ring[ss], a[p-1] = ring[ss+1], raw[p] -> a[p] = ring[ss+2], raw[p+1] = ring[ss+3]
-    float4 ra[NP][4], rb[NP][4];
-    unsigned cr[NP][4];   // neighbour codes of rows a (low half) and b (high half), same ring positions
+    // ---- register ring: rg[r][k] holds plane (c0-3+k+4j) of row r; at step s = 4j+ss:
+    //      a[p-2] = rg[.][ss], a[p-1] = rg[.][ss+1], raw[p] -> a[p] = rg[.][ss+2], raw[p+1] = rg[.][ss+3]
+    float4 rg[NRW][4];
+    unsigned cr[NRW / 2][4];   // neighbour codes, two rows per word, same ring positions
     mbar_wait(smem_u32(&mbar[0]), 0);
     mbar_wait(smem_u32(&mbar[1 % F_NB]), 0);
 #pragma unroll
-    for (int n = 0; n < NP; ++n) {
+    for (int r = 0; r < NRW; ++r) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            ra[n][k] = rb[n][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            cr[n][k] = 0;
+        for (int k = 0; k < 4; ++k) rg[r][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (doit) {
+            rg[r][1] = planes[i0 + r * LG];
+            rg[r][2] = planes[plane_f4 + i0 + r * LG];
         }
-        if (doit[n]) {
-            ra[n][1] = planes[idxa[n]];
-            rb[n][1] = planes[idxa[n] + LG];
-            ra[n][2] = planes[plane_f4 + idxa[n]];
-            rb[n][2] = planes[plane_f4 + idxa[n] + LG];
-            cr[n][2] = (unsigned)cplanes[cslot + idca[n]] | ((unsigned)cplanes[cslot + idca[n] + P.LGc] << 16);
-        }
+    }
+#pragma unroll
+    for (int q = 0; q < NRW / 2; ++q) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cr[q][k] = 0;
+        if (doit)
+            cr[q][2] = (unsigned)cplanes[cslot + ic0 + 2 * q * LGc] | ((unsigned)cplanes[cslot + ic0 + (2 * q + 1) * LGc] << 16);
     }
 
     unsigned umin = 0xffffffffu;   // guard word of every neighbour sum this thread divides
@@ -183,9 +222,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
             const int s = s4 + ss;
             if (s >= n_steps) break;
             const int p = c0 - 1 + s;   // plane receiving colour A; colour B goes to plane p-1
-            constexpr int kM2 = 0, kM1 = 1, kP = 2, kP1 = 3;
-            const int iM2 = (ss + kM2) & 3, iM1 = (ss + kM1) & 3, iP = (ss + kP) & 3, iP1 = (ss + kP1) & 3;
-            const bool a_is_xz = (((PA0 + ss) & 1) == 0);
+            const int iM2 = ss & 3, iM1 = (ss + 1) & 3, iP = (ss + 2) & 3, iP1 = (ss + 3) & 3;
             __syncthreads();            // ring slot of plane p-2 is free; a[p-1] is visible in its slot
             if (tid == 0 && s - 1 + F_NB < total_rel) issue(s - 1 + F_NB);
             mbar_wait(smem_u32(&mbar[(s + 2) % F_NB]), (uint32_t)(((s + 2) / F_NB) & 1));
@@ -196,42 +233,53 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
             const bool doA = (p >= P.a_lo) && (p < P.a_hi);
             const bool keepA = (p >= c0) && (p < c1);   // a[p] is read by colour B of plane p next step
             const bool doB = (s >= 2);
+            if (doit) {
 #pragma unroll
-            for (int n = 0; n < NP; ++n) {
-                if (!doit[n]) continue;
-                const int ia = idxa[n], ib = idxa[n] + LG;
-                ra[n][iP1] = bufP1[ia];
-                rb[n][iP1] = bufP1[ib];
-                cr[n][iP1] = (unsigned)codP1[idca[n]] | ((unsigned)codP1[idca[n] + P.LGc] << 16);
-                // scalar z neighbour: z-1 of .x (xz row) or z+1 of .w (yw row)
-                const int za = a_is_xz ? 4 * ia - 1 : 4 * ia + 4;
-                const int zb = a_is_xz ? 4 * ib + 4 : 4 * ib - 1;
-                if (doA) {
-                    const float4 dn = bufP[ia - LG], up = bufP[ib + LG];
-                    const float zsa = reinterpret_cast<const float *>(bufP)[za];
-                    const float zsb = reinterpret_cast<const float *>(bufP)[zb];
-                    const unsigned cda = cr[n][iP], cdb = cr[n][iP] >> 16;
-                    update_pair(a_is_xz, ra[n][iP], rb[n][iP], ra[n][iP1], ra[n][iM1], rb[n][iP1], rb[n][iM1], dn, up,
-                                           zsa, zsb, cda, cdb, s_div, P.omega, umin);
+                for (int r = 0; r < NRW; ++r) rg[r][iP1] = bufP1[i0 + r * LG];
+#pragma unroll
+                for (int q = 0; q < NRW / 2; ++q)
+                    cr[q][iP1] = (unsigned)codP1[ic0 + 2 * q * LGc] | ((unsigned)codP1[ic0 + (2 * q + 1) * LGc] << 16);
+            }
+            if (doA) {   // block-uniform
+                float zs[NRW];
+#pragma unroll
+                for (int r = 0; r < NRW; ++r)
+                    zs[r] = z_neighbour(((PA0 + ss + r) & 1) == 0, rg[r][iP], bufP, i0 + r * LG, lane, doit);
+                if (doit) {
+                    const float4 below = lds128(bufP + i0 - LG), above = lds128(bufP + i0 + NRW * LG);
+#pragma unroll
+                    for (int r = 0; r < NRW; ++r) {
+                        // neighbours inside the column are registers; each row only reads the components
+                        // its neighbours leave unchanged in this step
+                        const float4 &dn = (r == 0) ? below : rg[r - 1][iP];
+                        const float4 &up = (r == NRW - 1) ? above : rg[r + 1][iP];
+                        row_update(((PA0 + ss + r) & 1) == 0, rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r],
+                                   cr[r >> 1][iP] >> (16 * (r & 1)), s_div, P.omega, umin);
+                    }
                     if (keepA) {
-                        bufP[ia] = ra[n][iP];
-                        bufP[ib] = rb[n][iP];
+#pragma unroll
+                        for (int r = 0; r < NRW; ++r) bufP[i0 + r * LG] = rg[r][iP];
                     }
                 }
-                if (doB) {
-                    if (canBa[n] | canBb[n]) {
-                        const float4 dn = bufM1[ia - LG], up = bufM1[ib + LG];
-                        const float zsa = reinterpret_cast<const float *>(bufM1)[za];
-                        const float zsb = reinterpret_cast<const float *>(bufM1)[zb];
-                        const unsigned cda = cr[n][iM1], cdb = cr[n][iM1] >> 16;
-                        float4 oa = ra[n][iM1], ob = rb[n][iM1];
-                        update_pair(a_is_xz, oa, ob, ra[n][iP], ra[n][iM2], rb[n][iP], rb[n][iM2], dn, up, zsa, zsb, cda,
-                                               cdb, s_div, P.omega, umin);
-                        if (canBa[n]) *reinterpret_cast<float4 *>(dst_a[n]) = oa;
-                        if (canBb[n]) *reinterpret_cast<float4 *>(dst_a[n] + g.pitch) = ob;
+            }
+            if (doB) {   // block-uniform
+                float zs[NRW];
+#pragma unroll
+                for (int r = 0; r < NRW; ++r)
+                    zs[r] = z_neighbour(((PA0 + ss + r) & 1) == 0, rg[r][iM1], bufM1, i0 + r * LG, lane, doit);
+                if (canB) {
+                    const float4 below = lds128(bufM1 + i0 - LG), above = lds128(bufM1 + i0 + NRW * LG);
+#pragma unroll
+                    for (int r = 0; r < NRW; ++r) {
+                        const float4 &dn = (r == 0) ? below : rg[r - 1][iM1];
+                        const float4 &up = (r == NRW - 1) ? above : rg[r + 1][iM1];
+                        float4 out = rg[r][iM1];
+                        row_update(((PA0 + ss + r) & 1) == 0, out, rg[r][iP], rg[r][iM2], up, dn, zs[r],
+                                   cr[r >> 1][iM1] >> (16 * (r & 1)), s_div, P.omega, umin);
+                        if (canB & (1u << r)) *reinterpret_cast<float4 *>(dst0 + (int64_t)r * g.pitch) = out;
                     }
-                    dst_a[n] += ps;
                 }
+                dst0 += ps;
             }
         }
     }
@@ -247,31 +295,32 @@ static size_t fused_smem_bytes(int LR, int LG, int LGc)
     return F_NB * (slot + cslot) + F_NB * 8 + 16 * 8 + 128;           // + mbarriers, division table, alignment slack
 }
 
+constexpr int F_NRW = 4;   // rows per thread column
+
 struct TileChoice {
-    int NP, LR, LG, LGc, OR_, OG, tiles_j, tiles_k;
+    int LR, LG, LGc, OR_, OG, tiles_j, tiles_k;
     double eff;
 };
 
-// Tile = NPT row pairs x LG float4 groups (OG = LG - 2 of them are outputs).  TMA wants every box to
-// start on a 16-byte boundary and to be a multiple of 16 bytes wide; for the uint16 code box that
-// means OG (the tile step) is a multiple of 8 groups and the code box is LG rounded up to 8.  A box
-// is at most 256 elements wide (LG <= 64).  Pick the shape that wastes the fewest thread-items while
-// two CTAs still fit in one SM's shared memory.
+// Tile = NCT columns (of F_NRW rows) stacked in y x LG float4 groups (OG = LG - 2 of them are outputs);
+// one thread per (column, group).  TMA wants every box to start on a 16-byte boundary and to be a
+// multiple of 16 bytes wide; for the uint16 code box that means OG (the tile step) is a multiple of 8
+// groups and the code box is LG rounded up to 8.  A box is at most 256 elements wide (LG <= 64).  Pick
+// the shape that wastes the fewest threads while two CTAs still fit in one SM's shared memory.
 static TileChoice choose_tile(const taub_geom &g)
 {
     const int ng = interior_groups(g.Nz);
     TileChoice best{};
     best.eff = -1.0;
-    const int NP = 2;
     for (int OG = 8; OG <= 56; OG += 8) {
         const int LG = OG + 2, LGc = ((LG + 7) / 8) * 8;
-        int NPT = (NP * F_NT) / LG;   // row pairs the CTA's thread-items can cover
-        while (NPT >= 2 && fused_smem_bytes(2 * NPT + 2, LG, LGc) > 115000) --NPT;
-        if (NPT < 2) continue;
-        const int NR = 2 * NPT, OR_ = NR - 2, LR = NR + 2;
+        int NCT = F_NT / LG;   // columns the CTA's threads can cover
+        while (NCT >= 1 && fused_smem_bytes(F_NRW * NCT + 2, LG, LGc) > 115000) --NCT;
+        if (NCT < 1) continue;
+        const int NR = F_NRW * NCT, OR_ = NR - 2, LR = NR + 2;
         const int tj = ceil_div(g.Ny, OR_), tk = ceil_div(ng, OG);
-        const double eff = ((double)g.Ny * ng) / ((double)tj * tk * NP * F_NT * 2);   // 2 rows per item
-        if (eff > best.eff + 1e-12) best = TileChoice{NP, LR, LG, LGc, OR_, OG, tj, tk, eff};
+        const double eff = ((double)g.Ny * ng) / ((double)tj * tk * F_NT * F_NRW);
+        if (eff > best.eff + 1e-12) best = TileChoice{LR, LG, LGc, OR_, OG, tj, tk, eff};
         if (OG >= ng) break;          // one tile already spans the row
     }
     return best;
@@ -417,12 +466,12 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     // parity of loaded row 1 (row a of every pair) at step 0, i.e. at plane c0-1: 0 -> x,z active.
     // Tile row offsets (multiples of the even OR_) and chunk starts (multiples of the even
     // chunk_len) do not change it, so it is one number for the whole grid.
-    const int pa0 = (1 - G + g.i_offset + P.colourA + (i_lo - 1)) & 1;
+    const int pa0 = (1 - G + g.i_offset + P.colourA + (i_lo - 1)) & 1;   // row lr = 1 is row 0 of a column
 #define TAUB_LAUNCH_FUSED(PA_)                                                                                    \
     do {                                                                                                          \
-        TAUB_CUDA(cudaFuncSetAttribute(fused_sweep2_kernel<2, PA_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+        TAUB_CUDA(cudaFuncSetAttribute(fused_sweep2_kernel<F_NRW, PA_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                        (int)smem));                                                               \
-        fused_sweep2_kernel<2, PA_><<<grid, F_NT, smem, s>>>(P, tmap, cmap);                                            \
+        fused_sweep2_kernel<F_NRW, PA_><<<grid, F_NT, smem, s>>>(P, tmap, cmap);                                            \
     } while (0)
     if (pa0 == 0)
         TAUB_LAUNCH_FUSED(0);
