@@ -36,7 +36,8 @@ struct FusedParams {
     int colourA;
     int i_lo, i_hi;    // output planes (local)
     int a_lo, a_hi;    // planes that receive the colour-A update (output planes +-1, clipped to real planes)
-    int LR, LG, LGc;   // loaded rows, loaded float4 groups, code-box width (LG rounded up to 8)
+    int LR, LG, LGc;   // loaded rows, box width in float4 groups (odd: see choose_tile), code-box width
+    int LGt;           // groups per row that threads work on (= OG + 2 <= LG)
     int OR_, OG;       // output rows / groups per tile
     int tiles_k;
     int chunk_len;     // output planes per CTA
@@ -91,7 +92,7 @@ __device__ __forceinline__ float4 lds128(const float4 *p)
 // neighbour that lives in the adjacent group (.w of the left group / .x of the right group).
 __device__ __forceinline__ void row_update(const bool is_xz, float4 &c, const float4 &xp, const float4 &xm,
                                            const float4 &up, const float4 &dn, float zs, unsigned code,
-                                           const float2 *s_div, float omega, unsigned &umin)
+                                           const float *s_div, float omega, unsigned &umin)
 {
     float n0, n1;
     if (is_xz) {
@@ -141,7 +142,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     float4 *planes = reinterpret_cast<float4 *>(smem_raw);
     uint16_t *cplanes = reinterpret_cast<uint16_t *>(smem_raw + (size_t)F_NB * plane_f4 * 16);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(cplanes + (size_t)F_NB * cslot);
-    float2 *s_div = reinterpret_cast<float2 *>(mbar + F_NB);
+    float *s_div = reinterpret_cast<float *>(mbar + F_NB);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int tk = blockIdx.x % P.tiles_k, tj = blockIdx.x / P.tiles_k;
@@ -153,7 +154,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     const int total_rel = c1 - c0 + 4;           // planes c0-2 .. c1+1
     const int64_t ps = g.plane_stride;
 
-    if (tid < 16) s_div[tid] = div_entry(tid);
+    if (tid < 16) s_div[tid] = rcp_entry(tid);
     if (tid == 0) {
         for (int n = 0; n < F_NB; ++n) mbar_init(smem_u32(&mbar[n]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -177,11 +178,12 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
 
     // ---- this thread's column: rows lr0 .. lr0+NRW-1 of the tile, group gg
     const int NCT = (LR - 2) / NRW;          // columns stacked in the tile
-    const int m = tid / LG, gg = tid - m * LG;
+    const int LGt = P.LGt;
+    const int m = tid / LGt, gg = tid - m * LGt;
     const int lr0 = 1 + NRW * m;
     const int Ra = R0 + lr0, Gs = G0 + gg;
     const bool doit = (m < NCT) && (Gs < PG) && (Ra < g.rows);
-    const bool colB = gg >= 1 && gg < LG - 1 && Gs >= 1 && Gs < 1 + interior_groups(g.Nz);
+    const bool colB = gg >= 1 && gg < LGt - 1 && Gs >= 1 && Gs < 1 + interior_groups(g.Nz);
     unsigned canB = 0;                       // bit r: row r of the column is an output row
 #pragma unroll
     for (int r = 0; r < NRW; ++r)
@@ -257,8 +259,12 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                                    cr[r >> 1][iP] >> (16 * (r & 1)), s_div, P.omega, umin);
                     }
                     if (keepA) {
+                        // other threads read the column's first and last row (their above / below) and,
+                        // at the two ends of a warp, the neighbour lane's group (z_neighbour fall-back)
+                        const bool edge_lane = (lane == 0) || (lane == 31);
 #pragma unroll
-                        for (int r = 0; r < NRW; ++r) bufP[i0 + r * LG] = rg[r][iP];
+                        for (int r = 0; r < NRW; ++r)
+                            if (r == 0 || r == NRW - 1 || edge_lane) bufP[i0 + r * LG] = rg[r][iP];
                     }
                 }
             }
@@ -292,13 +298,13 @@ static size_t fused_smem_bytes(int LR, int LG, int LGc)
 {
     const size_t slot = ((size_t)(LR * LG + 7) / 8) * 8 * 16;         // fp32 box, 128-byte multiple
     const size_t cslot = ((size_t)(LR * LGc * 2 + 127) / 128) * 128;  // uint16 box
-    return F_NB * (slot + cslot) + F_NB * 8 + 16 * 8 + 128;           // + mbarriers, division table, alignment slack
+    return F_NB * (slot + cslot) + F_NB * 8 + 16 * 4 + 128;           // + mbarriers, reciprocal table, alignment slack
 }
 
 constexpr int F_NRW = 4;   // rows per thread column
 
 struct TileChoice {
-    int LR, LG, LGc, OR_, OG, tiles_j, tiles_k;
+    int LR, LG, LGc, LGt, OR_, OG, tiles_j, tiles_k;
     double eff;
 };
 
@@ -313,14 +319,17 @@ static TileChoice choose_tile(const taub_geom &g)
     TileChoice best{};
     best.eff = -1.0;
     for (int OG = 8; OG <= 56; OG += 8) {
-        const int LG = OG + 2, LGc = ((LG + 7) / 8) * 8;
-        int NCT = F_NT / LG;   // columns the CTA's threads can cover
+        // threads work on OG + 2 groups per row; the box (= shared-memory row pitch) is one group wider
+        // so that it is ODD: columns are F_NRW rows apart, and 4*LG float4 is a multiple of 32 banks
+        // only when LG is even -- an odd pitch keeps warps that straddle two columns conflict-free
+        const int LGt = OG + 2, LG = LGt + 1, LGc = ((LG + 7) / 8) * 8;
+        int NCT = F_NT / LGt;   // columns the CTA's threads can cover
         while (NCT >= 1 && fused_smem_bytes(F_NRW * NCT + 2, LG, LGc) > 115000) --NCT;
         if (NCT < 1) continue;
         const int NR = F_NRW * NCT, OR_ = NR - 2, LR = NR + 2;
         const int tj = ceil_div(g.Ny, OR_), tk = ceil_div(ng, OG);
         const double eff = ((double)g.Ny * ng) / ((double)tj * tk * F_NT * F_NRW);
-        if (eff > best.eff + 1e-12) best = TileChoice{LR, LG, LGc, OR_, OG, tj, tk, eff};
+        if (eff > best.eff + 1e-12) best = TileChoice{LR, LG, LGc, LGt, OR_, OG, tj, tk, eff};
         if (OG >= ng) break;          // one tile already spans the row
     }
     return best;
@@ -441,7 +450,7 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     P.i_hi = i_hi;
     P.a_lo = max(i_lo - 1, -g.i_offset);
     P.a_hi = min(i_hi + 1, g.Nx_global - g.i_offset);
-    P.LR = t.LR; P.LG = t.LG; P.LGc = t.LGc; P.OR_ = t.OR_; P.OG = t.OG;   // OR_ is even, OG % 8 == 0
+    P.LR = t.LR; P.LG = t.LG; P.LGc = t.LGc; P.LGt = t.LGt; P.OR_ = t.OR_; P.OG = t.OG;   // OR_ even, OG % 8 == 0
     P.tiles_k = t.tiles_k;
     const int n_planes = i_hi - i_lo;
     const int64_t tiles = (int64_t)t.tiles_j * t.tiles_k * g.bs;
