@@ -319,13 +319,16 @@ static TileChoice choose_tile(const taub_geom &g)
     TileChoice best{};
     best.eff = -1.0;
     for (int OG = 8; OG <= 56; OG += 8) {
-        // threads work on OG + 2 groups per row; the box (= shared-memory row pitch) is one group wider
-        // so that it is ODD: columns are F_NRW rows apart, and 4*LG float4 is a multiple of 32 banks
-        // only when LG is even -- an odd pitch keeps warps that straddle two columns conflict-free
-        const int LGt = OG + 2, LG = LGt + 1, LGc = ((LG + 7) / 8) * 8;
+        // threads work on LGt = OG + 2 groups per row.  Columns are F_NRW rows apart and 4*LG float4 is
+        // a multiple of 32 banks when LG is even, so warps that straddle two columns bank-conflict; a
+        // box one group wider (odd pitch) avoids that -- taken when it does not cost a column.
+        const int LGt = OG + 2;
         int NCT = F_NT / LGt;   // columns the CTA's threads can cover
-        while (NCT >= 1 && fused_smem_bytes(F_NRW * NCT + 2, LG, LGc) > 115000) --NCT;
+        while (NCT >= 1 && fused_smem_bytes(F_NRW * NCT + 2, LGt, ((LGt + 7) / 8) * 8) > 115000) --NCT;
         if (NCT < 1) continue;
+        int LG = LGt;
+        if (fused_smem_bytes(F_NRW * NCT + 2, LGt + 1, ((LGt + 8) / 8) * 8) <= 115000) LG = LGt + 1;
+        const int LGc = ((LG + 7) / 8) * 8;
         const int NR = F_NRW * NCT, OR_ = NR - 2, LR = NR + 2;
         const int tj = ceil_div(g.Ny, OR_), tk = ceil_div(ng, OG);
         const double eff = ((double)g.Ny * ng) / ((double)tj * tk * F_NT * F_NRW);
