@@ -55,16 +55,17 @@ static inline __host__ __device__ int interior_groups(int Nz) { return (Nz + 3) 
 // (c, r) = (0, 0), which yields q = 0 = s / inf without a special case.  The guard is evaluated once
 // per group of updates (a branch per update would stop the compiler from interleaving the chains).
 // ------------------------------------------------------------------------------------------
-// Table entry n: correctly rounded 1/n for n = 1..8, 0 otherwise (one 4-byte shared load per
-// update; the divisor itself is an int-to-float conversion of the 4-bit code).
-__device__ __forceinline__ float rcp_entry(int code)
+// Table entry n: (n, correctly rounded 1/n) for n = 1..8, (0, 0) otherwise.  The table is a STATIC
+// shared array so its address is a compile-time constant: a lookup is shift + mask + one LDS.64.
+__device__ __forceinline__ float2 div_entry(int code)
 {
-    return (code >= 1 && code <= 8) ? __frcp_rn((float)code) : 0.0f;
+    const float c = (code >= 1 && code <= 8) ? (float)code : 0.0f;
+    return make_float2(c, (c > 0.0f) ? __frcp_rn(c) : 0.0f);
 }
 
-__device__ __forceinline__ float2 div_pair(unsigned nib, const float *s_rcp)
+__device__ __forceinline__ float2 div_pair(unsigned nib, const float2 *s_div)
 {
-    return make_float2((float)nib, s_rcp[nib]);
+    return s_div[nib];
 }
 
 // Fast quotient (exact for s == 0 and for every |s| >= 2^-100) plus the guard word of s:
@@ -118,14 +119,14 @@ static __device__ __noinline__ float sor_exact(float c, float xp, float xm, floa
 // The *_fast forms return the new values in n0/n1 and fold the guard into umin; commit_* writes them
 // after the (single, rare) exactness check of the caller.
 __device__ __forceinline__ void xz_fast(const float4 &c, const float4 &xp, const float4 &xm, const float4 &up,
-                                        const float4 &dn, float zs, unsigned code, const float *s_div, float omega,
+                                        const float4 &dn, float zs, unsigned code, const float2 *s_div, float omega,
                                         float &n0, float &n1, unsigned &umin)
 {
     n0 = sor_fast(c.x, xp.x, xm.x, up.x, dn.x, c.y, zs, div_pair(code & 15u, s_div), omega, umin);
     n1 = sor_fast(c.z, xp.z, xm.z, up.z, dn.z, c.w, c.y, div_pair((code >> 8) & 15u, s_div), omega, umin);
 }
 __device__ __forceinline__ void yw_fast(const float4 &c, const float4 &xp, const float4 &xm, const float4 &up,
-                                        const float4 &dn, float zs, unsigned code, const float *s_div, float omega,
+                                        const float4 &dn, float zs, unsigned code, const float2 *s_div, float omega,
                                         float &n0, float &n1, unsigned &umin)
 {
     n0 = sor_fast(c.y, xp.y, xm.y, up.y, dn.y, c.z, c.x, div_pair((code >> 4) & 15u, s_div), omega, umin);
@@ -146,7 +147,7 @@ __device__ __forceinline__ void yw_exact(const float4 &c, const float4 &xp, cons
 
 // Single-row forms (generic kernel): fast path, one exactness check per row group.
 __device__ __forceinline__ void update_xz(float4 &c, const float4 &xp, const float4 &xm, const float4 &up,
-                                          const float4 &dn, float zs, unsigned code, const float *s_div, float omega)
+                                          const float4 &dn, float zs, unsigned code, const float2 *s_div, float omega)
 {
     float n0, n1;
     unsigned umin = 0xffffffffu;
@@ -156,7 +157,7 @@ __device__ __forceinline__ void update_xz(float4 &c, const float4 &xp, const flo
     c.z = n1;
 }
 __device__ __forceinline__ void update_yw(float4 &c, const float4 &xp, const float4 &xm, const float4 &up,
-                                          const float4 &dn, float zs, unsigned code, const float *s_div, float omega)
+                                          const float4 &dn, float zs, unsigned code, const float2 *s_div, float omega)
 {
     float n0, n1;
     unsigned umin = 0xffffffffu;
@@ -172,7 +173,7 @@ __device__ __forceinline__ void update_yw(float4 &c, const float4 &xp, const flo
 __device__ __forceinline__ void update_pair(const bool A_IS_XZ, float4 &ca, float4 &cb, const float4 &axp,
                                             const float4 &axm, const float4 &bxp, const float4 &bxm, const float4 &a_dn,
                                             const float4 &b_up, float zsa, float zsb, unsigned cda, unsigned cdb,
-                                            const float *s_div, float omega, unsigned &umin)
+                                            const float2 *s_div, float omega, unsigned &umin)
 {
     // row a: up neighbour is row b, down neighbour comes from shared memory; row b: the mirror image.
     // Each row only reads components of the other that this step leaves unchanged.

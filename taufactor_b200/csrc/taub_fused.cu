@@ -92,7 +92,7 @@ __device__ __forceinline__ float4 lds128(const float4 *p)
 // neighbour that lives in the adjacent group (.w of the left group / .x of the right group).
 __device__ __forceinline__ void row_update(const bool is_xz, float4 &c, const float4 &xp, const float4 &xm,
                                            const float4 &up, const float4 &dn, float zs, unsigned code,
-                                           const float *s_div, float omega, unsigned &umin)
+                                           const float2 *s_div, float omega, unsigned &umin)
 {
     float n0, n1;
     if (is_xz) {
@@ -142,7 +142,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     float4 *planes = reinterpret_cast<float4 *>(smem_raw);
     uint16_t *cplanes = reinterpret_cast<uint16_t *>(smem_raw + (size_t)F_NB * plane_f4 * 16);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(cplanes + (size_t)F_NB * cslot);
-    float *s_div = reinterpret_cast<float *>(mbar + F_NB);
+    __shared__ float2 s_div[16];   // static: constant address, no address arithmetic per lookup
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int tk = blockIdx.x % P.tiles_k, tj = blockIdx.x / P.tiles_k;
@@ -154,7 +154,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     const int total_rel = c1 - c0 + 4;           // planes c0-2 .. c1+1
     const int64_t ps = g.plane_stride;
 
-    if (tid < 16) s_div[tid] = rcp_entry(tid);
+    if (tid < 16) s_div[tid] = div_entry(tid);
     if (tid == 0) {
         for (int n = 0; n < F_NB; ++n) mbar_init(smem_u32(&mbar[n]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -298,7 +298,8 @@ static size_t fused_smem_bytes(int LR, int LG, int LGc)
 {
     const size_t slot = ((size_t)(LR * LG + 7) / 8) * 8 * 16;         // fp32 box, 128-byte multiple
     const size_t cslot = ((size_t)(LR * LGc * 2 + 127) / 128) * 128;  // uint16 box
-    return F_NB * (slot + cslot) + F_NB * 8 + 16 * 4 + 128;           // + mbarriers, reciprocal table, alignment slack
+    return F_NB * (slot + cslot) + F_NB * 8 + 128;                    // + mbarriers, alignment slack (the division
+                                                                      // table is 128 bytes of static shared memory)
 }
 
 constexpr int F_NRW = 4;   // rows per thread column

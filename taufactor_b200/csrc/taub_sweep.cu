@@ -66,11 +66,11 @@ half_sweep_kernel(taub_geom g, const float *__restrict__ src, float *__restrict_
                   const uint16_t *__restrict__ codes, const uint8_t *__restrict__ labels,
                   const float *__restrict__ lut, int L, float omega, int colour, int i_lo, int n_planes)
 {
-    __shared__ float s_div[16];
+    __shared__ float2 s_div[16];
     extern __shared__ float s_lut[];  // MULTI: (L+1)^2
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     if (!MULTI) {
-        if (tid < 16) s_div[tid] = rcp_entry(tid);
+        if (tid < 16) s_div[tid] = div_entry(tid);
     } else {
         for (int t = tid; t < (L + 1) * (L + 1); t += blockDim.x * blockDim.y) s_lut[t] = lut[t];
     }
