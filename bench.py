@@ -255,7 +255,11 @@ def run_ours(args):
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get(roofline["kernel"])
+            t = json.load(open(traffic_file)).get(roofline["kernel"])
+            roofline["traffic"] = t["bytes_per_launch"] if isinstance(t, dict) else t
+            roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full on the "
+                                        "512^3 volume (profiles/traffic.json); algorithmic bytes per launch = "
+                                        f"{BYTES_PER_LUP} B x LUPs per launch")
         except Exception:
             pass
 

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TAUB_ABI_VERSION 1
+#define TAUB_ABI_VERSION 2
 #define TAUB_GHOST 2            /* ghost width in x (planes), y (rows) and z (columns) */
 #define TAUB_COL0 4             /* column of interior voxel k = 0 */
 #define TAUB_MAX_LABELS 64      /* dense phase indices 0..L-1, L <= 64; index L = "outside" */
@@ -71,6 +71,8 @@ typedef struct taub_problem {
     float *lut;                 /* multi-phase: (L+1)*(L+1) fp32 harmonic means, device */
     float omega;                /* over-relaxation factor rounded once to fp32 (taufactor.py:224) */
     int32_t cur;                /* index of the buffer that holds the current field */
+    int32_t *stop;              /* optional device flag: while *stop != 0 every sweep / refresh / check
+                                 * kernel of this problem returns at once (set by taub_check_async) */
 } taub_problem;
 
 /* -- library ------------------------------------------------------------------------------ */
@@ -140,6 +142,19 @@ int taub_iterate(taub_problem *p, int64_t iter, int n, int flags, void *stream);
  * order (deterministic), results rounded to fp32.  Outputs are device pointers. */
 int taub_plane_means(const taub_problem *p, void *workspace, float *flux_mean, float *field_mean,
                      void *stream);
+
+/* The same reduction followed by the reference's stop rule ON THE DEVICE (check_convergence,
+ * taufactor.py:143-153, with compute_metrics :296-305 in the reference's float32 NumPy arithmetic,
+ * including NumPy's pairwise summation order for the mean flux), so that the host can queue the next
+ * block of sweeps without waiting for this check.  Needs the whole volume (i_offset == 0, Nx == Nx_global).
+ *   D_mean[bs], old_tau[bs] (in/out, starts at 0), record[2 + 2*bs] (out): device fp32 arrays;
+ *   record[0] = status (0 continue, 1 converged, 2 a slice flux is exactly 0 -> the host must run the
+ *   percolation check, 3 the check did not run because *stop was already set), record[1] = reserved,
+ *   record[2..2+bs) = tau, record[2+bs..2+2bs) = relative error.
+ * On status 1 or 2 the kernel sets *p->stop (p->stop must be non-NULL): sweeps already queued behind
+ * it become no-ops, so the field stays exactly at the iteration of this check. */
+int taub_check_async(const taub_problem *p, void *workspace, float *flux_mean, float *field_mean,
+                     const float *D_mean, float *old_tau, float conv_crit, float *record, void *stream);
 
 #ifdef __cplusplus
 }

@@ -27,7 +27,7 @@ class Geom(ctypes.Structure):
 class Problem(ctypes.Structure):
     _fields_ = [("g", Geom), ("kind", ctypes.c_int32), ("L", ctypes.c_int32),
                 ("field", c_vp * 2), ("codes", c_vp), ("labels", c_vp), ("lut", c_vp),
-                ("omega", ctypes.c_float), ("cur", ctypes.c_int32)]
+                ("omega", ctypes.c_float), ("cur", ctypes.c_int32), ("stop", c_vp)]
 
 
 # name -> (restype, argtypes); must list every symbol include/taub200.h declares
@@ -51,6 +51,7 @@ SIGNATURES = {
     "taub_can_fuse": (c_int, [ctypes.POINTER(Problem)]),
     "taub_iterate": (c_int, [ctypes.POINTER(Problem), c_i64, c_int, c_int, c_vp]),
     "taub_plane_means": (c_int, [ctypes.POINTER(Problem), c_vp, c_vp, c_vp, c_vp]),
+    "taub_check_async": (c_int, [ctypes.POINTER(Problem), c_vp, c_vp, c_vp, c_vp, c_vp, c_float, c_vp, c_vp]),
 }
 
 _lib = None
@@ -72,7 +73,7 @@ def load():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.taub_abi_version() != 1:
+        if lib.taub_abi_version() != 2:
             raise ImportError("libtaub200.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib

@@ -41,6 +41,7 @@ struct FusedParams {
     int OR_, OG;       // output rows / groups per tile
     int tiles_k;
     int chunk_len;     // output planes per CTA
+    const int *stop;   // optional device flag: non-zero -> the kernel returns at once
     int slot_f4;       // float4 per field ring slot
     int cslot_h;       // uint16 per code ring slot
 };
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(F_NT, 2)
 fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tmap,
                     const __grid_constant__ CUtensorMap cmap)
 {
+    if (P.stop && *P.stop) return;
     extern __shared__ unsigned char smem_dyn[];
     // TMA destinations need 128-byte alignment: align the base, slots are multiples of 128 B
     unsigned char *smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
@@ -449,6 +451,7 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     P.dst = p->field[p->cur ^ 1];
     P.codes = p->codes;
     P.omega = p->omega;
+    P.stop = p->stop;
     P.colourA = (int)(iter & 1);
     P.i_lo = i_lo;
     P.i_hi = i_hi;

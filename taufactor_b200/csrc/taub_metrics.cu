@@ -21,8 +21,9 @@ template <bool MULTI>
 __global__ void __launch_bounds__(SUM_THREADS)
 plane_sums_kernel(taub_geom g, const float *__restrict__ f, const uint16_t *__restrict__ codes,
                   const uint8_t *__restrict__ labels, const float *__restrict__ lut, int L,
-                  int n_flux, double2 *__restrict__ partial)
+                  int n_flux, double2 *__restrict__ partial, const int *__restrict__ stop)
 {
+    if (stop && *stop) return;
     extern __shared__ float s_lut[];
     __shared__ double s_red[2][SUM_THREADS / 32];
     if (MULTI) {
@@ -95,8 +96,10 @@ plane_sums_kernel(taub_geom g, const float *__restrict__ f, const uint16_t *__re
 }
 
 __global__ void finalize_means_kernel(taub_geom g, const double2 *__restrict__ partial, int nchunks,
-                                      int n_flux, float *__restrict__ flux_mean, float *__restrict__ field_mean)
+                                      int n_flux, float *__restrict__ flux_mean, float *__restrict__ field_mean,
+                                      const int *__restrict__ stop)
 {
+    if (stop && *stop) return;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= g.bs * g.Nx) return;
     const int b = t / g.Nx, il = t - b * g.Nx;
@@ -111,6 +114,84 @@ __global__ void finalize_means_kernel(taub_geom g, const double2 *__restrict__ p
     if (il < n_flux) flux_mean[(int64_t)b * n_flux + il] = (float)(a / n);
 }
 
+// NumPy's float32 add.reduce along a contiguous axis (loops_utils.h.src, pairwise sum): plain loop
+// below 8 elements, 8 interleaved accumulators up to 128, recursive halving (multiples of 8) above.
+__device__ float np_pairwise_sum(const float *a, int n)
+{
+    if (n < 8) {
+        float res = 0.0f;
+        for (int i = 0; i < n; ++i) res = __fadd_rn(res, a[i]);
+        return res;
+    }
+    if (n <= 128) {
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = a[j];
+        int i = 8;
+        for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], a[i + j]);
+        }
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                              __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __fadd_rn(res, a[i]);
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __fadd_rn(np_pairwise_sum(a, n2), np_pairwise_sum(a + n2, n - n2));
+}
+
+// The reference's compute_metrics scalars (taufactor.py:297-305) and check_convergence decision
+// (:143-153) in the same float32 arithmetic NumPy uses on the host.  One thread per image, one block.
+__global__ void stop_rule_kernel(int bs, int Nx, const float *__restrict__ flux_mean, const float *__restrict__ D_mean,
+                                 float *__restrict__ old_tau, float conv_crit, float *__restrict__ record,
+                                 int *__restrict__ stop)
+{
+    __shared__ int s_all_conv, s_needs_host;
+    __shared__ float s_tau_err;
+    if (*stop) {                        // a previous check already stopped the solve
+        if (threadIdx.x == 0) record[0] = 3.0f;
+        return;
+    }
+    if (threadIdx.x == 0) {
+        s_all_conv = 1;
+        s_needs_host = 0;
+        s_tau_err = 0.0f;
+    }
+    __syncthreads();
+    const int n = Nx - 1;
+    for (int b = threadIdx.x; b < bs; b += blockDim.x) {
+        const float *fl = flux_mean + (size_t)b * n;
+        float fmax = fl[0], fmin = fl[0];
+        for (int i = 1; i < n; ++i) {
+            fmax = fmaxf(fmax, fl[i]);   // NaN handling differs from np.max only when the field is NaN
+            fmin = fminf(fmin, fl[i]);
+        }
+        const float mean_fl = __fdiv_rn(np_pairwise_sum(fl, n), (float)n);
+        float rel = (fmax != 0.0f) ? __fdiv_rn(__fsub_rn(fmax, fmin), fmax) : __int_as_float(0x7fc00000);
+        const float D_rel = __fmul_rn(mean_fl, (float)Nx);                     // / abs(top_bc - bot_bc) == 1
+        const float tau = (D_rel != 0.0f) ? __fdiv_rn(D_mean[b], D_rel) : __int_as_float(0x7fc00000);
+        if (fmin == 0.0f || fmax == 0.0f || mean_fl == 0.0f) s_needs_host = 1;  // percolation check, host only
+        if (mean_fl != mean_fl) rel = 0.0f;                                     // NaN counts as converged
+        record[2 + b] = tau;
+        record[2 + bs + b] = rel;
+        if (!(rel < conv_crit)) s_all_conv = 0;
+        const float err = fabsf(__fsub_rn(tau, old_tau[b]));
+        if (!(err < 2e-3f)) atomicExch(reinterpret_cast<int *>(&s_tau_err), __float_as_int(1.0f));  // any failure
+    }
+    __syncthreads();
+    const bool converged = s_all_conv && !(s_tau_err > 0.0f);
+    if (!s_needs_host && !converged)
+        for (int b = threadIdx.x; b < bs; b += blockDim.x) old_tau[b] = record[2 + b];   // ref:144,149
+    if (threadIdx.x == 0) {
+        const int status = s_needs_host ? 2 : (converged ? 1 : 0);
+        record[0] = (float)status;
+        record[1] = 0.0f;
+        if (status) *stop = status;
+    }
+}
+
 }  // namespace taub
 
 using namespace taub;
@@ -122,8 +203,32 @@ size_t taub_sums_ws_bytes(const taub_geom *g)
     return sizeof(double2) * (size_t)g->bs * g->Nx * sum_chunks(*g);
 }
 
+static int plane_means(const taub_problem *p, void *workspace, float *flux_mean, float *field_mean,
+                       const int *stop, void *stream);
+
 int taub_plane_means(const taub_problem *p, void *workspace, float *flux_mean, float *field_mean,
                      void *stream)
+{
+    return plane_means(p, workspace, flux_mean, field_mean, nullptr, stream);
+}
+
+int taub_check_async(const taub_problem *p, void *workspace, float *flux_mean, float *field_mean,
+                     const float *D_mean, float *old_tau, float conv_crit, float *record, void *stream)
+{
+    TAUB_REQUIRE(p && D_mean && old_tau && record, "taub_check_async: null pointer");
+    TAUB_REQUIRE(p->stop != nullptr, "taub_check_async: the problem has no stop flag");
+    TAUB_REQUIRE(p->g.i_offset == 0 && p->g.Nx == p->g.Nx_global && p->g.Nx >= 2,
+                 "taub_check_async needs the whole volume on this device and Nx >= 2");
+    if (int rc = plane_means(p, workspace, flux_mean, field_mean, p->stop, stream)) return rc;
+    stop_rule_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(p->g.bs, p->g.Nx, flux_mean, D_mean, old_tau, conv_crit,
+                                                        record, p->stop);
+    TAUB_CUDA(cudaGetLastError());
+    count_launch();
+    return TAUB_OK;
+}
+
+static int plane_means(const taub_problem *p, void *workspace, float *flux_mean, float *field_mean,
+                       const int *stop, void *stream)
 {
     TAUB_REQUIRE(p && workspace && flux_mean && field_mean, "taub_plane_means: null pointer");
     const taub_geom &g = p->g;
@@ -136,16 +241,16 @@ int taub_plane_means(const taub_problem *p, void *workspace, float *flux_mean, f
     dim3 grid(nchunks, g.Nx, g.bs);
     if (p->kind == TAUB_BINARY) {
         plane_sums_kernel<false><<<grid, SUM_THREADS, 0, s>>>(g, f, p->codes, nullptr, nullptr, 0, n_flux,
-                                                              (double2 *)workspace);
+                                                              (double2 *)workspace, stop);
     } else {
         const size_t smem = sizeof(float) * (p->L + 1) * (p->L + 1);
         plane_sums_kernel<true><<<grid, SUM_THREADS, smem, s>>>(g, f, nullptr, p->labels, p->lut, p->L,
-                                                                n_flux, (double2 *)workspace);
+                                                                n_flux, (double2 *)workspace, stop);
     }
     TAUB_CUDA(cudaGetLastError());
     count_launch();
     finalize_means_kernel<<<ceil_div(g.bs * g.Nx, 128), 128, 0, s>>>(g, (const double2 *)workspace, nchunks,
-                                                                    n_flux, flux_mean, field_mean);
+                                                                    n_flux, flux_mean, field_mean, stop);
     TAUB_CUDA(cudaGetLastError());
     count_launch();
     return TAUB_OK;

@@ -17,8 +17,9 @@ namespace taub {
 // {2,3,Nz+4,Nz+5} of the interior rows, := image of the wrapped interior voxel.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-refresh_ghosts_kernel(taub_geom g, float *__restrict__ f, int p_lo)
+refresh_ghosts_kernel(taub_geom g, float *__restrict__ f, int p_lo, const int *__restrict__ stop)
 {
+    if (stop && *stop) return;
     // items: the 2G ghost rows as float4 groups (pitch/4 each), then for every interior row the left
     // and the right ghost column pair (one float2 each; columns 2,3 and Nz+4,Nz+5 are 8-byte aligned
     // when Nz is even, otherwise the pair is moved as two scalars).
@@ -64,8 +65,10 @@ template <bool MULTI>
 __global__ void __launch_bounds__(256)
 half_sweep_kernel(taub_geom g, const float *__restrict__ src, float *__restrict__ dst,
                   const uint16_t *__restrict__ codes, const uint8_t *__restrict__ labels,
-                  const float *__restrict__ lut, int L, float omega, int colour, int i_lo, int n_planes)
+                  const float *__restrict__ lut, int L, float omega, int colour, int i_lo, int n_planes,
+                  const int *__restrict__ stop)
 {
+    if (stop && *stop) return;
     __shared__ float2 s_div[16];
     extern __shared__ float s_lut[];  // MULTI: (L+1)^2
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -143,7 +146,14 @@ using namespace taub;
 
 extern "C" {
 
+static int refresh_ghosts(const taub_geom *g, float *field, int p_lo, int p_hi, const int *stop, void *stream);
+
 int taub_refresh_ghosts(const taub_geom *g, float *field, int p_lo, int p_hi, void *stream)
+{
+    return refresh_ghosts(g, field, p_lo, p_hi, nullptr, stream);
+}
+
+static int refresh_ghosts(const taub_geom *g, float *field, int p_lo, int p_hi, const int *stop, void *stream)
 {
     TAUB_REQUIRE(g && field, "taub_refresh_ghosts: null pointer");
     TAUB_REQUIRE(p_lo >= 0 && p_hi <= g->planes && p_lo < p_hi, "taub_refresh_ghosts: planes [%d, %d) invalid", p_lo, p_hi);
@@ -151,7 +161,7 @@ int taub_refresh_ghosts(const taub_geom *g, float *field, int p_lo, int p_hi, vo
     for (int b0 = 0; b0 < g->bs; b0 += 65535) {
         dim3 grid(ceil_div(total, 256), p_hi - p_lo, min(g->bs - b0, 65535));
         refresh_ghosts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-            *g, field + (int64_t)b0 * g->image_stride, p_lo);
+            *g, field + (int64_t)b0 * g->image_stride, p_lo, stop);
     }
     TAUB_CUDA(cudaGetLastError());
     count_launch();
@@ -178,13 +188,13 @@ int taub_half_sweep(const taub_problem *p, int64_t iter, int i_lo, int i_hi, voi
     if (p->kind == TAUB_BINARY) {
         TAUB_REQUIRE(p->codes, "taub_half_sweep: binary problem without codes");
         half_sweep_kernel<false><<<grid, block, 0, s>>>(g, src, dst, p->codes, nullptr, nullptr, 0,
-                                                        p->omega, colour, i_lo, n_planes);
+                                                        p->omega, colour, i_lo, n_planes, p->stop);
     } else {
         TAUB_REQUIRE(p->labels && p->lut && p->L >= 1 && p->L <= TAUB_MAX_LABELS,
                      "taub_half_sweep: multi-phase problem without labels / table");
         const size_t smem = sizeof(float) * (p->L + 1) * (p->L + 1);
         half_sweep_kernel<true><<<grid, block, smem, s>>>(g, src, dst, nullptr, p->labels, p->lut,
-                                                          p->L, p->omega, colour, i_lo, n_planes);
+                                                          p->L, p->omega, colour, i_lo, n_planes, p->stop);
     }
     TAUB_CUDA(cudaGetLastError());
     count_launch();
@@ -201,7 +211,7 @@ int taub_iterate(taub_problem *p, int64_t iter, int n, int flags, void *stream)
     int done = 0;
     while (done < n) {
         if (g.periodic) {
-            if (int rc = taub_refresh_ghosts(&g, p->field[p->cur], 0, g.planes, stream)) return rc;
+            if (int rc = refresh_ghosts(&g, p->field[p->cur], 0, g.planes, p->stop, stream)) return rc;
         }
         if (fuse_ok && n - done >= 2) {
             if (int rc = taub_fused_sweep2(p, iter + done, 0, g.Nx, stream)) return rc;

@@ -218,6 +218,8 @@ class DistributedSolver(Solver):
         self.overlap = overlap
         self._report = (self.rank == 0)
 
+    pipeline = False   # the stop rule runs on the gathered profiles, on the host of every rank
+
     # ---- the loop: refresh (periodic) -> halo exchange -> pass, two iterations per pass when fused.
     # With overlap, the ghost exchange and the BW boundary planes of each side run on a side stream
     # while the interior planes (which need no ghost data) run on the compute stream.

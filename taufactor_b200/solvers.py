@@ -178,8 +178,8 @@ class SORSolver:
                               (g.image_stride, g.plane_stride, g.pitch, 1), off)
 
     # ------------------------------------------------------------------ the check (ref:109-153)
-    def check_convergence(self, verbose, conv_crit, plot_interval):
-        self.tau, relative_error = self.compute_metrics()
+    def check_convergence(self, verbose, conv_crit, plot_interval, profiles=None):
+        self.tau, relative_error = self.compute_metrics(profiles)
         if (verbose == 'per_iter' or verbose == 'debug') and self._report:
             i = np.argmax(relative_error)
             print(f'Iter: {self.iter}, conv error: {abs(relative_error[i]):.3E}, '
@@ -207,9 +207,9 @@ class SORSolver:
         mean = host[nf:].reshape(bs, Nx).copy()
         return flux, mean
 
-    def compute_metrics(self):
+    def compute_metrics(self, profiles=None):
         """ref:293-331 -- identical host post-processing of the two per-slice profiles."""
-        self.flux_1d, c_mean = self._plane_means()
+        self.flux_1d, c_mean = profiles if profiles is not None else self._plane_means()
         fl = self.flux_1d
         with np.errstate(invalid="ignore", divide="ignore"):
             fl_max, fl_min, mean_fl = fl.max(axis=1), fl.min(axis=1), fl.mean(axis=1)
@@ -258,6 +258,8 @@ class SORSolver:
         if verbose:
             torch.cuda.reset_peak_memory_stats(device=self.device)
         start = timer()
+        if self.pipeline and self._can_pipeline():
+            self._solve_pipelined(iter_limit, verbose, conv_crit, plot_interval)
         while not self.converged and self.iter < iter_limit:
             self._advance(min(100 - self.iter % 100, iter_limit - self.iter))
             if self.iter % 100 == 0:
@@ -268,6 +270,94 @@ class SORSolver:
         if self.tau_x is None:
             return self.tau
         return self.tau_x
+
+    # ------------------------------------------------------------------ pipelined checks
+    pipeline = True      # queue the next 100 iterations before the previous check is read back
+    PIPELINE_DEPTH = 2   # blocks of (100 iterations + check) in flight
+
+    def _can_pipeline(self):
+        return self.Nx >= 2 and self._geom.i_offset == 0 and self._geom.Nx == self._geom.Nx_global
+
+    def _solve_pipelined(self, iter_limit, verbose, conv_crit, plot_interval):
+        """The reference loop (ref:174-185) with the stop rule evaluated ON THE DEVICE
+        (taub_check_async): the host keeps PIPELINE_DEPTH blocks of 100 iterations + check queued and
+        reads the per-check records from pinned memory as they complete, so the GPU never waits for
+        the host.  When a check fires, the blocks queued behind it see the device stop flag and do
+        nothing: field and iteration count are exactly those of the reference's stopping check.  The
+        host re-evaluates every record with the reference's NumPy code for tau / D_eff / tau_x (and
+        for the zero-flux percolation branch, which only the host can run)."""
+        from collections import deque
+        lib, dev = self._lib, self.device
+        lib.taub_set_device(self._dev_index)
+        bs = self.batch_size
+        nprof, nrec = self._prof_dev.numel(), 2 + 2 * bs
+        if getattr(self, "_pipe", None) is None:
+            with torch.cuda.device(dev):
+                self._pipe = dict(
+                    ctl=torch.zeros(1, dtype=torch.int32, device=dev),
+                    old_tau=torch.zeros(bs, dtype=torch.float32, device=dev),
+                    D_mean=torch.from_numpy(np.atleast_1d(np.asarray(self.D_mean, np.float64)).copy()).to(dev),
+                    rec=torch.zeros(nrec, dtype=torch.float32, device=dev),
+                    host=torch.zeros((self.PIPELINE_DEPTH + 1, nprof + nrec), dtype=torch.float32).pin_memory())
+        P = self._pipe
+        P["ctl"].zero_()
+        P["old_tau"].copy_(torch.from_numpy(np.broadcast_to(np.asarray(self.old_tau, np.float32), (bs,)).copy()))
+        self._prob.stop = P["ctl"].data_ptr()
+        flags = 1 if self.force_generic else 0
+        stream = self._stream()
+        pending, slot, queued_iter = deque(), 0, self.iter
+        self.rule_mismatches = getattr(self, "rule_mismatches", 0)
+        try:
+            while not self.converged:
+                while (len(pending) < self.PIPELINE_DEPTH and queued_iter % 100 == 0
+                       and queued_iter + 100 <= iter_limit):
+                    self._call(lib.taub_iterate(self._prob, queued_iter, 100, flags, stream), "taub_iterate")
+                    self._call(lib.taub_check_async(self._prob, self._ws.data_ptr(), self._flux_dev.data_ptr(),
+                                                    self._mean_dev.data_ptr(), P["D_mean"].data_ptr(),
+                                                    P["old_tau"].data_ptr(), float(conv_crit), P["rec"].data_ptr(),
+                                                    stream), "taub_check_async")
+                    h = P["host"][slot]
+                    h[:nprof].copy_(self._prof_dev, non_blocking=True)
+                    h[nprof:].copy_(P["rec"], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    queued_iter += 100
+                    pending.append((ev, slot, queued_iter))
+                    slot = (slot + 1) % (self.PIPELINE_DEPTH + 1)
+                if not pending:
+                    break
+                ev, sl, it = pending.popleft()
+                ev.synchronize()
+                h = P["host"][sl].numpy()
+                status = int(h[nprof])
+                if status == 3:          # queued behind a check that stopped the solve: it did nothing
+                    continue
+                self.iter = it
+                nf = self._flux_dev.numel()
+                prof = (h[: bs * (self.Nx - 1)].reshape(bs, self.Nx - 1).copy(), h[nf:nprof].reshape(bs, self.Nx).copy())
+                host_says = self.check_convergence(verbose, conv_crit, plot_interval, profiles=prof)
+                if status == 2:
+                    # a slice flux is exactly 0: only the host can run the percolation check (ref:318-327);
+                    # its decision stands.  Everything queued behind was a no-op: drop it and resume.
+                    for e, _, _ in pending:
+                        e.synchronize()
+                    pending.clear()
+                    queued_iter = it
+                    self.converged = host_says
+                    if not host_says:
+                        P["old_tau"].copy_(torch.from_numpy(np.asarray(self.old_tau, np.float32).reshape(bs).copy()))
+                        P["ctl"].zero_()
+                    continue
+                if host_says != (status == 1):
+                    self.rule_mismatches += 1     # never observed: device and NumPy float32 rules are the same
+                    if status == 1:
+                        self.tau[self.tau == 0] = np.inf
+                    else:
+                        self.old_tau = self.tau
+                self.converged = (status == 1)
+        finally:
+            torch.cuda.synchronize(dev)
+            self._prob.stop = None
 
     def _advance(self, n):
         """n reference iterations on the device, no check, no host sync (ref:175-182 x n)."""
@@ -326,9 +416,8 @@ class Solver(ThroughTransportSolver):
     _kind = _lib.BINARY
 
     def __init__(self, img, omega=None, D_0=1, device='cuda'):
-        self._check_binary_labels(img)
         self.conductive_labels = [1]
-        img4 = _expand_to_4d(img)
+        img4 = _expand_to_4d(self._check_binary_labels(img))
         u8 = _as_uint8_labels(img4)
 
         def prepare(hist):
@@ -342,16 +431,24 @@ class Solver(ThroughTransportSolver):
 
     @staticmethod
     def _check_binary_labels(img):
-        """ref:387-397 -- every voxel must be exactly 0 or 1."""
-        a = np.asarray(img)
-        if a.size and not np.logical_or(a == 0, a == 1).all():
-            raise ValueError(
-                "Input image must only contain 0s and 1s. "
-                "Your image must be segmented to use this tool. "
-                "If your image has been segmented, ensure your labels are "
-                "0 for non-conductive and 1 for conductive phase. "
-                f"Your image has the following labels: {np.unique(a)}. "
-                "If you have more than one conductive phase, use the multi-phase solver.")
+        """ref:387-397 -- every voxel must be exactly 0 or 1 (one min/max pass instead of the
+        reference's three np.unique sorts).  Returns the image unchanged."""
+        if isinstance(img, np.ndarray) and img.size:
+            ok = img.dtype == np.bool_
+            if not ok:
+                lo, hi = img.min(), img.max()
+                ok = (lo == 0 or lo == 1) and (hi == 0 or hi == 1)
+                if ok and img.dtype.kind not in "ui":          # floats: nothing strictly between 0 and 1
+                    ok = bool(np.logical_or(img == 0, img == 1).all())
+            if not ok:
+                raise ValueError(
+                    "Input image must only contain 0s and 1s. "
+                    "Your image must be segmented to use this tool. "
+                    "If your image has been segmented, ensure your labels are "
+                    "0 for non-conductive and 1 for conductive phase. "
+                    f"Your image has the following labels: {np.unique(img)}. "
+                    "If you have more than one conductive phase, use the multi-phase solver.")
+        return img
 
     def _init_binary(self, p, img_dev, vec):
         codes = torch.empty(self._lib.taub_codes_elems(p.g), dtype=torch.int16, device=self.device)

@@ -224,6 +224,20 @@ def test_uniform_block_analytic_256(tau):
     assert abs(float(S.tau[0]) - 1.0) < 1e-5
 
 
+@pytest.mark.parametrize("name", ["rand40", "ref_deadend", "batch3_blobs48", "blobs3_48_pmp", "ref_non_percolating",
+                                  "flat2d_per_batch", "odd_11_13_9_per"])
+def test_pipelined_and_synchronous_solves_agree(tau, name):
+    """The device-side stop rule (taub_check_async) takes the same decisions as the host rule."""
+    A, skw = make(tau, name)                       # pipelined (default)
+    B, _ = make(tau, name, pipeline=False)         # one host sync per check, like the reference
+    A.solve(verbose=False, **skw)
+    B.solve(verbose=False, **skw)
+    assert A.iter == B.iter and A.converged == B.converged
+    assert np.array_equal(A.tau, B.tau, equal_nan=True) and np.array_equal(A.D_eff, B.D_eff, equal_nan=True)
+    assert np.array_equal(A.field.cpu().numpy(), B.field.cpu().numpy(), equal_nan=True)
+    assert getattr(A, "rule_mismatches", 0) == 0
+
+
 def test_zz_fused_fast_division_was_exact_everywhere(tau):
     """Runs last: no thread of the fused kernel ever divided a sub-2^-100 sum on the fast path, so
     every fused trajectory above was bit-identical to IEEE division (taub_inexact_events)."""
