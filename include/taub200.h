@@ -147,14 +147,14 @@ int taub_plane_means(const taub_problem *p, void *workspace, float *flux_mean, f
  * taufactor.py:143-153, with compute_metrics :296-305 in the reference's float32 NumPy arithmetic,
  * including NumPy's pairwise summation order for the mean flux), so that the host can queue the next
  * block of sweeps without waiting for this check.  Needs the whole volume (i_offset == 0, Nx == Nx_global).
- *   D_mean[bs], old_tau[bs] (in/out, starts at 0), record[2 + 2*bs] (out): device fp32 arrays;
+ *   D_mean[bs] device fp64; old_tau[bs] (in/out, starts at 0) and record[2 + 2*bs] (out) device fp32;
  *   record[0] = status (0 continue, 1 converged, 2 a slice flux is exactly 0 -> the host must run the
  *   percolation check, 3 the check did not run because *stop was already set), record[1] = reserved,
  *   record[2..2+bs) = tau, record[2+bs..2+2bs) = relative error.
  * On status 1 or 2 the kernel sets *p->stop (p->stop must be non-NULL): sweeps already queued behind
  * it become no-ops, so the field stays exactly at the iteration of this check. */
 int taub_check_async(const taub_problem *p, void *workspace, float *flux_mean, float *field_mean,
-                     const float *D_mean, float *old_tau, float conv_crit, float *record, void *stream);
+                     const double *D_mean, float *old_tau, float conv_crit, float *record, void *stream);
 
 #ifdef __cplusplus
 }

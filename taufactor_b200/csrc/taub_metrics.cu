@@ -144,7 +144,7 @@ __device__ float np_pairwise_sum(const float *a, int n)
 
 // The reference's compute_metrics scalars (taufactor.py:297-305) and check_convergence decision
 // (:143-153) in the same float32 arithmetic NumPy uses on the host.  One thread per image, one block.
-__global__ void stop_rule_kernel(int bs, int Nx, const float *__restrict__ flux_mean, const float *__restrict__ D_mean,
+__global__ void stop_rule_kernel(int bs, int Nx, const float *__restrict__ flux_mean, const double *__restrict__ D_mean,
                                  float *__restrict__ old_tau, float conv_crit, float *__restrict__ record,
                                  int *__restrict__ stop)
 {
@@ -171,7 +171,9 @@ __global__ void stop_rule_kernel(int bs, int Nx, const float *__restrict__ flux_
         const float mean_fl = __fdiv_rn(np_pairwise_sum(fl, n), (float)n);
         float rel = (fmax != 0.0f) ? __fdiv_rn(__fsub_rn(fmax, fmin), fmax) : __int_as_float(0x7fc00000);
         const float D_rel = __fmul_rn(mean_fl, (float)Nx);                     // / abs(top_bc - bot_bc) == 1
-        const float tau = (D_rel != 0.0f) ? __fdiv_rn(D_mean[b], D_rel) : __int_as_float(0x7fc00000);
+        // np.divide(D_mean, D_rel, out=float32): D_mean is float32 (binary) or float64 (multi-phase); the
+        // double quotient rounded to float equals the float32 quotient of float32 operands (53 >= 2*24+2)
+        const float tau = (D_rel != 0.0f) ? (float)(D_mean[b] / (double)D_rel) : __int_as_float(0x7fc00000);
         if (fmin == 0.0f || fmax == 0.0f || mean_fl == 0.0f) s_needs_host = 1;  // percolation check, host only
         if (mean_fl != mean_fl) rel = 0.0f;                                     // NaN counts as converged
         record[2 + b] = tau;
@@ -213,7 +215,7 @@ int taub_plane_means(const taub_problem *p, void *workspace, float *flux_mean, f
 }
 
 int taub_check_async(const taub_problem *p, void *workspace, float *flux_mean, float *field_mean,
-                     const float *D_mean, float *old_tau, float conv_crit, float *record, void *stream)
+                     const double *D_mean, float *old_tau, float conv_crit, float *record, void *stream)
 {
     TAUB_REQUIRE(p && D_mean && old_tau && record, "taub_check_async: null pointer");
     TAUB_REQUIRE(p->stop != nullptr, "taub_check_async: the problem has no stop flag");
