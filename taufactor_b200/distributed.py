@@ -241,11 +241,12 @@ class DistributedSolver(Solver):
             self._side = torch.cuda.Stream(device=self.device) if self._overlap else None
         done = 0
         main = torch.cuda.current_stream(self.device)
+        fresh = False     # the fused kernel leaves a fresh periodic ghost frame in its destination
         while done < n:
             cur = self._bufs[p.cur]
             fused = self._fuse and not self.force_generic and n - done >= 2
             it = self.iter + done
-            if self._periodic:
+            if self._periodic and not fresh:
                 self._call(lib.taub_refresh_ghosts(g, cur.data_ptr(), G, G + g.Nx, self._stream()), "taub_refresh_ghosts")
             if self._overlap:
                 side = self._side
@@ -263,6 +264,7 @@ class DistributedSolver(Solver):
                                                            self.rank, self.world, self.group)
                 self._sweep(it, fused, 0, g.Nx)
             done += 2 if fused else 1
+            fresh = bool(fused)
             p.cur ^= 1
         self.iter += n
 
@@ -316,6 +318,90 @@ class DistributedSolver(Solver):
         return torch.cat([out[r][:, : h - l] for r, (l, h) in enumerate(self.bounds)], dim=1)
 
 
+class BatchShardedSolver:
+    """A batch of independent images sharded one (or a few) per GPU -- BASELINE configs[2].
+
+    Every rank runs an ordinary single-GPU solver on its share of the batch; there is no data-path
+    collective.  The reference applies its stop rule JOINTLY to the whole batch (np.all / np.max over
+    the batch, taufactor.py:143-147), so at every check the ranks all-gather (relative error, tau) of
+    their images -- two floats per image -- and take the same decision.  ``tau`` / ``D_eff`` hold the
+    whole batch on every rank after ``solve()``.
+    """
+
+    def __init__(self, imgs, solver="Solver", group=None, device=None, **kw):
+        from . import solvers
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        imgs = _expand_to_4d(imgs)
+        self.batch_size = imgs.shape[0]
+        cuts = [self.batch_size * r // self.world for r in range(self.world + 1)]
+        self.shares = [(cuts[r], cuts[r + 1]) for r in range(self.world)]
+        lo, hi = self.shares[self.rank]
+        if hi <= lo:
+            raise ValueError(f"rank {self.rank} has no image: batch of {self.batch_size} over {self.world} ranks")
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.local = getattr(solvers, solver)(imgs[lo:hi], device=device, **kw)
+        self.local.pipeline = False          # the joint rule needs every rank's numbers at each check
+        self.local._report = (self.rank == 0)
+        self.device = self.local.device
+        self.global_voxels = int(np.prod(imgs.shape))
+        self.local_shape = imgs[lo:hi].shape
+        self.iter, self.converged, self.tau, self.D_eff = 0, False, None, None
+        self.old_tau = 0
+
+    def _gather(self, arr):
+        nmax = max(h - l for l, h in self.shares)
+        pad = torch.zeros(nmax, dtype=torch.float32, device=self.device)
+        pad[: len(arr)] = torch.from_numpy(np.asarray(arr, np.float32)).to(self.device)
+        out = torch.zeros(self.world * nmax, dtype=torch.float32, device=self.device)
+        all_gather_flat(out, pad, self.group)
+        out = out.cpu().numpy().reshape(self.world, nmax)
+        return np.concatenate([out[r, : h - l] for r, (l, h) in enumerate(self.shares)])
+
+    def solve(self, iter_limit=10000, verbose=True, conv_crit=1e-2, plot_interval=10):
+        S = self.local
+        start = timer()
+        while not self.converged and self.iter < iter_limit:
+            n = min(100 - self.iter % 100, iter_limit - self.iter)
+            S._advance(n)
+            self.iter += n
+            if self.iter % 100 == 0:
+                tau_l, rel_l = S.compute_metrics()
+                S.tau = tau_l
+                self.tau, rel = self._gather(tau_l), self._gather(rel_l)
+                self.D_eff = self._gather(S.D_eff)
+                if verbose == 'per_iter' and self.rank == 0:
+                    i = int(np.argmax(rel))
+                    print(f'Iter: {self.iter}, conv error: {abs(rel[i]):.3E}, tau: {self.tau[i]:.5f} (batch element {i})')
+                # ref:143-153 on the whole batch
+                if np.all(rel < conv_crit) and np.max(np.abs(self.tau - self.old_tau)) < 2e-3:
+                    self.tau[self.tau == 0] = np.inf
+                    self.converged = True
+                else:
+                    self.old_tau = self.tau
+        torch.cuda.synchronize(self.device)
+        self.walltime = timer() - start
+        S.converged, S.walltime = self.converged, self.walltime
+        if self.rank == 0 and verbose:
+            print(f"{'converged to' if self.converged else 'unconverged value of tau'}: {self.tau} after: {self.iter} "
+                  f"iterations in: {np.around(self.walltime, 4)} s")
+        return self.tau
+
+    # bench.py drives these
+    Nx = property(lambda self: self.local.Nx)
+    cpu_img = property(lambda self: self.local.cpu_img)
+
+    def _advance(self, n):
+        self.local._advance(n)
+
+    def _check_only(self):
+        return self.local._check_only()
+
+    def sweep_kernel_name(self):
+        return self.local.sweep_kernel_name()
+
+
 # ----------------------------------------------------------------------------- bench helper
 def make_bench_solver(args, rank, world, dev):
     """Workloads of ``bench.py --gpus N`` (N > 1)."""
@@ -325,16 +411,10 @@ def make_bench_solver(args, rank, world, dev):
     import cases
     if args.workload == "batch":
         # BASELINE configs[2]: one independent 384^3 image per GPU
-        from . import Solver as Single
-        img = cases.blobs(384, 0.5, seed=384 + rank)
-        host = torch.empty(img.shape, dtype=torch.uint8).pin_memory()
-        host.numpy()[...] = img
-
-        class Batch(Single):
-            global_voxels = img.size * world
-            local_shape = img.shape
-        return (lambda: Batch(host.numpy(), device=dev), f"batched Solver: {world} x 384^3 independent volumes, one per GPU",
-                f"batch sharded, {world} ranks, no data-path collective", host.numpy())
+        imgs = np.zeros((world, 384, 384, 384), np.uint8)      # every rank only fills (and uses) its own image
+        imgs[rank] = cases.blobs(384, 0.5, seed=384 + rank)
+        return (lambda: BatchShardedSolver(imgs, device=dev), f"batched Solver: {world} x 384^3 independent volumes, one per GPU",
+                f"batch sharded, {world} ranks, joint stop rule (2 floats per image all-gathered per check)", imgs[rank])
     # BASELINE configs[4]: the periodic 512^3 blob tiled to side*side*side, x-slab partitioned
     side = args.size if args.size > 512 else 2048
     reps = side // 512

@@ -93,6 +93,26 @@ def test_field_bitwise_vs_oracle_after_57_iterations(tau, name, generic):
     assert np.allclose(np.atleast_1d(S.D_mean), np.atleast_1d(st["D_mean"]), rtol=1e-7)
 
 
+@pytest.mark.parametrize("shape", [(12, 2, 2), (16, 6, 10), (20, 22, 30), (24, 40, 64), (9, 4, 66), (2, 64, 8)])
+def test_periodic_fused_kernel_writes_its_own_ghost_frame(tau, shape):
+    """Periodic solvers, even Ny/Nz: the fused kernel produces the destination's periodic ghost frame
+    itself (no refresh kernel between passes); Nz % 4 == 2 and 2-wide dimensions included."""
+    import torch
+    img = cases.random_img(shape, 0.75, seed=sum(shape))
+    A = tau.PeriodicSolver(img, device="cuda")
+    B = tau.PeriodicSolver(img, device="cuda")
+    B.force_generic = True
+    assert A.sweep_kernel_name() == "fused_sweep2_kernel"
+    for n in (2, 6, 49, 100):
+        A._advance(n)
+        B._advance(n)
+        assert torch.equal(A.field, B.field), (shape, A.iter)
+    from oracle import sor_c, sor_numpy as orc
+    st = orc.build_binary(img, periodic=True)
+    sor_c.sweep(st, A.iter)
+    assert np.array_equal(A.field.cpu().numpy()[:, 1:-1, 1:-1, 1:-1], st["field"][:, 1:-1, 1:-1, 1:-1])
+
+
 # ------------------------------------------------------------------ end-to-end solves
 @pytest.mark.parametrize("name", list(cases.CASES))
 def test_solve_matches_reference(tau, name):

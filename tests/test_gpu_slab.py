@@ -71,3 +71,34 @@ def test_slabs_equal_single_gpu(tmp_path, shape, periodic, world, mode):
     assert np.array_equal(B.flux_1d, got["flux"])
     assert np.array_equal(B.tau, got["tau"]) and np.array_equal(B.D_eff, got["D_eff"])
     assert int(got["sent"]) > 0
+
+
+def _batch_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.cuda.set_device(0)
+        from taufactor_b200.distributed import BatchShardedSolver
+        S = BatchShardedSolver(cases.stacked_blobs(), device="cuda:0")
+        S.solve(verbose=False)
+        if rank == 0:
+            np.savez(out, tau=S.tau, D_eff=S.D_eff, iters=S.iter)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_batch_sharded_joint_stop_rule(tmp_path):
+    """the joint rule matters at the 1e-4 level -- the third image alone stops at 200
+    iterations, in the batch at 300.  Sharded over ranks it must behave like the single-GPU batch."""
+    import json
+    import torch.multiprocessing as mp
+    import taufactor_b200 as tau
+    out = str(tmp_path / "batch.npz")
+    mp.spawn(_batch_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    B = tau.Solver(cases.stacked_blobs(), device="cuda")
+    B.solve(verbose=False)
+    assert int(got["iters"]) == B.iter == 300
+    assert np.array_equal(got["tau"], B.tau) and np.array_equal(got["D_eff"], B.D_eff)
