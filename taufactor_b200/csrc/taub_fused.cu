@@ -188,9 +188,17 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     const bool doit = (m < NCT) && (Gs < PG) && (Ra < g.rows);
     const bool colB = gg >= 1 && gg < LGt - 1 && Gs >= 1 && Gs < 1 + interior_groups(g.Nz);
     unsigned canB = 0;                       // bit r: row r of the column is an output row
+    unsigned wrapf = 0;                      // PER: bit r / 8+r: row r also goes to the bottom / top ghost rows,
+                                             //      bit 16 / 17: first / last interior group (ghost columns)
 #pragma unroll
     for (int r = 0; r < NRW; ++r)
-        if (doit && colB && lr0 + r >= 2 && lr0 + r < LR - 2 && Ra + r >= G && Ra + r < G + g.Ny) canB |= 1u << r;
+        if (doit && colB && lr0 + r >= 2 && lr0 + r < LR - 2 && Ra + r >= G && Ra + r < G + g.Ny) {
+            canB |= 1u << r;
+            if (Ra + r < 2 * G) wrapf |= 1u << r;
+            if (Ra + r >= g.Ny) wrapf |= 1u << (8 + r);
+        }
+    if (canB && Gs == 1) wrapf |= 1u << 16;
+    if (canB && Gs == interior_groups(g.Nz)) wrapf |= 1u << 17;
     const int i0 = lr0 * LG + gg;            // float4 index of row 0 inside a ring slot (row r: + r*LG)
     const int ic0 = lr0 * LGc + gg;          // uint16 index of row 0's code (row r: + r*LGc)
     // colour B first writes plane c0 (at step 2)
@@ -288,22 +296,21 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                         if (canB & (1u << r)) {
                             float *d = dst0 + (int64_t)r * g.pitch;
                             *reinterpret_cast<float4 *>(d) = out;
-                            if (PER) {
+                            if (PER && wrapf) {   // edge threads only
                                 // periodic images (apply_boundary_conditions, ref:501-505, done at the source):
                                 // rows j = 0,1 -> ghost rows Ny+2, Ny+3; rows Ny-2, Ny-1 -> ghost rows 0, 1;
                                 // columns k = 0,1 -> ghost columns Nz+4, Nz+5; k = Nz-2, Nz-1 -> columns 2, 3
-                                const int R = Ra + r;
                                 const int64_t wrap_dn = (int64_t)g.Ny * g.pitch;
-                                const bool to_bottom = R < 2 * G, to_top = R >= g.Ny;
+                                const bool to_bottom = wrapf & (1u << r), to_top = wrapf & (1u << (8 + r));
                                 if (to_bottom) *reinterpret_cast<float4 *>(d + wrap_dn) = out;
                                 if (to_top) *reinterpret_cast<float4 *>(d - wrap_dn) = out;
-                                if (Gs == 1) {
+                                if (wrapf & (1u << 16)) {
                                     const float2 v = make_float2(out.x, out.y);
                                     *reinterpret_cast<float2 *>(d + g.Nz) = v;
                                     if (to_bottom) *reinterpret_cast<float2 *>(d + wrap_dn + g.Nz) = v;
                                     if (to_top) *reinterpret_cast<float2 *>(d - wrap_dn + g.Nz) = v;
                                 }
-                                if (Gs == interior_groups(g.Nz)) {
+                                if (wrapf & (1u << 17)) {
                                     const float2 v = (g.Nz & 3) ? make_float2(out.x, out.y) : make_float2(out.z, out.w);
                                     float *e = d - 4 * Gs + COL0 - G;
                                     *reinterpret_cast<float2 *>(e) = v;
