@@ -123,6 +123,31 @@ __device__ __forceinline__ float z_neighbour(const bool is_xz, const float4 &v, 
     return zs;
 }
 
+// Periodic images of one freshly produced float4 group (apply_boundary_conditions, ref:501-505, done at
+// the source): rows j = 0,1 -> ghost rows Ny+2, Ny+3; rows Ny-2, Ny-1 -> ghost rows 0, 1; columns
+// k = 0,1 -> ghost columns Nz+4, Nz+5; k = Nz-2, Nz-1 -> columns 2, 3; corners included.  Out of line:
+// only the threads on the edge of the volume ever call it.
+static __device__ __noinline__ void wrap_store(float *d, float4 out, unsigned wrapf, int r, int Gs, int Ny, int Nz, int pitch)
+{
+    const int64_t wrap_dn = (int64_t)Ny * pitch;
+    const bool to_bottom = wrapf & (1u << r), to_top = wrapf & (1u << (8 + r));
+    if (to_bottom) *reinterpret_cast<float4 *>(d + wrap_dn) = out;
+    if (to_top) *reinterpret_cast<float4 *>(d - wrap_dn) = out;
+    if (wrapf & (1u << 16)) {
+        const float2 v = make_float2(out.x, out.y);
+        *reinterpret_cast<float2 *>(d + Nz) = v;
+        if (to_bottom) *reinterpret_cast<float2 *>(d + wrap_dn + Nz) = v;
+        if (to_top) *reinterpret_cast<float2 *>(d - wrap_dn + Nz) = v;
+    }
+    if (wrapf & (1u << 17)) {
+        const float2 v = (Nz & 3) ? make_float2(out.x, out.y) : make_float2(out.z, out.w);
+        float *e = d - 4 * Gs + COL0 - G;
+        *reinterpret_cast<float2 *>(e) = v;
+        if (to_bottom) *reinterpret_cast<float2 *>(e + wrap_dn) = v;
+        if (to_top) *reinterpret_cast<float2 *>(e - wrap_dn) = v;
+    }
+}
+
 // Thread work item = a COLUMN of NRW vertically adjacent rows x one float4 group.  In every step the
 // rows of a column alternate between "xz" and "yw" rows and swap roles each step; the column's internal
 // y-neighbours stay in registers, only the rows above and below it come from shared memory.  PA0 = parity
@@ -296,28 +321,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                         if (canB & (1u << r)) {
                             float *d = dst0 + (int64_t)r * g.pitch;
                             *reinterpret_cast<float4 *>(d) = out;
-                            if (PER && wrapf) {   // edge threads only
-                                // periodic images (apply_boundary_conditions, ref:501-505, done at the source):
-                                // rows j = 0,1 -> ghost rows Ny+2, Ny+3; rows Ny-2, Ny-1 -> ghost rows 0, 1;
-                                // columns k = 0,1 -> ghost columns Nz+4, Nz+5; k = Nz-2, Nz-1 -> columns 2, 3
-                                const int64_t wrap_dn = (int64_t)g.Ny * g.pitch;
-                                const bool to_bottom = wrapf & (1u << r), to_top = wrapf & (1u << (8 + r));
-                                if (to_bottom) *reinterpret_cast<float4 *>(d + wrap_dn) = out;
-                                if (to_top) *reinterpret_cast<float4 *>(d - wrap_dn) = out;
-                                if (wrapf & (1u << 16)) {
-                                    const float2 v = make_float2(out.x, out.y);
-                                    *reinterpret_cast<float2 *>(d + g.Nz) = v;
-                                    if (to_bottom) *reinterpret_cast<float2 *>(d + wrap_dn + g.Nz) = v;
-                                    if (to_top) *reinterpret_cast<float2 *>(d - wrap_dn + g.Nz) = v;
-                                }
-                                if (wrapf & (1u << 17)) {
-                                    const float2 v = (g.Nz & 3) ? make_float2(out.x, out.y) : make_float2(out.z, out.w);
-                                    float *e = d - 4 * Gs + COL0 - G;
-                                    *reinterpret_cast<float2 *>(e) = v;
-                                    if (to_bottom) *reinterpret_cast<float2 *>(e + wrap_dn) = v;
-                                    if (to_top) *reinterpret_cast<float2 *>(e - wrap_dn) = v;
-                                }
-                            }
+                            if (PER && wrapf) wrap_store(d, out, wrapf, r, Gs, g.Ny, g.Nz, g.pitch);   // edge threads only
                         }
                     }
                 }
