@@ -120,8 +120,6 @@ int taub_refresh_ghosts(const taub_geom *g, float *field, int p_lo, int p_hi, vo
 int taub_half_sweep(const taub_problem *p, int64_t iter, int i_lo, int i_hi, void *stream);
 /* TWO consecutive reference iterations (iter, iter+1) fused in one pass over HBM: temporally
  * blocked, TMA-bulk staged shared-memory tiles, register-rotating plane march.  Binary kind.
- * For periodic problems the kernel also writes the periodic ghost frame of the destination planes, so a
- * following pass needs no taub_refresh_ghosts (the SOURCE must have a fresh frame).
  * Returns TAUB_ERR_UNSUPPORTED when the problem does not qualify (see taub_can_fuse). */
 int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, void *stream);
 int taub_can_fuse(const taub_problem *p);

@@ -123,38 +123,12 @@ __device__ __forceinline__ float z_neighbour(const bool is_xz, const float4 &v, 
     return zs;
 }
 
-// Periodic images of one freshly produced float4 group (apply_boundary_conditions, ref:501-505, done at
-// the source): rows j = 0,1 -> ghost rows Ny+2, Ny+3; rows Ny-2, Ny-1 -> ghost rows 0, 1; columns
-// k = 0,1 -> ghost columns Nz+4, Nz+5; k = Nz-2, Nz-1 -> columns 2, 3; corners included.  Out of line:
-// only the threads on the edge of the volume ever call it.
-static __device__ __noinline__ void wrap_store(float *d, float4 out, unsigned wrapf, int r, int Gs, int Ny, int Nz, int pitch)
-{
-    const int64_t wrap_dn = (int64_t)Ny * pitch;
-    const bool to_bottom = wrapf & (1u << r), to_top = wrapf & (1u << (8 + r));
-    if (to_bottom) *reinterpret_cast<float4 *>(d + wrap_dn) = out;
-    if (to_top) *reinterpret_cast<float4 *>(d - wrap_dn) = out;
-    if (wrapf & (1u << 16)) {
-        const float2 v = make_float2(out.x, out.y);
-        *reinterpret_cast<float2 *>(d + Nz) = v;
-        if (to_bottom) *reinterpret_cast<float2 *>(d + wrap_dn + Nz) = v;
-        if (to_top) *reinterpret_cast<float2 *>(d - wrap_dn + Nz) = v;
-    }
-    if (wrapf & (1u << 17)) {
-        const float2 v = (Nz & 3) ? make_float2(out.x, out.y) : make_float2(out.z, out.w);
-        float *e = d - 4 * Gs + COL0 - G;
-        *reinterpret_cast<float2 *>(e) = v;
-        if (to_bottom) *reinterpret_cast<float2 *>(e + wrap_dn) = v;
-        if (to_top) *reinterpret_cast<float2 *>(e - wrap_dn) = v;
-    }
-}
-
 // Thread work item = a COLUMN of NRW vertically adjacent rows x one float4 group.  In every step the
 // rows of a column alternate between "xz" and "yw" rows and swap roles each step; the column's internal
 // y-neighbours stay in registers, only the rows above and below it come from shared memory.  PA0 = parity
 // of the column's first row at step 0 (uniform over the whole grid, chosen by the host), so every step
-// body is branch-free.  PER: periodic y/z -- the kernel also writes the destination's ghost frame (the
-// periodic images of the rows / columns it has just produced), so the next pass needs no refresh kernel.
-template <int NRW, int PA0, bool PER>
+// body is branch-free.
+template <int NRW, int PA0>
 __global__ void __launch_bounds__(F_NT, 2)
 fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tmap,
                     const __grid_constant__ CUtensorMap cmap)
@@ -213,17 +187,9 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     const bool doit = (m < NCT) && (Gs < PG) && (Ra < g.rows);
     const bool colB = gg >= 1 && gg < LGt - 1 && Gs >= 1 && Gs < 1 + interior_groups(g.Nz);
     unsigned canB = 0;                       // bit r: row r of the column is an output row
-    unsigned wrapf = 0;                      // PER: bit r / 8+r: row r also goes to the bottom / top ghost rows,
-                                             //      bit 16 / 17: first / last interior group (ghost columns)
 #pragma unroll
     for (int r = 0; r < NRW; ++r)
-        if (doit && colB && lr0 + r >= 2 && lr0 + r < LR - 2 && Ra + r >= G && Ra + r < G + g.Ny) {
-            canB |= 1u << r;
-            if (Ra + r < 2 * G) wrapf |= 1u << r;
-            if (Ra + r >= g.Ny) wrapf |= 1u << (8 + r);
-        }
-    if (canB && Gs == 1) wrapf |= 1u << 16;
-    if (canB && Gs == interior_groups(g.Nz)) wrapf |= 1u << 17;
+        if (doit && colB && lr0 + r >= 2 && lr0 + r < LR - 2 && Ra + r >= G && Ra + r < G + g.Ny) canB |= 1u << r;
     const int i0 = lr0 * LG + gg;            // float4 index of row 0 inside a ring slot (row r: + r*LG)
     const int ic0 = lr0 * LGc + gg;          // uint16 index of row 0's code (row r: + r*LGc)
     // colour B first writes plane c0 (at step 2)
@@ -318,11 +284,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                         float4 out = rg[r][iM1];
                         row_update(((PA0 + ss + r) & 1) == 0, out, rg[r][iP], rg[r][iM2], up, dn, zs[r],
                                    cr[r >> 1][iM1] >> (16 * (r & 1)), s_div, P.omega, umin);
-                        if (canB & (1u << r)) {
-                            float *d = dst0 + (int64_t)r * g.pitch;
-                            *reinterpret_cast<float4 *>(d) = out;
-                            if (PER && wrapf) wrap_store(d, out, wrapf, r, Gs, g.Ny, g.Nz, g.pitch);   // edge threads only
-                        }
+                        if (canB & (1u << r)) *reinterpret_cast<float4 *>(dst0 + (int64_t)r * g.pitch) = out;
                     }
                 }
                 dst0 += ps;
@@ -521,17 +483,16 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     // Tile row offsets (multiples of the even OR_) and chunk starts (multiples of the even
     // chunk_len) do not change it, so it is one number for the whole grid.
     const int pa0 = (1 - G + g.i_offset + P.colourA + (i_lo - 1)) & 1;   // row lr = 1 is row 0 of a column
-#define TAUB_LAUNCH_FUSED(PA_, PER_)                                                                                  \
-    do {                                                                                                              \
-        TAUB_CUDA(cudaFuncSetAttribute(fused_sweep2_kernel<F_NRW, PA_, PER_>,                                         \
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
-        fused_sweep2_kernel<F_NRW, PA_, PER_><<<grid, F_NT, smem, s>>>(P, tmap, cmap);                                \
+#define TAUB_LAUNCH_FUSED(PA_)                                                                                    \
+    do {                                                                                                          \
+        TAUB_CUDA(cudaFuncSetAttribute(fused_sweep2_kernel<F_NRW, PA_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                       (int)smem));                                                               \
+        fused_sweep2_kernel<F_NRW, PA_><<<grid, F_NT, smem, s>>>(P, tmap, cmap);                                            \
     } while (0)
-    if (g.periodic) {
-        if (pa0 == 0) TAUB_LAUNCH_FUSED(0, true); else TAUB_LAUNCH_FUSED(1, true);
-    } else {
-        if (pa0 == 0) TAUB_LAUNCH_FUSED(0, false); else TAUB_LAUNCH_FUSED(1, false);
-    }
+    if (pa0 == 0)
+        TAUB_LAUNCH_FUSED(0);
+    else
+        TAUB_LAUNCH_FUSED(1);
 #undef TAUB_LAUNCH_FUSED
     TAUB_CUDA(cudaGetLastError());
     count_launch();

@@ -209,19 +209,16 @@ int taub_iterate(taub_problem *p, int64_t iter, int n, int flags, void *stream)
                  "taub_iterate drives a whole volume; slabs interleave halo exchange in the caller");
     const bool fuse_ok = !(flags & 1) && taub_can_fuse(p) == 1;
     int done = 0;
-    bool ghosts_fresh = false;   // the fused kernel writes the periodic ghost frame of its destination
     while (done < n) {
-        if (g.periodic && !ghosts_fresh) {
+        if (g.periodic) {
             if (int rc = refresh_ghosts(&g, p->field[p->cur], 0, g.planes, p->stop, stream)) return rc;
         }
         if (fuse_ok && n - done >= 2) {
             if (int rc = taub_fused_sweep2(p, iter + done, 0, g.Nx, stream)) return rc;
             done += 2;
-            ghosts_fresh = true;
         } else {
             if (int rc = taub_half_sweep(p, iter + done, 0, g.Nx, stream)) return rc;
             done += 1;
-            ghosts_fresh = false;
         }
         p->cur ^= 1;
     }

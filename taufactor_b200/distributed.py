@@ -241,12 +241,11 @@ class DistributedSolver(Solver):
             self._side = torch.cuda.Stream(device=self.device) if self._overlap else None
         done = 0
         main = torch.cuda.current_stream(self.device)
-        fresh = False     # the fused kernel leaves a fresh periodic ghost frame in its destination
         while done < n:
             cur = self._bufs[p.cur]
             fused = self._fuse and not self.force_generic and n - done >= 2
             it = self.iter + done
-            if self._periodic and not fresh:
+            if self._periodic:
                 self._call(lib.taub_refresh_ghosts(g, cur.data_ptr(), G, G + g.Nx, self._stream()), "taub_refresh_ghosts")
             if self._overlap:
                 side = self._side
@@ -264,7 +263,6 @@ class DistributedSolver(Solver):
                                                            self.rank, self.world, self.group)
                 self._sweep(it, fused, 0, g.Nx)
             done += 2 if fused else 1
-            fresh = bool(fused)
             p.cur ^= 1
         self.iter += n
 

@@ -94,9 +94,8 @@ def test_field_bitwise_vs_oracle_after_57_iterations(tau, name, generic):
 
 
 @pytest.mark.parametrize("shape", [(12, 2, 2), (16, 6, 10), (20, 22, 30), (24, 40, 64), (9, 4, 66), (2, 64, 8)])
-def test_periodic_fused_kernel_writes_its_own_ghost_frame(tau, shape):
-    """Periodic solvers, even Ny/Nz: the fused kernel produces the destination's periodic ghost frame
-    itself (no refresh kernel between passes); Nz % 4 == 2 and 2-wide dimensions included."""
+def test_periodic_fused_vs_generic_small_and_odd_group_shapes(tau, shape):
+    """Periodic solvers, even Ny/Nz, on the fused kernel: Nz % 4 == 2 and 2-wide dimensions included."""
     import torch
     img = cases.random_img(shape, 0.75, seed=sum(shape))
     A = tau.PeriodicSolver(img, device="cuda")
