@@ -42,7 +42,11 @@ typedef enum taub_status {
     TAUB_ERR_UNSUPPORTED = -3   /* path not available for this problem (e.g. fused sweep) */
 } taub_status;
 
-typedef enum taub_kind { TAUB_BINARY = 0, TAUB_MULTIPHASE = 1 } taub_kind;
+typedef enum taub_kind {
+    TAUB_BINARY = 0,       /* Solver, PeriodicSolver */
+    TAUB_MULTIPHASE = 1,   /* MultiPhaseSolver, PeriodicMultiPhaseSolver */
+    TAUB_ANISOTROPIC = 2   /* AnisotropicSolver: binary codes, lut = device float[2] {Ky, Kz} (taufactor.py:455-456) */
+} taub_kind;
 
 /* Geometry of one rank's slab.  Filled by taub_geom_init. */
 typedef struct taub_geom {
@@ -58,7 +62,8 @@ typedef struct taub_geom {
 
 /* Everything a sweep needs.  Mirrors the state SORSolver.__init__ builds (taufactor.py:24-67):
  * field (two ping-pong copies), the per-voxel prefactor in compressed form (4-bit neighbour
- * count per voxel for the binary solvers instead of the fp32 `factor` tensor; 1-byte dense
+ * count per voxel for the binary solvers instead of the fp32 `factor` tensor (0 = non-conductive,
+ * 1..8 = count, 9 = conductive voxel without a conductive neighbour); 1-byte dense
  * phase index + an (L+1)x(L+1) harmonic-mean table for the multi-phase solvers instead of
  * D_x, D_y, D_z, factor), and omega.  No chequerboard tensors: parity is computed on the fly. */
 typedef struct taub_problem {

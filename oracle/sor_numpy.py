@@ -123,6 +123,32 @@ def build_binary(img, periodic=False, omega=None, D_0=1):
     return st
 
 
+def build_anisotropic(img, spacing, omega=None, D_0=1):
+    """AnisotropicSolver state (ref:447-471): neighbour weights Ky = (dx/dy)^2, Kz = (dx/dz)^2."""
+    dx, dy, dz = spacing
+    Ky, Kz = (dx / dy) ** 2, (dx / dz) ** 2
+    img4 = expand_to_4d(img)
+    mask = img4.astype(F32)
+    st = _common_state(img4, mask, omega)
+    m = np.zeros((mask.shape[0], mask.shape[1] + 2, mask.shape[2] + 2, mask.shape[3] + 2), F32)
+    m[:, 1:-1, 1:-1, 1:-1] = mask
+    m[:, 0, 1:-1, 1:-1] = 2
+    m[:, -1, 1:-1, 1:-1] = 2
+    # ref:462-467 -- nn += roll(img2, dr, dim) * factor[dim-1] for dim in x,y,z, dr in (+1, -1), fp32
+    nn = np.zeros_like(mask)
+    nn = (nn + m[:, :-2, 1:-1, 1:-1] * F32(1.0)).astype(F32)
+    nn = (nn + m[:, 2:, 1:-1, 1:-1] * F32(1.0)).astype(F32)
+    nn = (nn + (m[:, 1:-1, :-2, 1:-1] * F32(Ky)).astype(F32)).astype(F32)
+    nn = (nn + (m[:, 1:-1, 2:, 1:-1] * F32(Ky)).astype(F32)).astype(F32)
+    nn = (nn + (m[:, 1:-1, 1:-1, :-2] * F32(Kz)).astype(F32)).astype(F32)
+    nn = (nn + (m[:, 1:-1, 1:-1, 2:] * F32(Kz)).astype(F32)).astype(F32)
+    nn[mask == 0] = np.inf
+    nn[nn == 0] = np.inf
+    st.update(kind="anisotropic", periodic=False, factor=nn, D_0=D_0, Ky=Ky, Kz=Kz,
+              D_mean=np.mean(st["vol_x"], axis=1), conductive_labels=[1])
+    return st
+
+
 def harmonic_mean(a, b):
     """ref:577-583 -- ((2*a)*b)/(a+b) where a+b > 0 else 0, every step rounded to fp32."""
     a = a.astype(F32)
@@ -190,6 +216,11 @@ def refresh_periodic_ghosts(f):
 def neighbour_sum(st):
     """ref:95-103 (binary) / ref:606-613 (multi-phase): left-to-right fp32 adds."""
     f = st["field"]
+    if st["kind"] == "anisotropic":   # ref:473-478: (x+ + x-) + Ky*(y+ + y-) + Kz*(z+ + z-)
+        s = f[:, 2:, 1:-1, 1:-1] + f[:, :-2, 1:-1, 1:-1]
+        s = s + F32(st["Ky"]) * (f[:, 1:-1, 2:, 1:-1] + f[:, 1:-1, :-2, 1:-1])
+        s = s + F32(st["Kz"]) * (f[:, 1:-1, 1:-1, 2:] + f[:, 1:-1, 1:-1, :-2])
+        return s
     if st["kind"] == "binary":
         s = f[:, 2:, 1:-1, 1:-1] + f[:, :-2, 1:-1, 1:-1]
         s = s + f[:, 1:-1, 2:, 1:-1]
@@ -225,7 +256,7 @@ def vertical_flux(st):
     """ref:412-419 (binary, masked) / ref:615-620 (multi-phase, weighted)."""
     f = st["field"]
     vf = f[:, 2:-1, 1:-1, 1:-1] - f[:, 1:-2, 1:-1, 1:-1]
-    if st["kind"] == "binary":
+    if st["kind"] in ("binary", "anisotropic"):
         vf[st["factor"][:, 0:-1] > 8] = 0
         vf[st["factor"][:, 1:] > 8] = 0
         return vf

@@ -13,7 +13,7 @@ c_int, c_i64, c_vp, c_float = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, cty
 GHOST = 2
 COL0 = 4
 MAX_LABELS = 64
-BINARY, MULTIPHASE = 0, 1
+BINARY, MULTIPHASE, ANISOTROPIC = 0, 1, 2
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3
 
 

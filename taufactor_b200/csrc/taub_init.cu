@@ -80,6 +80,7 @@ init_binary_kernel(taub_geom g, ImgView v, const float *__restrict__ vec, float 
                         c = nn_weight(v, b, i + 1, jj, k) + nn_weight(v, b, i - 1, jj, k) +
                             nn_weight(v, b, i, jj + 1, k) + nn_weight(v, b, i, jj - 1, k) +
                             nn_weight(v, b, i, jj, k + 1) + nn_weight(v, b, i, jj, k - 1);
+                        if (c == 0) c = 9;   // conductive but isolated: factor = inf, yet part of the mask
                     }
                 }
             }
@@ -224,7 +225,7 @@ int taub_init_binary(const taub_problem *p, const uint8_t *img, int img_i0, int 
                      const float *vec, void *stream)
 {
     TAUB_REQUIRE(p && img && vec, "taub_init_binary: null pointer");
-    TAUB_REQUIRE(p->kind == TAUB_BINARY && p->field[0] && p->field[1] && p->codes,
+    TAUB_REQUIRE((p->kind == TAUB_BINARY || p->kind == TAUB_ANISOTROPIC) && p->field[0] && p->field[1] && p->codes,
                  "taub_init_binary: problem is not a bound binary problem");
     const taub_geom &g = p->g;
     if (int rc = check_img_cover(g, img_i0, img_n, G + 1)) return rc;

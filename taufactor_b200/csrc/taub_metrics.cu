@@ -17,13 +17,14 @@ static int sum_chunks(const taub_geom &g)
     return chunks > 64 ? 64 : (chunks < 1 ? 1 : chunks);
 }
 
-template <bool MULTI>
+template <int KIND>
 __global__ void __launch_bounds__(SUM_THREADS)
 plane_sums_kernel(taub_geom g, const float *__restrict__ f, const uint16_t *__restrict__ codes,
                   const uint8_t *__restrict__ labels, const float *__restrict__ lut, int L,
                   int n_flux, double2 *__restrict__ partial, const int *__restrict__ stop)
 {
     if (stop && *stop) return;
+    constexpr bool MULTI = (KIND == TAUB_MULTIPHASE);
     extern __shared__ float s_lut[];
     __shared__ double s_red[2][SUM_THREADS / 32];
     if (MULTI) {
@@ -50,10 +51,10 @@ plane_sums_kernel(taub_geom g, const float *__restrict__ f, const uint16_t *__re
         if (has_flux) {
             const float4 n4 = *reinterpret_cast<const float4 *>(f + o + g.plane_stride);
             n[0] = n4.x; n[1] = n4.y; n[2] = n4.z; n[3] = n4.w;
-            if (!MULTI) {
+            if (KIND == TAUB_BINARY) {
                 ca = codes[o >> 2];
                 cn = codes[(o + g.plane_stride) >> 2];
-            } else {
+            } else if (MULTI) {
                 la = *reinterpret_cast<const uint32_t *>(labels + o);
                 ln = *reinterpret_cast<const uint32_t *>(labels + o + g.plane_stride);
             }
@@ -64,9 +65,18 @@ plane_sums_kernel(taub_geom g, const float *__restrict__ f, const uint16_t *__re
                 fsum += (double)a[q];
                 if (has_flux) {
                     float v = __fsub_rn(n[q], a[q]);
-                    if (!MULTI) {
-                        const bool open = ((ca >> (4 * q)) & 15u) != 0 && ((cn >> (4 * q)) & 15u) != 0;
+                    if (KIND == TAUB_BINARY) {
+                        // factor > 8 (inf) on either side zeroes the flux (ref:417-418): codes 1..8 are finite
+                        const bool open = (((ca >> (4 * q)) & 15u) - 1u) < 8u && (((cn >> (4 * q)) & 15u) - 1u) < 8u;
                         v = open ? v : 0.0f;
+                    } else if (KIND == TAUB_ANISOTROPIC) {
+                        // same test on the weighted prefactor, which may legitimately exceed 8
+                        const int ig = il + g.i_offset;
+                        const float fa = aniso_factor_at(codes, o >> 2, q, g.plane_stride >> 2, g.pitch >> 2, ig,
+                                                         g.Nx_global, lut[0], lut[1]);
+                        const float fn = aniso_factor_at(codes, (o + g.plane_stride) >> 2, q, g.plane_stride >> 2,
+                                                         g.pitch >> 2, ig + 1, g.Nx_global, lut[0], lut[1]);
+                        v = (fa > 8.0f || fn > 8.0f) ? 0.0f : v;
                     } else {
                         v = __fmul_rn(s_lut[((la >> (8 * q)) & 255u) * (L + 1) + ((ln >> (8 * q)) & 255u)], v);
                     }
@@ -242,11 +252,14 @@ static int plane_means(const taub_problem *p, void *workspace, float *flux_mean,
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid(nchunks, g.Nx, g.bs);
     if (p->kind == TAUB_BINARY) {
-        plane_sums_kernel<false><<<grid, SUM_THREADS, 0, s>>>(g, f, p->codes, nullptr, nullptr, 0, n_flux,
-                                                              (double2 *)workspace, stop);
+        plane_sums_kernel<TAUB_BINARY><<<grid, SUM_THREADS, 0, s>>>(g, f, p->codes, nullptr, nullptr, 0, n_flux,
+                                                                    (double2 *)workspace, stop);
+    } else if (p->kind == TAUB_ANISOTROPIC) {
+        plane_sums_kernel<TAUB_ANISOTROPIC><<<grid, SUM_THREADS, 0, s>>>(g, f, p->codes, nullptr, p->lut, 0, n_flux,
+                                                                         (double2 *)workspace, stop);
     } else {
         const size_t smem = sizeof(float) * (p->L + 1) * (p->L + 1);
-        plane_sums_kernel<true><<<grid, SUM_THREADS, smem, s>>>(g, f, nullptr, p->labels, p->lut, p->L,
+        plane_sums_kernel<TAUB_MULTIPHASE><<<grid, SUM_THREADS, smem, s>>>(g, f, nullptr, p->labels, p->lut, p->L,
                                                                 n_flux, (double2 *)workspace, stop);
     }
     TAUB_CUDA(cudaGetLastError());

@@ -61,7 +61,7 @@ refresh_ghosts_kernel(taub_geom g, float *__restrict__ f, int p_lo, const int *_
 // voxels of the active colour are updated (warp-uniform branch on the row parity).  blockDim = (32, 8):
 // x -> groups along z (coalesced 512 B per warp), y -> rows; grid.z -> (image, plane).
 // ------------------------------------------------------------------------------------------
-template <bool MULTI>
+template <int KIND>   // 0 binary, 1 multi-phase, 2 anisotropic
 __global__ void __launch_bounds__(256)
 half_sweep_kernel(taub_geom g, const float *__restrict__ src, float *__restrict__ dst,
                   const uint16_t *__restrict__ codes, const uint8_t *__restrict__ labels,
@@ -69,6 +69,7 @@ half_sweep_kernel(taub_geom g, const float *__restrict__ src, float *__restrict_
                   const int *__restrict__ stop)
 {
     if (stop && *stop) return;
+    constexpr bool MULTI = (KIND == TAUB_MULTIPHASE);
     __shared__ float2 s_div[16];
     extern __shared__ float s_lut[];  // MULTI: (L+1)^2
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -100,12 +101,29 @@ half_sweep_kernel(taub_geom g, const float *__restrict__ src, float *__restrict_
         // voxel q is active when (i + j + k) % 2 == colour; k = 4*grp + q so only q matters.
         // par0 is uniform over a warp (one row per warp): 0 -> x,z active, 1 -> y,w active.
         const int par0 = (ig + j + colour) & 1;
-        if (!MULTI) {
+        if (KIND == TAUB_BINARY) {
             const unsigned code = codes[o >> 2];
             if (par0 == 0)
                 update_xz(c4, xp4, xm4, yp4, ym4, src[o - 1], code, s_div, omega);
             else
                 update_yw(c4, xp4, xm4, yp4, ym4, src[o + 4], code, s_div, omega);
+        } else if (KIND == TAUB_ANISOTROPIC) {
+            const float Ky = lut[0], Kz = lut[1];
+            const int64_t ci = o >> 2, cps = ps >> 2;
+            const int cpitch = pitch >> 2;
+            if (par0 == 0) {
+                const float f0 = aniso_factor_at(codes, ci, 0, cps, cpitch, ig, g.Nx_global, Ky, Kz);
+                const float f2 = aniso_factor_at(codes, ci, 2, cps, cpitch, ig, g.Nx_global, Ky, Kz);
+                const float cy = c4.y;
+                c4.x = sor_aniso(c4.x, xp4.x, xm4.x, yp4.x, ym4.x, cy, src[o - 1], f0, Ky, Kz, omega);
+                c4.z = sor_aniso(c4.z, xp4.z, xm4.z, yp4.z, ym4.z, c4.w, cy, f2, Ky, Kz, omega);
+            } else {
+                const float f1 = aniso_factor_at(codes, ci, 1, cps, cpitch, ig, g.Nx_global, Ky, Kz);
+                const float f3 = aniso_factor_at(codes, ci, 3, cps, cpitch, ig, g.Nx_global, Ky, Kz);
+                const float cz = c4.z;
+                c4.y = sor_aniso(c4.y, xp4.y, xm4.y, yp4.y, ym4.y, cz, c4.x, f1, Ky, Kz, omega);
+                c4.w = sor_aniso(c4.w, xp4.w, xm4.w, yp4.w, ym4.w, src[o + 4], cz, f3, Ky, Kz, omega);
+            }
         } else {
             const uint32_t lc = *reinterpret_cast<const uint32_t *>(labels + o);
             const uint32_t lxp = *reinterpret_cast<const uint32_t *>(labels + o + ps);
@@ -187,13 +205,18 @@ int taub_half_sweep(const taub_problem *p, int64_t iter, int i_lo, int i_hi, voi
     cudaStream_t s = (cudaStream_t)stream;
     if (p->kind == TAUB_BINARY) {
         TAUB_REQUIRE(p->codes, "taub_half_sweep: binary problem without codes");
-        half_sweep_kernel<false><<<grid, block, 0, s>>>(g, src, dst, p->codes, nullptr, nullptr, 0,
-                                                        p->omega, colour, i_lo, n_planes, p->stop);
+        half_sweep_kernel<TAUB_BINARY><<<grid, block, 0, s>>>(g, src, dst, p->codes, nullptr, nullptr, 0,
+                                                              p->omega, colour, i_lo, n_planes, p->stop);
+    } else if (p->kind == TAUB_ANISOTROPIC) {
+        TAUB_REQUIRE(p->codes && p->lut, "taub_half_sweep: anisotropic problem without codes / weights");
+        TAUB_REQUIRE(!g.periodic, "taub_half_sweep: the anisotropic solver has no periodic variant");
+        half_sweep_kernel<TAUB_ANISOTROPIC><<<grid, block, 0, s>>>(g, src, dst, p->codes, nullptr, p->lut, 0,
+                                                                   p->omega, colour, i_lo, n_planes, p->stop);
     } else {
         TAUB_REQUIRE(p->labels && p->lut && p->L >= 1 && p->L <= TAUB_MAX_LABELS,
                      "taub_half_sweep: multi-phase problem without labels / table");
         const size_t smem = sizeof(float) * (p->L + 1) * (p->L + 1);
-        half_sweep_kernel<true><<<grid, block, smem, s>>>(g, src, dst, nullptr, p->labels, p->lut,
+        half_sweep_kernel<TAUB_MULTIPHASE><<<grid, block, smem, s>>>(g, src, dst, nullptr, p->labels, p->lut,
                                                           p->L, p->omega, colour, i_lo, n_planes, p->stop);
     }
     TAUB_CUDA(cudaGetLastError());

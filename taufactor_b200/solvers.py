@@ -467,8 +467,54 @@ class Solver(ThroughTransportSolver):
         c = codes.to(torch.int32) & 0xFFFF
         nib = torch.stack([(c >> (4 * q)) & 15 for q in range(4)], dim=-1).reshape(g.bs, g.Nx, g.Ny, -1)
         nib = nib[..., _lib.COL0:_lib.COL0 + g.Nz].to(torch.float32)
-        nib[nib == 0] = torch.inf
+        nib[(nib == 0) | (nib == 9)] = torch.inf      # 9: conductive voxel without a conductive neighbour
         return nib
+
+
+class AnisotropicSolver(Solver):
+    """Binary solver with voxel-spacing corrections (ref:422-478): y neighbours weigh
+    ``Ky = (dx/dy)**2`` and z neighbours ``Kz = (dx/dz)**2`` in the stencil and in the prefactor.
+
+    Args:
+        img: binary image.
+        spacing: voxel spacing ``(dx, dy, dz)``.
+    """
+    _kind = _lib.ANISOTROPIC
+
+    def __init__(self, img, spacing, omega=None, D_0=1, device='cuda'):
+        if not isinstance(spacing, (list, tuple)) or len(spacing) != 3:
+            raise ValueError("spacing must be a list or tuple with three elements (dx, dy, dz)")
+        if not all(isinstance(x, (int, float)) for x in spacing):
+            raise ValueError("All elements in spacing must be integers or floats")
+        if (np.max(spacing) / np.min(spacing) > 10):
+            warnings.warn("This computation is very questionable for largely different spacings e.g. dz >> dx.")
+        dx, dy, dz = spacing
+        self.Ky = (dx / dy) ** 2
+        self.Kz = (dx / dz) ** 2
+        super().__init__(img, omega=omega, D_0=D_0, device=device)
+
+    def _init_binary(self, p, img_dev, vec):
+        weights = torch.tensor([self.Ky, self.Kz], dtype=torch.float32, device=self.device)   # rounded to fp32 like
+        p.lut = weights.data_ptr()                                                           # torch's tensor * scalar
+        return super()._init_binary(p, img_dev, vec) + (weights,)
+
+    @property
+    def factor(self):
+        """ref:459-471 rebuilt from the conductive mask (test / inspection only)."""
+        g, G = self._geom, _lib.GHOST
+        codes = self._keep[0].view(g.bs, g.planes, g.rows, g.pitch // 4).to(torch.int32) & 0xFFFF
+        m = torch.stack([(codes >> (4 * q)) & 15 for q in range(4)], dim=-1).reshape(g.bs, g.planes, g.rows, -1)
+        m = (m != 0).to(torch.float32)[:, G - 1:G + g.Nx + 1, G - 1:G + g.Ny + 1, _lib.COL0 - 1:_lib.COL0 + g.Nz + 1]
+        m[:, 0, 1:-1, 1:-1], m[:, -1, 1:-1, 1:-1] = 2, 2
+        Ky, Kz = np.float32(self.Ky), np.float32(self.Kz)
+        nn = m[:, :-2, 1:-1, 1:-1] + m[:, 2:, 1:-1, 1:-1]
+        nn = nn + m[:, 1:-1, :-2, 1:-1] * Ky
+        nn = nn + m[:, 1:-1, 2:, 1:-1] * Ky
+        nn = nn + m[:, 1:-1, 1:-1, :-2] * Kz
+        nn = nn + m[:, 1:-1, 1:-1, 2:] * Kz
+        nn[m[:, 1:-1, 1:-1, 1:-1] == 0] = torch.inf
+        nn[nn == 0] = torch.inf
+        return nn
 
 
 class PeriodicSolver(Solver):

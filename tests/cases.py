@@ -158,13 +158,18 @@ CASES = {
     "odd3_pmp":             ("PeriodicMultiPhaseSolver", odd_random3, {"diffusivities": {0: 0.2, 1: 1.0, 2: 0.0}}, {"iter_limit": 300}, None),
     "flat2d":               ("Solver", flat_2d, {}, {"iter_limit": 600}, None),
     "flat2d_per_batch":     ("PeriodicSolver", img_2d_batch, {}, {"iter_limit": 600}, None),
+    # AnisotropicSolver (ref:422-478; SURVEY 8f "next" #1)
+    "aniso_iso":            ("AnisotropicSolver", lambda: random_img((24, 20, 16), 0.7, 11), {"spacing": (1, 1, 1)}, {}, None),
+    "aniso_fib":            ("AnisotropicSolver", lambda: random_img((20, 24, 18), 0.75, 12), {"spacing": (1.0, 1.0, 2.5)}, {}, None),
+    "aniso_odd":            ("AnisotropicSolver", lambda: odd_random(8), {"spacing": (2.0, 1.0, 3.0)}, {"iter_limit": 300}, None),
+    "aniso_blobs48":        ("AnisotropicSolver", lambda: blobs(48, 0.5, seed=48), {"spacing": (1.0, 0.8, 1.6)}, {}, None),
     "omega_custom":         ("Solver", lambda: random_img((24, 20, 16), 0.7, 11), {"omega": 1.7}, {"conv_crit": 1e-3}, None),
 }
 
 # cases whose field is snapshotted bit-for-bit after these iteration counts
 SNAPSHOT_ITERS = (1, 2, 3, 100, 101)
 SNAPSHOT_CASES = ("odd_11_13_9", "odd_11_13_9_per", "odd3_mp", "odd3_pmp", "flat2d",
-                  "flat2d_per_batch", "ref_slanted", "ref_per_slanted_odd")
+                  "flat2d_per_batch", "ref_slanted", "ref_per_slanted_odd", "aniso_odd", "aniso_fib")
 
 # fast subset for the GPU parity run through the product API
 GPU_SOLVE_CASES = tuple(CASES)

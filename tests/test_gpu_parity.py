@@ -47,6 +47,8 @@ def oracle_state(name):
         if "MultiPhase" in cls:
             d = ckw.get("diffusivities")
             return orc.build_multiphase(build(), dict(d) if d else None, periodic=periodic, omega=ckw.get("omega"))
+        if cls == "AnisotropicSolver":
+            return orc.build_anisotropic(build(), ckw["spacing"], omega=ckw.get("omega"))
         return orc.build_binary(build(), periodic=periodic, omega=ckw.get("omega"))
 
 
