@@ -169,25 +169,41 @@ def run_ours(args):
     del w
 
     if world == 1:
-        img = blob_image(args.size)
+        if args.size > 512:     # the multi-GPU workload on one GPU (strong-scaling reference point)
+            reps = args.size // 512
+            img = np.tile(blob_image(512), (reps, reps, reps))
+            workload = f"tau.Solver on {512 * reps}^3 volume (512^3 blob tiled {reps}x{reps}x{reps}), single GPU"
+        else:
+            img = blob_image(args.size)
+            workload = f"tau.Solver on {args.size}^3 synthetic blob microstructure (porosity 0.5, seed {args.size})"
         pinned = torch.empty(img.shape, dtype=torch.uint8).pin_memory()
         pinned.numpy()[...] = img
         host_img = pinned.numpy()
-        workload = f"tau.Solver on {args.size}^3 synthetic blob microstructure (porosity 0.5, seed {args.size})"
+        del img
         make = lambda: tau.Solver(host_img, device=dev)
         parallelism = "single GPU"
     else:
         from taufactor_b200.distributed import make_bench_solver
         make, workload, parallelism, host_img = make_bench_solver(args, rank, world, dev)
 
-    # ---- e2e: the user-facing call with HOST buffers: ctor (H2D of the image, state build) +
-    #      solve() to the reference's default stop rule (D2H of the flux profiles every check)
-    sync_all()
-    t0 = time.perf_counter()
-    S = make()
-    S.solve(verbose=False, iter_limit=args.e2e_iter_limit)
-    sync_all()
-    t_e2e = time.perf_counter() - t0
+    # ---- e2e: the user-facing call with HOST buffers: ctor (H2D of the pinned image, state build) +
+    #      solve() to the reference's default stop rule (D2H of the flux profiles every check).
+    #      Run twice back to back: the first run also pays one-time process costs (first large
+    #      cudaMalloc of the caching allocator, lazy module loading, pinned-buffer allocation) and is
+    #      reported as "first_run_s"; the headline is the second, steady-state run.
+    first_run = None
+    for attempt in range(2):
+        S = None
+        sync_all()
+        t0 = time.perf_counter()
+        S = make()
+        torch.cuda.synchronize(dev)
+        t_ctor = time.perf_counter() - t0
+        S.solve(verbose=False, iter_limit=args.e2e_iter_limit)
+        sync_all()
+        t_e2e = time.perf_counter() - t0
+        if attempt == 0:
+            first_run = t_e2e
     if world > 1:
         tt = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -198,7 +214,7 @@ def run_ours(args):
     e2e = {"value": voxels_total * e2e_iters / t_e2e / 1e9, "unit": "GLUPS",
            "h2d_bytes_per_step": int(host_img.nbytes // e2e_checks),
            "d2h_bytes_per_step": int(4 * (2 * S.Nx - 1) * S.batch_size),
-           "time_to_converged_s": t_e2e, "iterations": e2e_iters, "converged": bool(S.converged), "tau": e2e_tau}
+           "time_to_converged_s": t_e2e, "ctor_s": t_ctor, "solve_s": t_e2e - t_ctor, "first_run_s": first_run, "iterations": e2e_iters, "converged": bool(S.converged), "tau": e2e_tau}
 
     # ---- device-resident throughput: K steps of (100 iterations + flux check), CUDA events
     def step():
@@ -271,7 +287,7 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample on the host cores
     cpu = None
     if world == 1 and not args.no_cpu:
-        sample = np.ascontiguousarray(host_img[: max(8, args.size // 4)])
+        sample = np.ascontiguousarray(host_img[: max(8, min(args.size, 512) // 4), :512, :512])
         _, _, dt4 = cpu_reference(sample, 4)
         n_cpu = int(min(400, max(8, 12.0 / max(dt4 / 4, 1e-4))))      # about 12 s of CPU work
         v, threads, dt = cpu_reference(sample, n_cpu)
