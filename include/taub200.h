@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TAUB_ABI_VERSION 2
+#define TAUB_ABI_VERSION 3
 #define TAUB_GHOST 2            /* ghost width in x (planes), y (rows) and z (columns) */
 #define TAUB_COL0 4             /* column of interior voxel k = 0 */
 #define TAUB_MAX_LABELS 64      /* dense phase indices 0..L-1, L <= 64; index L = "outside" */
@@ -45,7 +45,10 @@ typedef enum taub_status {
 typedef enum taub_kind {
     TAUB_BINARY = 0,       /* Solver, PeriodicSolver */
     TAUB_MULTIPHASE = 1,   /* MultiPhaseSolver, PeriodicMultiPhaseSolver */
-    TAUB_ANISOTROPIC = 2   /* AnisotropicSolver: binary codes, lut = device float[2] {Ky, Kz} (taufactor.py:455-456) */
+    TAUB_ANISOTROPIC = 2,  /* AnisotropicSolver: binary codes, lut = device float[2] {Ky, Kz} (taufactor.py:455-456) */
+    TAUB_MULTIPHASE_CLASS = 3  /* multi-phase through a stencil-class table: codes = one uint16 class id per
+                                * storage voxel, lut = device float[L][8] rows {w_x+, w_x-, w_y+, w_y-, w_z+,
+                                * w_z-, prefactor, 0}, L = number of classes (see taub_multiphase_keys) */
 } taub_kind;
 
 /* Geometry of one rank's slab.  Filled by taub_geom_init. */
@@ -109,6 +112,12 @@ int taub_init_binary(const taub_problem *p, const uint8_t *img, int img_i0, int 
  * phase conducts (D > 0); p->lut must already hold the harmonic-mean table. */
 int taub_init_multiphase(const taub_problem *p, const uint8_t *img, int img_i0, int img_n,
                          const uint8_t *map256, const float *cond, const float *vec, void *stream);
+/* Multi-phase only: keys[b][i][j][k] (int32, device, bs*Nx*Ny*Nz) = the seven dense phase indices that
+ * determine a voxel's stencil (own | x- <<4 | x+ <<8 | y- <<12 | y+ <<16 | z- <<20 | z+ <<24) plus bit 28 /
+ * 29 = first / last global plane (the Dirichlet face counts twice, taufactor.py:601-602).  Needs L <= 15.
+ * Voxels with equal keys have identical face conductances and prefactor, so the caller can replace the
+ * labels by the index into the table of distinct keys (TAUB_MULTIPHASE_CLASS). */
+int taub_multiphase_keys(const taub_problem *p, int32_t *keys, void *stream);
 /* counts[b][i] (int64, device) = voxels of local plane i whose raw label has sel256[label] != 0
  * (numerator of vol_x, taufactor.py:42); hist[b][256] (int64, device, may be NULL) = label
  * histogram (numerators of VF, taufactor.py:564-567). */

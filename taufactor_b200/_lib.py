@@ -13,7 +13,7 @@ c_int, c_i64, c_vp, c_float = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, cty
 GHOST = 2
 COL0 = 4
 MAX_LABELS = 64
-BINARY, MULTIPHASE, ANISOTROPIC = 0, 1, 2
+BINARY, MULTIPHASE, ANISOTROPIC, MULTIPHASE_CLASS = 0, 1, 2, 3
 OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3
 
 
@@ -43,6 +43,7 @@ SIGNATURES = {
     "taub_sums_ws_bytes": (ctypes.c_size_t, [ctypes.POINTER(Geom)]),
     "taub_init_binary": (c_int, [ctypes.POINTER(Problem), c_vp, c_int, c_int, c_vp, c_vp]),
     "taub_init_multiphase": (c_int, [ctypes.POINTER(Problem), c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "taub_multiphase_keys": (c_int, [ctypes.POINTER(Problem), c_vp, c_vp]),
     "taub_plane_counts": (c_int, [ctypes.POINTER(Geom), c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "taub_refresh_ghosts": (c_int, [ctypes.POINTER(Geom), c_vp, c_int, c_int, c_vp]),
     "taub_half_sweep": (c_int, [ctypes.POINTER(Problem), c_i64, c_int, c_int, c_vp]),
@@ -73,7 +74,7 @@ def load():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.taub_abi_version() != 2:
+        if lib.taub_abi_version() != 3:
             raise ImportError("libtaub200.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib

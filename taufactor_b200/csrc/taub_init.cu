@@ -185,6 +185,28 @@ plane_counts_kernel(taub_geom g, ImgView v, const uint8_t *__restrict__ sel256,
             if (s_hist[t]) atomicAdd(&hist[(int64_t)b * 256 + t], (unsigned long long)s_hist[t]);
 }
 
+// One thread per interior voxel: pack the seven dense phase indices of its stencil.
+__global__ void __launch_bounds__(256)
+multiphase_keys_kernel(taub_geom g, const uint8_t *__restrict__ labels, int32_t *__restrict__ keys)
+{
+    const int64_t total = (int64_t)g.bs * g.Nx * g.Ny * g.Nz;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(t % g.Nz);
+        int64_t r = t / g.Nz;
+        const int j = (int)(r % g.Ny);
+        r /= g.Ny;
+        const int i = (int)(r % g.Nx);
+        const int b = (int)(r / g.Nx);
+        const int64_t o = (int64_t)b * g.image_stride + (int64_t)(i + G) * g.plane_stride + (int64_t)(j + G) * g.pitch + COL0 + k;
+        const int ig = i + g.i_offset;
+        int key = labels[o] | (labels[o - g.plane_stride] << 4) | (labels[o + g.plane_stride] << 8) |
+                  (labels[o - g.pitch] << 12) | (labels[o + g.pitch] << 16) | (labels[o - 1] << 20) | (labels[o + 1] << 24);
+        if (ig == 0) key |= 1 << 28;
+        if (ig == g.Nx_global - 1) key |= 1 << 29;
+        keys[t] = key;
+    }
+}
+
 static int check_img_cover(const taub_geom &g, int img_i0, int img_n, int halo)
 {
     const int lo = max(0, g.i_offset - halo), hi = min(g.Nx_global, g.i_offset + g.Nx + halo);
@@ -250,6 +272,18 @@ int taub_init_multiphase(const taub_problem *p, const uint8_t *img, int img_i0, 
     const int64_t total = (int64_t)taub_codes_elems(&g);
     init_multi_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         g, make_view(g, img, img_i0, img_n), p->L, map256, cond, vec, p->field[0], p->field[1], p->labels);
+    TAUB_CUDA(cudaGetLastError());
+    count_launch();
+    return TAUB_OK;
+}
+
+int taub_multiphase_keys(const taub_problem *p, int32_t *keys, void *stream)
+{
+    TAUB_REQUIRE(p && keys && p->labels, "taub_multiphase_keys: null pointer");
+    TAUB_REQUIRE(p->L >= 1 && p->L <= 15, "taub_multiphase_keys: needs at most 15 phases (got %d)", p->L);
+    const taub_geom &g = p->g;
+    const int64_t total = (int64_t)g.bs * g.Nx * g.Ny * g.Nz;
+    multiphase_keys_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(g, p->labels, keys);
     TAUB_CUDA(cudaGetLastError());
     count_launch();
     return TAUB_OK;

@@ -69,6 +69,9 @@ plane_sums_kernel(taub_geom g, const float *__restrict__ f, const uint16_t *__re
                         // factor > 8 (inf) on either side zeroes the flux (ref:417-418): codes 1..8 are finite
                         const bool open = (((ca >> (4 * q)) & 15u) - 1u) < 8u && (((cn >> (4 * q)) & 15u) - 1u) < 8u;
                         v = open ? v : 0.0f;
+                    } else if (KIND == TAUB_MULTIPHASE_CLASS) {
+                        // D_x face conductance towards plane i+1 = first entry of the voxel's class row
+                        v = __fmul_rn(__ldg(lut + 8 * (int)codes[o + q]), v);
                     } else if (KIND == TAUB_ANISOTROPIC) {
                         // same test on the weighted prefactor, which may legitimately exceed 8
                         const int ig = il + g.i_offset;
@@ -254,6 +257,9 @@ static int plane_means(const taub_problem *p, void *workspace, float *flux_mean,
     if (p->kind == TAUB_BINARY) {
         plane_sums_kernel<TAUB_BINARY><<<grid, SUM_THREADS, 0, s>>>(g, f, p->codes, nullptr, nullptr, 0, n_flux,
                                                                     (double2 *)workspace, stop);
+    } else if (p->kind == TAUB_MULTIPHASE_CLASS) {
+        plane_sums_kernel<TAUB_MULTIPHASE_CLASS><<<grid, SUM_THREADS, 0, s>>>(g, f, p->codes, nullptr, p->lut, p->L, n_flux,
+                                                                              (double2 *)workspace, stop);
     } else if (p->kind == TAUB_ANISOTROPIC) {
         plane_sums_kernel<TAUB_ANISOTROPIC><<<grid, SUM_THREADS, 0, s>>>(g, f, p->codes, nullptr, p->lut, 0, n_flux,
                                                                          (double2 *)workspace, stop);

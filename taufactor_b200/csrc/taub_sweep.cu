@@ -61,7 +61,7 @@ refresh_ghosts_kernel(taub_geom g, float *__restrict__ f, int p_lo, const int *_
 // voxels of the active colour are updated (warp-uniform branch on the row parity).  blockDim = (32, 8):
 // x -> groups along z (coalesced 512 B per warp), y -> rows; grid.z -> (image, plane).
 // ------------------------------------------------------------------------------------------
-template <int KIND>   // 0 binary, 1 multi-phase, 2 anisotropic
+template <int KIND>   // 0 binary, 1 multi-phase (labels), 2 anisotropic, 3 multi-phase (stencil classes)
 __global__ void __launch_bounds__(256)
 half_sweep_kernel(taub_geom g, const float *__restrict__ src, float *__restrict__ dst,
                   const uint16_t *__restrict__ codes, const uint8_t *__restrict__ labels,
@@ -107,6 +107,32 @@ half_sweep_kernel(taub_geom g, const float *__restrict__ src, float *__restrict_
                 update_xz(c4, xp4, xm4, yp4, ym4, src[o - 1], code, s_div, omega);
             else
                 update_yw(c4, xp4, xm4, yp4, ym4, src[o + 4], code, s_div, omega);
+        } else if (KIND == TAUB_MULTIPHASE_CLASS) {
+            // codes: one uint16 class id per voxel; lut row = {w_x+, w_x-, w_y+, w_y-, w_z+, w_z-, prefactor, 0}
+            const uint2 cw = *reinterpret_cast<const uint2 *>(codes + o);
+            const float4 *tab = reinterpret_cast<const float4 *>(lut);
+#define TAUB_CLASS_Q(CLS, CEN, XP, XM, YP, YM, ZP, ZM)                                                     \
+    {                                                                                                      \
+        const float4 wa = __ldg(tab + 2 * (CLS)), wb = __ldg(tab + 2 * (CLS) + 1);                          \
+        float s = __fadd_rn(__fmul_rn(XP, wa.x), __fmul_rn(XM, wa.y));                                       \
+        s = __fadd_rn(s, __fmul_rn(YP, wa.z));                                                              \
+        s = __fadd_rn(s, __fmul_rn(YM, wa.w));                                                              \
+        s = __fadd_rn(s, __fmul_rn(ZP, wb.x));                                                              \
+        s = __fadd_rn(s, __fmul_rn(ZM, wb.y));                                                              \
+        CEN = relax(CEN, __fdiv_rn(s, wb.z), omega);                                                        \
+    }
+            if (par0 == 0) {
+                const float zl = src[o - 1];
+                const float cy = c4.y;
+                TAUB_CLASS_Q(cw.x & 0xffffu, c4.x, xp4.x, xm4.x, yp4.x, ym4.x, cy, zl)
+                TAUB_CLASS_Q(cw.y & 0xffffu, c4.z, xp4.z, xm4.z, yp4.z, ym4.z, c4.w, cy)
+            } else {
+                const float zr = src[o + 4];
+                const float cz = c4.z;
+                TAUB_CLASS_Q(cw.x >> 16, c4.y, xp4.y, xm4.y, yp4.y, ym4.y, cz, c4.x)
+                TAUB_CLASS_Q(cw.y >> 16, c4.w, xp4.w, xm4.w, yp4.w, ym4.w, zr, cz)
+            }
+#undef TAUB_CLASS_Q
         } else if (KIND == TAUB_ANISOTROPIC) {
             const float Ky = lut[0], Kz = lut[1];
             const int64_t ci = o >> 2, cps = ps >> 2;
@@ -207,6 +233,10 @@ int taub_half_sweep(const taub_problem *p, int64_t iter, int i_lo, int i_hi, voi
         TAUB_REQUIRE(p->codes, "taub_half_sweep: binary problem without codes");
         half_sweep_kernel<TAUB_BINARY><<<grid, block, 0, s>>>(g, src, dst, p->codes, nullptr, nullptr, 0,
                                                               p->omega, colour, i_lo, n_planes, p->stop);
+    } else if (p->kind == TAUB_MULTIPHASE_CLASS) {
+        TAUB_REQUIRE(p->codes && p->lut && p->L >= 1 && p->L <= 65536, "taub_half_sweep: class problem without table");
+        half_sweep_kernel<TAUB_MULTIPHASE_CLASS><<<grid, block, 0, s>>>(g, src, dst, p->codes, nullptr, p->lut, p->L,
+                                                                        p->omega, colour, i_lo, n_planes, p->stop);
     } else if (p->kind == TAUB_ANISOTROPIC) {
         TAUB_REQUIRE(p->codes && p->lut, "taub_half_sweep: anisotropic problem without codes / weights");
         TAUB_REQUIRE(!g.periodic, "taub_half_sweep: the anisotropic solver has no periodic variant");

@@ -611,7 +611,53 @@ class MultiPhaseSolver(ThroughTransportSolver):
         self._call(self._lib.taub_init_multiphase(p, img_dev.data_ptr(), 0, self.Nx, m256.data_ptr(),
                                                   cond.data_ptr(), vec.data_ptr(), self._stream()),
                    "taub_init_multiphase")
-        return (labels, lut, cond, m256, vec)
+        keep = (labels, lut, cond, m256, vec)
+        if self.use_class_table and self._L <= 15:
+            keep += self._build_class_table(p)
+        return keep
+
+    use_class_table = True   # False: recompute the face conductances from the labels in the kernel
+
+    def _build_class_table(self, p):
+        """Replace (label, harmonic-mean table) by (stencil class, per-class weights).
+
+        The six face conductances and the prefactor of a voxel (ref:594-603) depend only on the phase
+        of the voxel and of its six neighbours (+ whether the Dirichlet face counts twice).  The
+        distinct combinations that occur are few (<= 3 * L^7, in practice hundreds): each becomes a
+        class with one 8-float row {w_x+, w_x-, w_y+, w_y-, w_z+, w_z-, prefactor, 0}, computed here in
+        the reference's fp32 op order; the sweep then reads one uint16 class id per voxel and one row
+        instead of seven labels and six table look-ups (TAUB_MULTIPHASE_CLASS)."""
+        g, dev = p.g, self.device
+        n = g.bs * g.Nx * g.Ny * g.Nz
+        keys = torch.empty(n, dtype=torch.int32, device=dev)
+        self._call(self._lib.taub_multiphase_keys(p, keys.data_ptr(), self._stream()), "taub_multiphase_keys")
+        uniq, inv = torch.unique(keys, return_inverse=True)
+        del keys
+        if uniq.numel() > 65535:
+            return ()
+        k = uniq.cpu().numpy().astype(np.int64)
+        lut = self.harmonic_table(self._dense_D)
+        own = k & 15
+        wxm, wxp = lut[own, (k >> 4) & 15], lut[own, (k >> 8) & 15]
+        wym, wyp = lut[own, (k >> 12) & 15], lut[own, (k >> 16) & 15]
+        wzm, wzp = lut[own, (k >> 20) & 15], lut[own, (k >> 24) & 15]
+        first, last = ((k >> 28) & 1).astype(bool), ((k >> 29) & 1).astype(bool)
+        fac = (wxm + wxp).astype(np.float32)                      # ref:598-600, left to right in fp32
+        for w in (wym, wyp, wzm, wzp):
+            fac = (fac + w).astype(np.float32)
+        fac[first] = (fac[first] + wxm[first]).astype(np.float32)   # ref:601
+        fac[last] = (fac[last] + wxp[last]).astype(np.float32)      # ref:602
+        fac[fac == 0] = np.inf                                      # ref:603
+        table = np.stack([wxp, wxm, wyp, wym, wzp, wzm, fac, np.zeros_like(fac)], axis=1).astype(np.float32)
+        table_dev = torch.from_numpy(np.ascontiguousarray(table)).to(dev)
+        classes = torch.zeros(self._lib.taub_field_elems(g), dtype=torch.int16, device=dev)
+        G = _lib.GHOST
+        classes.view(g.bs, g.planes, g.rows, g.pitch)[:, G:G + g.Nx, G:G + g.Ny, _lib.COL0:_lib.COL0 + g.Nz] = \
+            inv.view(g.bs, g.Nx, g.Ny, g.Nz).to(torch.int16)
+        del inv
+        p.kind, p.codes, p.lut, p.L = _lib.MULTIPHASE_CLASS, classes.data_ptr(), table_dev.data_ptr(), int(len(k))
+        self.n_stencil_classes = int(len(k))
+        return (classes, table_dev)
 
 
 class PeriodicMultiPhaseSolver(MultiPhaseSolver):

@@ -245,6 +245,28 @@ def test_uniform_block_analytic_256(tau):
     assert abs(float(S.tau[0]) - 1.0) < 1e-5
 
 
+@pytest.mark.parametrize("name", ["odd3_mp", "odd3_pmp", "blobs3_48_mp", "blobs3_48_pmp", "ref_mp_batched", "ref_mp_strip123",
+                                  "ref_mp_label0"])
+def test_multiphase_class_table_equals_label_kernel(tau, name):
+    """The stencil-class path (one uint16 class id + one table row per voxel) and the label path
+    (seven labels + six look-ups) are the same arithmetic: identical bits, identical flux profile."""
+    import torch
+    cls = getattr(tau, cases.CASES[name][0])
+    A, skw = make(tau, name)
+    try:
+        cls.use_class_table = False
+        B, _ = make(tau, name)
+    finally:
+        cls.use_class_table = True
+    assert getattr(A, "n_stencil_classes", 0) > 0 and not hasattr(B, "n_stencil_classes")
+    A._advance(57)
+    B._advance(57)
+    assert torch.equal(A.field, B.field)
+    fa, ma = A._check_only()
+    fb, mb = B._check_only()
+    assert np.array_equal(fa, fb) and np.array_equal(ma, mb)
+
+
 @pytest.mark.parametrize("name", ["rand40", "ref_deadend", "batch3_blobs48", "blobs3_48_pmp", "ref_non_percolating",
                                   "flat2d_per_batch", "odd_11_13_9_per"])
 def test_pipelined_and_synchronous_solves_agree(tau, name):
