@@ -217,6 +217,26 @@ __device__ __forceinline__ float sor_multi(float c, float xp, float xm, float yp
 }
 
 // ------------------------------------------------------------------------------------------
+// Multi-phase through stencil classes (TAUB_MULTIPHASE_CLASS).  Table row of class c (two float4):
+//   {w_x+, w_x-, w_y+, w_y-}  {w_z+, w_z-, b, r}   with b = prefactor and r = RN(1/b) -- or b = r = 0
+//   where the prefactor is inf (non-conductive voxel), which yields q = 0 without a special case.
+// s as in taufactor.py:606-613 (each product rounded, summed left to right); q = s / b by
+// q0 = RN(s*r), rem = s - q0*b (exact FMA), q = RN(q0 + rem*r): the fast path of IEEE division with the
+// exactly rounded reciprocal (checked against s / b on 6e8 random pairs; same guard word as div_fast).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sor_class(float c, float xp, float xm, float yp, float ym, float zp, float zm,
+                                           unsigned cls, const float4 *__restrict__ tab, float omega, unsigned &umin)
+{
+    const float4 wa = __ldg(tab + 2 * cls), wb = __ldg(tab + 2 * cls + 1);
+    float s = __fadd_rn(__fmul_rn(xp, wa.x), __fmul_rn(xm, wa.y));
+    s = __fadd_rn(s, __fmul_rn(yp, wa.z));
+    s = __fadd_rn(s, __fmul_rn(ym, wa.w));
+    s = __fadd_rn(s, __fmul_rn(zp, wb.x));
+    s = __fadd_rn(s, __fmul_rn(zm, wb.y));
+    return relax(c, div_fast(s, make_float2(wb.z, wb.w), umin), omega);
+}
+
+// ------------------------------------------------------------------------------------------
 // AnisotropicSolver (taufactor.py:422-478).  The neighbour codes double as the conductive mask
 // (code != 0; 9 = conductive voxel without conductive neighbour).  Prefactor, in the reference's fp32
 // accumulation order (:462-467): ((((x- + x+) + Ky*y-) + Ky*y+) + Kz*z-) + Kz*z+ with the Dirichlet

@@ -31,7 +31,8 @@ struct FusedParams {
     taub_geom g;
     const float *src;
     float *dst;
-    const uint16_t *codes;
+    const uint16_t *codes;   // binary: one uint16 (four 4-bit counts) per group; class kind: one uint16 per voxel
+    const float *table;      // class kind: [n_classes][8] weight rows
     float omega;
     int colourA;
     int i_lo, i_hi;    // output planes (local)
@@ -107,6 +108,24 @@ __device__ __forceinline__ void row_update(const bool is_xz, float4 &c, const fl
     }
 }
 
+// Class kind: cls2 = the row's four uint16 class ids (x | y << 16, z | w << 16).
+__device__ __forceinline__ void row_update_class(const bool is_xz, float4 &c, const float4 &xp, const float4 &xm,
+                                                 const float4 &up, const float4 &dn, float zs, uint2 cls2,
+                                                 const float4 *tab, float omega, unsigned &umin)
+{
+    if (is_xz) {
+        const float n0 = sor_class(c.x, xp.x, xm.x, up.x, dn.x, c.y, zs, cls2.x & 0xffffu, tab, omega, umin);
+        const float n1 = sor_class(c.z, xp.z, xm.z, up.z, dn.z, c.w, c.y, cls2.y & 0xffffu, tab, omega, umin);
+        c.x = n0;
+        c.z = n1;
+    } else {
+        const float n0 = sor_class(c.y, xp.y, xm.y, up.y, dn.y, c.z, c.x, cls2.x >> 16, tab, omega, umin);
+        const float n1 = sor_class(c.w, xp.w, xm.w, up.w, dn.w, zs, c.z, cls2.y >> 16, tab, omega, umin);
+        c.y = n0;
+        c.w = n1;
+    }
+}
+
 // The z neighbour from the adjacent lane's registers (one crossbar pass instead of a 4-way conflicted
 // shared load); the two lanes at the warp ends read shared memory.  All 32 lanes must call this.
 __device__ __forceinline__ float z_neighbour(const bool is_xz, const float4 &v, const float4 *buf, int i4, int lane,
@@ -128,7 +147,7 @@ __device__ __forceinline__ float z_neighbour(const bool is_xz, const float4 &v, 
 // y-neighbours stay in registers, only the rows above and below it come from shared memory.  PA0 = parity
 // of the column's first row at step 0 (uniform over the whole grid, chosen by the host), so every step
 // body is branch-free.
-template <int NRW, int PA0>
+template <int NRW, int PA0, int KIND>   // KIND: TAUB_BINARY (4-bit codes) or TAUB_MULTIPHASE_CLASS (class ids)
 __global__ void __launch_bounds__(F_NT, 2)
 fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tmap,
                     const __grid_constant__ CUtensorMap cmap)
@@ -138,7 +157,10 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     // TMA destinations need 128-byte alignment: align the base, slots are multiples of 128 B
     unsigned char *smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
     const taub_geom &g = P.g;
+    constexpr bool CLS = (KIND == TAUB_MULTIPHASE_CLASS);
+    constexpr int CPG = CLS ? 4 : 1;             // uint16 side-array elements per float4 group
     const int LR = P.LR, LG = P.LG, LGc = P.LGc;
+    const float4 *tab = reinterpret_cast<const float4 *>(P.table);
     const int plane_f4 = P.slot_f4;              // ring slot size in float4 (>= LR*LG, multiple of 8)
     const int cslot = P.cslot_h;
     float4 *planes = reinterpret_cast<float4 *>(smem_raw);
@@ -170,10 +192,10 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
         const int slot = rel % F_NB;
         const uint32_t bar = smem_u32(&mbar[slot]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, (uint32_t)(LR * (LG * 16 + LGc * 2)));
+        mbar_expect_tx(bar, (uint32_t)(LR * (LG * 16 + LGc * CPG * 2)));
         const int pl = b * g.planes + (c0 - 2 + rel + G);
         tma_load_3d(smem_u32(planes + (size_t)slot * plane_f4), &tmap, 4 * G0, R0, pl, bar);
-        tma_load_3d(smem_u32(cplanes + (size_t)slot * cslot), &cmap, G0, R0, pl, bar);
+        tma_load_3d(smem_u32(cplanes + (size_t)slot * cslot), &cmap, G0 * CPG, R0, pl, bar);
     };
     if (tid == 0)
         for (int rel = 0; rel < min(F_NB - 1, total_rel); ++rel) issue(rel);
@@ -191,14 +213,14 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     for (int r = 0; r < NRW; ++r)
         if (doit && colB && lr0 + r >= 2 && lr0 + r < LR - 2 && Ra + r >= G && Ra + r < G + g.Ny) canB |= 1u << r;
     const int i0 = lr0 * LG + gg;            // float4 index of row 0 inside a ring slot (row r: + r*LG)
-    const int ic0 = lr0 * LGc + gg;          // uint16 index of row 0's code (row r: + r*LGc)
+    const int ic0 = (lr0 * LGc + gg) * CPG;  // uint16 index of row 0's code / class ids (row r: + r*LGc*CPG)
     // colour B first writes plane c0 (at step 2)
     float *dst0 = P.dst + (int64_t)b * g.image_stride + 4 * Gs + (int64_t)(c0 + G) * ps + (int64_t)Ra * g.pitch;
 
     // ---- register ring: rg[r][k] holds plane (c0-3+k+4j) of row r; at step s = 4j+ss:
     //      a[p-2] = rg[.][ss], a[p-1] = rg[.][ss+1], raw[p] -> a[p] = rg[.][ss+2], raw[p+1] = rg[.][ss+3]
     float4 rg[NRW][4];
-    unsigned cr[NRW / 2][4];   // neighbour codes, two rows per word, same ring positions
+    unsigned cr[NRW / 2][4];   // binary: neighbour codes, two rows per word, same ring positions
     mbar_wait(smem_u32(&mbar[0]), 0);
     mbar_wait(smem_u32(&mbar[1 % F_NB]), 0);
 #pragma unroll
@@ -214,7 +236,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     for (int q = 0; q < NRW / 2; ++q) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) cr[q][k] = 0;
-        if (doit)
+        if (doit && !CLS)
             cr[q][2] = (unsigned)cplanes[cslot + ic0 + 2 * q * LGc] | ((unsigned)cplanes[cslot + ic0 + (2 * q + 1) * LGc] << 16);
     }
 
@@ -234,15 +256,19 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
             float4 *bufP = planes + (size_t)((s + 1) % F_NB) * plane_f4;
             const float4 *bufP1 = planes + (size_t)((s + 2) % F_NB) * plane_f4;
             const uint16_t *codP1 = cplanes + (size_t)((s + 2) % F_NB) * cslot;
+            const uint16_t *codP = cplanes + (size_t)((s + 1) % F_NB) * cslot;    // class kind reads ids in place
+            const uint16_t *codM1 = cplanes + (size_t)(s % F_NB) * cslot;
             const bool doA = (p >= P.a_lo) && (p < P.a_hi);
             const bool keepA = (p >= c0) && (p < c1);   // a[p] is read by colour B of plane p next step
             const bool doB = (s >= 2);
             if (doit) {
 #pragma unroll
                 for (int r = 0; r < NRW; ++r) rg[r][iP1] = bufP1[i0 + r * LG];
+                if (!CLS) {
 #pragma unroll
-                for (int q = 0; q < NRW / 2; ++q)
-                    cr[q][iP1] = (unsigned)codP1[ic0 + 2 * q * LGc] | ((unsigned)codP1[ic0 + (2 * q + 1) * LGc] << 16);
+                    for (int q = 0; q < NRW / 2; ++q)
+                        cr[q][iP1] = (unsigned)codP1[ic0 + 2 * q * LGc] | ((unsigned)codP1[ic0 + (2 * q + 1) * LGc] << 16);
+                }
             }
             if (doA) {   // block-uniform
                 float zs[NRW];
@@ -257,8 +283,12 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                         // its neighbours leave unchanged in this step
                         const float4 &dn = (r == 0) ? below : rg[r - 1][iP];
                         const float4 &up = (r == NRW - 1) ? above : rg[r + 1][iP];
-                        row_update(((PA0 + ss + r) & 1) == 0, rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r],
-                                   cr[r >> 1][iP] >> (16 * (r & 1)), s_div, P.omega, umin);
+                        if (CLS)
+                            row_update_class(((PA0 + ss + r) & 1) == 0, rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r],
+                                             *reinterpret_cast<const uint2 *>(codP + ic0 + r * LGc * CPG), tab, P.omega, umin);
+                        else
+                            row_update(((PA0 + ss + r) & 1) == 0, rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r],
+                                       cr[r >> 1][iP] >> (16 * (r & 1)), s_div, P.omega, umin);
                     }
                     if (keepA) {
                         // other threads read the column's first and last row (their above / below) and,
@@ -282,8 +312,12 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                         const float4 &dn = (r == 0) ? below : rg[r - 1][iM1];
                         const float4 &up = (r == NRW - 1) ? above : rg[r + 1][iM1];
                         float4 out = rg[r][iM1];
-                        row_update(((PA0 + ss + r) & 1) == 0, out, rg[r][iP], rg[r][iM2], up, dn, zs[r],
-                                   cr[r >> 1][iM1] >> (16 * (r & 1)), s_div, P.omega, umin);
+                        if (CLS)
+                            row_update_class(((PA0 + ss + r) & 1) == 0, out, rg[r][iP], rg[r][iM2], up, dn, zs[r],
+                                             *reinterpret_cast<const uint2 *>(codM1 + ic0 + r * LGc * CPG), tab, P.omega, umin);
+                        else
+                            row_update(((PA0 + ss + r) & 1) == 0, out, rg[r][iP], rg[r][iM2], up, dn, zs[r],
+                                       cr[r >> 1][iM1] >> (16 * (r & 1)), s_div, P.omega, umin);
                         if (canB & (1u << r)) *reinterpret_cast<float4 *>(dst0 + (int64_t)r * g.pitch) = out;
                     }
                 }
@@ -296,10 +330,10 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     if (umin < GUARD_T) atomicAdd(&g_inexact_events, 1ULL);
 }
 
-static size_t fused_smem_bytes(int LR, int LG, int LGc)
+static size_t fused_smem_bytes(int LR, int LG, int LGc, int cpg)
 {
-    const size_t slot = ((size_t)(LR * LG + 7) / 8) * 8 * 16;         // fp32 box, 128-byte multiple
-    const size_t cslot = ((size_t)(LR * LGc * 2 + 127) / 128) * 128;  // uint16 box
+    const size_t slot = ((size_t)(LR * LG + 7) / 8) * 8 * 16;               // fp32 box, 128-byte multiple
+    const size_t cslot = ((size_t)(LR * LGc * cpg * 2 + 127) / 128) * 128;  // uint16 box (codes / class ids)
     return F_NB * (slot + cslot) + F_NB * 8 + 128;                    // + mbarriers, alignment slack (the division
                                                                       // table is 128 bytes of static shared memory)
 }
@@ -316,7 +350,7 @@ struct TileChoice {
 // multiple of 16 bytes wide; for the uint16 code box that means OG (the tile step) is a multiple of 8
 // groups and the code box is LG rounded up to 8.  A box is at most 256 elements wide (LG <= 64).  Pick
 // the shape that wastes the fewest threads while two CTAs still fit in one SM's shared memory.
-static TileChoice choose_tile(const taub_geom &g)
+static TileChoice choose_tile(const taub_geom &g, int cpg)
 {
     const int ng = interior_groups(g.Nz);
     TileChoice best{};
@@ -327,10 +361,10 @@ static TileChoice choose_tile(const taub_geom &g)
         // box one group wider (odd pitch) avoids that -- taken when it does not cost a column.
         const int LGt = OG + 2;
         int NCT = F_NT / LGt;   // columns the CTA's threads can cover
-        while (NCT >= 1 && fused_smem_bytes(F_NRW * NCT + 2, LGt, ((LGt + 7) / 8) * 8) > 115000) --NCT;
+        while (NCT >= 1 && fused_smem_bytes(F_NRW * NCT + 2, LGt, ((LGt + 7) / 8) * 8, cpg) > 115000) --NCT;
         if (NCT < 1) continue;
         int LG = LGt;
-        if (fused_smem_bytes(F_NRW * NCT + 2, LGt + 1, ((LGt + 8) / 8) * 8) <= 115000) LG = LGt + 1;
+        if (fused_smem_bytes(F_NRW * NCT + 2, LGt + 1, ((LGt + 8) / 8) * 8, cpg) <= 115000) LG = LGt + 1;
         const int LGc = ((LG + 7) / 8) * 8;
         const int NR = F_NRW * NCT, OR_ = NR - 2, LR = NR + 2;
         const int tj = ceil_div(g.Ny, OR_), tk = ceil_div(ng, OG);
@@ -375,15 +409,16 @@ static int make_field_map(CUtensorMap *map, const taub_geom &g, const float *bas
     return TAUB_OK;
 }
 
-// Same view of the neighbour codes: (groups = pitch/4, rows, bs * planes), uint16, box = LGc x LR x 1.
-static int make_code_map(CUtensorMap *map, const taub_geom &g, const uint16_t *base, int LR, int LGc)
+// Same view of the uint16 side array (cpg elements per float4 group: 1 = neighbour codes, 4 = class ids):
+// (pitch/4 * cpg, rows, bs * planes), box = LGc*cpg x LR x 1.
+static int make_code_map(CUtensorMap *map, const taub_geom &g, const uint16_t *base, int LR, int LGc, int cpg)
 {
     EncodeTiledFn enc = encode_tiled_fn();
     TAUB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
-    const cuuint64_t PG = (cuuint64_t)(g.pitch >> 2);
+    const cuuint64_t PG = (cuuint64_t)(g.pitch >> 2) * cpg;
     const cuuint64_t dims[3] = {PG, (cuuint64_t)g.rows, (cuuint64_t)g.bs * g.planes};
     const cuuint64_t strides[2] = {PG * 2, (cuuint64_t)g.rows * PG * 2};
-    const cuuint32_t box[3] = {(cuuint32_t)LGc, (cuuint32_t)LR, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)(LGc * cpg), (cuuint32_t)LR, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<uint16_t *>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -427,13 +462,15 @@ unsigned long long taub_inexact_events(void)
 
 int taub_can_fuse(const taub_problem *p)
 {
-    if (!p || p->kind != TAUB_BINARY || !p->codes || !p->field[0] || !p->field[1]) return 0;
+    if (!p || (p->kind != TAUB_BINARY && p->kind != TAUB_MULTIPHASE_CLASS) || !p->codes || !p->field[0] || !p->field[1])
+        return 0;
+    if (p->kind == TAUB_MULTIPHASE_CLASS && !p->lut) return 0;
     const taub_geom &g = p->g;
     // periodic wrap with odd Ny/Nz couples two voxels of the SAME colour (reference reads a ghost
     // snapshot); the in-place shared-memory colour update cannot express that -> generic path.
     if (g.periodic && ((g.Ny & 1) || (g.Nz & 1))) return 0;
     if (g.bs > 65535) return 0;
-    return choose_tile(g).eff > 0.0 ? 1 : 0;
+    return choose_tile(g, p->kind == TAUB_MULTIPHASE_CLASS ? 4 : 1).eff > 0.0 ? 1 : 0;
 }
 
 int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, void *stream)
@@ -444,12 +481,14 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     }
     const taub_geom &g = p->g;
     TAUB_REQUIRE(i_lo >= 0 && i_hi <= g.Nx && i_lo < i_hi, "taub_fused_sweep2: planes [%d, %d) outside the slab", i_lo, i_hi);
-    const TileChoice t = choose_tile(g);
+    const int cpg = (p->kind == TAUB_MULTIPHASE_CLASS) ? 4 : 1;
+    const TileChoice t = choose_tile(g, cpg);
     FusedParams P;
     P.g = g;
     P.src = p->field[p->cur];
     P.dst = p->field[p->cur ^ 1];
     P.codes = p->codes;
+    P.table = p->lut;
     P.omega = p->omega;
     P.stop = p->stop;
     P.colourA = (int)(iter & 1);
@@ -472,27 +511,28 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     P.chunk_len = chunk_len;
     TAUB_REQUIRE(chunks <= 65535, "taub_fused_sweep2: too many plane chunks");
     P.slot_f4 = ((t.LR * t.LG + 7) / 8) * 8;
-    P.cslot_h = ((t.LR * t.LGc * 2 + 127) / 128) * 64;
-    const size_t smem = fused_smem_bytes(t.LR, t.LG, t.LGc);
+    P.cslot_h = ((t.LR * t.LGc * cpg * 2 + 127) / 128) * 64;
+    const size_t smem = fused_smem_bytes(t.LR, t.LG, t.LGc, cpg);
     dim3 grid(t.tiles_j * t.tiles_k, chunks, g.bs);
     cudaStream_t s = (cudaStream_t)stream;
     CUtensorMap tmap, cmap;
     if (int rc = make_field_map(&tmap, g, P.src, t.LR, t.LG)) return rc;
-    if (int rc = make_code_map(&cmap, g, P.codes, t.LR, t.LGc)) return rc;
+    if (int rc = make_code_map(&cmap, g, P.codes, t.LR, t.LGc, cpg)) return rc;
     // parity of loaded row 1 (row a of every pair) at step 0, i.e. at plane c0-1: 0 -> x,z active.
     // Tile row offsets (multiples of the even OR_) and chunk starts (multiples of the even
     // chunk_len) do not change it, so it is one number for the whole grid.
     const int pa0 = (1 - G + g.i_offset + P.colourA + (i_lo - 1)) & 1;   // row lr = 1 is row 0 of a column
-#define TAUB_LAUNCH_FUSED(PA_)                                                                                    \
+#define TAUB_LAUNCH_FUSED(PA_, KIND_)                                                                             \
     do {                                                                                                          \
-        TAUB_CUDA(cudaFuncSetAttribute(fused_sweep2_kernel<F_NRW, PA_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                       (int)smem));                                                               \
-        fused_sweep2_kernel<F_NRW, PA_><<<grid, F_NT, smem, s>>>(P, tmap, cmap);                                            \
+        TAUB_CUDA(cudaFuncSetAttribute(fused_sweep2_kernel<F_NRW, PA_, KIND_>,                                    \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
+        fused_sweep2_kernel<F_NRW, PA_, KIND_><<<grid, F_NT, smem, s>>>(P, tmap, cmap);                           \
     } while (0)
-    if (pa0 == 0)
-        TAUB_LAUNCH_FUSED(0);
-    else
-        TAUB_LAUNCH_FUSED(1);
+    if (p->kind == TAUB_MULTIPHASE_CLASS) {
+        if (pa0 == 0) TAUB_LAUNCH_FUSED(0, TAUB_MULTIPHASE_CLASS); else TAUB_LAUNCH_FUSED(1, TAUB_MULTIPHASE_CLASS);
+    } else {
+        if (pa0 == 0) TAUB_LAUNCH_FUSED(0, TAUB_BINARY); else TAUB_LAUNCH_FUSED(1, TAUB_BINARY);
+    }
 #undef TAUB_LAUNCH_FUSED
     TAUB_CUDA(cudaGetLastError());
     count_launch();

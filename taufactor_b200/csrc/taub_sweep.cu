@@ -108,7 +108,8 @@ half_sweep_kernel(taub_geom g, const float *__restrict__ src, float *__restrict_
             else
                 update_yw(c4, xp4, xm4, yp4, ym4, src[o + 4], code, s_div, omega);
         } else if (KIND == TAUB_MULTIPHASE_CLASS) {
-            // codes: one uint16 class id per voxel; lut row = {w_x+, w_x-, w_y+, w_y-, w_z+, w_z-, prefactor, 0}
+            // codes: one uint16 class id per voxel; lut row = {w_x+, w_x-, w_y+, w_y-, w_z+, w_z-, b, 1/b}
+            // (b = 0 stands for an infinite prefactor); true IEEE division here, the fused kernel uses 1/b
             const uint2 cw = *reinterpret_cast<const uint2 *>(codes + o);
             const float4 *tab = reinterpret_cast<const float4 *>(lut);
 #define TAUB_CLASS_Q(CLS, CEN, XP, XM, YP, YM, ZP, ZM)                                                     \
@@ -119,7 +120,7 @@ half_sweep_kernel(taub_geom g, const float *__restrict__ src, float *__restrict_
         s = __fadd_rn(s, __fmul_rn(YM, wa.w));                                                              \
         s = __fadd_rn(s, __fmul_rn(ZP, wb.x));                                                              \
         s = __fadd_rn(s, __fmul_rn(ZM, wb.y));                                                              \
-        CEN = relax(CEN, __fdiv_rn(s, wb.z), omega);                                                        \
+        CEN = relax(CEN, __fdiv_rn(s, wb.z != 0.0f ? wb.z : __int_as_float(0x7f800000)), omega);            \
     }
             if (par0 == 0) {
                 const float zl = src[o - 1];

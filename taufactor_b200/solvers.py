@@ -624,7 +624,7 @@ class MultiPhaseSolver(ThroughTransportSolver):
         The six face conductances and the prefactor of a voxel (ref:594-603) depend only on the phase
         of the voxel and of its six neighbours (+ whether the Dirichlet face counts twice).  The
         distinct combinations that occur are few (<= 3 * L^7, in practice hundreds): each becomes a
-        class with one 8-float row {w_x+, w_x-, w_y+, w_y-, w_z+, w_z-, prefactor, 0}, computed here in
+        class with one 8-float row {w_x+, w_x-, w_y+, w_y-, w_z+, w_z-, prefactor, 1/prefactor}, computed here in
         the reference's fp32 op order; the sweep then reads one uint16 class id per voxel and one row
         instead of seven labels and six table look-ups (TAUB_MULTIPHASE_CLASS)."""
         g, dev = p.g, self.device
@@ -647,8 +647,10 @@ class MultiPhaseSolver(ThroughTransportSolver):
             fac = (fac + w).astype(np.float32)
         fac[first] = (fac[first] + wxm[first]).astype(np.float32)   # ref:601
         fac[last] = (fac[last] + wxp[last]).astype(np.float32)      # ref:602
-        fac[fac == 0] = np.inf                                      # ref:603
-        table = np.stack([wxp, wxm, wyp, wym, wzp, wzm, fac, np.zeros_like(fac)], axis=1).astype(np.float32)
+        # ref:603 turns a zero prefactor into inf; the table keeps b = 0 with reciprocal 0 for it (q = 0)
+        with np.errstate(divide="ignore"):
+            rcp = np.where(fac > 0, (1.0 / fac.astype(np.float64)), 0.0).astype(np.float32)   # RN(1/b)
+        table = np.stack([wxp, wxm, wyp, wym, wzp, wzm, fac, rcp], axis=1).astype(np.float32)
         table_dev = torch.from_numpy(np.ascontiguousarray(table)).to(dev)
         classes = torch.zeros(self._lib.taub_field_elems(g), dtype=torch.int16, device=dev)
         G = _lib.GHOST
