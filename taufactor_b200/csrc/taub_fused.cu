@@ -352,6 +352,9 @@ struct TileChoice {
 // the shape that wastes the fewest threads while two CTAs still fit in one SM's shared memory.
 static TileChoice choose_tile(const taub_geom &g, int cpg)
 {
+    // shared-memory budget per CTA (two CTAs per SM).  The class kind reads its weight rows through L1,
+    // which shares the 228 KB with shared memory: leave it ~32 KB.
+    const size_t budget = (cpg == 1) ? 115000 : 98000;
     const int ng = interior_groups(g.Nz);
     TileChoice best{};
     best.eff = -1.0;
@@ -361,10 +364,10 @@ static TileChoice choose_tile(const taub_geom &g, int cpg)
         // box one group wider (odd pitch) avoids that -- taken when it does not cost a column.
         const int LGt = OG + 2;
         int NCT = F_NT / LGt;   // columns the CTA's threads can cover
-        while (NCT >= 1 && fused_smem_bytes(F_NRW * NCT + 2, LGt, ((LGt + 7) / 8) * 8, cpg) > 115000) --NCT;
+        while (NCT >= 1 && fused_smem_bytes(F_NRW * NCT + 2, LGt, ((LGt + 7) / 8) * 8, cpg) > budget) --NCT;
         if (NCT < 1) continue;
         int LG = LGt;
-        if (fused_smem_bytes(F_NRW * NCT + 2, LGt + 1, ((LGt + 8) / 8) * 8, cpg) <= 115000) LG = LGt + 1;
+        if (fused_smem_bytes(F_NRW * NCT + 2, LGt + 1, ((LGt + 8) / 8) * 8, cpg) <= budget) LG = LGt + 1;
         const int LGc = ((LG + 7) / 8) * 8;
         const int NR = F_NRW * NCT, OR_ = NR - 2, LR = NR + 2;
         const int tj = ceil_div(g.Ny, OR_), tk = ceil_div(ng, OG);

@@ -633,7 +633,7 @@ class MultiPhaseSolver(ThroughTransportSolver):
         self._call(self._lib.taub_multiphase_keys(p, keys.data_ptr(), self._stream()), "taub_multiphase_keys")
         uniq, inv = torch.unique(keys, return_inverse=True)
         del keys
-        if uniq.numel() > 65535:
+        if uniq.numel() > 65534:
             return ()
         k = uniq.cpu().numpy().astype(np.int64)
         lut = self.harmonic_table(self._dense_D)
@@ -651,13 +651,27 @@ class MultiPhaseSolver(ThroughTransportSolver):
         with np.errstate(divide="ignore"):
             rcp = np.where(fac > 0, (1.0 / fac.astype(np.float64)), 0.0).astype(np.float32)   # RN(1/b)
         table = np.stack([wxp, wxm, wyp, wym, wzp, wzm, fac, rcp], axis=1).astype(np.float32)
+        # one more, INERT class (all zeros: a voxel that stays what it is -- 0) for everything outside
+        # the volume: ghost frame of the no-flux solvers, Dirichlet planes, row padding
+        inert = len(k)
+        table = np.concatenate([table, np.zeros((1, 8), np.float32)])
         table_dev = torch.from_numpy(np.ascontiguousarray(table)).to(dev)
-        classes = torch.zeros(self._lib.taub_field_elems(g), dtype=torch.int16, device=dev)
-        G = _lib.GHOST
-        classes.view(g.bs, g.planes, g.rows, g.pitch)[:, G:G + g.Nx, G:G + g.Ny, _lib.COL0:_lib.COL0 + g.Nz] = \
-            inv.view(g.bs, g.Nx, g.Ny, g.Nz).to(torch.int16)
+        classes = torch.full((self._lib.taub_field_elems(g),), inert, dtype=torch.int32, device=dev).to(torch.int16)
+        G, C0 = _lib.GHOST, _lib.COL0
+        cv = classes.view(g.bs, g.planes, g.rows, g.pitch)
+        cv[:, G:G + g.Nx, G:G + g.Ny, C0:C0 + g.Nz] = inv.view(g.bs, g.Nx, g.Ny, g.Nz).to(torch.int16)
         del inv
-        p.kind, p.codes, p.lut, p.L = _lib.MULTIPHASE_CLASS, classes.data_ptr(), table_dev.data_ptr(), int(len(k))
+        if self._periodic:
+            # the fused kernel applies colour A on the first ghost ring too: ghost voxels carry the class
+            # of their periodic image (rows first, then columns over all rows -> corners included)
+            own = cv[:, G:G + g.Nx]
+            for w in range(G):
+                own[:, :, G - 1 - w] = own[:, :, G + g.Ny - 1 - (w % g.Ny)]
+                own[:, :, G + g.Ny + w] = own[:, :, G + (w % g.Ny)]
+            for w in range(G):
+                own[:, :, :, C0 - 1 - w] = own[:, :, :, C0 + g.Nz - 1 - (w % g.Nz)]
+                own[:, :, :, C0 + g.Nz + w] = own[:, :, :, C0 + (w % g.Nz)]
+        p.kind, p.codes, p.lut, p.L = _lib.MULTIPHASE_CLASS, classes.data_ptr(), table_dev.data_ptr(), int(len(table))
         self.n_stencil_classes = int(len(k))
         return (classes, table_dev)
 
