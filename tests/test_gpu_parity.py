@@ -217,6 +217,22 @@ def test_three_phase_96_goldens(tau):
     assert abs(float(a.D_eff[0]) / 0.2418978 - 1) < RTOL and abs(float(b.D_eff[0]) / 0.2461410 - 1) < RTOL
 
 
+def test_config4_analogue_256_goldens(tau):
+    """BASELINE config 4 at 256^3 (the largest size the reference was run at in the survey):
+    three-phase blobs seed 768, D = {0:0, 1:1, 2:0.3}.  Reference (CPU) values and iteration counts."""
+    img = cases.blobs3(256, seed=768)
+    Ds = {0: 0.0, 1: 1.0, 2: 0.3}
+    for cls, kw, img_, tau_ref, deff_ref, its in (
+            ("MultiPhaseSolver", {"diffusivities": dict(Ds)}, img, 1.5867065, 0.2678515, 800),
+            ("PeriodicMultiPhaseSolver", {"diffusivities": dict(Ds)}, img, 1.5538672, 0.2735122, 800),
+            ("PeriodicSolver", {}, (img > 0).astype(np.uint8), 1.5259533, 0.3931996, 900)):
+        S = getattr(tau, cls)(img_, device="cuda", **kw)
+        S.solve(verbose=False)
+        assert S.iter == its, (cls, S.iter)
+        assert abs(float(S.tau[0]) / tau_ref - 1) < RTOL and abs(float(S.D_eff[0]) / deff_ref - 1) < RTOL, (cls, S.tau, S.D_eff)
+        assert S.sweep_kernel_name() == "fused_sweep2_kernel"
+
+
 # ------------------------------------------------------------------ full-size properties
 def test_full_size_properties_384(tau):
     """At a size the oracle cannot sweep in seconds: (i) the fused and the generic kernels give
