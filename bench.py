@@ -142,6 +142,33 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ----------------------------------------------------------------------------- multi-GPU workloads
+def make_bench_solver(args, rank, world, dev):
+    """Workloads of ``bench.py --gpus N`` (N > 1)."""
+    import torch
+    import cases
+    from taufactor_b200.distributed import BatchShardedSolver, DistributedSolver, image_window, slab_bounds
+    if args.workload == "batch":
+        # BASELINE configs[2]: one independent 384^3 image per GPU
+        imgs = np.zeros((world, 384, 384, 384), np.uint8)      # every rank only fills (and uses) its own image
+        imgs[rank] = cases.blobs(384, 0.5, seed=384 + rank)
+        return (lambda: BatchShardedSolver(imgs, device=dev), f"batched Solver: {world} x 384^3 independent volumes, one per GPU",
+                f"batch sharded, {world} ranks, joint stop rule (2 floats per image all-gathered per check)", imgs[rank])
+    # BASELINE configs[4]: the periodic 512^3 blob tiled to side*side*side, x-slab partitioned
+    side = args.size if args.size > 512 else 2048
+    reps = side // 512
+    blob = cases.blobs(512, 0.5, seed=512)
+    lo, hi = slab_bounds(side, world)[rank]
+    w0, w1 = image_window(lo, hi, side)
+    planes = np.arange(w0, w1) % 512
+    window = torch.empty((w1 - w0, side, side), dtype=torch.uint8).pin_memory()
+    window.numpy()[...] = np.tile(blob[planes], (1, reps, reps))
+    host = window.numpy()
+    make = lambda: DistributedSolver(host, device=dev, window=(w0, w1), shape=(side, side, side))
+    return (make, f"tau.Solver on {side}^3 volume (512^3 blob tiled {reps}x{reps}x{reps}), x-slab partitioned",
+            f"{world} x-slabs of {side // world} planes, 2-plane ghost exchange per fused pass (NCCL send/recv)", host)
+
+
 # ----------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -183,7 +210,6 @@ def run_ours(args):
         make = lambda: tau.Solver(host_img, device=dev)
         parallelism = "single GPU"
     else:
-        from taufactor_b200.distributed import make_bench_solver
         make, workload, parallelism, host_img = make_bench_solver(args, rank, world, dev)
 
     # ---- e2e: the user-facing call with HOST buffers: ctor (H2D of the pinned image, state build) +
