@@ -212,6 +212,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
 #pragma unroll
     for (int r = 0; r < NRW; ++r)
         if (doit && colB && lr0 + r >= 2 && lr0 + r < LR - 2 && Ra + r >= G && Ra + r < G + g.Ny) canB |= 1u << r;
+    const bool all_rows = (canB == (1u << NRW) - 1u);   // interior columns: every row is an output row
     const int i0 = lr0 * LG + gg;            // float4 index of row 0 inside a ring slot (row r: + r*LG)
     const int ic0 = (lr0 * LGc + gg) * CPG;  // uint16 index of row 0's code / class ids (row r: + r*LGc*CPG)
     // colour B first writes plane c0 (at step 2)
@@ -318,7 +319,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                         else
                             row_update(((PA0 + ss + r) & 1) == 0, out, rg[r][iP], rg[r][iM2], up, dn, zs[r],
                                        cr[r >> 1][iM1] >> (16 * (r & 1)), s_div, P.omega, umin);
-                        if (canB & (1u << r)) *reinterpret_cast<float4 *>(dst0 + (int64_t)r * g.pitch) = out;
+                        if (all_rows || (canB & (1u << r))) *reinterpret_cast<float4 *>(dst0 + (int64_t)r * g.pitch) = out;
                     }
                 }
                 dst0 += ps;
