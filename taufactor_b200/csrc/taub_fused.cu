@@ -396,9 +396,46 @@ static EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
+// Encoding a tensor map costs a driver call; a solve alternates between the same few (buffer, box)
+// combinations thousands of times, so keep the last few maps (per host thread).
+struct MapKey {
+    const void *base;
+    int pitch, rows, planes_total, box_w, box_h, elem;
+    bool operator==(const MapKey &o) const
+    {
+        return base == o.base && pitch == o.pitch && rows == o.rows && planes_total == o.planes_total &&
+               box_w == o.box_w && box_h == o.box_h && elem == o.elem;
+    }
+};
+struct MapCache {
+    static constexpr int N = 8;
+    MapKey key[N];
+    CUtensorMap map[N];
+    int used = 0, next = 0;
+    const CUtensorMap *find(const MapKey &k) const
+    {
+        for (int i = 0; i < used; ++i)
+            if (key[i] == k) return &map[i];
+        return nullptr;
+    }
+    void put(const MapKey &k, const CUtensorMap &m)
+    {
+        key[next] = k;
+        map[next] = m;
+        next = (next + 1) % N;
+        if (used < N) ++used;
+    }
+};
+static thread_local MapCache g_maps;
+
 // 3-D view of one ping-pong buffer: (columns = pitch, rows, bs * planes), fp32, box = LG*4 x LR x 1.
 static int make_field_map(CUtensorMap *map, const taub_geom &g, const float *base, int LR, int LG)
 {
+    const MapKey key{base, g.pitch, g.rows, g.bs * g.planes, LG * 4, LR, 4};
+    if (const CUtensorMap *hit = g_maps.find(key)) {
+        *map = *hit;
+        return TAUB_OK;
+    }
     EncodeTiledFn enc = encode_tiled_fn();
     TAUB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[3] = {(cuuint64_t)g.pitch, (cuuint64_t)g.rows, (cuuint64_t)g.bs * g.planes};
@@ -410,6 +447,7 @@ static int make_field_map(CUtensorMap *map, const taub_geom &g, const float *bas
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     TAUB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (pitch %d rows %d planes %lld box %dx%d)",
                  (int)r, g.pitch, g.rows, (long long)g.bs * g.planes, LG * 4, LR);
+    g_maps.put(key, *map);
     return TAUB_OK;
 }
 
@@ -417,6 +455,11 @@ static int make_field_map(CUtensorMap *map, const taub_geom &g, const float *bas
 // (pitch/4 * cpg, rows, bs * planes), box = LGc*cpg x LR x 1.
 static int make_code_map(CUtensorMap *map, const taub_geom &g, const uint16_t *base, int LR, int LGc, int cpg)
 {
+    const MapKey key{base, g.pitch * cpg / 4, g.rows, g.bs * g.planes, LGc * cpg, LR, 2};
+    if (const CUtensorMap *hit = g_maps.find(key)) {
+        *map = *hit;
+        return TAUB_OK;
+    }
     EncodeTiledFn enc = encode_tiled_fn();
     TAUB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t PG = (cuuint64_t)(g.pitch >> 2) * cpg;
@@ -428,6 +471,7 @@ static int make_code_map(CUtensorMap *map, const taub_geom &g, const uint16_t *b
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     TAUB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (codes) failed with CUresult %d", (int)r);
+    g_maps.put(key, *map);
     return TAUB_OK;
 }
 
@@ -504,12 +548,10 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     P.tiles_k = t.tiles_k;
     const int n_planes = i_hi - i_lo;
     const int64_t tiles = (int64_t)t.tiles_j * t.tiles_k * g.bs;
+    int dev_ord = 0;
+    TAUB_CUDA(cudaGetDevice(&dev_ord));
     static int sm_count = 0;
-    if (!sm_count) {
-        int dev = 0;
-        TAUB_CUDA(cudaGetDevice(&dev));
-        TAUB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    }
+    if (!sm_count) TAUB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev_ord));
     int chunk_len, chunks;
     choose_chunks(n_planes, tiles, 2 * sm_count, &chunk_len, &chunks);
     P.chunk_len = chunk_len;
@@ -528,8 +570,12 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     const int pa0 = (1 - G + g.i_offset + P.colourA + (i_lo - 1)) & 1;   // row lr = 1 is row 0 of a column
 #define TAUB_LAUNCH_FUSED(PA_, KIND_)                                                                             \
     do {                                                                                                          \
-        TAUB_CUDA(cudaFuncSetAttribute(fused_sweep2_kernel<F_NRW, PA_, KIND_>,                                    \
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                  \
+        static size_t smem_set[64] = {0};   /* per device: raise the opt-in limit only when it grows */         \
+        if (smem > smem_set[dev_ord & 63]) {                                                                      \
+            TAUB_CUDA(cudaFuncSetAttribute(fused_sweep2_kernel<F_NRW, PA_, KIND_>,                                \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+            smem_set[dev_ord & 63] = smem;                                                                        \
+        }                                                                                                         \
         fused_sweep2_kernel<F_NRW, PA_, KIND_><<<grid, F_NT, smem, s>>>(P, tmap, cmap);                           \
     } while (0)
     if (p->kind == TAUB_MULTIPHASE_CLASS) {
