@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TAUB_ABI_VERSION 3
+#define TAUB_ABI_VERSION 4
 #define TAUB_GHOST 2            /* ghost width in x (planes), y (rows) and z (columns) */
 #define TAUB_COL0 4             /* column of interior voxel k = 0 */
 #define TAUB_MAX_LABELS 64      /* dense phase indices 0..L-1, L <= 64; index L = "outside" */
@@ -82,6 +82,11 @@ typedef struct taub_problem {
     int32_t cur;                /* index of the buffer that holds the current field */
     int32_t *stop;              /* optional device flag: while *stop != 0 every sweep / refresh / check
                                  * kernel of this problem returns at once (set by taub_check_async) */
+    float *peer_lo[2];          /* optional, x-slab runs with equal slabs: the two ping-pong buffers of the rank */
+    float *peer_hi[2];          /* below / above, mapped into this process (NVLink peer memory).  The fused
+                                 * kernel then stores its first / last TAUB_GHOST output planes straight into
+                                 * the neighbour's ghost planes of the destination buffer (one-sided halo
+                                 * exchange; the caller orders passes with device-side signals). */
 } taub_problem;
 
 /* -- library ------------------------------------------------------------------------------ */

@@ -27,7 +27,8 @@ class Geom(ctypes.Structure):
 class Problem(ctypes.Structure):
     _fields_ = [("g", Geom), ("kind", ctypes.c_int32), ("L", ctypes.c_int32),
                 ("field", c_vp * 2), ("codes", c_vp), ("labels", c_vp), ("lut", c_vp),
-                ("omega", ctypes.c_float), ("cur", ctypes.c_int32), ("stop", c_vp)]
+                ("omega", ctypes.c_float), ("cur", ctypes.c_int32), ("stop", c_vp),
+                ("peer_lo", c_vp * 2), ("peer_hi", c_vp * 2)]
 
 
 # name -> (restype, argtypes); must list every symbol include/taub200.h declares
@@ -74,7 +75,7 @@ def load():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.taub_abi_version() != 3:
+        if lib.taub_abi_version() != 4:
             raise ImportError("libtaub200.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib

@@ -43,6 +43,8 @@ struct FusedParams {
     int tiles_k;
     int chunk_len;     // output planes per CTA
     const int *stop;   // optional device flag: non-zero -> the kernel returns at once
+    float *peer_lo;    // optional: destination buffer of the rank below / above (peer memory); the first /
+    float *peer_hi;    // last G output planes are also stored into its upper / lower ghost planes
     int slot_f4;       // float4 per field ring slot
     int cslot_h;       // uint16 per code ring slot
 };
@@ -262,6 +264,9 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
             const bool doA = (p >= P.a_lo) && (p < P.a_hi);
             const bool keepA = (p >= c0) && (p < c1);   // a[p] is read by colour B of plane p next step
             const bool doB = (s >= 2);
+            // one-sided halo exchange: output plane p-1 is one of the neighbour's ghost planes
+            const bool send_lo = P.peer_lo != nullptr && (p - 1) < G;
+            const bool send_hi = P.peer_hi != nullptr && (p - 1) >= g.Nx - G;
             if (doit) {
 #pragma unroll
                 for (int r = 0; r < NRW; ++r) rg[r][iP1] = bufP1[i0 + r * LG];
@@ -319,7 +324,12 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                         else
                             row_update(((PA0 + ss + r) & 1) == 0, out, rg[r][iP], rg[r][iM2], up, dn, zs[r],
                                        cr[r >> 1][iM1] >> (16 * (r & 1)), s_div, P.omega, umin);
-                        if (all_rows || (canB & (1u << r))) *reinterpret_cast<float4 *>(dst0 + (int64_t)r * g.pitch) = out;
+                        if (all_rows || (canB & (1u << r))) {
+                            float *d = dst0 + (int64_t)r * g.pitch;
+                            *reinterpret_cast<float4 *>(d) = out;
+                            if (send_lo) *reinterpret_cast<float4 *>(P.peer_lo + (d - P.dst) + (int64_t)g.Nx * ps) = out;
+                            if (send_hi) *reinterpret_cast<float4 *>(P.peer_hi + (d - P.dst) - (int64_t)g.Nx * ps) = out;
+                        }
                     }
                 }
                 dst0 += ps;
@@ -539,6 +549,8 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     P.table = p->lut;
     P.omega = p->omega;
     P.stop = p->stop;
+    P.peer_lo = p->peer_lo[p->cur ^ 1];
+    P.peer_hi = p->peer_hi[p->cur ^ 1];
     P.colourA = (int)(iter & 1);
     P.i_lo = i_lo;
     P.i_hi = i_hi;

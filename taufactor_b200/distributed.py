@@ -118,10 +118,14 @@ class DistributedSolver(Solver):
         group: process group (default: the world group).
         overlap: run the ghost exchange + boundary planes on a side stream, concurrently with the
             interior planes (default on; needs slabs of at least 32 planes).
+        p2p: one-sided halo exchange over NVLink peer memory (default on; needs equal slabs, the fused
+            kernel and torch symmetric memory -- otherwise NCCL send/recv): the boundary kernels store
+            their first / last 2 output planes straight into the neighbour's ghost planes, passes are
+            ordered by device-side signals, no halo message is ever sent.
     """
 
     def __init__(self, img, omega=None, D_0=1, device=None, periodic=False, group=None, window=None, shape=None,
-                 overlap=True):
+                 overlap=True, p2p=True):
         self._lib = _lib.load()
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
@@ -164,7 +168,21 @@ class DistributedSolver(Solver):
         self._geom = g
         n = self._lib.taub_field_elems(g)
         with torch.cuda.device(dev):
-            self._bufs = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(2)]
+            self._symm = None
+            equal_slabs = len({h - l for l, h in self.bounds}) == 1
+            if p2p and self.world > 1 and equal_slabs and dist.get_backend(group) == "nccl":
+                try:      # peer-addressable field buffers (same size on every rank)
+                    import torch.distributed._symmetric_memory as symm
+                    grp = group if group is not None else dist.group.WORLD
+                    if not symm.is_symm_mem_enabled_for_group(grp.group_name):
+                        symm.enable_symm_mem_for_group(grp.group_name)
+                    bufs = [symm.empty(n, dtype=torch.float32, device=dev) for _ in range(2)]
+                    self._symm = [symm.rendezvous(b, grp) for b in bufs]
+                    self._bufs = bufs
+                except Exception as e:   # no P2P / fabric support here: fall back to NCCL messages
+                    self._symm, self._p2p_error = None, repr(e)
+            if self._symm is None:
+                self._bufs = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(2)]
             # only the planes this rank needs travel to the device
             sub = np.ascontiguousarray(_as_uint8_labels(img4[:, need[0] - window[0]: need[1] - window[0]]))
             img_dev = torch.from_numpy(sub).to(dev)
@@ -176,6 +194,11 @@ class DistributedSolver(Solver):
             p.field[0], p.field[1] = self._bufs[0].data_ptr(), self._bufs[1].data_ptr()
             p.omega = float(np.float32(omega))
             p.cur = 0
+            if self._symm is not None:
+                for i, h in enumerate(self._symm):
+                    ptrs = list(h.buffer_ptrs)
+                    p.peer_lo[i] = ptrs[self.rank - 1] if self.rank > 0 else None
+                    p.peer_hi[i] = ptrs[self.rank + 1] if self.rank < self.world - 1 else None
             codes = torch.empty(self._lib.taub_codes_elems(g), dtype=torch.int16, device=dev)
             p.codes = codes.data_ptr()
             self._prob = p
@@ -214,6 +237,8 @@ class DistributedSolver(Solver):
         self.D_0 = D_0
         self.D_mean = np.mean(self.vol_x, axis=1)
         self.halo_bytes_sent = 0
+        self._sig_pending = False     # p2p: neighbours' signals of the last pass not yet consumed
+        self._ghost_stale = False     # p2p: the last pass was generic, ghosts need an NCCL exchange
         self._fuse = None
         self.overlap = overlap
         self._report = (self.rank == 0)
@@ -232,6 +257,33 @@ class DistributedSolver(Solver):
         else:
             self._call(lib.taub_half_sweep(p, it, lo, hi, self._stream()), "taub_half_sweep")
 
+    SIGNAL_TIMEOUT_MS = 20000
+
+    def _p2p_signal(self):
+        """Tell both neighbours that this rank's boundary kernels of the current pass are done."""
+        h = self._symm[0]
+        for peer in (self.rank - 1, self.rank + 1):
+            if 0 <= peer < self.world:
+                h.put_signal(peer, 0, self.SIGNAL_TIMEOUT_MS)
+        self._sig_pending = True
+
+    def _p2p_wait(self, buf):
+        """Wait (on the current stream) until both neighbours have finished the pass that wrote this
+        rank's ghost planes of ``buf``; periodic solvers then complete the ghost frame of those planes."""
+        if not self._sig_pending:
+            return
+        h, g = self._symm[0], self._geom
+        for peer in (self.rank - 1, self.rank + 1):
+            if 0 <= peer < self.world:
+                h.wait_signal(peer, 0, self.SIGNAL_TIMEOUT_MS)
+        self._sig_pending = False
+        if self._periodic:
+            lib = self._lib
+            if self.rank > 0:
+                self._call(lib.taub_refresh_ghosts(g, buf.data_ptr(), 0, G, self._stream()), "taub_refresh_ghosts")
+            if self.rank < self.world - 1:
+                self._call(lib.taub_refresh_ghosts(g, buf.data_ptr(), G + g.Nx, g.planes, self._stream()), "taub_refresh_ghosts")
+
     def _advance(self, n):
         lib, p, g = self._lib, self._prob, self._geom
         lib.taub_set_device(self._dev_index)
@@ -239,29 +291,54 @@ class DistributedSolver(Solver):
             self._fuse = lib.taub_can_fuse(p) == 1
             self._overlap = (self.overlap and self.world > 1 and g.Nx >= 4 * self.BW and g.Ny * g.Nz >= 128 * 128)
             self._side = torch.cuda.Stream(device=self.device) if self._overlap else None
+            self.p2p_active = self._symm is not None and self._fuse
+            if not self.p2p_active:      # the kernel must not store into peers unless the protocol runs
+                for i in range(2):
+                    p.peer_lo[i] = None
+                    p.peer_hi[i] = None
         done = 0
         main = torch.cuda.current_stream(self.device)
         while done < n:
             cur = self._bufs[p.cur]
             fused = self._fuse and not self.force_generic and n - done >= 2
             it = self.iter + done
+            p2p = self.p2p_active and fused
             if self._periodic:
                 self._call(lib.taub_refresh_ghosts(g, cur.data_ptr(), G, G + g.Nx, self._stream()), "taub_refresh_ghosts")
+
+            def halo():   # make this rank's ghost planes of `cur` current (runs on the current stream)
+                if self.p2p_active and not self._ghost_stale:
+                    self._p2p_wait(cur)
+                elif self.world > 1:
+                    self.halo_bytes_sent += exchange_halos(cur, g.bs, g.image_stride, g.plane_stride, g.Nx,
+                                                           self.rank, self.world, self.group)
+                    self._ghost_stale = False
+
+            if self.p2p_active and not p2p:      # a generic pass inside a p2p run: no peer stores this pass
+                saved = [(p.peer_lo[i], p.peer_hi[i]) for i in range(2)]
+                for i in range(2):
+                    p.peer_lo[i] = None
+                    p.peer_hi[i] = None
             if self._overlap:
                 side = self._side
                 side.wait_stream(main)                      # previous pass (and the refresh) done
                 with torch.cuda.stream(side):
-                    self.halo_bytes_sent += exchange_halos(cur, g.bs, g.image_stride, g.plane_stride, g.Nx,
-                                                           self.rank, self.world, self.group)
+                    halo()
                     self._sweep(it, fused, 0, self.BW)
                     self._sweep(it, fused, g.Nx - self.BW, g.Nx)
+                    if p2p:
+                        self._p2p_signal()
                 self._sweep(it, fused, self.BW, g.Nx - self.BW)   # interior: no ghost dependency
                 main.wait_stream(side)
             else:
-                if self.world > 1:
-                    self.halo_bytes_sent += exchange_halos(cur, g.bs, g.image_stride, g.plane_stride, g.Nx,
-                                                           self.rank, self.world, self.group)
+                halo()
                 self._sweep(it, fused, 0, g.Nx)
+                if p2p:
+                    self._p2p_signal()
+            if self.p2p_active and not p2p:
+                for i in range(2):
+                    p.peer_lo[i], p.peer_hi[i] = saved[i]
+                self._ghost_stale = True
             done += 2 if fused else 1
             p.cur ^= 1
         self.iter += n
@@ -269,7 +346,9 @@ class DistributedSolver(Solver):
     def _plane_means(self):
         lib, p, g = self._lib, self._prob, self._geom
         cur = self._bufs[p.cur]
-        if self.world > 1:   # the face to the next slab reads the upper ghost plane: make it current
+        if getattr(self, "p2p_active", False) and not self._ghost_stale:
+            self._p2p_wait(cur)  # the neighbours stored the ghost planes themselves: just wait for them
+        elif self.world > 1:     # the face to the next slab reads the upper ghost plane: make it current
             self.halo_bytes_sent += exchange_halos(cur, g.bs, g.image_stride, g.plane_stride, g.Nx, self.rank,
                                                    self.world, self.group, width=1)
         self._call(lib.taub_plane_means(p, self._ws.data_ptr(), self._flux_dev.data_ptr(), self._mean_dev.data_ptr(),

@@ -24,7 +24,7 @@ def test_header_symbols_exported(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in taub200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes prototype"
-    assert lib.taub_abi_version() == 3
+    assert lib.taub_abi_version() == 4
 
 
 def test_struct_layout_matches_header(lib):
@@ -32,8 +32,8 @@ def test_struct_layout_matches_header(lib):
     from taufactor_b200 import _lib
     assert ctypes.sizeof(_lib.Geom) == 10 * 4 + 2 * 8
     assert _lib.Problem.field.offset == ctypes.sizeof(_lib.Geom) + 8
-    assert ctypes.sizeof(_lib.Problem) == ctypes.sizeof(_lib.Geom) + 8 + 5 * 8 + 8 + 8
-    assert _lib.Problem.stop.offset == ctypes.sizeof(_lib.Problem) - 8
+    assert ctypes.sizeof(_lib.Problem) == ctypes.sizeof(_lib.Geom) + 8 + 5 * 8 + 8 + 8 + 4 * 8
+    assert _lib.Problem.stop.offset == ctypes.sizeof(_lib.Problem) - 5 * 8
 
 
 @pytest.mark.parametrize("shape", [(1, 512, 512, 512), (3, 11, 13, 9), (2, 30, 28, 1), (1, 8, 8, 2049)])

@@ -11,7 +11,9 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 import taufactor_b200 as tau
 from taufactor_b200.distributed import DistributedSolver
 ok = True
-for shape, periodic in [((256, 200, 232), False), ((192, 256, 256), True)]:
+import warnings
+warnings.filterwarnings("ignore")
+for shape, periodic in [((256, 200, 232), False), ((192, 256, 256), True), ((130, 64, 72), True)]:
     img = cases.blobs(shape, 0.5, seed=7)
     S = DistributedSolver(img, periodic=periodic)
     S.solve(verbose=False, conv_crit=2e-2)
@@ -22,20 +24,21 @@ for shape, periodic in [((256, 200, 232), False), ((192, 256, 256), True)]:
         A.solve(verbose=False, conv_crit=2e-2)
         same = torch.equal(A.field[:, 1:-1, 1:-1, 1:-1], full)
         print(shape, "periodic" if periodic else "", "slab iters", S.iter, "single", A.iter, "tau", S.tau, A.tau,
-              "field bitwise equal:", same, "halo MB sent by rank0:", S.halo_bytes_sent / 1e6, flush=True)
+              "field bitwise equal:", same, "halo MB sent by rank0:", S.halo_bytes_sent / 1e6,
+              "p2p:", getattr(S, "p2p_active", None), getattr(S, "_p2p_error", None), flush=True)
         ok &= same and S.iter == A.iter and np.array_equal(S.tau, A.tau)
 # overlap on / off timing on a larger volume
 import time
 img = cases.random_img((512, 768, 768), 0.5, seed=3)
-for ov in (False, True):
-    S = DistributedSolver(img, overlap=ov)
+for ov, pp in ((False, False), (True, False), (False, True), (True, True)):
+    S = DistributedSolver(img, overlap=ov, p2p=pp)
     S._advance(20); torch.cuda.synchronize(); dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); S._advance(200); e1.record(); torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda"); dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     f = S.gather_field()
     if rank == 0:
-        print(f"overlap={ov}: {ms.item() / 200 * 1e3:.1f} us/iter, {img.size * 200 / ms.item() / 1e6:.1f} GLUPS, checksum {float(f.double().sum()):.10e}", flush=True)
+        print(f"overlap={ov} p2p={pp} (active={getattr(S, 'p2p_active', None)}, err={getattr(S, '_p2p_error', None)}): {ms.item() / 200 * 1e3:.1f} us/iter, {img.size * 200 / ms.item() / 1e6:.1f} GLUPS, checksum {float(f.double().sum()):.10e}", flush=True)
     del S
 if rank == 0:
     print("NCCL SLAB CHECK", "OK" if ok else "FAILED", flush=True)
