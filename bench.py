@@ -166,7 +166,8 @@ def make_bench_solver(args, rank, world, dev):
     host = window.numpy()
     make = lambda: DistributedSolver(host, device=dev, window=(w0, w1), shape=(side, side, side))
     return (make, f"tau.Solver on {side}^3 volume (512^3 blob tiled {reps}x{reps}x{reps}), x-slab partitioned",
-            f"{world} x-slabs of {side // world} planes, 2-plane ghost exchange per fused pass (NCCL send/recv)", host)
+            f"{world} x-slabs of {side // world} planes; per fused pass the boundary kernels store 2 ghost planes per "
+            f"neighbour over NVLink peer memory (device-side signals), overlapped with the interior planes", host)
 
 
 # ----------------------------------------------------------------------------- our arm
