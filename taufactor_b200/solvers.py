@@ -419,8 +419,13 @@ class Solver(ThroughTransportSolver):
         self.conductive_labels = [1]
         img4 = _expand_to_4d(self._check_binary_labels(img))
         u8 = _as_uint8_labels(img4)
+        if u8 is None:                                   # not integer-valued in 0..255: cannot be binary
+            self._raise_not_binary(np.unique(img4))
 
         def prepare(hist):
+            present = np.flatnonzero(hist.sum(axis=0))
+            if present.size and present.max() > 1:       # device-side label check for large images
+                self._raise_not_binary(present)
             sel = np.zeros(256, np.uint8)
             sel[1] = 1
             return sel
@@ -429,26 +434,32 @@ class Solver(ThroughTransportSolver):
         self.D_0 = D_0
         self.D_mean = np.mean(self.vol_x, axis=1)     # ref:385
 
-    @staticmethod
-    def _check_binary_labels(img):
-        """ref:387-397 -- every voxel must be exactly 0 or 1 (one min/max pass instead of the
-        reference's three np.unique sorts).  Returns the image unchanged."""
-        if isinstance(img, np.ndarray) and img.size:
-            ok = img.dtype == np.bool_
+    _HOST_CHECK_MAX = 1 << 22   # larger images are validated from the device histogram instead
+
+    @classmethod
+    def _check_binary_labels(cls, img):
+        """ref:387-397 -- every voxel must be exactly 0 or 1.  Small images are checked on the host
+        before any device work (like the reference); large ones from the label histogram the state
+        build computes on the device anyway (`_setup` -> `prepare`), which avoids two host passes over
+        the volume.  Returns the image unchanged."""
+        if isinstance(img, np.ndarray) and img.size and img.size <= cls._HOST_CHECK_MAX and img.dtype != np.bool_:
+            lo, hi = img.min(), img.max()
+            ok = (lo == 0 or lo == 1) and (hi == 0 or hi == 1)
+            if ok and img.dtype.kind not in "ui":          # floats: nothing strictly between 0 and 1
+                ok = bool(np.logical_or(img == 0, img == 1).all())
             if not ok:
-                lo, hi = img.min(), img.max()
-                ok = (lo == 0 or lo == 1) and (hi == 0 or hi == 1)
-                if ok and img.dtype.kind not in "ui":          # floats: nothing strictly between 0 and 1
-                    ok = bool(np.logical_or(img == 0, img == 1).all())
-            if not ok:
-                raise ValueError(
-                    "Input image must only contain 0s and 1s. "
-                    "Your image must be segmented to use this tool. "
-                    "If your image has been segmented, ensure your labels are "
-                    "0 for non-conductive and 1 for conductive phase. "
-                    f"Your image has the following labels: {np.unique(img)}. "
-                    "If you have more than one conductive phase, use the multi-phase solver.")
+                cls._raise_not_binary(np.unique(img))
         return img
+
+    @staticmethod
+    def _raise_not_binary(labels):
+        raise ValueError(
+            "Input image must only contain 0s and 1s. "
+            "Your image must be segmented to use this tool. "
+            "If your image has been segmented, ensure your labels are "
+            "0 for non-conductive and 1 for conductive phase. "
+            f"Your image has the following labels: {labels}. "
+            "If you have more than one conductive phase, use the multi-phase solver.")
 
     def _init_binary(self, p, img_dev, vec):
         codes = torch.empty(self._lib.taub_codes_elems(p.g), dtype=torch.int16, device=self.device)

@@ -150,6 +150,16 @@ def test_deadend_reference_assertions(tau):
     assert S.tau == np.inf
 
 
+def test_large_non_binary_image_is_rejected_from_the_device_histogram(tau):
+    """ref:387-397 for images above the host-check threshold."""
+    img = np.zeros((170, 170, 170), np.uint8)
+    img[3, 4, 5] = 2
+    with pytest.raises(ValueError, match="only contain 0s and 1s"):
+        tau.Solver(img, device="cuda")
+    with pytest.raises(ValueError, match="only contain 0s and 1s"):
+        tau.Solver(np.full((170, 170, 170), 0.5), device="cuda")
+
+
 def test_missing_diffusivities_warn(tau):
     """ref tests/test_taufactor.py:170-178."""
     N = 10
