@@ -167,28 +167,6 @@ __device__ __forceinline__ void update_yw(float4 &c, const float4 &xp, const flo
     c.w = n1;
 }
 
-// A row PAIR (a below b) in one step of the fused kernel: the xz row and the yw row on the fast path
-// only.  A_IS_XZ (a constant after unrolling) selects which of the two rows updates x,z; ca/cb are
-// updated in place; umin accumulates the guard word (see taub_inexact_events()).
-__device__ __forceinline__ void update_pair(const bool A_IS_XZ, float4 &ca, float4 &cb, const float4 &axp,
-                                            const float4 &axm, const float4 &bxp, const float4 &bxm, const float4 &a_dn,
-                                            const float4 &b_up, float zsa, float zsb, unsigned cda, unsigned cdb,
-                                            const float2 *s_div, float omega, unsigned &umin)
-{
-    // row a: up neighbour is row b, down neighbour comes from shared memory; row b: the mirror image.
-    // Each row only reads components of the other that this step leaves unchanged.
-    float a0, a1, b0, b1;
-    if (A_IS_XZ) {
-        xz_fast(ca, axp, axm, cb, a_dn, zsa, cda, s_div, omega, a0, a1, umin);
-        yw_fast(cb, bxp, bxm, b_up, ca, zsb, cdb, s_div, omega, b0, b1, umin);
-        ca.x = a0; ca.z = a1; cb.y = b0; cb.w = b1;
-    } else {
-        yw_fast(ca, axp, axm, cb, a_dn, zsa, cda, s_div, omega, a0, a1, umin);
-        xz_fast(cb, bxp, bxm, b_up, ca, zsb, cdb, s_div, omega, b0, b1, umin);
-        ca.y = a0; ca.w = a1; cb.x = b0; cb.z = b1;
-    }
-}
-
 // One multi-phase voxel update (taufactor.py:606-613, :598-603): each neighbour times its face
 // conductance (separately rounded), summed left to right; prefactor = sum of the six face
 // conductances in the reference's order (+ the Dirichlet face once more on the first / last
