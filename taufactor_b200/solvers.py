@@ -226,7 +226,7 @@ class SORSolver:
             self.tau_x = np.divide(eps * dc, fl, out=np.full_like(dc, np.nan), where=fl != 0)
         for b in range(self.batch_size):
             if fl_min[b] == 0 or fl_max[b] == 0 or mean_fl[b] == 0:
-                if _through_fraction_is_zero(self._host_conductive_mask(b)):
+                if self._no_percolating_path(b):
                     if self._report:
                         print(f"Warning: batch element {b} has no percolating path!")
                     relative_error[b] = 0
@@ -236,6 +236,14 @@ class SORSolver:
         relative_error[np.isnan(mean_fl)] = 0   # NaN counts as converged, ref:328-329
         self.D_eff = self.D_0 * D_rel
         return tau, relative_error
+
+    def _no_percolating_path(self, b):
+        """ref:320-322 -- the connectivity of the (static) image is computed once per batch element and
+        remembered; the reference re-labels the whole volume at every check of a zero-flux sample."""
+        cache = self.__dict__.setdefault("_percolation_cache", {})
+        if b not in cache:
+            cache[b] = _through_fraction_is_zero(self._host_conductive_mask(b))
+        return cache[b]
 
     def _host_conductive_mask(self, b):
         """Boolean conductive mask of image b on the host (only the zero-flux branch needs it)."""
