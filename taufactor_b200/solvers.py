@@ -177,6 +177,15 @@ class SORSolver:
         return buf.as_strided((g.bs, g.Nx + 2, g.Ny + 2, g.Nz + 2),
                               (g.image_stride, g.plane_stride, g.pitch, 1), off)
 
+    @property
+    def cb(self):
+        """The reference's two chequerboard tensors omega * [(a+b+c) % 2 == 0 / 1] (ref:218-225), built
+        on demand for inspection only -- the kernels compute the parity on the fly."""
+        idx = [torch.arange(n, device=self.device) for n in (self.Nx, self.Ny, self.Nz)]
+        par = (idx[0][:, None, None] + idx[1][None, :, None] + idx[2][None, None, :]) % 2
+        w = float(np.float32(self.omega))
+        return [(par == 0).to(torch.float32) * w, (par == 1).to(torch.float32) * w]
+
     # ------------------------------------------------------------------ the check (ref:109-153)
     def check_convergence(self, verbose, conv_crit, plot_interval, profiles=None):
         self.tau, relative_error = self.compute_metrics(profiles)

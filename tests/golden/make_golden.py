@@ -92,6 +92,20 @@ def main():
                 S2.solve(iter_limit=k, verbose=False)
                 assert S2.iter == k or S2.converged
                 fields[f"{name}@{k}"] = S2.field.numpy().copy()
+    # the Python surface the drop-in must keep: constructor / solve() signatures and the public
+    # attributes a solved object carries (names only)
+    import inspect
+    api = {}
+    for cls in ("Solver", "PeriodicSolver", "AnisotropicSolver", "MultiPhaseSolver", "PeriodicMultiPhaseSolver"):
+        C = getattr(tau, cls)
+        def sig(f):
+            return [[n, None if p.default is inspect._empty else repr(p.default)]
+                    for n, p in inspect.signature(f).parameters.items() if n != "self"]
+        api[cls] = {"init": sig(C.__init__), "solve": sig(C.solve), "bases": [b.__name__ for b in C.__mro__[1:-1]]}
+    S, _ = run_case("rand40")[1], None
+    api["solved_attributes"] = sorted(a for a in vars(S) if not a.startswith("_"))
+    with open(os.path.join(HERE, "api.json"), "w") as fh:
+        json.dump(api, fh, indent=1)
     with open(os.path.join(HERE, "solve.json"), "w") as fh:
         json.dump(solve, fh, indent=1)
     np.savez_compressed(os.path.join(HERE, "fields.npz"), **fields)

@@ -102,3 +102,28 @@ def test_harmonic_table_matches_oracle():
     t = MultiPhaseSolver.harmonic_table(D)
     ref = orc.harmonic_mean(np.repeat(D[:, None], len(D), 1), np.repeat(D[None, :], len(D), 0))
     assert np.array_equal(t, ref) and np.array_equal(t, t.T)
+
+
+def test_python_surface_matches_reference_signatures():
+    """Drop-in check against tests/golden/api.json (generated from the unmodified reference by
+    tests/golden/make_golden.py): same constructor / solve() parameter names, order and defaults, same
+    class hierarchy names."""
+    import inspect
+    import json
+    import taufactor_b200 as tau
+    api = json.load(open(os.path.join(ROOT, "tests", "golden", "api.json")))
+    for cls, ref in api.items():
+        if cls == "solved_attributes":
+            continue
+        C = getattr(tau, cls)
+        for meth in ("init", "solve"):
+            f = C.__init__ if meth == "init" else C.solve
+            got = [[n, None if p.default is inspect._empty else repr(p.default)]
+                   for n, p in inspect.signature(f).parameters.items() if n != "self"]
+            for (gn, gd), (rn, rd) in zip(got, ref[meth]):
+                assert gn == rn, (cls, meth, gn, rn)
+                if rn != "device":        # the reference's AnisotropicSolver default is a torch.device object
+                    assert gd == rd, (cls, meth, gn, gd, rd)
+            assert len(got) == len(ref[meth]), (cls, meth)
+        names = [b.__name__ for b in C.__mro__[1:-1]]
+        assert [n for n in ref["bases"] if n != "ABC"] == names, (cls, names)

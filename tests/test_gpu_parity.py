@@ -142,6 +142,18 @@ def test_solve_matches_reference(tau, name):
     assert S.tau_x.shape == (S.batch_size, S.Nx - 1) and S.c_x.shape == (S.batch_size, S.Nx)
 
 
+def test_solved_object_carries_the_reference_attributes(tau):
+    """Every public attribute a solved reference object has (tests/golden/api.json) exists here too."""
+    api = json.load(open(os.path.join(HERE, "golden", "api.json")))
+    S, skw = make(tau, "rand40")
+    S.solve(verbose=False)
+    missing = [a for a in api["solved_attributes"] if not hasattr(S, a)]
+    assert not missing, missing
+    assert tuple(S.field.shape) == (1, 42, 42, 42) and tuple(S.factor.shape) == (1, 40, 40, 40)
+    assert len(S.cb) == 2 and tuple(S.cb[0].shape) == (40, 40, 40)
+    assert float(S.cb[0][0, 0, 0]) == float(np.float32(S.omega)) and float(S.cb[1][0, 0, 0]) == 0.0
+
+
 def test_deadend_reference_assertions(tau):
     """ref tests/test_taufactor.py:68-76."""
     S, _ = make(tau, "ref_deadend")
