@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TAUB_ABI_VERSION 4
+#define TAUB_ABI_VERSION 5
 #define TAUB_GHOST 2            /* ghost width in x (planes), y (rows) and z (columns) */
 #define TAUB_COL0 4             /* column of interior voxel k = 0 */
 #define TAUB_MAX_LABELS 64      /* dense phase indices 0..L-1, L <= 64; index L = "outside" */
@@ -118,12 +118,14 @@ int taub_init_binary(const taub_problem *p, const uint8_t *img, int img_i0, int 
  * phase conducts (D > 0); p->lut must already hold the harmonic-mean table. */
 int taub_init_multiphase(const taub_problem *p, const uint8_t *img, int img_i0, int img_n,
                          const uint8_t *map256, const float *cond, const float *vec, void *stream);
-/* Multi-phase only: keys[b][i][j][k] (int32, device, bs*Nx*Ny*Nz) = the seven dense phase indices that
+/* Multi-phase only: keys[b][i][j][k] (int32, device, bs*(i_hi-i_lo)*Ny*Nz) for the local planes [i_lo, i_hi)
+ * (a slab may include its first ghost plane on either side, where the fused kernel also applies colour A)
+ * = the seven dense phase indices that
  * determine a voxel's stencil (own | x- <<4 | x+ <<8 | y- <<12 | y+ <<16 | z- <<20 | z+ <<24) plus bit 28 /
  * 29 = first / last global plane (the Dirichlet face counts twice, taufactor.py:601-602).  Needs L <= 15.
  * Voxels with equal keys have identical face conductances and prefactor, so the caller can replace the
  * labels by the index into the table of distinct keys (TAUB_MULTIPHASE_CLASS). */
-int taub_multiphase_keys(const taub_problem *p, int32_t *keys, void *stream);
+int taub_multiphase_keys(const taub_problem *p, int i_lo, int i_hi, int32_t *keys, void *stream);
 /* counts[b][i] (int64, device) = voxels of local plane i whose raw label has sel256[label] != 0
  * (numerator of vol_x, taufactor.py:42); hist[b][256] (int64, device, may be NULL) = label
  * histogram (numerators of VF, taufactor.py:564-567). */

@@ -44,7 +44,7 @@ SIGNATURES = {
     "taub_sums_ws_bytes": (ctypes.c_size_t, [ctypes.POINTER(Geom)]),
     "taub_init_binary": (c_int, [ctypes.POINTER(Problem), c_vp, c_int, c_int, c_vp, c_vp]),
     "taub_init_multiphase": (c_int, [ctypes.POINTER(Problem), c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
-    "taub_multiphase_keys": (c_int, [ctypes.POINTER(Problem), c_vp, c_vp]),
+    "taub_multiphase_keys": (c_int, [ctypes.POINTER(Problem), c_int, c_int, c_vp, c_vp]),
     "taub_plane_counts": (c_int, [ctypes.POINTER(Geom), c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "taub_refresh_ghosts": (c_int, [ctypes.POINTER(Geom), c_vp, c_int, c_int, c_vp]),
     "taub_half_sweep": (c_int, [ctypes.POINTER(Problem), c_i64, c_int, c_int, c_vp]),
@@ -75,7 +75,7 @@ def load():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.taub_abi_version() != 4:
+        if lib.taub_abi_version() != 5:
             raise ImportError("libtaub200.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib

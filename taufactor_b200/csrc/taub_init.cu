@@ -187,16 +187,16 @@ plane_counts_kernel(taub_geom g, ImgView v, const uint8_t *__restrict__ sel256,
 
 // One thread per interior voxel: pack the seven dense phase indices of its stencil.
 __global__ void __launch_bounds__(256)
-multiphase_keys_kernel(taub_geom g, const uint8_t *__restrict__ labels, int32_t *__restrict__ keys)
+multiphase_keys_kernel(taub_geom g, const uint8_t *__restrict__ labels, int32_t *__restrict__ keys, int i_lo, int n_i)
 {
-    const int64_t total = (int64_t)g.bs * g.Nx * g.Ny * g.Nz;
+    const int64_t total = (int64_t)g.bs * n_i * g.Ny * g.Nz;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int k = (int)(t % g.Nz);
         int64_t r = t / g.Nz;
         const int j = (int)(r % g.Ny);
         r /= g.Ny;
-        const int i = (int)(r % g.Nx);
-        const int b = (int)(r / g.Nx);
+        const int i = i_lo + (int)(r % n_i);
+        const int b = (int)(r / n_i);
         const int64_t o = (int64_t)b * g.image_stride + (int64_t)(i + G) * g.plane_stride + (int64_t)(j + G) * g.pitch + COL0 + k;
         const int ig = i + g.i_offset;
         int key = labels[o] | (labels[o - g.plane_stride] << 4) | (labels[o + g.plane_stride] << 8) |
@@ -277,13 +277,16 @@ int taub_init_multiphase(const taub_problem *p, const uint8_t *img, int img_i0, 
     return TAUB_OK;
 }
 
-int taub_multiphase_keys(const taub_problem *p, int32_t *keys, void *stream)
+int taub_multiphase_keys(const taub_problem *p, int i_lo, int i_hi, int32_t *keys, void *stream)
 {
     TAUB_REQUIRE(p && keys && p->labels, "taub_multiphase_keys: null pointer");
     TAUB_REQUIRE(p->L >= 1 && p->L <= 15, "taub_multiphase_keys: needs at most 15 phases (got %d)", p->L);
     const taub_geom &g = p->g;
-    const int64_t total = (int64_t)g.bs * g.Nx * g.Ny * g.Nz;
-    multiphase_keys_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(g, p->labels, keys);
+    TAUB_REQUIRE(i_lo >= -(G - 1) && i_hi <= g.Nx + (G - 1) && i_lo < i_hi && i_lo + g.i_offset >= 0 &&
+                     i_hi + g.i_offset <= g.Nx_global,
+                 "taub_multiphase_keys: planes [%d, %d) are not voxel planes held by this slab", i_lo, i_hi);
+    const int64_t total = (int64_t)g.bs * (i_hi - i_lo) * g.Ny * g.Nz;
+    multiphase_keys_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(g, p->labels, keys, i_lo, i_hi - i_lo);
     TAUB_CUDA(cudaGetLastError());
     count_launch();
     return TAUB_OK;

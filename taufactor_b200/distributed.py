@@ -25,7 +25,8 @@ import torch.distributed as dist
 
 from . import _lib
 from ._lib import Geom, Problem
-from .solvers import BOT_BC, TOP_BC, SORSolver, Solver, _as_uint8_labels, _expand_to_4d
+from .solvers import (BOT_BC, TOP_BC, MultiPhaseSolver, SORSolver, Solver, _as_uint8_labels, _expand_to_4d,
+                      build_class_table, validated_diffusivities)
 
 G = _lib.GHOST
 
@@ -108,9 +109,11 @@ def assemble_profiles(parts, bounds, bs):
 
 # ----------------------------------------------------------------------------- the solver
 class DistributedSolver(Solver):
-    """``Solver`` / ``PeriodicSolver`` on an x-slab partition (binary labels).
+    """``Solver`` / ``PeriodicSolver`` -- or, with ``diffusivities``, ``MultiPhaseSolver`` /
+    ``PeriodicMultiPhaseSolver`` -- on an x-slab partition.
 
     Args:
+        diffusivities, D_scaling: as MultiPhaseSolver (ref:524); None = binary labels, label 1 conducts.
         img: either the FULL label image on every rank, or -- with ``window=(g_lo, g_hi)`` -- only
             the global planes [g_lo, g_hi) of it, which must cover ``image_window`` of this rank.
         shape: global (Nx, Ny, Nz) when ``img`` is a window.
@@ -125,14 +128,22 @@ class DistributedSolver(Solver):
     """
 
     def __init__(self, img, omega=None, D_0=1, device=None, periodic=False, group=None, window=None, shape=None,
-                 overlap=True, p2p=True):
+                 overlap=True, p2p=True, diffusivities=None, D_scaling=None):
         self._lib = _lib.load()
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self._periodic = bool(periodic)
         self.conductive_labels = [1]
         img4 = _expand_to_4d(img)
-        self._check_binary_labels(img4)
+        self._multi = diffusivities is not None
+        if self._multi:
+            self.Ds = validated_diffusivities(diffusivities)
+            if _as_uint8_labels(img4[:, :1]) is None:
+                raise ValueError("the distributed multi-phase solver needs integer labels in 0..255")
+            if D_scaling is not None:
+                D_0 = D_scaling
+        else:
+            self._check_binary_labels(img4)
         if window is None:
             window = (0, img4.shape[1])
             Nx_g, Ny, Nz = img4.shape[1:]
@@ -184,13 +195,15 @@ class DistributedSolver(Solver):
             if self._symm is None:
                 self._bufs = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(2)]
             # only the planes this rank needs travel to the device
-            sub = np.ascontiguousarray(_as_uint8_labels(img4[:, need[0] - window[0]: need[1] - window[0]]))
-            img_dev = torch.from_numpy(sub).to(dev)
+            sub = _as_uint8_labels(img4[:, need[0] - window[0]: need[1] - window[0]])
+            img_dev = None if sub is None else torch.from_numpy(np.ascontiguousarray(sub)).to(dev)
             sh = 1 / (2 * Nx_g)
             vec = torch.linspace(TOP_BC + sh, BOT_BC - sh, Nx_g, dtype=torch.float32).to(dev)
+            if sub is None:
+                raise ValueError("the distributed multi-phase solver needs integer labels in 0..255")
             p = Problem()
             p.g = g
-            p.kind = _lib.BINARY
+            p.kind = _lib.MULTIPHASE if self._multi else _lib.BINARY
             p.field[0], p.field[1] = self._bufs[0].data_ptr(), self._bufs[1].data_ptr()
             p.omega = float(np.float32(omega))
             p.cur = 0
@@ -199,17 +212,51 @@ class DistributedSolver(Solver):
                     ptrs = list(h.buffer_ptrs)
                     p.peer_lo[i] = ptrs[self.rank - 1] if self.rank > 0 else None
                     p.peer_hi[i] = ptrs[self.rank + 1] if self.rank < self.world - 1 else None
-            codes = torch.empty(self._lib.taub_codes_elems(g), dtype=torch.int16, device=dev)
-            p.codes = codes.data_ptr()
             self._prob = p
-            self._call(self._lib.taub_init_binary(p, img_dev.data_ptr(), need[0], need[1] - need[0],
-                                                  vec.data_ptr(), self._stream()), "taub_init_binary")
-            sel = torch.zeros(256, dtype=torch.uint8, device=dev)
-            sel[1] = 1
             counts = torch.zeros(self.batch_size * g.Nx, dtype=torch.int64, device=dev)
+            sel = torch.zeros(256, dtype=torch.uint8, device=dev)
+            if not self._multi:
+                codes = torch.empty(self._lib.taub_codes_elems(g), dtype=torch.int16, device=dev)
+                p.codes = codes.data_ptr()
+                self._call(self._lib.taub_init_binary(p, img_dev.data_ptr(), need[0], need[1] - need[0],
+                                                      vec.data_ptr(), self._stream()), "taub_init_binary")
+                sel[1] = 1
+                self._keep = (codes, vec)
+            else:
+                # global label histogram (ref:564-567): every rank counts its own planes, then all-reduce;
+                # all ranks derive the same dense phase numbering from it
+                hist = torch.zeros(self.batch_size * 256, dtype=torch.int64, device=dev)
+                self._call(self._lib.taub_plane_counts(g, img_dev.data_ptr(), need[0], need[1] - need[0], sel.data_ptr(),
+                                                       counts.data_ptr(), hist.data_ptr(), self._stream()), "taub_plane_counts")
+                if self.world > 1:
+                    dist.all_reduce(hist, group=group)
+                self._hist = hist.cpu().numpy().reshape(self.batch_size, 256)
+                sel = torch.from_numpy(MultiPhaseSolver._dense_phase_tables(self, self._hist)).to(dev)
+                labels = torch.empty(n, dtype=torch.uint8, device=dev)
+                lut = torch.from_numpy(MultiPhaseSolver.harmonic_table(self._dense_D)).contiguous().to(dev)
+                cond = torch.from_numpy((self._dense_D > 0).astype(np.float32)).to(dev)
+                m256 = torch.from_numpy(self._map256).to(dev)
+                p.labels, p.lut, p.L = labels.data_ptr(), lut.data_ptr(), self._L
+                self._call(self._lib.taub_init_multiphase(p, img_dev.data_ptr(), need[0], need[1] - need[0], m256.data_ptr(),
+                                                          cond.data_ptr(), vec.data_ptr(), self._stream()), "taub_init_multiphase")
+                self._keep = (labels, lut, cond, m256, vec)
+                if self.use_class_table and self._L <= 15:
+                    # the fused kernel applies colour A on the first ghost plane of either side as well:
+                    # class ids are needed there too, from the neighbour's labels held in the ghost planes
+                    i_lo = -1 if self.lo > 0 else 0
+                    i_hi = g.Nx + (1 if self.hi < Nx_g else 0)
+                    out = build_class_table(self._lib, p, self._dense_D, self._periodic, dev, self._stream(), i_lo, i_hi)
+                    # every rank must run the same kernel kind (fused passes do two iterations per exchange)
+                    ok = torch.tensor([1 if out else 0], dtype=torch.int64, device=dev)
+                    if self.world > 1:
+                        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+                    if int(ok.item()) and out:
+                        self._keep += out[:2]
+                        self.n_stencil_classes = out[2]
+                    elif out:     # somebody else overflowed the class table: back to the label kernel
+                        p.kind, p.codes, p.lut, p.L = _lib.MULTIPHASE, None, lut.data_ptr(), self._L
             self._call(self._lib.taub_plane_counts(g, img_dev.data_ptr(), need[0], need[1] - need[0], sel.data_ptr(),
                                                    counts.data_ptr(), None, self._stream()), "taub_plane_counts")
-            self._keep = (codes, vec)
             self._ws = torch.empty(max(self._lib.taub_sums_ws_bytes(g), 16), dtype=torch.uint8, device=dev)
             self._n_flux = g.Nx - 1 + (1 if self.hi < Nx_g else 0)
             self._max_local = max(h - l for l, h in self.bounds)
@@ -235,7 +282,13 @@ class DistributedSolver(Solver):
         self.D_eff = None
         self.force_generic = False
         self.D_0 = D_0
-        self.D_mean = np.mean(self.vol_x, axis=1)
+        if self._multi:
+            present_u8, present_raw = self._present
+            N = float(Nx_g) * Ny * Nz
+            self.VF = {int(r): self._hist[:, int(v)].astype(np.float64) / N for v, r in zip(present_u8, present_raw)}
+            self.D_mean = np.sum([self.VF[z] * self.Ds.get(z, 0.0) for z in self.VF], axis=0)   # ref:569
+        else:
+            self.D_mean = np.mean(self.vol_x, axis=1)
         self.halo_bytes_sent = 0
         self._sig_pending = False     # p2p: neighbours' signals of the last pass not yet consumed
         self._ghost_stale = False     # p2p: the last pass was generic, ghosts need an NCCL exchange
@@ -244,6 +297,7 @@ class DistributedSolver(Solver):
         self._report = (self.rank == 0)
 
     pipeline = False   # the stop rule runs on the gathered profiles, on the host of every rank
+    use_class_table = True
 
     # ---- the loop: refresh (periodic) -> halo exchange -> pass, two iterations per pass when fused.
     # With overlap, the ghost exchange and the BW boundary planes of each side run on a side stream

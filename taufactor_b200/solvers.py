@@ -562,17 +562,7 @@ class MultiPhaseSolver(ThroughTransportSolver):
     _kind = _lib.MULTIPHASE
 
     def __init__(self, img, diffusivities=None, D_scaling=1, omega=None, device='cuda'):
-        if diffusivities is None:
-            diffusivities = {0: 0, 1: 1}
-        if not isinstance(diffusivities, dict):
-            raise TypeError("diffusivities must be a dictionary mapping phase labels to diffusivities")
-        for phase, D_p in diffusivities.items():
-            if not isinstance(phase, (int, np.integer)):
-                raise TypeError(f"Phase label must be integer, got {type(phase).__name__}")
-            D_p = float(D_p)
-            if (not np.isfinite(D_p)) or (D_p < 0):
-                raise ValueError(f"Diffusivity for label {phase} must be finite and >= 0, got {D_p}")
-        self.Ds = diffusivities
+        self.Ds = validated_diffusivities(diffusivities)
         img4 = _expand_to_4d(img)
         u8 = _as_uint8_labels(img4)
         if u8 is None:
@@ -587,29 +577,7 @@ class MultiPhaseSolver(ThroughTransportSolver):
         to_raw = (lambda v: raw_of_u8[v]) if raw_of_u8 is not None else (lambda v: v)
 
         def prepare(hist):
-            present_u8 = np.flatnonzero(hist.sum(axis=0))
-            present_raw = [to_raw(int(v)) for v in present_u8]
-            missing = sorted(int(l) for l in present_raw if l not in self.Ds)   # ref:550-558
-            if missing:
-                warnings.warn("No diffusivity provided for phase label(s) "
-                              f"{missing}; assuming these phases are isolating.", UserWarning)
-                for lbl in missing:
-                    self.Ds[lbl] = 0.0
-            self.conductive_labels = [lbl for lbl, D_p in self.Ds.items() if D_p > 0]   # ref:560
-            L = len(present_u8)
-            if L > _lib.MAX_LABELS:
-                raise ValueError(f"at most {_lib.MAX_LABELS} distinct phases are supported, got {L}")
-            # dense phase tables: D per dense index (+ the isolating pseudo-phase L), ref:586-588
-            D = np.zeros(L + 1, np.float32)
-            map256 = np.full(256, L, np.uint8)
-            sel = np.zeros(256, np.uint8)
-            for d, v in enumerate(present_u8):
-                D[d] = np.float32(self.Ds[to_raw(int(v))])
-                map256[v] = d
-                sel[v] = 1 if D[d] > 0 else 0
-            self._dense_D, self._map256, self._L = D, map256, L
-            self._present = (present_u8, present_raw)
-            return sel
+            return self._dense_phase_tables(hist, to_raw)
 
         self._setup(img4, omega, device, u8, prepare, self._init_multi)
         present_u8, present_raw = self._present
@@ -617,6 +585,33 @@ class MultiPhaseSolver(ThroughTransportSolver):
         self.VF = {int(r): self._hist[:, int(v)].astype(np.float64) / N for v, r in zip(present_u8, present_raw)}
         self.D_0 = D_scaling
         self.D_mean = np.sum([self.VF[z] * self.Ds.get(z, 0.0) for z in self.VF], axis=0)   # ref:569
+
+    def _dense_phase_tables(self, hist, to_raw=int):
+        """From the label histogram: warn about / isolate labels without a diffusivity (ref:550-558), then
+        the dense phase tables (D per dense index + the isolating pseudo-phase L, ref:586-588).  Returns
+        the 256-entry "conducts" selector used for the per-slice volume fractions."""
+        present_u8 = np.flatnonzero(hist.sum(axis=0))
+        present_raw = [to_raw(int(v)) for v in present_u8]
+        missing = sorted(int(l) for l in present_raw if l not in self.Ds)
+        if missing:
+            warnings.warn("No diffusivity provided for phase label(s) "
+                          f"{missing}; assuming these phases are isolating.", UserWarning)
+            for lbl in missing:
+                self.Ds[lbl] = 0.0
+        self.conductive_labels = [lbl for lbl, D_p in self.Ds.items() if D_p > 0]   # ref:560
+        L = len(present_u8)
+        if L > _lib.MAX_LABELS:
+            raise ValueError(f"at most {_lib.MAX_LABELS} distinct phases are supported, got {L}")
+        D = np.zeros(L + 1, np.float32)
+        map256 = np.full(256, L, np.uint8)
+        sel = np.zeros(256, np.uint8)
+        for d, v in enumerate(present_u8):
+            D[d] = np.float32(self.Ds[to_raw(int(v))])
+            map256[v] = d
+            sel[v] = 1 if D[d] > 0 else 0
+        self._dense_D, self._map256, self._L = D, map256, L
+        self._present = (present_u8, present_raw)
+        return sel
 
     @staticmethod
     def harmonic_table(D):
@@ -647,67 +642,90 @@ class MultiPhaseSolver(ThroughTransportSolver):
     use_class_table = True   # False: recompute the face conductances from the labels in the kernel
 
     def _build_class_table(self, p):
-        """Replace (label, harmonic-mean table) by (stencil class, per-class weights).
+        out = build_class_table(self._lib, p, self._dense_D, self._periodic, self.device, self._stream(), 0, p.g.Nx)
+        if out:
+            self.n_stencil_classes = out[2]
+            return out[:2]
+        return ()
 
-        The six face conductances and the prefactor of a voxel (ref:594-603) depend only on the phase
-        of the voxel and of its six neighbours (+ whether the Dirichlet face counts twice).  The
-        distinct combinations that occur are few (<= 3 * L^7, in practice hundreds): each becomes a
-        class with one 8-float row {w_x+, w_x-, w_y+, w_y-, w_z+, w_z-, prefactor, 1/prefactor}, computed here in
-        the reference's fp32 op order; the sweep then reads one uint16 class id per voxel and one row
-        instead of seven labels and six table look-ups (TAUB_MULTIPHASE_CLASS)."""
-        g, dev = p.g, self.device
-        n = g.bs * g.Nx * g.Ny * g.Nz
-        keys = torch.empty(n, dtype=torch.int32, device=dev)
-        self._call(self._lib.taub_multiphase_keys(p, keys.data_ptr(), self._stream()), "taub_multiphase_keys")
-        uniq, inv, counts = torch.unique(keys, return_inverse=True, return_counts=True)
-        del keys
-        if uniq.numel() > 65534:
-            return ()
-        # most frequent classes first: the handful of "uniform interior" stencils that cover most voxels
-        # then share one or two cache lines of the weight table
-        order = torch.argsort(counts, descending=True, stable=True)
-        rank = torch.empty_like(order)
-        rank[order] = torch.arange(order.numel(), device=dev)
-        inv = rank[inv]
-        k = uniq[order].cpu().numpy().astype(np.int64)
-        lut = self.harmonic_table(self._dense_D)
-        own = k & 15
-        wxm, wxp = lut[own, (k >> 4) & 15], lut[own, (k >> 8) & 15]
-        wym, wyp = lut[own, (k >> 12) & 15], lut[own, (k >> 16) & 15]
-        wzm, wzp = lut[own, (k >> 20) & 15], lut[own, (k >> 24) & 15]
-        first, last = ((k >> 28) & 1).astype(bool), ((k >> 29) & 1).astype(bool)
-        fac = (wxm + wxp).astype(np.float32)                      # ref:598-600, left to right in fp32
-        for w in (wym, wyp, wzm, wzp):
-            fac = (fac + w).astype(np.float32)
-        fac[first] = (fac[first] + wxm[first]).astype(np.float32)   # ref:601
-        fac[last] = (fac[last] + wxp[last]).astype(np.float32)      # ref:602
-        # ref:603 turns a zero prefactor into inf; the table keeps b = 0 with reciprocal 0 for it (q = 0)
-        with np.errstate(divide="ignore"):
-            rcp = np.where(fac > 0, (1.0 / fac.astype(np.float64)), 0.0).astype(np.float32)   # RN(1/b)
-        table = np.stack([wxp, wxm, wyp, wym, wzp, wzm, fac, rcp], axis=1).astype(np.float32)
-        # one more, INERT class (all zeros: a voxel that stays what it is -- 0) for everything outside
-        # the volume: ghost frame of the no-flux solvers, Dirichlet planes, row padding
-        inert = len(k)
-        table = np.concatenate([table, np.zeros((1, 8), np.float32)])
-        table_dev = torch.from_numpy(np.ascontiguousarray(table)).to(dev)
-        classes = torch.full((self._lib.taub_field_elems(g),), inert, dtype=torch.int32, device=dev).to(torch.int16)
-        G, C0 = _lib.GHOST, _lib.COL0
-        cv = classes.view(g.bs, g.planes, g.rows, g.pitch)
-        cv[:, G:G + g.Nx, G:G + g.Ny, C0:C0 + g.Nz] = inv.view(g.bs, g.Nx, g.Ny, g.Nz).to(torch.int16)
-        del inv
-        if self._periodic:
-            # the fused kernel applies colour A on the first ghost ring too: ghost voxels carry the class
-            # of their periodic image (rows first, then columns over all rows -> corners included)
-            own = cv[:, G:G + g.Nx]
-            for w in range(G):
-                own[:, :, G - 1 - w] = own[:, :, G + g.Ny - 1 - (w % g.Ny)]
-                own[:, :, G + g.Ny + w] = own[:, :, G + (w % g.Ny)]
-            for w in range(G):
-                own[:, :, :, C0 - 1 - w] = own[:, :, :, C0 + g.Nz - 1 - (w % g.Nz)]
-                own[:, :, :, C0 + g.Nz + w] = own[:, :, :, C0 + (w % g.Nz)]
-        p.kind, p.codes, p.lut, p.L = _lib.MULTIPHASE_CLASS, classes.data_ptr(), table_dev.data_ptr(), int(len(table))
-        self.n_stencil_classes = int(len(k))
-        return (classes, table_dev)
+
+def validated_diffusivities(diffusivities):
+    """Argument checks of ref:524-545 (MultiPhaseSolver.__init__)."""
+    if diffusivities is None:
+        diffusivities = {0: 0, 1: 1}
+    if not isinstance(diffusivities, dict):
+        raise TypeError("diffusivities must be a dictionary mapping phase labels to diffusivities")
+    for phase, D_p in diffusivities.items():
+        if not isinstance(phase, (int, np.integer)):
+            raise TypeError(f"Phase label must be integer, got {type(phase).__name__}")
+        D_p = float(D_p)
+        if (not np.isfinite(D_p)) or (D_p < 0):
+            raise ValueError(f"Diffusivity for label {phase} must be finite and >= 0, got {D_p}")
+    return diffusivities
+
+
+def build_class_table(lib, p, dense_D, periodic, dev, stream, i_lo, i_hi):
+    """Replace (label, harmonic-mean table) by (stencil class, per-class weights) on the local planes
+    [i_lo, i_hi) of a bound multi-phase problem; switches ``p`` to TAUB_MULTIPHASE_CLASS.
+
+    The six face conductances and the prefactor of a voxel (ref:594-603) depend only on the phase of
+    the voxel and of its six neighbours (+ whether the Dirichlet face counts twice).  The distinct
+    combinations that occur are few (<= 3 * L^7, in practice hundreds): each becomes a class with one
+    8-float row {w_x+, w_x-, w_y+, w_y-, w_z+, w_z-, prefactor, 1/prefactor}, computed here in the
+    reference's fp32 op order; the sweep then reads one uint16 class id per voxel and one row instead of
+    seven labels and six table look-ups.  Returns (classes, table, n_classes) or None (too many classes)."""
+    g = p.g
+    n_i = i_hi - i_lo
+    keys = torch.empty(g.bs * n_i * g.Ny * g.Nz, dtype=torch.int32, device=dev)
+    check(lib.taub_multiphase_keys(p, i_lo, i_hi, keys.data_ptr(), stream), "taub_multiphase_keys")
+    uniq, inv, counts = torch.unique(keys, return_inverse=True, return_counts=True)
+    del keys
+    if uniq.numel() > 65534:
+        return None
+    # most frequent classes first: the handful of "uniform interior" stencils that cover most voxels
+    # then share one or two cache lines of the weight table
+    order = torch.argsort(counts, descending=True, stable=True)
+    rank = torch.empty_like(order)
+    rank[order] = torch.arange(order.numel(), device=dev)
+    inv = rank[inv]
+    k = uniq[order].cpu().numpy().astype(np.int64)
+    lut = MultiPhaseSolver.harmonic_table(dense_D)
+    own = k & 15
+    wxm, wxp = lut[own, (k >> 4) & 15], lut[own, (k >> 8) & 15]
+    wym, wyp = lut[own, (k >> 12) & 15], lut[own, (k >> 16) & 15]
+    wzm, wzp = lut[own, (k >> 20) & 15], lut[own, (k >> 24) & 15]
+    first, last = ((k >> 28) & 1).astype(bool), ((k >> 29) & 1).astype(bool)
+    fac = (wxm + wxp).astype(np.float32)                      # ref:598-600, left to right in fp32
+    for w in (wym, wyp, wzm, wzp):
+        fac = (fac + w).astype(np.float32)
+    fac[first] = (fac[first] + wxm[first]).astype(np.float32)   # ref:601
+    fac[last] = (fac[last] + wxp[last]).astype(np.float32)      # ref:602
+    # ref:603 turns a zero prefactor into inf; the table keeps b = 0 with reciprocal 0 for it (q = 0)
+    with np.errstate(divide="ignore"):
+        rcp = np.where(fac > 0, (1.0 / fac.astype(np.float64)), 0.0).astype(np.float32)   # RN(1/b)
+    table = np.stack([wxp, wxm, wyp, wym, wzp, wzm, fac, rcp], axis=1).astype(np.float32)
+    # one more, INERT class (all zeros: a voxel that stays what it is -- 0) for everything outside
+    # the volume: ghost frame of the no-flux solvers, Dirichlet planes, row padding
+    inert = len(k)
+    table = np.concatenate([table, np.zeros((1, 8), np.float32)])
+    table_dev = torch.from_numpy(np.ascontiguousarray(table)).to(dev)
+    classes = torch.full((lib.taub_field_elems(g),), inert, dtype=torch.int32, device=dev).to(torch.int16)
+    G, C0 = _lib.GHOST, _lib.COL0
+    cv = classes.view(g.bs, g.planes, g.rows, g.pitch)
+    cv[:, G + i_lo:G + i_hi, G:G + g.Ny, C0:C0 + g.Nz] = inv.view(g.bs, n_i, g.Ny, g.Nz).to(torch.int16)
+    del inv
+    if periodic:
+        # the fused kernel applies colour A on the first ghost ring too: ghost voxels carry the class
+        # of their periodic image (rows first, then columns over all rows -> corners included)
+        own_pl = cv[:, G + i_lo:G + i_hi]
+        for w in range(G):
+            own_pl[:, :, G - 1 - w] = own_pl[:, :, G + g.Ny - 1 - (w % g.Ny)]
+            own_pl[:, :, G + g.Ny + w] = own_pl[:, :, G + (w % g.Ny)]
+        for w in range(G):
+            own_pl[:, :, :, C0 - 1 - w] = own_pl[:, :, :, C0 + g.Nz - 1 - (w % g.Nz)]
+            own_pl[:, :, :, C0 + g.Nz + w] = own_pl[:, :, :, C0 + (w % g.Nz)]
+    p.kind, p.codes, p.lut, p.L = _lib.MULTIPHASE_CLASS, classes.data_ptr(), table_dev.data_ptr(), int(len(table))
+    return classes, table_dev, int(len(k))
 
 
 class PeriodicMultiPhaseSolver(MultiPhaseSolver):

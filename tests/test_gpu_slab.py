@@ -102,3 +102,64 @@ def test_batch_sharded_joint_stop_rule(tmp_path):
     B.solve(verbose=False)
     assert int(got["iters"]) == B.iter == 300
     assert np.array_equal(got["tau"], B.tau) and np.array_equal(got["D_eff"], B.D_eff)
+
+
+MP_D = {0: 0.0, 1: 1.0, 2: 0.3}
+
+
+def _mp_worker(rank, world, port, shape, periodic, mode, table, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.cuda.set_device(0)
+        from taufactor_b200.distributed import DistributedSolver, image_window, slab_bounds
+        DistributedSolver.use_class_table = table
+        img = cases.blobs3(shape, seed=sum(shape))
+        kw = dict(device="cuda:0", periodic=periodic, diffusivities=dict(MP_D), D_scaling=1)
+        if mode == "window":
+            lo, hi = slab_bounds(shape[0], world)[rank]
+            w = image_window(lo, hi, shape[0])
+            S = DistributedSolver(img[w[0]:w[1]], window=w, shape=shape, **kw)
+        else:
+            S = DistributedSolver(img, **kw)
+        S._advance(37)
+        f37 = S.gather_field().cpu().numpy()
+        S2 = DistributedSolver(img, **kw)
+        S2.solve(verbose=False, iter_limit=1500)
+        if rank == 0:
+            np.savez(out, f37=f37, tau=S2.tau, D_eff=S2.D_eff, iters=S2.iter, final=S2.gather_field().cpu().numpy(),
+                     flux=S2.flux_1d, D_mean=S2.D_mean, vol_x=S2.vol_x, kind=S2._prob.kind)
+        else:
+            S2.gather_field()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape,periodic,world,mode,table", [
+    ((24, 20, 28), False, 2, "full", True), ((30, 22, 16), True, 3, "window", True),
+    ((64, 48, 40), False, 2, "window", True), ((64, 40, 48), True, 2, "full", True),
+    ((26, 20, 24), True, 2, "window", False)])
+def test_multiphase_slabs_equal_single_gpu(tmp_path, shape, periodic, world, mode, table):
+    """MultiPhaseSolver / PeriodicMultiPhaseSolver on x-slabs (stencil-class table built per slab, with
+    class ids on the first ghost plane of either side) == the single-GPU solver, bit for bit."""
+    import torch.multiprocessing as mp
+    import taufactor_b200 as tau
+    from taufactor_b200 import _lib
+    out = str(tmp_path / "slab_mp.npz")
+    mp.spawn(_mp_worker, args=(world, _free_port(), shape, periodic, mode, table, out), nprocs=world, join=True)
+    got = np.load(out)
+    assert int(got["kind"]) == (_lib.MULTIPHASE_CLASS if table else _lib.MULTIPHASE)
+    img = cases.blobs3(shape, seed=sum(shape))
+    cls = tau.PeriodicMultiPhaseSolver if periodic else tau.MultiPhaseSolver
+    A = cls(img, diffusivities=dict(MP_D), device="cuda")
+    A._advance(37)
+    assert np.array_equal(A.field[:, 1:-1, 1:-1, 1:-1].cpu().numpy(), got["f37"])
+    B = cls(img, diffusivities=dict(MP_D), device="cuda")
+    B.solve(verbose=False, iter_limit=1500)
+    assert int(got["iters"]) == B.iter
+    assert np.array_equal(B.field[:, 1:-1, 1:-1, 1:-1].cpu().numpy(), got["final"])
+    assert np.array_equal(B.flux_1d, got["flux"])
+    assert np.array_equal(B.D_mean, got["D_mean"]) and np.array_equal(B.vol_x, got["vol_x"])
+    assert np.array_equal(B.tau, got["tau"]) and np.array_equal(B.D_eff, got["D_eff"])
