@@ -27,6 +27,28 @@ for shape, periodic in [((256, 200, 232), False), ((192, 256, 256), True), ((130
               "field bitwise equal:", same, "halo MB sent by rank0:", S.halo_bytes_sent / 1e6,
               "p2p:", getattr(S, "p2p_active", None), getattr(S, "_p2p_error", None), flush=True)
         ok &= same and S.iter == A.iter and np.array_equal(S.tau, A.tau)
+# multi-phase on slabs (stencil-class kernel, p2p ghost stores)
+MP_D = {0: 0.0, 1: 1.0, 2: 0.3}
+for shape, periodic in [((256, 192, 200), False), ((192, 256, 256), True)]:
+    img = cases.blobs3(shape, seed=9)
+    S = DistributedSolver(img, periodic=periodic, diffusivities=dict(MP_D))
+    S.solve(verbose=False, conv_crit=2e-2)
+    full = S.gather_field()
+    if rank == 0:
+        cls = tau.PeriodicMultiPhaseSolver if periodic else tau.MultiPhaseSolver
+        A = cls(img, diffusivities=dict(MP_D), device=f"cuda:{local}")
+        A.solve(verbose=False, conv_crit=2e-2)
+        same = torch.equal(A.field[:, 1:-1, 1:-1, 1:-1], full)
+        print("multi-phase", shape, "periodic" if periodic else "", "slab iters", S.iter, "single", A.iter, "tau", S.tau, A.tau,
+              "field bitwise equal:", same, "kind", S._prob.kind, "classes", getattr(S, "n_stencil_classes", None),
+              "p2p:", getattr(S, "p2p_active", None), flush=True)
+        ok &= same and S.iter == A.iter and np.array_equal(S.tau, A.tau)
+if os.environ.get("SLAB_CHECK_TIMING", "1") == "0":
+    if rank == 0:
+        print("NCCL SLAB CHECK", "OK" if ok else "FAILED", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0)
 # overlap on / off timing on a larger volume
 import time
 img = cases.random_img((512, 768, 768), 0.5, seed=3)
