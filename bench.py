@@ -310,6 +310,13 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    extra_cfg = {}
+    if world > 1 and args.workload == "slab":
+        extra_cfg = {"halo_exchange": ("one-sided stores over NVLink peer memory" if getattr(S, "p2p_active", False)
+                                       else "NCCL send/recv"),
+                     "overlap": bool(getattr(S, "_overlap", False)),
+                     "single_gpu_point": "strong-scaling base = `bench.py --size 2048` on 1 GPU (profiles/SCALING.md), "
+                                         "not the default 512^3 N=1 line"}
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample on the host cores
     cpu = None
@@ -326,8 +333,8 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak" if world == 1 or args.workload == "batch" else "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "parallelism": parallelism, "iterations_per_step": ITERS_PER_STEP,
-                       "l2": "inputs larger than L2 (field >= 0.5 GB per GPU vs 126 MB L2)"},
+            "config": dict({"workload": workload, "parallelism": parallelism, "iterations_per_step": ITERS_PER_STEP,
+                            "l2": "inputs larger than L2 (field >= 0.5 GB per GPU vs 126 MB L2)"}, **extra_cfg),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "true_updates_per_s": value * 1e9 / 2}
     print(json.dumps(line))

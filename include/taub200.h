@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TAUB_ABI_VERSION 5
+#define TAUB_ABI_VERSION 6
 #define TAUB_GHOST 2            /* ghost width in x (planes), y (rows) and z (columns) */
 #define TAUB_COL0 4             /* column of interior voxel k = 0 */
 #define TAUB_MAX_LABELS 64      /* dense phase indices 0..L-1, L <= 64; index L = "outside" */
@@ -161,7 +161,8 @@ int taub_iterate(taub_problem *p, int64_t iter, int n, int flags, void *stream);
  * through the face between local planes i and i+1 (the last entry uses the upper ghost plane
  * and exists only when this slab is not the last: Nx_out = Nx-1 + (i_offset+Nx < Nx_global));
  * field_mean[b][i], i in [0, Nx): mean of the field over plane i.  fp64 accumulation in a fixed
- * order (deterministic), results rounded to fp32.  Outputs are device pointers. */
+ * order (deterministic), results rounded to fp32.  Outputs are device pointers.  While *p->stop != 0
+ * (if p->stop is set) the outputs are left as they are. */
 int taub_plane_means(const taub_problem *p, void *workspace, float *flux_mean, float *field_mean,
                      void *stream);
 
@@ -177,6 +178,14 @@ int taub_plane_means(const taub_problem *p, void *workspace, float *flux_mean, f
  * it become no-ops, so the field stays exactly at the iteration of this check. */
 int taub_check_async(const taub_problem *p, void *workspace, float *flux_mean, float *field_mean,
                      const double *D_mean, float *old_tau, float conv_crit, float *record, void *stream);
+
+/* x-slab runs: the stop rule alone, on per-slice flux means of the WHOLE volume that the caller has
+ * assembled on the device (taub_plane_means of every slab, honouring p->stop, + an all-gather).  Same
+ * arithmetic, record layout and stop-flag protocol as taub_check_async; every rank evaluates the same
+ * numbers and therefore takes the same decision without a host round trip.
+ *   flux_mean[bs][Nx_global - 1] device fp32; stop: this rank's device flag (non-NULL). */
+int taub_stop_rule_async(int bs, int Nx_global, const float *flux_mean, const double *D_mean, float *old_tau,
+                         float conv_crit, float *record, int32_t *stop, void *stream);
 
 #ifdef __cplusplus
 }

@@ -224,7 +224,18 @@ static int plane_means(const taub_problem *p, void *workspace, float *flux_mean,
 int taub_plane_means(const taub_problem *p, void *workspace, float *flux_mean, float *field_mean,
                      void *stream)
 {
-    return plane_means(p, workspace, flux_mean, field_mean, nullptr, stream);
+    return plane_means(p, workspace, flux_mean, field_mean, p ? p->stop : nullptr, stream);
+}
+
+int taub_stop_rule_async(int bs, int Nx_global, const float *flux_mean, const double *D_mean, float *old_tau,
+                         float conv_crit, float *record, int32_t *stop, void *stream)
+{
+    TAUB_REQUIRE(flux_mean && D_mean && old_tau && record && stop, "taub_stop_rule_async: null pointer");
+    TAUB_REQUIRE(bs >= 1 && Nx_global >= 2, "taub_stop_rule_async: needs bs >= 1 and Nx_global >= 2");
+    stop_rule_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(bs, Nx_global, flux_mean, D_mean, old_tau, conv_crit, record, stop);
+    TAUB_CUDA(cudaGetLastError());
+    count_launch();
+    return TAUB_OK;
 }
 
 int taub_check_async(const taub_problem *p, void *workspace, float *flux_mean, float *field_mean,

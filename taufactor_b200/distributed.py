@@ -296,7 +296,8 @@ class DistributedSolver(Solver):
         self.overlap = overlap
         self._report = (self.rank == 0)
 
-    pipeline = False   # the stop rule runs on the gathered profiles, on the host of every rank
+    # pipeline = True (inherited): the stop rule runs on the device of every rank, on the all-gathered
+    # profiles, so the next block of sweeps is queued before the check is read back
     use_class_table = True
 
     # ---- the loop: refresh (periodic) -> halo exchange -> pass, two iterations per pass when fused.
@@ -338,7 +339,37 @@ class DistributedSolver(Solver):
             if self.rank < self.world - 1:
                 self._call(lib.taub_refresh_ghosts(g, buf.data_ptr(), G + g.Nx, g.planes, self._stream()), "taub_refresh_ghosts")
 
+    def _can_pipeline(self):
+        return self.Nx >= 2
+
+    def _pipeline_profiles(self):
+        if getattr(self, "_prof_glob", None) is None:
+            # index into the all-gathered per-rank records [world][flux|mean][bs][max_local] that lays the
+            # whole-volume profiles out as [flux (bs x (Nx-1)) | mean (bs x Nx)]
+            bs, ml, W = self.batch_size, self._max_local, self.world
+            idx = np.arange(W * 2 * bs * ml, dtype=np.int64).reshape(W, 2, bs, ml)
+            flux = np.concatenate([idx[r, 0, :, : (h - l) - 1 + (1 if h < self.Nx else 0)]
+                                   for r, (l, h) in enumerate(self.bounds)], axis=1)
+            mean = np.concatenate([idx[r, 1, :, : h - l] for r, (l, h) in enumerate(self.bounds)], axis=1)
+            assert flux.shape == (bs, self.Nx - 1) and mean.shape == (bs, self.Nx)
+            self._prof_idx = torch.from_numpy(np.concatenate([flux.ravel(), mean.ravel()])).to(self.device)
+            self._prof_glob = torch.zeros(self._prof_idx.numel(), dtype=torch.float32, device=self.device)
+        return self._prof_glob
+
+    def _queue_block(self, it, flags, conv_crit, P, stream):
+        self._advance_from(it, 100)
+        self._local_means()
+        src = self._gather if self.world > 1 else self._rec
+        torch.index_select(src, 0, self._prof_idx, out=self._prof_glob)
+        self._call(self._lib.taub_stop_rule_async(self.batch_size, self.Nx, self._prof_glob.data_ptr(), P["D_mean"].data_ptr(),
+                                                  P["old_tau"].data_ptr(), float(conv_crit), P["rec"].data_ptr(),
+                                                  P["ctl"].data_ptr(), stream), "taub_stop_rule_async")
+
     def _advance(self, n):
+        self._advance_from(self.iter, n)
+        self.iter += n
+
+    def _advance_from(self, it0, n):
         lib, p, g = self._lib, self._prob, self._geom
         lib.taub_set_device(self._dev_index)
         if self._fuse is None:
@@ -355,7 +386,7 @@ class DistributedSolver(Solver):
         while done < n:
             cur = self._bufs[p.cur]
             fused = self._fuse and not self.force_generic and n - done >= 2
-            it = self.iter + done
+            it = it0 + done
             p2p = self.p2p_active and fused
             if self._periodic:
                 self._call(lib.taub_refresh_ghosts(g, cur.data_ptr(), G, G + g.Nx, self._stream()), "taub_refresh_ghosts")
@@ -395,9 +426,9 @@ class DistributedSolver(Solver):
                 self._ghost_stale = True
             done += 2 if fused else 1
             p.cur ^= 1
-        self.iter += n
 
-    def _plane_means(self):
+    def _local_means(self):
+        """This slab's per-slice means, all-gathered into ``_gather`` (device; no host sync)."""
         lib, p, g = self._lib, self._prob, self._geom
         cur = self._bufs[p.cur]
         if getattr(self, "p2p_active", False) and not self._ghost_stale:
@@ -415,6 +446,11 @@ class DistributedSolver(Solver):
         rec[1, :, : g.Nx] = self._mean_dev.view(bs, g.Nx)
         if self.world > 1:
             all_gather_flat(self._gather, self._rec, self.group)
+
+    def _plane_means(self):
+        self._local_means()
+        bs, ml = self.batch_size, self._max_local
+        if self.world > 1:
             allr = self._gather.cpu().numpy().reshape(self.world, 2, bs, ml)
         else:
             allr = self._rec.cpu().numpy().reshape(1, 2, bs, ml)

@@ -307,7 +307,8 @@ class SORSolver:
         lib, dev = self._lib, self.device
         lib.taub_set_device(self._dev_index)
         bs = self.batch_size
-        nprof, nrec = self._prof_dev.numel(), 2 + 2 * bs
+        prof_dev = self._pipeline_profiles()
+        nprof, nrec = prof_dev.numel(), 2 + 2 * bs
         if getattr(self, "_pipe", None) is None:
             with torch.cuda.device(dev):
                 self._pipe = dict(
@@ -328,13 +329,9 @@ class SORSolver:
             while not self.converged:
                 while (len(pending) < self.PIPELINE_DEPTH and queued_iter % 100 == 0
                        and queued_iter + 100 <= iter_limit):
-                    self._call(lib.taub_iterate(self._prob, queued_iter, 100, flags, stream), "taub_iterate")
-                    self._call(lib.taub_check_async(self._prob, self._ws.data_ptr(), self._flux_dev.data_ptr(),
-                                                    self._mean_dev.data_ptr(), P["D_mean"].data_ptr(),
-                                                    P["old_tau"].data_ptr(), float(conv_crit), P["rec"].data_ptr(),
-                                                    stream), "taub_check_async")
+                    self._queue_block(queued_iter, flags, conv_crit, P, stream)
                     h = P["host"][slot]
-                    h[:nprof].copy_(self._prof_dev, non_blocking=True)
+                    h[:nprof].copy_(prof_dev, non_blocking=True)
                     h[nprof:].copy_(P["rec"], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record()
@@ -350,7 +347,7 @@ class SORSolver:
                 if status == 3:          # queued behind a check that stopped the solve: it did nothing
                     continue
                 self.iter = it
-                nf = self._flux_dev.numel()
+                nf = nprof - bs * self.Nx
                 prof = (h[: bs * (self.Nx - 1)].reshape(bs, self.Nx - 1).copy(), h[nf:nprof].reshape(bs, self.Nx).copy())
                 host_says = self.check_convergence(verbose, conv_crit, plot_interval, profiles=prof)
                 if status == 2:
@@ -375,6 +372,19 @@ class SORSolver:
         finally:
             torch.cuda.synchronize(dev)
             self._prob.stop = None
+
+    def _pipeline_profiles(self):
+        """Device record [flux (bs x (Nx-1)) | mean (bs x Nx)] of the whole volume that a queued check fills."""
+        return self._prof_dev
+
+    def _queue_block(self, it, flags, conv_crit, P, stream):
+        """Queue 100 iterations starting at iteration ``it`` and the device-side check that follows."""
+        lib = self._lib
+        self._call(lib.taub_iterate(self._prob, it, 100, flags, stream), "taub_iterate")
+        self._call(lib.taub_check_async(self._prob, self._ws.data_ptr(), self._flux_dev.data_ptr(),
+                                        self._mean_dev.data_ptr(), P["D_mean"].data_ptr(),
+                                        P["old_tau"].data_ptr(), float(conv_crit), P["rec"].data_ptr(),
+                                        stream), "taub_check_async")
 
     def _advance(self, n):
         """n reference iterations on the device, no check, no host sync (ref:175-182 x n)."""

@@ -40,6 +40,7 @@ def _worker(rank, world, port, shape, periodic, mode, out):
         f37 = S.gather_field().cpu().numpy()
         S.iter = 0   # restart the bookkeeping; the field keeps evolving from iteration 37 (odd parity)
         S2 = DistributedSolver(img, device="cuda:0", periodic=periodic)
+        S2.pipeline = (mode != "full")     # both the device-side (queued) and the host-side stop rule
         S2.solve(verbose=False)
         if rank == 0:
             np.savez(out, f37=f37, tau=S2.tau, D_eff=S2.D_eff, iters=S2.iter, final=S2.gather_field().cpu().numpy(),
