@@ -47,9 +47,10 @@ typedef enum taub_kind {
     TAUB_MULTIPHASE = 1,   /* MultiPhaseSolver, PeriodicMultiPhaseSolver */
     TAUB_ANISOTROPIC = 2,  /* AnisotropicSolver: binary codes, lut = device float[2] {Ky, Kz} (taufactor.py:455-456) */
     TAUB_MULTIPHASE_CLASS = 3  /* multi-phase through a stencil-class table: codes = one uint16 class id per
-                                * storage voxel, lut = device float[L][8] rows {w_x+, w_x-, w_y+, w_y-, w_z+,
-                                * w_z-, b, RN(1/b)} with b = prefactor (b = 1/b = 0 where it is infinite),
-                                * L = number of classes (see taub_multiphase_keys) */
+                                * storage voxel, lut = device float[2][L][4]: half rows {w_x+, w_x-, w_y+, w_y-}
+                                * of all L classes, then half rows {w_z+, w_z-, b, RN(1/b)} with b = prefactor
+                                * (b = 1/b = 0 where it is infinite), L = number of classes (see
+                                * taub_multiphase_keys) */
 } taub_kind;
 
 /* Geometry of one rank's slab.  Filled by taub_geom_init. */

@@ -203,9 +203,12 @@ __device__ __forceinline__ float sor_multi(float c, float xp, float xm, float yp
 // exactly rounded reciprocal (checked against s / b on 6e8 random pairs; same guard word as div_fast).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float sor_class(float c, float xp, float xm, float yp, float ym, float zp, float zm,
-                                           unsigned cls, const float4 *__restrict__ tab, float omega, unsigned &umin)
+                                           unsigned cls, const float4 *__restrict__ tabA, const float4 *__restrict__ tabB,
+                                           float omega, unsigned &umin)
 {
-    const float4 wa = __ldg(tab + 2 * cls), wb = __ldg(tab + 2 * cls + 1);
+    // two half-row arrays: a 32-byte sector holds the halves of two (frequency-adjacent) classes, so a
+    // warp's gather touches fewer sectors than with one 32-byte row per class
+    const float4 wa = __ldg(tabA + cls), wb = __ldg(tabB + cls);
     float s = __fadd_rn(__fmul_rn(xp, wa.x), __fmul_rn(xm, wa.y));
     s = __fadd_rn(s, __fmul_rn(yp, wa.z));
     s = __fadd_rn(s, __fmul_rn(ym, wa.w));

@@ -25,14 +25,15 @@
 namespace taub {
 
 constexpr int F_NT = 256;  // threads per CTA
-constexpr int F_NB = 6;    // ring depth (planes in shared memory)
+constexpr int F_NB = 6;    // ring depth (planes in shared memory) of the binary kind
 
 struct FusedParams {
     taub_geom g;
     const float *src;
     float *dst;
     const uint16_t *codes;   // binary: one uint16 (four 4-bit counts) per group; class kind: one uint16 per voxel
-    const float *table;      // class kind: [n_classes][8] weight rows
+    const float *table;      // class kind: [2][n_classes][4] weight half-rows
+    int n_classes;
     float omega;
     int colourA;
     int i_lo, i_hi;    // output planes (local)
@@ -113,16 +114,16 @@ __device__ __forceinline__ void row_update(const bool is_xz, float4 &c, const fl
 // Class kind: cls2 = the row's four uint16 class ids (x | y << 16, z | w << 16).
 __device__ __forceinline__ void row_update_class(const bool is_xz, float4 &c, const float4 &xp, const float4 &xm,
                                                  const float4 &up, const float4 &dn, float zs, uint2 cls2,
-                                                 const float4 *tab, float omega, unsigned &umin)
+                                                 const float4 *tab, const float4 *tabB, float omega, unsigned &umin)
 {
     if (is_xz) {
-        const float n0 = sor_class(c.x, xp.x, xm.x, up.x, dn.x, c.y, zs, cls2.x & 0xffffu, tab, omega, umin);
-        const float n1 = sor_class(c.z, xp.z, xm.z, up.z, dn.z, c.w, c.y, cls2.y & 0xffffu, tab, omega, umin);
+        const float n0 = sor_class(c.x, xp.x, xm.x, up.x, dn.x, c.y, zs, cls2.x & 0xffffu, tab, tabB, omega, umin);
+        const float n1 = sor_class(c.z, xp.z, xm.z, up.z, dn.z, c.w, c.y, cls2.y & 0xffffu, tab, tabB, omega, umin);
         c.x = n0;
         c.z = n1;
     } else {
-        const float n0 = sor_class(c.y, xp.y, xm.y, up.y, dn.y, c.z, c.x, cls2.x >> 16, tab, omega, umin);
-        const float n1 = sor_class(c.w, xp.w, xm.w, up.w, dn.w, zs, c.z, cls2.y >> 16, tab, omega, umin);
+        const float n0 = sor_class(c.y, xp.y, xm.y, up.y, dn.y, c.z, c.x, cls2.x >> 16, tab, tabB, omega, umin);
+        const float n1 = sor_class(c.w, xp.w, xm.w, up.w, dn.w, zs, c.z, cls2.y >> 16, tab, tabB, omega, umin);
         c.y = n0;
         c.w = n1;
     }
@@ -149,8 +150,8 @@ __device__ __forceinline__ float z_neighbour(const bool is_xz, const float4 &v, 
 // y-neighbours stay in registers, only the rows above and below it come from shared memory.  PA0 = parity
 // of the column's first row at step 0 (uniform over the whole grid, chosen by the host), so every step
 // body is branch-free.
-template <int NRW, int PA0, int KIND>   // KIND: TAUB_BINARY (4-bit codes) or TAUB_MULTIPHASE_CLASS (class ids)
-__global__ void __launch_bounds__(F_NT, 2)
+template <int NRW, int PA0, int KIND, int NB>   // KIND: TAUB_BINARY (4-bit codes) or TAUB_MULTIPHASE_CLASS (class ids)
+__global__ void __launch_bounds__(F_NT, 2)      // NB: ring depth (planes of the tile resident in shared memory)
 fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tmap,
                     const __grid_constant__ CUtensorMap cmap)
 {
@@ -162,12 +163,13 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     constexpr bool CLS = (KIND == TAUB_MULTIPHASE_CLASS);
     constexpr int CPG = CLS ? 4 : 1;             // uint16 side-array elements per float4 group
     const int LR = P.LR, LG = P.LG, LGc = P.LGc;
-    const float4 *tab = reinterpret_cast<const float4 *>(P.table);
+    const float4 *tab = reinterpret_cast<const float4 *>(P.table);   // class kind: half rows A, then half rows B
+    const float4 *tabB = tab + P.n_classes;
     const int plane_f4 = P.slot_f4;              // ring slot size in float4 (>= LR*LG, multiple of 8)
     const int cslot = P.cslot_h;
     float4 *planes = reinterpret_cast<float4 *>(smem_raw);
-    uint16_t *cplanes = reinterpret_cast<uint16_t *>(smem_raw + (size_t)F_NB * plane_f4 * 16);
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(cplanes + (size_t)F_NB * cslot);
+    uint16_t *cplanes = reinterpret_cast<uint16_t *>(smem_raw + (size_t)NB * plane_f4 * 16);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(cplanes + (size_t)NB * cslot);
     __shared__ float2 s_div[16];   // static: constant address, no address arithmetic per lookup
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -182,7 +184,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
 
     if (tid < 16) s_div[tid] = div_entry(tid);
     if (tid == 0) {
-        for (int n = 0; n < F_NB; ++n) mbar_init(smem_u32(&mbar[n]), 1);
+        for (int n = 0; n < NB; ++n) mbar_init(smem_u32(&mbar[n]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -191,7 +193,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     // (columns 4*G0.., rows R0.., one plane) plus the matching box of neighbour codes; the part of a
     // box outside the tensor reads as 0
     auto issue = [&](int rel) {
-        const int slot = rel % F_NB;
+        const int slot = rel % NB;
         const uint32_t bar = smem_u32(&mbar[slot]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(bar, (uint32_t)(LR * (LG * 16 + LGc * CPG * 2)));
@@ -200,7 +202,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
         tma_load_3d(smem_u32(cplanes + (size_t)slot * cslot), &cmap, G0 * CPG, R0, pl, bar);
     };
     if (tid == 0)
-        for (int rel = 0; rel < min(F_NB - 1, total_rel); ++rel) issue(rel);
+        for (int rel = 0; rel < min(NB - 1, total_rel); ++rel) issue(rel);
 
     // ---- this thread's column: rows lr0 .. lr0+NRW-1 of the tile, group gg
     const int NCT = (LR - 2) / NRW;          // columns stacked in the tile
@@ -225,7 +227,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     float4 rg[NRW][4];
     unsigned cr[NRW / 2][4];   // binary: neighbour codes, two rows per word, same ring positions
     mbar_wait(smem_u32(&mbar[0]), 0);
-    mbar_wait(smem_u32(&mbar[1 % F_NB]), 0);
+    mbar_wait(smem_u32(&mbar[1 % NB]), 0);
 #pragma unroll
     for (int r = 0; r < NRW; ++r) {
 #pragma unroll
@@ -253,14 +255,14 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
             const int p = c0 - 1 + s;   // plane receiving colour A; colour B goes to plane p-1
             const int iM2 = ss & 3, iM1 = (ss + 1) & 3, iP = (ss + 2) & 3, iP1 = (ss + 3) & 3;
             __syncthreads();            // ring slot of plane p-2 is free; a[p-1] is visible in its slot
-            if (tid == 0 && s - 1 + F_NB < total_rel) issue(s - 1 + F_NB);
-            mbar_wait(smem_u32(&mbar[(s + 2) % F_NB]), (uint32_t)(((s + 2) / F_NB) & 1));
-            const float4 *bufM1 = planes + (size_t)(s % F_NB) * plane_f4;
-            float4 *bufP = planes + (size_t)((s + 1) % F_NB) * plane_f4;
-            const float4 *bufP1 = planes + (size_t)((s + 2) % F_NB) * plane_f4;
-            const uint16_t *codP1 = cplanes + (size_t)((s + 2) % F_NB) * cslot;
-            const uint16_t *codP = cplanes + (size_t)((s + 1) % F_NB) * cslot;    // class kind reads ids in place
-            const uint16_t *codM1 = cplanes + (size_t)(s % F_NB) * cslot;
+            if (tid == 0 && s - 1 + NB < total_rel) issue(s - 1 + NB);
+            mbar_wait(smem_u32(&mbar[(s + 2) % NB]), (uint32_t)(((s + 2) / NB) & 1));
+            const float4 *bufM1 = planes + (size_t)(s % NB) * plane_f4;
+            float4 *bufP = planes + (size_t)((s + 1) % NB) * plane_f4;
+            const float4 *bufP1 = planes + (size_t)((s + 2) % NB) * plane_f4;
+            const uint16_t *codP1 = cplanes + (size_t)((s + 2) % NB) * cslot;
+            const uint16_t *codP = cplanes + (size_t)((s + 1) % NB) * cslot;    // class kind reads ids in place
+            const uint16_t *codM1 = cplanes + (size_t)(s % NB) * cslot;
             const bool doA = (p >= P.a_lo) && (p < P.a_hi);
             const bool keepA = (p >= c0) && (p < c1);   // a[p] is read by colour B of plane p next step
             const bool doB = (s >= 2);
@@ -291,7 +293,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                         const float4 &up = (r == NRW - 1) ? above : rg[r + 1][iP];
                         if (CLS)
                             row_update_class(((PA0 + ss + r) & 1) == 0, rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r],
-                                             *reinterpret_cast<const uint2 *>(codP + ic0 + r * LGc * CPG), tab, P.omega, umin);
+                                             *reinterpret_cast<const uint2 *>(codP + ic0 + r * LGc * CPG), tab, tabB, P.omega, umin);
                         else
                             row_update(((PA0 + ss + r) & 1) == 0, rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r],
                                        cr[r >> 1][iP] >> (16 * (r & 1)), s_div, P.omega, umin);
@@ -320,7 +322,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                         float4 out = rg[r][iM1];
                         if (CLS)
                             row_update_class(((PA0 + ss + r) & 1) == 0, out, rg[r][iP], rg[r][iM2], up, dn, zs[r],
-                                             *reinterpret_cast<const uint2 *>(codM1 + ic0 + r * LGc * CPG), tab, P.omega, umin);
+                                             *reinterpret_cast<const uint2 *>(codM1 + ic0 + r * LGc * CPG), tab, tabB, P.omega, umin);
                         else
                             row_update(((PA0 + ss + r) & 1) == 0, out, rg[r][iP], rg[r][iM2], up, dn, zs[r],
                                        cr[r >> 1][iM1] >> (16 * (r & 1)), s_div, P.omega, umin);
@@ -341,11 +343,11 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     if (umin < GUARD_T) atomicAdd(&g_inexact_events, 1ULL);
 }
 
-static size_t fused_smem_bytes(int LR, int LG, int LGc, int cpg)
+static size_t fused_smem_bytes(int LR, int LG, int LGc, int cpg, int nb)
 {
     const size_t slot = ((size_t)(LR * LG + 7) / 8) * 8 * 16;               // fp32 box, 128-byte multiple
     const size_t cslot = ((size_t)(LR * LGc * cpg * 2 + 127) / 128) * 128;  // uint16 box (codes / class ids)
-    return F_NB * (slot + cslot) + F_NB * 8 + 128;                    // + mbarriers, alignment slack (the division
+    return nb * (slot + cslot) + nb * 8 + 128;                    // + mbarriers, alignment slack (the division
                                                                       // table is 128 bytes of static shared memory)
 }
 
@@ -361,11 +363,18 @@ struct TileChoice {
 // multiple of 16 bytes wide; for the uint16 code box that means OG (the tile step) is a multiple of 8
 // groups and the code box is LG rounded up to 8.  A box is at most 256 elements wide (LG <= 64).  Pick
 // the shape that wastes the fewest threads while two CTAs still fit in one SM's shared memory.
+// Ring depth per kind.  The class kind carries 8 more bytes per float4 group in every slot and is bound by
+// the L1 gather of its weight rows, not by HBM latency: a shallower ring (one plane of prefetch) buys
+// ~1.6x larger tiles -> fewer halo re-loads and idle threads (measured: 6 -> 4 slots = +10 % at 384^3 / 512^3).
+constexpr int F_NB_CLS = 4;
+static int ring_depth(int cpg) { return cpg == 1 ? F_NB : F_NB_CLS; }
+
 static TileChoice choose_tile(const taub_geom &g, int cpg)
 {
+    const int nb = ring_depth(cpg);
     // shared-memory budget per CTA (two CTAs per SM).  The class kind reads its weight rows through L1,
-    // which shares the 228 KB with shared memory: leave it ~32 KB.
-    const size_t budget = (cpg == 1) ? 115000 : 98000;
+    // which shares the 256 KB with shared memory: leave it a little more.
+    const size_t budget = (cpg == 1) ? 115000 : 106000;
     const int ng = interior_groups(g.Nz);
     TileChoice best{};
     best.eff = -1.0;
@@ -375,10 +384,10 @@ static TileChoice choose_tile(const taub_geom &g, int cpg)
         // box one group wider (odd pitch) avoids that -- taken when it does not cost a column.
         const int LGt = OG + 2;
         int NCT = F_NT / LGt;   // columns the CTA's threads can cover
-        while (NCT >= 1 && fused_smem_bytes(F_NRW * NCT + 2, LGt, ((LGt + 7) / 8) * 8, cpg) > budget) --NCT;
+        while (NCT >= 1 && fused_smem_bytes(F_NRW * NCT + 2, LGt, ((LGt + 7) / 8) * 8, cpg, nb) > budget) --NCT;
         if (NCT < 1) continue;
         int LG = LGt;
-        if (fused_smem_bytes(F_NRW * NCT + 2, LGt + 1, ((LGt + 8) / 8) * 8, cpg) <= budget) LG = LGt + 1;
+        if (fused_smem_bytes(F_NRW * NCT + 2, LGt + 1, ((LGt + 8) / 8) * 8, cpg, nb) <= budget) LG = LGt + 1;
         const int LGc = ((LG + 7) / 8) * 8;
         const int NR = F_NRW * NCT, OR_ = NR - 2, LR = NR + 2;
         const int tj = ceil_div(g.Ny, OR_), tk = ceil_div(ng, OG);
@@ -547,6 +556,7 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     P.dst = p->field[p->cur ^ 1];
     P.codes = p->codes;
     P.table = p->lut;
+    P.n_classes = p->L;
     P.omega = p->omega;
     P.stop = p->stop;
     P.peer_lo = p->peer_lo[p->cur ^ 1];
@@ -570,7 +580,8 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     TAUB_REQUIRE(chunks <= 65535, "taub_fused_sweep2: too many plane chunks");
     P.slot_f4 = ((t.LR * t.LG + 7) / 8) * 8;
     P.cslot_h = ((t.LR * t.LGc * cpg * 2 + 127) / 128) * 64;
-    const size_t smem = fused_smem_bytes(t.LR, t.LG, t.LGc, cpg);
+    const int nb = ring_depth(cpg);
+    const size_t smem = fused_smem_bytes(t.LR, t.LG, t.LGc, cpg, nb);
     dim3 grid(t.tiles_j * t.tiles_k, chunks, g.bs);
     cudaStream_t s = (cudaStream_t)stream;
     CUtensorMap tmap, cmap;
@@ -580,20 +591,20 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     // Tile row offsets (multiples of the even OR_) and chunk starts (multiples of the even
     // chunk_len) do not change it, so it is one number for the whole grid.
     const int pa0 = (1 - G + g.i_offset + P.colourA + (i_lo - 1)) & 1;   // row lr = 1 is row 0 of a column
-#define TAUB_LAUNCH_FUSED(PA_, KIND_)                                                                             \
+#define TAUB_LAUNCH_FUSED(PA_, KIND_, NB_)                                                                        \
     do {                                                                                                          \
         static size_t smem_set[64] = {0};   /* per device: raise the opt-in limit only when it grows */         \
         if (smem > smem_set[dev_ord & 63]) {                                                                      \
-            TAUB_CUDA(cudaFuncSetAttribute(fused_sweep2_kernel<F_NRW, PA_, KIND_>,                                \
+            TAUB_CUDA(cudaFuncSetAttribute(fused_sweep2_kernel<F_NRW, PA_, KIND_, NB_>,                           \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
             smem_set[dev_ord & 63] = smem;                                                                        \
         }                                                                                                         \
-        fused_sweep2_kernel<F_NRW, PA_, KIND_><<<grid, F_NT, smem, s>>>(P, tmap, cmap);                           \
+        fused_sweep2_kernel<F_NRW, PA_, KIND_, NB_><<<grid, F_NT, smem, s>>>(P, tmap, cmap);                      \
     } while (0)
     if (p->kind == TAUB_MULTIPHASE_CLASS) {
-        if (pa0 == 0) TAUB_LAUNCH_FUSED(0, TAUB_MULTIPHASE_CLASS); else TAUB_LAUNCH_FUSED(1, TAUB_MULTIPHASE_CLASS);
+        if (pa0 == 0) TAUB_LAUNCH_FUSED(0, TAUB_MULTIPHASE_CLASS, F_NB_CLS); else TAUB_LAUNCH_FUSED(1, TAUB_MULTIPHASE_CLASS, F_NB_CLS);
     } else {
-        if (pa0 == 0) TAUB_LAUNCH_FUSED(0, TAUB_BINARY); else TAUB_LAUNCH_FUSED(1, TAUB_BINARY);
+        if (pa0 == 0) TAUB_LAUNCH_FUSED(0, TAUB_BINARY, F_NB); else TAUB_LAUNCH_FUSED(1, TAUB_BINARY, F_NB);
     }
 #undef TAUB_LAUNCH_FUSED
     TAUB_CUDA(cudaGetLastError());
