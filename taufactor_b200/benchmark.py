@@ -17,6 +17,7 @@ import time
 
 import torch
 
+from . import electrode as _electrode
 from . import solvers as _solvers
 from . import utils as _utils
 
@@ -26,6 +27,7 @@ DEFAULT_OUTFILE = "taufactor_benchmark_results.txt"
 SOLVER_REGISTRY = {name: getattr(_solvers, name)
                    for name in ("Solver", "PeriodicSolver", "AnisotropicSolver", "MultiPhaseSolver",
                                 "PeriodicMultiPhaseSolver")}
+SOLVER_REGISTRY.update({name: getattr(_electrode, name) for name in ("ElectrodeSolver", "PeriodicElectrodeSolver")})
 
 
 def _fcc_pores(N, features=None):

@@ -121,6 +121,8 @@ class SORSolver:
             self._call(self._lib.taub_plane_counts(g, img_dev.data_ptr(), 0, self.Nx, sel.data_ptr(),
                                                    counts.data_ptr(), None, self._stream()),
                        "taub_plane_counts")
+            self.vol_x = (counts.cpu().numpy().reshape(self.batch_size, self.Nx).astype(np.float32)
+                          / np.float32(self.Ny * self.Nz)).astype(np.float32)
             self._keep = extra_init(p, img_dev, vec)    # kind-specific tensors + init kernel
             ws = self._lib.taub_sums_ws_bytes(g)
             self._ws = torch.empty(max(ws, 16), dtype=torch.uint8, device=dev)
@@ -130,9 +132,7 @@ class SORSolver:
             self._prof_dev = torch.zeros(nf + self.batch_size * self.Nx, dtype=torch.float32, device=dev)
             self._prof_host = torch.zeros(self._prof_dev.numel(), dtype=torch.float32).pin_memory()
             self._flux_dev, self._mean_dev = self._prof_dev[:nf], self._prof_dev[nf:]
-            counts = counts.cpu().numpy().reshape(self.batch_size, self.Nx)
             del img_dev
-        self.vol_x = (counts.astype(np.float32) / np.float32(self.Ny * self.Nz)).astype(np.float32)
         # ref:62-67
         self.converged = False
         self.old_tau = 0
@@ -659,6 +659,19 @@ class MultiPhaseSolver(ThroughTransportSolver):
         return ()
 
 
+def fill_periodic_frame(planes, g):
+    """y/z ghost frame (width G, corners included) of storage planes [bs, n, rows, pitch] := periodic image
+    of the interior -- rows first, then columns over all rows.  The fused kernel applies colour A on the
+    first ghost ring too, so per-voxel side arrays (class ids) need their periodic images there."""
+    G, C0 = _lib.GHOST, _lib.COL0
+    for w in range(G):
+        planes[:, :, G - 1 - w] = planes[:, :, G + g.Ny - 1 - (w % g.Ny)]
+        planes[:, :, G + g.Ny + w] = planes[:, :, G + (w % g.Ny)]
+    for w in range(G):
+        planes[:, :, :, C0 - 1 - w] = planes[:, :, :, C0 + g.Nz - 1 - (w % g.Nz)]
+        planes[:, :, :, C0 + g.Nz + w] = planes[:, :, :, C0 + (w % g.Nz)]
+
+
 def validated_diffusivities(diffusivities):
     """Argument checks of ref:524-545 (MultiPhaseSolver.__init__)."""
     if diffusivities is None:
@@ -726,15 +739,7 @@ def build_class_table(lib, p, dense_D, periodic, dev, stream, i_lo, i_hi):
     cv[:, G + i_lo:G + i_hi, G:G + g.Ny, C0:C0 + g.Nz] = inv.view(g.bs, n_i, g.Ny, g.Nz).to(torch.int16)
     del inv
     if periodic:
-        # the fused kernel applies colour A on the first ghost ring too: ghost voxels carry the class
-        # of their periodic image (rows first, then columns over all rows -> corners included)
-        own_pl = cv[:, G + i_lo:G + i_hi]
-        for w in range(G):
-            own_pl[:, :, G - 1 - w] = own_pl[:, :, G + g.Ny - 1 - (w % g.Ny)]
-            own_pl[:, :, G + g.Ny + w] = own_pl[:, :, G + (w % g.Ny)]
-        for w in range(G):
-            own_pl[:, :, :, C0 - 1 - w] = own_pl[:, :, :, C0 + g.Nz - 1 - (w % g.Nz)]
-            own_pl[:, :, :, C0 + g.Nz + w] = own_pl[:, :, :, C0 + (w % g.Nz)]
+        fill_periodic_frame(cv[:, G + i_lo:G + i_hi], g)
     p.kind, p.codes, p.lut, p.L = _lib.MULTIPHASE_CLASS, classes.data_ptr(), table_dev.data_ptr(), int(len(table))
     return classes, table_dev, int(len(k))
 

@@ -172,9 +172,77 @@ def benchmark_goldens():
         json.dump(jsonable(out), fh, indent=1)
 
 
+# ----------------------------------------------------------------------------- electrode solvers
+from electrode_cases import electrode_cases  # noqa: E402
+
+
+def electrode_goldens():
+    from taufactor.electrode import ElectrodeSolver, PeriodicElectrodeSolver   # noqa: F401
+    import taufactor.electrode as el
+    out, arrays = {}, {}
+    for name, (cls, img, ckw, skw) in electrode_cases().items():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            S = getattr(el, cls)(img, device="cpu", **ckw)
+            small = S.field.numel() <= 20000
+            if small:
+                arrays[f"{name}@field0"] = S.field.numpy().copy()
+                arrays[f"{name}@factor"] = S.factor.numpy().copy()
+            trace = []
+            orig = S.compute_metrics
+
+            def logged():
+                t, r = orig()
+                trace.append([int(S.iter), float(np.max(r)), [float(x) for x in t]])
+                return t, r
+
+            S.compute_metrics = logged
+            S.solve(verbose=False, **skw)
+        out[name] = dict(solver=cls, iter=int(S.iter), converged=bool(S.converged),
+                         tau=[float(x) for x in np.asarray(S.tau)], k_0=[float(x) for x in S.k_0], trace=trace)
+        for attr in ("a_x", "c_x", "k_x", "tau_x", "vol_x"):
+            arrays[f"{name}@{attr}"] = np.asarray(getattr(S, attr))
+        arrays[f"{name}@Z_sim"] = np.asarray(S.Z_sim)
+        if small:
+            arrays[f"{name}@field"] = S.field.numpy().copy()
+        print("electrode", name, cls, S.iter, S.converged, S.tau, flush=True)
+    with open(os.path.join(HERE, "electrode.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+    np.savez_compressed(os.path.join(HERE, "electrode.npz"), **arrays)
+
+
+def api_goldens():
+    """The Python surface the drop-in must keep: constructor / solve() signatures and the public
+    attributes a solved object carries (names only)."""
+    import inspect
+
+    def sig(f):
+        return [[n, None if p.default is inspect._empty else repr(p.default)]
+                for n, p in inspect.signature(f).parameters.items() if n != "self"]
+
+    api = {}
+    for cls in ("Solver", "PeriodicSolver", "AnisotropicSolver", "MultiPhaseSolver", "PeriodicMultiPhaseSolver",
+                "ElectrodeSolver", "PeriodicElectrodeSolver"):
+        C = getattr(tau, cls)
+        api[cls] = {"init": sig(C.__init__), "solve": sig(C.solve), "bases": [b.__name__ for b in C.__mro__[1:-1]]}
+    S = run_case("rand40")[1]
+    api["solved_attributes"] = sorted(a for a in vars(S) if not a.startswith("_"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        E = tau.ElectrodeSolver(cases.random_img((24, 20, 16), 0.7, 11), device="cpu")
+        E.solve(verbose=False)
+    api["solved_attributes_electrode"] = sorted(a for a in vars(E) if not a.startswith("_"))
+    with open(os.path.join(HERE, "api.json"), "w") as fh:
+        json.dump(api, fh, indent=1)
+
+
 def main():
+    if "--api-only" in sys.argv:
+        return api_goldens()
     if "--benchmark-only" in sys.argv:
         return benchmark_goldens()
+    if "--electrode-only" in sys.argv:
+        return electrode_goldens()
     solve, fields = {}, {}
     for name in cases.CASES:
         out, S = run_case(name)
@@ -191,25 +259,13 @@ def main():
                 S2.solve(iter_limit=k, verbose=False)
                 assert S2.iter == k or S2.converged
                 fields[f"{name}@{k}"] = S2.field.numpy().copy()
-    # the Python surface the drop-in must keep: constructor / solve() signatures and the public
-    # attributes a solved object carries (names only)
-    import inspect
-    api = {}
-    for cls in ("Solver", "PeriodicSolver", "AnisotropicSolver", "MultiPhaseSolver", "PeriodicMultiPhaseSolver"):
-        C = getattr(tau, cls)
-        def sig(f):
-            return [[n, None if p.default is inspect._empty else repr(p.default)]
-                    for n, p in inspect.signature(f).parameters.items() if n != "self"]
-        api[cls] = {"init": sig(C.__init__), "solve": sig(C.solve), "bases": [b.__name__ for b in C.__mro__[1:-1]]}
-    S, _ = run_case("rand40")[1], None
-    api["solved_attributes"] = sorted(a for a in vars(S) if not a.startswith("_"))
-    with open(os.path.join(HERE, "api.json"), "w") as fh:
-        json.dump(api, fh, indent=1)
+    api_goldens()
     with open(os.path.join(HERE, "solve.json"), "w") as fh:
         json.dump(solve, fh, indent=1)
     np.savez_compressed(os.path.join(HERE, "fields.npz"), **fields)
     print("wrote", len(solve), "cases,", len(fields), "arrays")
     benchmark_goldens()
+    electrode_goldens()
 
 
 if __name__ == "__main__":

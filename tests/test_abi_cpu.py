@@ -113,7 +113,7 @@ def test_python_surface_matches_reference_signatures():
     import taufactor_b200 as tau
     api = json.load(open(os.path.join(ROOT, "tests", "golden", "api.json")))
     for cls, ref in api.items():
-        if cls == "solved_attributes":
+        if cls.startswith("solved_attributes"):
             continue
         C = getattr(tau, cls)
         for meth in ("init", "solve"):

@@ -79,10 +79,10 @@ def test_resolve_solver():
     assert bm.resolve_solver(None) is tau.PeriodicSolver
     assert bm.resolve_solver("MultiPhaseSolver") is tau.MultiPhaseSolver
     assert bm.resolve_solver(tau.Solver) is tau.Solver
-    assert sorted(bm.SOLVER_REGISTRY) == ["AnisotropicSolver", "MultiPhaseSolver", "PeriodicMultiPhaseSolver",
-                                          "PeriodicSolver", "Solver"]
+    assert sorted(bm.SOLVER_REGISTRY) == ["AnisotropicSolver", "ElectrodeSolver", "MultiPhaseSolver",
+                                          "PeriodicElectrodeSolver", "PeriodicMultiPhaseSolver", "PeriodicSolver", "Solver"]
     with pytest.raises(ValueError, match="Unknown solver"):
-        bm.resolve_solver("ElectrodeSolver")
+        bm.resolve_solver("ImpedanceSolver")
     with pytest.raises(TypeError):
         bm.resolve_solver(3)
 
