@@ -358,10 +358,21 @@ def test_pipelined_and_synchronous_solves_agree(tau, name):
     assert getattr(A, "rule_mismatches", 0) == 0
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _inexact_events_at_module_start():
+    """The counter is process-wide (other test files -- the electrode solvers -- legitimately raise it)."""
+    from taufactor_b200 import _lib
+    _EVENTS0.append(int(_lib.load().taub_inexact_events()))
+    yield
+
+
+_EVENTS0 = []
+
+
 def test_zz_fused_fast_division_was_exact_everywhere(tau):
-    """Runs last: no thread of the fused kernel ever divided a sub-2^-100 sum on the fast path, so
-    every fused trajectory above was bit-identical to IEEE division (taub_inexact_events)."""
+    """Runs last in this file: no thread of the fused kernel divided a sub-2^-100 sum on the fast path in any
+    through-transport test above, so every fused trajectory was bit-identical to IEEE division."""
     S, _ = make(tau, "rand40")
     S.solve(iter_limit=100, verbose=False)
     assert S.sweep_kernel_name() == "fused_sweep2_kernel"
-    assert S.inexact_events == 0
+    assert S.inexact_events == _EVENTS0[0]
