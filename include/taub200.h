@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TAUB_ABI_VERSION 6
+#define TAUB_ABI_VERSION 7
 #define TAUB_GHOST 2            /* ghost width in x (planes), y (rows) and z (columns) */
 #define TAUB_COL0 4             /* column of interior voxel k = 0 */
 #define TAUB_MAX_LABELS 64      /* dense phase indices 0..L-1, L <= 64; index L = "outside" */
@@ -187,6 +187,17 @@ int taub_check_async(const taub_problem *p, void *workspace, float *flux_mean, f
  *   flux_mean[bs][Nx_global - 1] device fp32; stop: this rank's device flag (non-NULL). */
 int taub_stop_rule_async(int bs, int Nx_global, const float *flux_mean, const double *D_mean, float *old_tau,
                          float conv_crit, float *record, int32_t *stop, void *stream);
+
+
+/* -- percolation check (replaces the host labelling of taufactor.py:318-327 ->
+ *    metrics/connectivity.py:138-213, extract_through_feature(mask, 1, 'x')) ------------------- */
+/* One round of a flood fill over the dense byte arrays mask / reach [bs][Nx][Ny][Nz] (device; mask != 0 =
+ * conductive): forward + backward marches along x, y and z that carry reach through 6-connected mask
+ * voxels (non-periodic).  The caller seeds reach with the mask of plane 0, repeats rounds until *changed
+ * (device int, written by the call) stays 0, and then reads plane Nx-1 of reach: no reached voxel there
+ * = no percolating path. */
+int taub_flood_round(const uint8_t *mask, uint8_t *reach, int bs, int Nx, int Ny, int Nz, int32_t *changed,
+                     void *stream);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,7 @@ SIGNATURES = {
     "taub_plane_means": (c_int, [ctypes.POINTER(Problem), c_vp, c_vp, c_vp, c_vp]),
     "taub_check_async": (c_int, [ctypes.POINTER(Problem), c_vp, c_vp, c_vp, c_vp, c_vp, c_float, c_vp, c_vp]),
     "taub_stop_rule_async": (c_int, [c_int, c_int, c_vp, c_vp, c_vp, c_float, c_vp, c_vp, c_vp]),
+    "taub_flood_round": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
 }
 
 _lib = None
@@ -76,7 +77,7 @@ def load():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.taub_abi_version() != 6:
+        if lib.taub_abi_version() != 7:
             raise ImportError("libtaub200.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib

@@ -56,18 +56,6 @@ def _as_uint8_labels(img4):
     return u8
 
 
-def _through_fraction_is_zero(mask3):
-    """True when no 6-connected cluster of ``mask3`` touches both x faces -- the condition the
-    reference derives from metrics.extract_through_feature(mask, 1, 'x') (ref:320-322)."""
-    from scipy.ndimage import label
-    if not mask3.any():
-        return True
-    lab, _ = label(mask3)
-    first = np.unique(lab[0])
-    last = np.unique(lab[-1])
-    return len(np.intersect1d(first[first != 0], last[last != 0])) == 0
-
-
 class SORSolver:
     """Shared machinery: device state, the iteration loop and the stop rule (ref:15-269)."""
 
@@ -251,8 +239,32 @@ class SORSolver:
         remembered; the reference re-labels the whole volume at every check of a zero-flux sample."""
         cache = self.__dict__.setdefault("_percolation_cache", {})
         if b not in cache:
-            cache[b] = _through_fraction_is_zero(self._host_conductive_mask(b))
+            cache[b] = self._device_no_percolating_path(self._host_conductive_mask(b))
         return cache[b]
+
+    MAX_FLOOD_ROUNDS = 100000
+
+    def _device_no_percolating_path(self, mask3):
+        """Flood fill from the first x plane through the 6-connected conductive voxels on the device
+        (taub_flood_round); True when the last plane is not reached -- the condition the reference derives
+        from a SciPy labelling of the whole volume on the host (ref:320-322)."""
+        dev = self.device
+        with torch.cuda.device(dev):
+            m = torch.from_numpy(np.ascontiguousarray(mask3, dtype=np.uint8)).to(dev)
+            if not bool(m[0].any()) or not bool(m[-1].any()):
+                return True
+            reach = torch.zeros_like(m)
+            reach[0] = m[0]
+            flag = torch.zeros(1, dtype=torch.int32, device=dev)
+            Nx, Ny, Nz = m.shape
+            for _ in range(self.MAX_FLOOD_ROUNDS):
+                self._call(self._lib.taub_flood_round(m.data_ptr(), reach.data_ptr(), 1, Nx, Ny, Nz, flag.data_ptr(),
+                                                      self._stream()), "taub_flood_round")
+                if bool(reach[-1].any()):
+                    return False                      # spanning cluster found: no need to finish the fill
+                if int(flag.item()) == 0:
+                    return True
+        raise RuntimeError("percolation flood fill did not converge")
 
     def _host_conductive_mask(self, b):
         """Boolean conductive mask of image b on the host (only the zero-flux branch needs it)."""
