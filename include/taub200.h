@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TAUB_ABI_VERSION 7
+#define TAUB_ABI_VERSION 8
 #define TAUB_GHOST 2            /* ghost width in x (planes), y (rows) and z (columns) */
 #define TAUB_COL0 4             /* column of interior voxel k = 0 */
 #define TAUB_MAX_LABELS 64      /* dense phase indices 0..L-1, L <= 64; index L = "outside" */
@@ -45,7 +45,9 @@ typedef enum taub_status {
 typedef enum taub_kind {
     TAUB_BINARY = 0,       /* Solver, PeriodicSolver */
     TAUB_MULTIPHASE = 1,   /* MultiPhaseSolver, PeriodicMultiPhaseSolver */
-    TAUB_ANISOTROPIC = 2,  /* AnisotropicSolver: binary codes, lut = device float[2] {Ky, Kz} (taufactor.py:455-456) */
+    TAUB_ANISOTROPIC = 2,  /* AnisotropicSolver (taufactor.py:422-478) through prefactor classes: codes = one uint16
+                            * class id (< 64) per storage voxel, lut = device float[130]: {b, RN(1/b)} per class
+                            * (b = weighted neighbour count :462-467; b = 1/b = 0 where it is infinite), then Ky, Kz */
     TAUB_MULTIPHASE_CLASS = 3  /* multi-phase through a stencil-class table: codes = one uint16 class id per
                                 * storage voxel, lut = device float[2][L][4]: half rows {w_x+, w_x-, w_y+, w_y-}
                                 * of all L classes, then half rows {w_z+, w_z-, b, RN(1/b)} with b = prefactor

@@ -218,43 +218,35 @@ __device__ __forceinline__ float sor_class(float c, float xp, float xm, float yp
 }
 
 // ------------------------------------------------------------------------------------------
-// AnisotropicSolver (taufactor.py:422-478).  The neighbour codes double as the conductive mask
-// (code != 0; 9 = conductive voxel without conductive neighbour).  Prefactor, in the reference's fp32
-// accumulation order (:462-467): ((((x- + x+) + Ky*y-) + Ky*y+) + Kz*z-) + Kz*z+ with the Dirichlet
-// planes counting 2; inf where the voxel is non-conductive or the sum is 0.
+// AnisotropicSolver (taufactor.py:422-478) through prefactor classes.  The prefactor, in the reference's
+// fp32 accumulation order (:462-467), is ((((x- + x+) + Ky*y-) + Ky*y+) + Kz*z-) + Kz*z+ with the Dirichlet
+// planes counting 2 -- it depends only on how many conductive neighbours a voxel has per axis, so at most
+// 5 x 3 x 3 values occur.  codes = one uint16 class id per voxel (< TAUB_ANISO_CLASSES); lut = float2
+// {b, RN(1/b)} per class (b = 1/b = 0: prefactor inf), then Ky, Kz.
+// s = ((x+ + x-) + Ky*(y+ + y-)) + Kz*(z+ + z-)  (:475-477).
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float aniso_factor(bool own, float wxm, float wxp, bool mym, bool myp, bool mzm, bool mzp,
-                                              float Ky, float Kz)
-{
-    float nn = __fadd_rn(wxm, wxp);
-    nn = __fadd_rn(nn, mym ? Ky : 0.0f);
-    nn = __fadd_rn(nn, myp ? Ky : 0.0f);
-    nn = __fadd_rn(nn, mzm ? Kz : 0.0f);
-    nn = __fadd_rn(nn, mzp ? Kz : 0.0f);
-    return (own && nn != 0.0f) ? nn : __int_as_float(0x7f800000);
-}
+constexpr int ANISO_CLASSES = 64;
 
-// prefactor of voxel q (0..3) of the float4 group at code index ci; ig = global x plane of the voxel
-__device__ __forceinline__ float aniso_factor_at(const uint16_t *__restrict__ codes, int64_t ci, int q, int64_t cps,
-                                                 int cpitch, int ig, int Nx_global, float Ky, float Kz)
-{
-    const unsigned c = codes[ci];
-    const auto nib = [](unsigned w, int k) { return ((w >> (4 * k)) & 15u) != 0; };
-    const float wxm = (ig == 0) ? 2.0f : (nib(codes[ci - cps], q) ? 1.0f : 0.0f);
-    const float wxp = (ig == Nx_global - 1) ? 2.0f : (nib(codes[ci + cps], q) ? 1.0f : 0.0f);
-    const bool mzm = (q > 0) ? nib(c, q - 1) : nib(codes[ci - 1], 3);
-    const bool mzp = (q < 3) ? nib(c, q + 1) : nib(codes[ci + 1], 0);
-    return aniso_factor(nib(c, q), wxm, wxp, nib(codes[ci - cpitch], q), nib(codes[ci + cpitch], q), mzm, mzp, Ky, Kz);
-}
-
-// s = ((x+ + x-) + Ky*(y+ + y-)) + Kz*(z+ + z-)  (:475-477), IEEE division by the prefactor.
-__device__ __forceinline__ float sor_aniso(float c, float xp, float xm, float yp, float ym, float zp, float zm,
-                                           float fac, float Ky, float Kz, float omega)
+__device__ __forceinline__ float aniso_sum(float xp, float xm, float yp, float ym, float zp, float zm, float Ky, float Kz)
 {
     float s = __fadd_rn(xp, xm);
     s = __fadd_rn(s, __fmul_rn(Ky, __fadd_rn(yp, ym)));
-    s = __fadd_rn(s, __fmul_rn(Kz, __fadd_rn(zp, zm)));
-    return relax(c, __fdiv_rn(s, fac), omega);
+    return __fadd_rn(s, __fmul_rn(Kz, __fadd_rn(zp, zm)));
+}
+
+// generic kernel: IEEE division by the prefactor
+__device__ __forceinline__ float sor_aniso(float c, float xp, float xm, float yp, float ym, float zp, float zm,
+                                           float2 br, float Ky, float Kz, float omega)
+{
+    const float fac = br.x != 0.0f ? br.x : __int_as_float(0x7f800000);
+    return relax(c, __fdiv_rn(aniso_sum(xp, xm, yp, ym, zp, zm, Ky, Kz), fac), omega);
+}
+
+// fused kernel: the exactly rounded reciprocal + one FMA correction (same fast path as div_fast)
+__device__ __forceinline__ float sor_aniso_fast(float c, float xp, float xm, float yp, float ym, float zp, float zm,
+                                                float2 br, float Ky, float Kz, float omega, unsigned &umin)
+{
+    return relax(c, div_fast(aniso_sum(xp, xm, yp, ym, zp, zm, Ky, Kz), br, umin), omega);
 }
 
 __device__ __forceinline__ int wrap(int a, int n)

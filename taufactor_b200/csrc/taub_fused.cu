@@ -129,6 +129,24 @@ __device__ __forceinline__ void row_update_class(const bool is_xz, float4 &c, co
     }
 }
 
+// Anisotropic kind: cls2 as above, the (b, 1/b) pair of a class from the static shared table.
+__device__ __forceinline__ void row_update_aniso(const bool is_xz, float4 &c, const float4 &xp, const float4 &xm,
+                                                 const float4 &up, const float4 &dn, float zs, uint2 cls2,
+                                                 const float2 *s_div, float Ky, float Kz, float omega, unsigned &umin)
+{
+    if (is_xz) {
+        const float n0 = sor_aniso_fast(c.x, xp.x, xm.x, up.x, dn.x, c.y, zs, s_div[cls2.x & 0xffffu], Ky, Kz, omega, umin);
+        const float n1 = sor_aniso_fast(c.z, xp.z, xm.z, up.z, dn.z, c.w, c.y, s_div[cls2.y & 0xffffu], Ky, Kz, omega, umin);
+        c.x = n0;
+        c.z = n1;
+    } else {
+        const float n0 = sor_aniso_fast(c.y, xp.y, xm.y, up.y, dn.y, c.z, c.x, s_div[cls2.x >> 16], Ky, Kz, omega, umin);
+        const float n1 = sor_aniso_fast(c.w, xp.w, xm.w, up.w, dn.w, zs, c.z, s_div[cls2.y >> 16], Ky, Kz, omega, umin);
+        c.y = n0;
+        c.w = n1;
+    }
+}
+
 // The z neighbour from the adjacent lane's registers (one crossbar pass instead of a 4-way conflicted
 // shared load); the two lanes at the warp ends read shared memory.  All 32 lanes must call this.
 __device__ __forceinline__ float z_neighbour(const bool is_xz, const float4 &v, const float4 *buf, int i4, int lane,
@@ -160,7 +178,8 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     // TMA destinations need 128-byte alignment: align the base, slots are multiples of 128 B
     unsigned char *smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
     const taub_geom &g = P.g;
-    constexpr bool CLS = (KIND == TAUB_MULTIPHASE_CLASS);
+    constexpr bool ANI = (KIND == TAUB_ANISOTROPIC);
+    constexpr bool CLS = (KIND == TAUB_MULTIPHASE_CLASS) || ANI;   // one uint16 id per voxel travels with the field
     constexpr int CPG = CLS ? 4 : 1;             // uint16 side-array elements per float4 group
     const int LR = P.LR, LG = P.LG, LGc = P.LGc;
     const float4 *tab = reinterpret_cast<const float4 *>(P.table);   // class kind: half rows A, then half rows B
@@ -170,7 +189,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     float4 *planes = reinterpret_cast<float4 *>(smem_raw);
     uint16_t *cplanes = reinterpret_cast<uint16_t *>(smem_raw + (size_t)NB * plane_f4 * 16);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(cplanes + (size_t)NB * cslot);
-    __shared__ float2 s_div[16];   // static: constant address, no address arithmetic per lookup
+    __shared__ float2 s_div[ANISO_CLASSES];   // static: constant address, no address arithmetic per lookup
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int tk = blockIdx.x % P.tiles_k, tj = blockIdx.x / P.tiles_k;
@@ -182,7 +201,9 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     const int total_rel = c1 - c0 + 4;           // planes c0-2 .. c1+1
     const int64_t ps = g.plane_stride;
 
-    if (tid < 16) s_div[tid] = div_entry(tid);
+    if (tid < ANISO_CLASSES)      // binary: (n, 1/n) of the neighbour count; anisotropic: (b, 1/b) of the class
+        s_div[tid] = ANI ? reinterpret_cast<const float2 *>(P.table)[tid] : div_entry(tid);
+    const float Ky = ANI ? P.table[2 * ANISO_CLASSES] : 0.0f, Kz = ANI ? P.table[2 * ANISO_CLASSES + 1] : 0.0f;
     if (tid == 0) {
         for (int n = 0; n < NB; ++n) mbar_init(smem_u32(&mbar[n]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -291,7 +312,10 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                         // its neighbours leave unchanged in this step
                         const float4 &dn = (r == 0) ? below : rg[r - 1][iP];
                         const float4 &up = (r == NRW - 1) ? above : rg[r + 1][iP];
-                        if (CLS)
+                        if (ANI)
+                            row_update_aniso(((PA0 + ss + r) & 1) == 0, rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r],
+                                             *reinterpret_cast<const uint2 *>(codP + ic0 + r * LGc * CPG), s_div, Ky, Kz, P.omega, umin);
+                        else if (CLS)
                             row_update_class(((PA0 + ss + r) & 1) == 0, rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r],
                                              *reinterpret_cast<const uint2 *>(codP + ic0 + r * LGc * CPG), tab, tabB, P.omega, umin);
                         else
@@ -320,7 +344,10 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                         const float4 &dn = (r == 0) ? below : rg[r - 1][iM1];
                         const float4 &up = (r == NRW - 1) ? above : rg[r + 1][iM1];
                         float4 out = rg[r][iM1];
-                        if (CLS)
+                        if (ANI)
+                            row_update_aniso(((PA0 + ss + r) & 1) == 0, out, rg[r][iP], rg[r][iM2], up, dn, zs[r],
+                                             *reinterpret_cast<const uint2 *>(codM1 + ic0 + r * LGc * CPG), s_div, Ky, Kz, P.omega, umin);
+                        else if (CLS)
                             row_update_class(((PA0 + ss + r) & 1) == 0, out, rg[r][iP], rg[r][iM2], up, dn, zs[r],
                                              *reinterpret_cast<const uint2 *>(codM1 + ic0 + r * LGc * CPG), tab, tabB, P.omega, umin);
                         else
@@ -529,15 +556,16 @@ unsigned long long taub_inexact_events(void)
 
 int taub_can_fuse(const taub_problem *p)
 {
-    if (!p || (p->kind != TAUB_BINARY && p->kind != TAUB_MULTIPHASE_CLASS) || !p->codes || !p->field[0] || !p->field[1])
+    if (!p || (p->kind != TAUB_BINARY && p->kind != TAUB_MULTIPHASE_CLASS && p->kind != TAUB_ANISOTROPIC) || !p->codes ||
+        !p->field[0] || !p->field[1])
         return 0;
-    if (p->kind == TAUB_MULTIPHASE_CLASS && !p->lut) return 0;
+    if (p->kind != TAUB_BINARY && !p->lut) return 0;
     const taub_geom &g = p->g;
     // periodic wrap with odd Ny/Nz couples two voxels of the SAME colour (reference reads a ghost
     // snapshot); the in-place shared-memory colour update cannot express that -> generic path.
     if (g.periodic && ((g.Ny & 1) || (g.Nz & 1))) return 0;
     if (g.bs > 65535) return 0;
-    return choose_tile(g, p->kind == TAUB_MULTIPHASE_CLASS ? 4 : 1).eff > 0.0 ? 1 : 0;
+    return choose_tile(g, (p->kind == TAUB_MULTIPHASE_CLASS || p->kind == TAUB_ANISOTROPIC) ? 4 : 1).eff > 0.0 ? 1 : 0;
 }
 
 int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, void *stream)
@@ -548,7 +576,7 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     }
     const taub_geom &g = p->g;
     TAUB_REQUIRE(i_lo >= 0 && i_hi <= g.Nx && i_lo < i_hi, "taub_fused_sweep2: planes [%d, %d) outside the slab", i_lo, i_hi);
-    const int cpg = (p->kind == TAUB_MULTIPHASE_CLASS) ? 4 : 1;
+    const int cpg = (p->kind == TAUB_MULTIPHASE_CLASS || p->kind == TAUB_ANISOTROPIC) ? 4 : 1;
     const TileChoice t = choose_tile(g, cpg);
     FusedParams P;
     P.g = g;
@@ -603,6 +631,8 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     } while (0)
     if (p->kind == TAUB_MULTIPHASE_CLASS) {
         if (pa0 == 0) TAUB_LAUNCH_FUSED(0, TAUB_MULTIPHASE_CLASS, F_NB_CLS); else TAUB_LAUNCH_FUSED(1, TAUB_MULTIPHASE_CLASS, F_NB_CLS);
+    } else if (p->kind == TAUB_ANISOTROPIC) {
+        if (pa0 == 0) TAUB_LAUNCH_FUSED(0, TAUB_ANISOTROPIC, F_NB_CLS); else TAUB_LAUNCH_FUSED(1, TAUB_ANISOTROPIC, F_NB_CLS);
     } else {
         if (pa0 == 0) TAUB_LAUNCH_FUSED(0, TAUB_BINARY, F_NB); else TAUB_LAUNCH_FUSED(1, TAUB_BINARY, F_NB);
     }

@@ -247,7 +247,7 @@ int taub_init_binary(const taub_problem *p, const uint8_t *img, int img_i0, int 
                      const float *vec, void *stream)
 {
     TAUB_REQUIRE(p && img && vec, "taub_init_binary: null pointer");
-    TAUB_REQUIRE((p->kind == TAUB_BINARY || p->kind == TAUB_ANISOTROPIC) && p->field[0] && p->field[1] && p->codes,
+    TAUB_REQUIRE(p->kind == TAUB_BINARY && p->field[0] && p->field[1] && p->codes,
                  "taub_init_binary: problem is not a bound binary problem");
     const taub_geom &g = p->g;
     if (int rc = check_img_cover(g, img_i0, img_n, G + 1)) return rc;

@@ -73,13 +73,11 @@ plane_sums_kernel(taub_geom g, const float *__restrict__ f, const uint16_t *__re
                         // D_x face conductance towards plane i+1 = first entry of the voxel's class row
                         v = __fmul_rn(__ldg(lut + 4 * (int)codes[o + q]), v);
                     } else if (KIND == TAUB_ANISOTROPIC) {
-                        // same test on the weighted prefactor, which may legitimately exceed 8
-                        const int ig = il + g.i_offset;
-                        const float fa = aniso_factor_at(codes, o >> 2, q, g.plane_stride >> 2, g.pitch >> 2, ig,
-                                                         g.Nx_global, lut[0], lut[1]);
-                        const float fn = aniso_factor_at(codes, (o + g.plane_stride) >> 2, q, g.plane_stride >> 2,
-                                                         g.pitch >> 2, ig + 1, g.Nx_global, lut[0], lut[1]);
-                        v = (fa > 8.0f || fn > 8.0f) ? 0.0f : v;
+                        // the reference's factor > 8 test (:417-418) on the weighted prefactors of both voxels
+                        // (b = 0 encodes inf); the prefactor may legitimately exceed 8 here
+                        const float fa = __ldg(lut + 2 * (int)codes[o + q]);
+                        const float fn = __ldg(lut + 2 * (int)codes[o + g.plane_stride + q]);
+                        v = (fa == 0.0f || fa > 8.0f || fn == 0.0f || fn > 8.0f) ? 0.0f : v;
                     } else {
                         v = __fmul_rn(s_lut[((la >> (8 * q)) & 255u) * (L + 1) + ((ln >> (8 * q)) & 255u)], v);
                     }

@@ -135,21 +135,18 @@ half_sweep_kernel(taub_geom g, const float *__restrict__ src, float *__restrict_
             }
 #undef TAUB_CLASS_Q
         } else if (KIND == TAUB_ANISOTROPIC) {
-            const float Ky = lut[0], Kz = lut[1];
-            const int64_t ci = o >> 2, cps = ps >> 2;
-            const int cpitch = pitch >> 2;
+            // codes: one uint16 prefactor-class id per voxel; lut = {b, 1/b} per class, then Ky, Kz
+            const float2 *tab = reinterpret_cast<const float2 *>(lut);
+            const float Ky = lut[2 * ANISO_CLASSES], Kz = lut[2 * ANISO_CLASSES + 1];
+            const uint2 cw = *reinterpret_cast<const uint2 *>(codes + o);
             if (par0 == 0) {
-                const float f0 = aniso_factor_at(codes, ci, 0, cps, cpitch, ig, g.Nx_global, Ky, Kz);
-                const float f2 = aniso_factor_at(codes, ci, 2, cps, cpitch, ig, g.Nx_global, Ky, Kz);
                 const float cy = c4.y;
-                c4.x = sor_aniso(c4.x, xp4.x, xm4.x, yp4.x, ym4.x, cy, src[o - 1], f0, Ky, Kz, omega);
-                c4.z = sor_aniso(c4.z, xp4.z, xm4.z, yp4.z, ym4.z, c4.w, cy, f2, Ky, Kz, omega);
+                c4.x = sor_aniso(c4.x, xp4.x, xm4.x, yp4.x, ym4.x, cy, src[o - 1], __ldg(tab + (cw.x & 0xffffu)), Ky, Kz, omega);
+                c4.z = sor_aniso(c4.z, xp4.z, xm4.z, yp4.z, ym4.z, c4.w, cy, __ldg(tab + (cw.y & 0xffffu)), Ky, Kz, omega);
             } else {
-                const float f1 = aniso_factor_at(codes, ci, 1, cps, cpitch, ig, g.Nx_global, Ky, Kz);
-                const float f3 = aniso_factor_at(codes, ci, 3, cps, cpitch, ig, g.Nx_global, Ky, Kz);
                 const float cz = c4.z;
-                c4.y = sor_aniso(c4.y, xp4.y, xm4.y, yp4.y, ym4.y, cz, c4.x, f1, Ky, Kz, omega);
-                c4.w = sor_aniso(c4.w, xp4.w, xm4.w, yp4.w, ym4.w, src[o + 4], cz, f3, Ky, Kz, omega);
+                c4.y = sor_aniso(c4.y, xp4.y, xm4.y, yp4.y, ym4.y, cz, c4.x, __ldg(tab + (cw.x >> 16)), Ky, Kz, omega);
+                c4.w = sor_aniso(c4.w, xp4.w, xm4.w, yp4.w, ym4.w, src[o + 4], cz, __ldg(tab + (cw.y >> 16)), Ky, Kz, omega);
             }
         } else {
             const uint32_t lc = *reinterpret_cast<const uint32_t *>(labels + o);
@@ -239,7 +236,7 @@ int taub_half_sweep(const taub_problem *p, int64_t iter, int i_lo, int i_hi, voi
         half_sweep_kernel<TAUB_MULTIPHASE_CLASS><<<grid, block, 0, s>>>(g, src, dst, p->codes, nullptr, p->lut, p->L,
                                                                         p->omega, colour, i_lo, n_planes, p->stop);
     } else if (p->kind == TAUB_ANISOTROPIC) {
-        TAUB_REQUIRE(p->codes && p->lut, "taub_half_sweep: anisotropic problem without codes / weights");
+        TAUB_REQUIRE(p->codes && p->lut, "taub_half_sweep: anisotropic problem without class ids / table");
         TAUB_REQUIRE(!g.periodic, "taub_half_sweep: the anisotropic solver has no periodic variant");
         half_sweep_kernel<TAUB_ANISOTROPIC><<<grid, block, 0, s>>>(g, src, dst, p->codes, nullptr, p->lut, 0,
                                                                    p->omega, colour, i_lo, n_planes, p->stop);

@@ -19,7 +19,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from .solvers import SORSolver, _as_uint8_labels, _expand_to_4d, fill_periodic_frame
+from .solvers import (SORSolver, _as_uint8_labels, _expand_to_4d, fill_periodic_frame, neighbour_count_axis,
+                      shift_zero)
 
 __all__ = ["ElectrodeSolver", "PeriodicElectrodeSolver", "compute_impedance", "compute_impedance_batched"]
 
@@ -98,30 +99,14 @@ class ElectrodeSolver(SORSolver):
         self.c_x = 0
 
     # ------------------------------------------------------------------ state build (device tensor ops)
-    @staticmethod
-    def _shift(a, dim, step):
-        """a moved by ``step`` along ``dim`` with zeros entering (the reference's zero padding)."""
-        out = torch.zeros_like(a)
-        n = a.shape[dim]
-        if abs(step) < n:
-            src = [slice(None)] * a.dim()
-            dst = [slice(None)] * a.dim()
-            src[dim] = slice(0, n - step) if step > 0 else slice(-step, n)
-            dst[dim] = slice(step, n) if step > 0 else slice(0, n + step)
-            out[tuple(dst)] = a[tuple(src)]
-        return out
-
     def _neighbour_count(self, a, left_ghost):
         """Number of set 6-neighbours of every voxel of ``a`` (int8 0/1, [bs,Nx,Ny,Nz]); the left x ghost
         plane counts ``left_ghost``, the right one 0; y/z ghosts 0, or the periodic image
         (ref electrode.py:48-64 / :136-150 with taufactor.py:228-253)."""
-        n = self._shift(a, 1, 1) + self._shift(a, 1, -1)
+        n = neighbour_count_axis(a, 1, False)
         n[:, 0] += left_ghost
         for dim in (2, 3):
-            if self._periodic:
-                n += torch.roll(a, 1, dim) + torch.roll(a, -1, dim)
-            else:
-                n += self._shift(a, dim, 1) + self._shift(a, dim, -1)
+            n += neighbour_count_axis(a, dim, self._periodic)
         return n
 
     def _init_electrode(self, p, img_dev, vec_unused):
@@ -159,7 +144,7 @@ class ElectrodeSolver(SORSolver):
         table = np.concatenate(rows + [np.zeros((1, 8), np.float32)])         # last row: inert (non-conductive)
         inert = len(table) - 1
         table_dev = torch.from_numpy(np.ascontiguousarray(np.concatenate([table[:, :4], table[:, 4:]]))).to(dev)
-        xp = self._shift(cond, 1, -1)
+        xp = shift_zero(cond, 1, -1)
         ids = ((cond_nn.to(torch.int32) * _N_REAC + reac_nn.to(torch.int32)) * 2 + xp.to(torch.int32))
         ids += (torch.arange(bs, device=dev, dtype=torch.int32) * n_img).view(bs, 1, 1, 1)
         ids = torch.where(cond.bool(), ids, torch.full_like(ids, inert)).to(torch.int16)

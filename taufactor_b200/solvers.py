@@ -543,28 +543,62 @@ class AnisotropicSolver(Solver):
         self.Kz = (dx / dz) ** 2
         super().__init__(img, omega=omega, D_0=D_0, device=device)
 
+    N_CLASSES = 64          # taub_common.cuh: ANISO_CLASSES
+    _INERT = 63             # non-conductive voxels and everything outside the volume
+
     def _init_binary(self, p, img_dev, vec):
-        weights = torch.tensor([self.Ky, self.Kz], dtype=torch.float32, device=self.device)   # rounded to fp32 like
-        p.lut = weights.data_ptr()                                                           # torch's tensor * scalar
-        return super()._init_binary(p, img_dev, vec) + (weights,)
+        """State = the binary solver's start field + one prefactor-class id per voxel.  The weighted
+        neighbour count (ref:459-471) depends only on the number of conductive neighbours per axis
+        (x: 0..4 with the Dirichlet planes counting 2; y, z: 0..2), so it is a 45-entry table of
+        (b, RN(1/b)) pairs built here in the reference's fp32 accumulation order."""
+        lib, dev, g = self._lib, self.device, p.g
+        G, C0 = _lib.GHOST, _lib.COL0
+        # start field through the binary state build (its neighbour codes are not kept)
+        tmp = Problem()
+        ctypes_copy(tmp, p)
+        tmp.kind = _lib.BINARY
+        scratch = torch.empty(lib.taub_codes_elems(g), dtype=torch.int16, device=dev)
+        tmp.codes = scratch.data_ptr()
+        self._call(lib.taub_init_binary(tmp, img_dev.data_ptr(), 0, self.Nx, vec.data_ptr(), self._stream()),
+                   "taub_init_binary")
+        cond = (img_dev == 1).to(torch.int8)
+        nx = neighbour_count_axis(cond, 1, False)
+        nx[:, 0] += 2
+        nx[:, -1] += 2
+        ny = neighbour_count_axis(cond, 2, False)
+        nz = neighbour_count_axis(cond, 3, False)
+        ids = ((nx.to(torch.int16) * 3 + ny) * 3 + nz)
+        ids = torch.where(cond.bool(), ids, torch.full_like(ids, self._INERT))
+        del nx, ny, nz, cond
+        classes = torch.full((lib.taub_field_elems(g),), self._INERT, dtype=torch.int16, device=dev)
+        classes.view(g.bs, g.planes, g.rows, g.pitch)[:, G:G + self.Nx, G:G + self.Ny, C0:C0 + self.Nz] = ids
+        del ids, scratch
+        Ky, Kz = np.float32(self.Ky), np.float32(self.Kz)       # rounded to fp32 like torch's tensor * scalar
+        lut = np.zeros(2 * self.N_CLASSES + 2, np.float32)
+        for cx in range(5):
+            for cy in range(3):
+                for cz in range(3):
+                    b = np.float32(cx)                                # (x- + x+): small integers, exact
+                    for w, n in ((Ky, cy), (Kz, cz)):                 # + K*m for the two neighbours of the axis
+                        for k in range(2):
+                            b = np.float32(b + (w if k < n else np.float32(0.0)))
+                    i = (cx * 3 + cy) * 3 + cz
+                    if b > 0:                                         # b == 0 -> prefactor inf: (0, 0)
+                        lut[2 * i], lut[2 * i + 1] = b, np.float32(1.0 / np.float64(b))
+        lut[2 * self.N_CLASSES], lut[2 * self.N_CLASSES + 1] = Ky, Kz
+        table = torch.from_numpy(lut).to(dev)
+        p.codes, p.lut, p.L = classes.data_ptr(), table.data_ptr(), self.N_CLASSES
+        return (classes, vec, table)
 
     @property
     def factor(self):
-        """ref:459-471 rebuilt from the conductive mask (test / inspection only)."""
-        g, G = self._geom, _lib.GHOST
-        codes = self._keep[0].view(g.bs, g.planes, g.rows, g.pitch // 4).to(torch.int32) & 0xFFFF
-        m = torch.stack([(codes >> (4 * q)) & 15 for q in range(4)], dim=-1).reshape(g.bs, g.planes, g.rows, -1)
-        m = (m != 0).to(torch.float32)[:, G - 1:G + g.Nx + 1, G - 1:G + g.Ny + 1, _lib.COL0 - 1:_lib.COL0 + g.Nz + 1]
-        m[:, 0, 1:-1, 1:-1], m[:, -1, 1:-1, 1:-1] = 2, 2
-        Ky, Kz = np.float32(self.Ky), np.float32(self.Kz)
-        nn = m[:, :-2, 1:-1, 1:-1] + m[:, 2:, 1:-1, 1:-1]
-        nn = nn + m[:, 1:-1, :-2, 1:-1] * Ky
-        nn = nn + m[:, 1:-1, 2:, 1:-1] * Ky
-        nn = nn + m[:, 1:-1, 1:-1, :-2] * Kz
-        nn = nn + m[:, 1:-1, 1:-1, 2:] * Kz
-        nn[m[:, 1:-1, 1:-1, 1:-1] == 0] = torch.inf
-        nn[nn == 0] = torch.inf
-        return nn
+        """ref:459-471: the weighted neighbour count per voxel (inf where non-conductive or 0), from the
+        class ids (test / inspection only)."""
+        g, G, C0 = self._geom, _lib.GHOST, _lib.COL0
+        classes, _, table = self._keep
+        ids = classes.view(g.bs, g.planes, g.rows, g.pitch)[:, G:G + g.Nx, G:G + g.Ny, C0:C0 + g.Nz]
+        b = table[: 2 * self.N_CLASSES: 2][ids.to(torch.int64)]
+        return torch.where(b > 0, b, torch.full_like(b, float("inf")))
 
 
 class PeriodicSolver(Solver):
@@ -669,6 +703,32 @@ class MultiPhaseSolver(ThroughTransportSolver):
             self.n_stencil_classes = out[2]
             return out[:2]
         return ()
+
+
+def ctypes_copy(dst, src):
+    """Field-by-field copy of a ctypes structure."""
+    import ctypes
+    ctypes.memmove(ctypes.byref(dst), ctypes.byref(src), ctypes.sizeof(src))
+
+
+def shift_zero(a, dim, step):
+    """``a`` moved by ``step`` along ``dim`` with zeros entering (the reference's zero padding, ref:228-238)."""
+    out = torch.zeros_like(a)
+    n = a.shape[dim]
+    if abs(step) < n:
+        src = [slice(None)] * a.dim()
+        dst = [slice(None)] * a.dim()
+        src[dim] = slice(0, n - step) if step > 0 else slice(-step, n)
+        dst[dim] = slice(step, n) if step > 0 else slice(0, n + step)
+        out[tuple(dst)] = a[tuple(src)]
+    return out
+
+
+def neighbour_count_axis(a, dim, periodic):
+    """Number of set neighbours along one axis of a 0/1 int8 tensor [bs,Nx,Ny,Nz] (zero or periodic ends)."""
+    if periodic:
+        return torch.roll(a, 1, dim) + torch.roll(a, -1, dim)
+    return shift_zero(a, dim, 1) + shift_zero(a, dim, -1)
 
 
 def fill_periodic_frame(planes, g):
