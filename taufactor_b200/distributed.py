@@ -25,7 +25,7 @@ import torch.distributed as dist
 
 from . import _lib
 from ._lib import Geom, Problem
-from .solvers import (BOT_BC, TOP_BC, MultiPhaseSolver, SORSolver, Solver, _as_uint8_labels, _expand_to_4d,
+from .solvers import (BOT_BC, TOP_BC, MultiPhaseSolver, Solver, _as_uint8_labels, _expand_to_4d,
                       build_class_table, validated_diffusivities)
 
 G = _lib.GHOST

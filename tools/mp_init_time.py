@@ -1,7 +1,7 @@
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-import numpy as np, torch
+import torch
 import taufactor_b200 as tau
 import cases
 img = cases.blobs3(384, seed=768)

@@ -50,7 +50,7 @@ if os.environ.get("SLAB_CHECK_TIMING", "1") == "0":
     dist.destroy_process_group()
     sys.exit(0)
 # overlap on / off timing on a larger volume
-import time
+
 img = cases.random_img((512, 768, 768), 0.5, seed=3)
 for ov, pp in ((False, False), (True, False), (False, True), (True, True)):
     S = DistributedSolver(img, overlap=ov, p2p=pp)
