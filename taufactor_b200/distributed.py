@@ -107,6 +107,18 @@ def assemble_profiles(parts, bounds, bs):
     return flux, mean
 
 
+def profile_gather_index(bounds, bs, max_local):
+    """Index into the all-gathered per-rank records ``[world][flux | mean][bs][max_local]`` (flattened) that
+    lays the whole-volume profiles out as ``[flux (bs x (Nx-1)) | mean (bs x Nx)]`` -- the device-side twin of
+    ``assemble_profiles`` (one ``index_select`` instead of a host round trip)."""
+    W, Nx = len(bounds), bounds[-1][1]
+    idx = np.arange(W * 2 * bs * max_local, dtype=np.int64).reshape(W, 2, bs, max_local)
+    flux = np.concatenate([idx[r, 0, :, : (h - l) - 1 + (1 if h < Nx else 0)] for r, (l, h) in enumerate(bounds)], axis=1)
+    mean = np.concatenate([idx[r, 1, :, : h - l] for r, (l, h) in enumerate(bounds)], axis=1)
+    assert flux.shape == (bs, Nx - 1) and mean.shape == (bs, Nx), (flux.shape, mean.shape)
+    return np.concatenate([flux.ravel(), mean.ravel()])
+
+
 # ----------------------------------------------------------------------------- the solver
 class DistributedSolver(Solver):
     """``Solver`` / ``PeriodicSolver`` -- or, with ``diffusivities``, ``MultiPhaseSolver`` /
@@ -344,15 +356,8 @@ class DistributedSolver(Solver):
 
     def _pipeline_profiles(self):
         if getattr(self, "_prof_glob", None) is None:
-            # index into the all-gathered per-rank records [world][flux|mean][bs][max_local] that lays the
-            # whole-volume profiles out as [flux (bs x (Nx-1)) | mean (bs x Nx)]
-            bs, ml, W = self.batch_size, self._max_local, self.world
-            idx = np.arange(W * 2 * bs * ml, dtype=np.int64).reshape(W, 2, bs, ml)
-            flux = np.concatenate([idx[r, 0, :, : (h - l) - 1 + (1 if h < self.Nx else 0)]
-                                   for r, (l, h) in enumerate(self.bounds)], axis=1)
-            mean = np.concatenate([idx[r, 1, :, : h - l] for r, (l, h) in enumerate(self.bounds)], axis=1)
-            assert flux.shape == (bs, self.Nx - 1) and mean.shape == (bs, self.Nx)
-            self._prof_idx = torch.from_numpy(np.concatenate([flux.ravel(), mean.ravel()])).to(self.device)
+            idx = profile_gather_index(self.bounds, self.batch_size, self._max_local)
+            self._prof_idx = torch.from_numpy(idx).to(self.device)
             self._prof_glob = torch.zeros(self._prof_idx.numel(), dtype=torch.float32, device=self.device)
         return self._prof_glob
 

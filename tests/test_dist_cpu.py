@@ -104,3 +104,22 @@ def test_two_slabs_equal_monolithic_oracle(tmp_path, name, world):
     assert np.array_equal(got["field"], st["field"][0, 1:-1, 1:-1, 1:-1])
     fl, mn = orc.plane_means(st)
     assert np.array_equal(got["flux"], fl) and np.array_equal(got["mean"], mn)
+
+
+@pytest.mark.parametrize("Nx,world,bs", [(10, 2, 1), (17, 3, 2), (64, 8, 3), (9, 4, 1)])
+def test_device_profile_index_equals_host_assembly(Nx, world, bs):
+    """profile_gather_index (what the pipelined slab solver feeds to index_select on the device) lays the
+    all-gathered padded records out exactly like assemble_profiles does on the host."""
+    from taufactor_b200.distributed import assemble_profiles, profile_gather_index, slab_bounds
+    bounds = slab_bounds(Nx, world)
+    ml = max(h - l for l, h in bounds)
+    rng = np.random.default_rng(Nx * world + bs)
+    gathered = rng.random((world, 2, bs, ml)).astype(np.float32)
+    parts = []
+    for r, (l, h) in enumerate(bounds):
+        nf = (h - l) - 1 + (1 if h < Nx else 0)
+        parts.append((gathered[r, 0, :, :nf], gathered[r, 1, :, : h - l]))
+    fl, mn = assemble_profiles(parts, bounds, bs)
+    flat = gathered.ravel()[profile_gather_index(bounds, bs, ml)]
+    assert np.array_equal(flat[: bs * (Nx - 1)].reshape(bs, Nx - 1), fl)
+    assert np.array_equal(flat[bs * (Nx - 1):].reshape(bs, Nx), mn)
