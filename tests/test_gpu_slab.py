@@ -42,9 +42,14 @@ def _worker(rank, world, port, shape, periodic, mode, out):
         S2 = DistributedSolver(img, device="cuda:0", periodic=periodic)
         S2.pipeline = (mode != "full")     # both the device-side (queued) and the host-side stop rule
         S2.solve(verbose=False)
+        # resumed solve: a limit that is not a multiple of 100 (queued blocks + remainder), then to convergence
+        S3 = DistributedSolver(img, device="cuda:0", periodic=periodic)
+        S3.solve(verbose=False, iter_limit=250)
+        it_a, conv_a = S3.iter, S3.converged
+        S3.solve(verbose=False)
         if rank == 0:
             np.savez(out, f37=f37, tau=S2.tau, D_eff=S2.D_eff, iters=S2.iter, final=S2.gather_field().cpu().numpy(),
-                     flux=S2.flux_1d, sent=S2.halo_bytes_sent)
+                     flux=S2.flux_1d, sent=S2.halo_bytes_sent, it_a=it_a, conv_a=conv_a, it_b=S3.iter, tau_b=S3.tau)
         else:
             S2.gather_field()
     finally:
@@ -72,6 +77,11 @@ def test_slabs_equal_single_gpu(tmp_path, shape, periodic, world, mode):
     assert np.array_equal(B.flux_1d, got["flux"])
     assert np.array_equal(B.tau, got["tau"]) and np.array_equal(B.D_eff, got["D_eff"])
     assert int(got["sent"]) > 0
+    C = cls(img, device="cuda")
+    C.solve(verbose=False, iter_limit=250)
+    assert (C.iter, bool(C.converged)) == (int(got["it_a"]), bool(got["conv_a"]))
+    C.solve(verbose=False)
+    assert C.iter == int(got["it_b"]) and np.array_equal(C.tau, got["tau_b"])
 
 
 def _batch_worker(rank, world, port, out):
