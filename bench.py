@@ -117,8 +117,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    img = blob_image(args.size)
-    sample = img[: max(8, args.size // 4)]        # bounded sample: a quarter of the planes
+    base = min(args.size, 512)                    # --size > 512 means the 512^3 blob tiled: one tile is the sample
+    img = blob_image(base)
+    sample = img[: max(8, base // 4)]             # bounded sample: a quarter of the planes
     n_it = 4
     vals = []
     for _ in range(args.warmup):
@@ -128,14 +129,26 @@ def run_reference(args):
         v, threads, dt = cpu_reference(sample, n_it)
         vals.append(v); t_all += dt
     value = float(np.mean(vals))
-    desc = (f"{n_it} iterations per step on the first {sample.shape[0]} planes of the {args.size}^3 blob volume "
-            f"({sample.shape[0]}x{args.size}x{args.size}), PyTorch-eager port of the reference loop")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and args.workload == "slab":
+        # the N-GPU arm runs the 512^3 blob tiled to 2048^3: a 128 x 512 x 512 block of one tile is a sample of it
+        side = args.size if args.size > 512 else 2048
+        workload = f"tau.Solver on {side}^3 volume (512^3 blob tiled {side // 512}x{side // 512}x{side // 512}), x-slab partitioned"
+        desc = (f"{n_it} iterations per step on a {sample.shape[0]}x{base}x{base} block of one tile of that volume, "
+                f"PyTorch-eager port of the reference loop on the host cores (rank 0 only)")
+    else:
+        if args.size > 512:
+            workload = f"tau.Solver on {args.size}^3 volume (512^3 blob tiled), single GPU"
+        else:
+            workload = f"tau.Solver on {args.size}^3 synthetic blob microstructure (porosity 0.5, seed {args.size})"
+        desc = (f"{n_it} iterations per step on the first {sample.shape[0]} planes of the {base}^3 blob volume "
+                f"({sample.shape[0]}x{base}x{base}), PyTorch-eager port of the reference loop")
     line = {"impl": "reference", "metric": "stencil_sweep_throughput", "value": value, "unit": "GLUPS",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * t_all / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": 1e3 * t_all / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "strong" if (world > 1 and args.workload == "slab") else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"tau.Solver on {args.size}^3 synthetic blob microstructure (porosity 0.5, seed {args.size})",
-                       "l2": "inputs larger than L2"},
+            "config": {"workload": workload, "l2": "inputs larger than L2"},
             "cpu_baseline": {"value": value, "unit": "GLUPS", "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": "GLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
