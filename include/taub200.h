@@ -155,7 +155,11 @@ int taub_can_fuse(const taub_problem *p);
  * kernel and the reference.  Synchronises the device. */
 unsigned long long taub_inexact_events(void);
 /* n iterations starting at iter on the whole local slab (single-rank use): refreshes periodic
- * ghosts, picks fused pairs where possible, flips p->cur.  flags bit0: force the generic path. */
+ * ghosts, picks fused pairs where possible, flips p->cur.  flags bit 0: force the generic path;
+ * bit 1 (experimental, off by default): launch the fused passes with programmatic dependent launch
+ * (cudaLaunchAttributeProgrammaticStreamSerialization) -- the next pass's launch and shared-memory
+ * prologue overlap the tail of the previous one; its first read waits for the previous grid to
+ * complete (griddepcontrol.wait), so results are unchanged. */
 int taub_iterate(taub_problem *p, int64_t iter, int n, int flags, void *stream);
 
 /* -- the check (replaces vertical_flux :412-419 / :615-620 and the two torch.mean reductions in

@@ -17,6 +17,7 @@ constexpr int COL0 = TAUB_COL0;
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);   // bumps the counter behind taub_launch_count()
+extern thread_local bool g_fused_pdl;   // taub_fused.cu: launch fused passes as programmatic dependents (opt-in)
 
 #define TAUB_CUDA(call)                                                                    \
     do {                                                                                   \

@@ -173,7 +173,10 @@ __global__ void __launch_bounds__(F_NT, 2)      // NB: ring depth (planes of the
 fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tmap,
                     const __grid_constant__ CUtensorMap cmap)
 {
-    if (P.stop && *P.stop) return;
+    // Programmatic dependent launch (opt-in, taub_iterate flags bit 1): let the next pass of the stream be
+    // scheduled as soon as every CTA of this one has started, so that its launch latency and shared-memory
+    // prologue overlap this pass's tail.  A no-op for an ordinary launch.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ unsigned char smem_dyn[];
     // TMA destinations need 128-byte alignment: align the base, slots are multiples of 128 B
     unsigned char *smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
@@ -209,6 +212,11 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // everything above touches only parameters, shared memory and tables no kernel writes; from here on the
+    // kernel reads what the previous grid of the stream produced (stop flag, source field): wait for it to
+    // complete and flush (returns at once when this grid was not launched as a programmatic dependent)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (P.stop && *P.stop) return;
 
     // one thread stages plane rel (local plane c0-2+rel) into ring slot rel % NB with one TMA box
     // (columns 4*G0.., rows R0.., one plane) plus the matching box of neighbour codes; the part of a
@@ -474,6 +482,9 @@ struct MapCache {
 };
 static thread_local MapCache g_maps;
 
+// taub_iterate flags bit 1 (per host thread): launch the fused passes as programmatic dependents
+thread_local bool g_fused_pdl = false;
+
 // 3-D view of one ping-pong buffer: (columns = pitch, rows, bs * planes), fp32, box = LG*4 x LR x 1.
 static int make_field_map(CUtensorMap *map, const taub_geom &g, const float *base, int LR, int LG)
 {
@@ -627,7 +638,17 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
             smem_set[dev_ord & 63] = smem;                                                                        \
         }                                                                                                         \
-        fused_sweep2_kernel<F_NRW, PA_, KIND_, NB_><<<grid, F_NT, smem, s>>>(P, tmap, cmap);                      \
+        cudaLaunchConfig_t cfg = {};                                                                              \
+        cfg.gridDim = grid;                                                                                       \
+        cfg.blockDim = dim3(F_NT);                                                                                \
+        cfg.dynamicSmemBytes = smem;                                                                              \
+        cfg.stream = s;                                                                                           \
+        cudaLaunchAttribute attr[1];                                                                              \
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                          \
+        attr[0].val.programmaticStreamSerializationAllowed = 1;                                                   \
+        cfg.attrs = attr;                                                                                         \
+        cfg.numAttrs = g_fused_pdl ? 1 : 0;                                                                       \
+        TAUB_CUDA(cudaLaunchKernelEx(&cfg, fused_sweep2_kernel<F_NRW, PA_, KIND_, NB_>, P, tmap, cmap));          \
     } while (0)
     if (p->kind == TAUB_MULTIPHASE_CLASS) {
         if (pa0 == 0) TAUB_LAUNCH_FUSED(0, TAUB_MULTIPHASE_CLASS, F_NB_CLS); else TAUB_LAUNCH_FUSED(1, TAUB_MULTIPHASE_CLASS, F_NB_CLS);

@@ -259,6 +259,11 @@ int taub_iterate(taub_problem *p, int64_t iter, int n, int flags, void *stream)
     TAUB_REQUIRE(g.i_offset == 0 && g.Nx == g.Nx_global,
                  "taub_iterate drives a whole volume; slabs interleave halo exchange in the caller");
     const bool fuse_ok = !(flags & 1) && taub_can_fuse(p) == 1;
+    struct PdlScope {   // bit 1: the fused passes of THIS call are launched as programmatic dependents
+        bool saved;
+        explicit PdlScope(bool on) : saved(g_fused_pdl) { g_fused_pdl = on; }
+        ~PdlScope() { g_fused_pdl = saved; }
+    } pdl_scope((flags & 2) != 0);
     int done = 0;
     while (done < n) {
         if (g.periodic) {

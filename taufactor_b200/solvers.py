@@ -12,6 +12,7 @@ PyTorch-eager fallback: without a CUDA device or without ``libtaub200.so`` const
 from __future__ import annotations
 
 import math
+import os
 import warnings
 from timeit import default_timer as timer
 
@@ -333,7 +334,7 @@ class SORSolver:
         P["ctl"].zero_()
         P["old_tau"].copy_(torch.from_numpy(np.broadcast_to(np.asarray(self.old_tau, np.float32), (bs,)).copy()))
         self._prob.stop = P["ctl"].data_ptr()
-        flags = 1 if self.force_generic else 0
+        flags = self._iterate_flags()
         stream = self._stream()
         pending, slot, queued_iter = deque(), 0, self.iter
         self.rule_mismatches = getattr(self, "rule_mismatches", 0)
@@ -401,9 +402,17 @@ class SORSolver:
     def _advance(self, n):
         """n reference iterations on the device, no check, no host sync (ref:175-182 x n)."""
         self._lib.taub_set_device(self._dev_index)
-        flags = 1 if self.force_generic else 0
-        self._call(self._lib.taub_iterate(self._prob, self.iter, int(n), flags, self._stream()), "taub_iterate")
+        self._call(self._lib.taub_iterate(self._prob, self.iter, int(n), self._iterate_flags(), self._stream()),
+                   "taub_iterate")
         self.iter += int(n)
+
+    # programmatic dependent launch of the fused passes (taub_iterate bit 1): the next pass's launch latency and
+    # prologue overlap the previous pass's tail -- bit-identical, 100^3: 5.1 -> 3.7 us / iteration.  Opt-in
+    # (TAUB_PDL=1 or ``solver.use_pdl = True``) until the whole GPU suite has run with it.
+    use_pdl = os.environ.get("TAUB_PDL", "0") == "1"
+
+    def _iterate_flags(self):
+        return (1 if self.force_generic else 0) | (2 if self.use_pdl else 0)
 
     def _check_only(self):
         """The reduction + device->host read of one convergence check, without the stop rule."""
