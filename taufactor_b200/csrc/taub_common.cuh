@@ -17,7 +17,34 @@ constexpr int COL0 = TAUB_COL0;
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);   // bumps the counter behind taub_launch_count()
-extern thread_local bool g_fused_pdl;   // taub_fused.cu: launch fused passes as programmatic dependents (opt-in)
+extern thread_local bool g_fused_pdl;   // taub_fused.cu: launch the passes of taub_iterate as programmatic dependents
+
+// Launch with or without cudaLaunchAttributeProgrammaticStreamSerialization (g_fused_pdl).  A kernel launched
+// through this must execute pdl_wait() in EVERY thread before its first access to global memory that an
+// earlier grid of the stream may have written (and before any exit), and may call pdl_trigger() first.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_maybe_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                    Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_fused_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#ifdef __CUDACC__
+// The next grid of the stream may be scheduled once every CTA of this one has got here (or exited).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Block until the previous grid of the stream has completed and its writes are visible; returns at once in a
+// grid that was not launched as a programmatic dependent.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 
 #define TAUB_CUDA(call)                                                                    \
     do {                                                                                   \

@@ -176,7 +176,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     // Programmatic dependent launch (opt-in, taub_iterate flags bit 1): let the next pass of the stream be
     // scheduled as soon as every CTA of this one has started, so that its launch latency and shared-memory
     // prologue overlap this pass's tail.  A no-op for an ordinary launch.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    pdl_trigger();
     extern __shared__ unsigned char smem_dyn[];
     // TMA destinations need 128-byte alignment: align the base, slots are multiples of 128 B
     unsigned char *smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
@@ -204,19 +204,20 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     const int total_rel = c1 - c0 + 4;           // planes c0-2 .. c1+1
     const int64_t ps = g.plane_stride;
 
-    if (tid < ANISO_CLASSES)      // binary: (n, 1/n) of the neighbour count; anisotropic: (b, 1/b) of the class
-        s_div[tid] = ANI ? reinterpret_cast<const float2 *>(P.table)[tid] : div_entry(tid);
-    const float Ky = ANI ? P.table[2 * ANISO_CLASSES] : 0.0f, Kz = ANI ? P.table[2 * ANISO_CLASSES + 1] : 0.0f;
+    if (!ANI && tid < ANISO_CLASSES) s_div[tid] = div_entry(tid);   // binary: (n, 1/n) of the neighbour count
     if (tid == 0) {
         for (int n = 0; n < NB; ++n) mbar_init(smem_u32(&mbar[n]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // everything above touches only parameters, shared memory and tables no kernel writes; from here on the
-    // kernel reads what the previous grid of the stream produced (stop flag, source field): wait for it to
-    // complete and flush (returns at once when this grid was not launched as a programmatic dependent)
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // everything above touches only parameters and shared memory; from here on the kernel reads global memory
+    // (stop flag, tables, source field): wait for the previous grid of the stream to complete and flush
+    // (returns at once when this grid was not launched as a programmatic dependent)
+    pdl_wait();
     if (P.stop && *P.stop) return;
+    // anisotropic: (b, 1/b) of the prefactor classes; first used after the step loop's first __syncthreads
+    if (ANI && tid < ANISO_CLASSES) s_div[tid] = reinterpret_cast<const float2 *>(P.table)[tid];
+    const float Ky = ANI ? P.table[2 * ANISO_CLASSES] : 0.0f, Kz = ANI ? P.table[2 * ANISO_CLASSES + 1] : 0.0f;
 
     // one thread stages plane rel (local plane c0-2+rel) into ring slot rel % NB with one TMA box
     // (columns 4*G0.., rows R0.., one plane) plus the matching box of neighbour codes; the part of a
@@ -638,17 +639,8 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
             smem_set[dev_ord & 63] = smem;                                                                        \
         }                                                                                                         \
-        cudaLaunchConfig_t cfg = {};                                                                              \
-        cfg.gridDim = grid;                                                                                       \
-        cfg.blockDim = dim3(F_NT);                                                                                \
-        cfg.dynamicSmemBytes = smem;                                                                              \
-        cfg.stream = s;                                                                                           \
-        cudaLaunchAttribute attr[1];                                                                              \
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                          \
-        attr[0].val.programmaticStreamSerializationAllowed = 1;                                                   \
-        cfg.attrs = attr;                                                                                         \
-        cfg.numAttrs = g_fused_pdl ? 1 : 0;                                                                       \
-        TAUB_CUDA(cudaLaunchKernelEx(&cfg, fused_sweep2_kernel<F_NRW, PA_, KIND_, NB_>, P, tmap, cmap));          \
+        TAUB_CUDA(launch_maybe_pdl(fused_sweep2_kernel<F_NRW, PA_, KIND_, NB_>, grid, dim3(F_NT), smem, s, P, tmap,    \
+                                   cmap));                                                                        \
     } while (0)
     if (p->kind == TAUB_MULTIPHASE_CLASS) {
         if (pa0 == 0) TAUB_LAUNCH_FUSED(0, TAUB_MULTIPHASE_CLASS, F_NB_CLS); else TAUB_LAUNCH_FUSED(1, TAUB_MULTIPHASE_CLASS, F_NB_CLS);

@@ -19,6 +19,8 @@ namespace taub {
 __global__ void __launch_bounds__(256)
 refresh_ghosts_kernel(taub_geom g, float *__restrict__ f, int p_lo, const int *__restrict__ stop)
 {
+    pdl_trigger();
+    pdl_wait();      // before the first global read and before any thread exits (see launch_maybe_pdl)
     if (stop && *stop) return;
     // items: the 2G ghost rows as float4 groups (pitch/4 each), then for every interior row the left
     // and the right ghost column pair (one float2 each; columns 2,3 and Nz+4,Nz+5 are 8-byte aligned
@@ -68,6 +70,8 @@ half_sweep_kernel(taub_geom g, const float *__restrict__ src, float *__restrict_
                   const float *__restrict__ lut, int L, float omega, int colour, int i_lo, int n_planes,
                   const int *__restrict__ stop)
 {
+    pdl_trigger();
+    pdl_wait();      // before the first global read and before any thread exits (see launch_maybe_pdl)
     if (stop && *stop) return;
     constexpr bool MULTI = (KIND == TAUB_MULTIPHASE);
     __shared__ float2 s_div[16];
@@ -202,8 +206,8 @@ static int refresh_ghosts(const taub_geom *g, float *field, int p_lo, int p_hi, 
     const int total = 2 * G * (g->pitch >> 2) + 2 * g->Ny;
     for (int b0 = 0; b0 < g->bs; b0 += 65535) {
         dim3 grid(ceil_div(total, 256), p_hi - p_lo, min(g->bs - b0, 65535));
-        refresh_ghosts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-            *g, field + (int64_t)b0 * g->image_stride, p_lo, stop);
+        TAUB_CUDA(launch_maybe_pdl(refresh_ghosts_kernel, grid, dim3(256), 0, (cudaStream_t)stream, *g,
+                                   field + (int64_t)b0 * g->image_stride, p_lo, stop));
     }
     TAUB_CUDA(cudaGetLastError());
     count_launch();
@@ -229,23 +233,23 @@ int taub_half_sweep(const taub_problem *p, int64_t iter, int i_lo, int i_hi, voi
     cudaStream_t s = (cudaStream_t)stream;
     if (p->kind == TAUB_BINARY) {
         TAUB_REQUIRE(p->codes, "taub_half_sweep: binary problem without codes");
-        half_sweep_kernel<TAUB_BINARY><<<grid, block, 0, s>>>(g, src, dst, p->codes, nullptr, nullptr, 0,
-                                                              p->omega, colour, i_lo, n_planes, p->stop);
+        TAUB_CUDA(launch_maybe_pdl(half_sweep_kernel<TAUB_BINARY>, grid, block, 0, s, g, src, dst, p->codes, nullptr, nullptr,
+                                   0, p->omega, colour, i_lo, n_planes, p->stop));
     } else if (p->kind == TAUB_MULTIPHASE_CLASS) {
         TAUB_REQUIRE(p->codes && p->lut && p->L >= 1 && p->L <= 65536, "taub_half_sweep: class problem without table");
-        half_sweep_kernel<TAUB_MULTIPHASE_CLASS><<<grid, block, 0, s>>>(g, src, dst, p->codes, nullptr, p->lut, p->L,
-                                                                        p->omega, colour, i_lo, n_planes, p->stop);
+        TAUB_CUDA(launch_maybe_pdl(half_sweep_kernel<TAUB_MULTIPHASE_CLASS>, grid, block, 0, s, g, src, dst, p->codes, nullptr,
+                                   p->lut, p->L, p->omega, colour, i_lo, n_planes, p->stop));
     } else if (p->kind == TAUB_ANISOTROPIC) {
         TAUB_REQUIRE(p->codes && p->lut, "taub_half_sweep: anisotropic problem without class ids / table");
         TAUB_REQUIRE(!g.periodic, "taub_half_sweep: the anisotropic solver has no periodic variant");
-        half_sweep_kernel<TAUB_ANISOTROPIC><<<grid, block, 0, s>>>(g, src, dst, p->codes, nullptr, p->lut, 0,
-                                                                   p->omega, colour, i_lo, n_planes, p->stop);
+        TAUB_CUDA(launch_maybe_pdl(half_sweep_kernel<TAUB_ANISOTROPIC>, grid, block, 0, s, g, src, dst, p->codes, nullptr,
+                                   p->lut, 0, p->omega, colour, i_lo, n_planes, p->stop));
     } else {
         TAUB_REQUIRE(p->labels && p->lut && p->L >= 1 && p->L <= TAUB_MAX_LABELS,
                      "taub_half_sweep: multi-phase problem without labels / table");
         const size_t smem = sizeof(float) * (p->L + 1) * (p->L + 1);
-        half_sweep_kernel<TAUB_MULTIPHASE><<<grid, block, smem, s>>>(g, src, dst, nullptr, p->labels, p->lut,
-                                                          p->L, p->omega, colour, i_lo, n_planes, p->stop);
+        TAUB_CUDA(launch_maybe_pdl(half_sweep_kernel<TAUB_MULTIPHASE>, grid, block, smem, s, g, src, dst, nullptr, p->labels,
+                                   p->lut, p->L, p->omega, colour, i_lo, n_planes, p->stop));
     }
     TAUB_CUDA(cudaGetLastError());
     count_launch();

@@ -406,13 +406,29 @@ class SORSolver:
                    "taub_iterate")
         self.iter += int(n)
 
-    # programmatic dependent launch of the fused passes (taub_iterate bit 1): the next pass's launch latency and
-    # prologue overlap the previous pass's tail -- bit-identical, 100^3: 5.1 -> 3.7 us / iteration.  Opt-in
-    # (TAUB_PDL=1 or ``solver.use_pdl = True``) until the whole GPU suite has run with it.
-    use_pdl = os.environ.get("TAUB_PDL", "0") == "1"
+    # Programmatic dependent launch of the kernels queued by taub_iterate (flags bit 1): the next kernel's launch
+    # latency and prologue overlap the previous kernel's tail; every kernel waits for its predecessor's
+    # completion before its first global read, so results are bit-identical (tests/test_gpu_parity.py,
+    # tools/pdl_check.py).  Measured (us / iteration, plain -> dependent launches): Solver 100^3 5.12 -> 3.71,
+    # 256^3 19.5 -> 18.5, 512^3 113.8 -> 112.9; PeriodicSolver 100^3 7.17 -> 5.12 but 256^3 22.6 -> 23.4 and
+    # 512^3 126.7 -> 129.2 (fused CTAs parked on the SMs while the ghost refresh runs cost more than the hidden
+    # launch).  None = automatic: on, except for periodic solvers above PDL_PERIODIC_MAX_VOXELS;
+    # TAUB_PDL=0 / 1 or ``solver.use_pdl = False / True`` override.
+    use_pdl = None
+    PDL_PERIODIC_MAX_VOXELS = 1 << 22
+
+    def _pdl_on(self):
+        if self.use_pdl is not None:
+            return bool(self.use_pdl)
+        env = os.environ.get("TAUB_PDL")
+        if env is not None:
+            return env != "0"
+        if not self._periodic:
+            return True
+        return self.batch_size * self.Nx * self.Ny * self.Nz <= self.PDL_PERIODIC_MAX_VOXELS
 
     def _iterate_flags(self):
-        return (1 if self.force_generic else 0) | (2 if self.use_pdl else 0)
+        return (1 if self.force_generic else 0) | (2 if self._pdl_on() else 0)
 
     def _check_only(self):
         """The reduction + device->host read of one convergence check, without the stop rule."""

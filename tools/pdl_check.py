@@ -48,11 +48,11 @@ def main():
         print(f"{cls.__name__:28s} solve: {A.iter} / {B.iter} iterations, tau {A.tau} / {B.tau}: {same}", flush=True)
     print("inexact events:", A.inexact_events, flush=True)
     sizes = [int(x) for x in sys.argv[1:]] or [100, 256, 512]
-    for N in sizes:
+    for N, cls in [(n, c) for n in sizes for c in (tau.Solver, tau.PeriodicSolver)]:
         img = cases.random_img(N, 0.6, seed=N)
         res = {}
         for pdl in (False, True, False, True):
-            S = tau.Solver(img, device="cuda")
+            S = cls(img, device="cuda")
             S.use_pdl = pdl
             n = 2000 if N <= 128 else (600 if N <= 256 else 200)
             S._advance(n // 4)
@@ -62,7 +62,7 @@ def main():
             torch.cuda.synchronize()
             res.setdefault(pdl, []).append(1e3 * e0.elapsed_time(e1) / n)
             del S
-        print(f"Solver {N}^3: us/iteration plain {min(res[False]):.2f}  pdl {min(res[True]):.2f}  "
+        print(f"{cls.__name__} {N}^3: us/iteration plain {min(res[False]):.2f}  pdl {min(res[True]):.2f}  "
               f"({N ** 3 / min(res[False]) / 1e3:.0f} -> {N ** 3 / min(res[True]) / 1e3:.0f} GLUPS)", flush=True)
     print("ALL BITWISE EQUAL" if ok else "MISMATCH", f"({time.time() - t00:.0f} s)")
     return 0 if ok else 1
