@@ -156,10 +156,11 @@ int taub_can_fuse(const taub_problem *p);
 unsigned long long taub_inexact_events(void);
 /* n iterations starting at iter on the whole local slab (single-rank use): refreshes periodic
  * ghosts, picks fused pairs where possible, flips p->cur.  flags bit 0: force the generic path;
- * bit 1 (experimental, off by default): launch the fused passes with programmatic dependent launch
+ * bit 1: launch the queued kernels (fused / generic sweeps, ghost refresh) with programmatic dependent launch
  * (cudaLaunchAttributeProgrammaticStreamSerialization) -- the next pass's launch and shared-memory
  * prologue overlap the tail of the previous one; its first read waits for the previous grid to
- * complete (griddepcontrol.wait), so results are unchanged. */
+ * complete (griddepcontrol.wait), so results are unchanged.  bit 2 (with bit 1, periodic solvers): the ghost
+ * refresh releases the sweep behind it when it has finished, not when it starts. */
 int taub_iterate(taub_problem *p, int64_t iter, int n, int flags, void *stream);
 
 /* -- the check (replaces vertical_flux :412-419 / :615-620 and the two torch.mean reductions in

@@ -17,9 +17,11 @@ namespace taub {
 // {2,3,Nz+4,Nz+5} of the interior rows, := image of the wrapped interior voxel.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-refresh_ghosts_kernel(taub_geom g, float *__restrict__ f, int p_lo, const int *__restrict__ stop)
+refresh_ghosts_kernel(taub_geom g, float *__restrict__ f, int p_lo, const int *__restrict__ stop, int early_trigger)
 {
-    pdl_trigger();
+    // early_trigger = 0 (taub_iterate flags bit 2): the sweep behind this refresh is released when the refresh
+    // has finished instead of being parked on the SMs while it runs
+    if (early_trigger) pdl_trigger();
     pdl_wait();      // before the first global read and before any thread exits (see launch_maybe_pdl)
     if (stop && *stop) return;
     // items: the 2G ghost rows as float4 groups (pitch/4 each), then for every interior row the left
@@ -190,6 +192,8 @@ half_sweep_kernel(taub_geom g, const float *__restrict__ src, float *__restrict_
 
 using namespace taub;
 
+static thread_local bool g_refresh_late_trigger = false;   // taub_iterate flags bit 2
+
 extern "C" {
 
 static int refresh_ghosts(const taub_geom *g, float *field, int p_lo, int p_hi, const int *stop, void *stream);
@@ -207,7 +211,7 @@ static int refresh_ghosts(const taub_geom *g, float *field, int p_lo, int p_hi, 
     for (int b0 = 0; b0 < g->bs; b0 += 65535) {
         dim3 grid(ceil_div(total, 256), p_hi - p_lo, min(g->bs - b0, 65535));
         TAUB_CUDA(launch_maybe_pdl(refresh_ghosts_kernel, grid, dim3(256), 0, (cudaStream_t)stream, *g,
-                                   field + (int64_t)b0 * g->image_stride, p_lo, stop));
+                                   field + (int64_t)b0 * g->image_stride, p_lo, stop, g_refresh_late_trigger ? 0 : 1));
     }
     TAUB_CUDA(cudaGetLastError());
     count_launch();
@@ -268,6 +272,11 @@ int taub_iterate(taub_problem *p, int64_t iter, int n, int flags, void *stream)
         explicit PdlScope(bool on) : saved(g_fused_pdl) { g_fused_pdl = on; }
         ~PdlScope() { g_fused_pdl = saved; }
     } pdl_scope((flags & 2) != 0);
+    struct LateScope {
+        bool saved;
+        explicit LateScope(bool on) : saved(g_refresh_late_trigger) { g_refresh_late_trigger = on; }
+        ~LateScope() { g_refresh_late_trigger = saved; }
+    } late_scope((flags & 4) != 0);
     int done = 0;
     while (done < n) {
         if (g.periodic) {

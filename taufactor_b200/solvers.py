@@ -427,8 +427,11 @@ class SORSolver:
             return True
         return self.batch_size * self.Nx * self.Ny * self.Nz <= self.PDL_PERIODIC_MAX_VOXELS
 
+    pdl_refresh_late = False    # experimental (flags bit 2): the periodic ghost refresh releases the next sweep late
+
     def _iterate_flags(self):
-        return (1 if self.force_generic else 0) | (2 if self._pdl_on() else 0)
+        pdl = self._pdl_on()
+        return (1 if self.force_generic else 0) | (2 if pdl else 0) | (4 if pdl and self.pdl_refresh_late else 0)
 
     def _check_only(self):
         """The reduction + device->host read of one convergence check, without the stop rule."""

@@ -51,9 +51,12 @@ def main():
     for N, cls in [(n, c) for n in sizes for c in (tau.Solver, tau.PeriodicSolver)]:
         img = cases.random_img(N, 0.6, seed=N)
         res = {}
-        for pdl in (False, True, False, True):
+        for pdl in (False, True, "late") * 2:
+            if pdl == "late" and cls is not tau.PeriodicSolver:
+                continue
             S = cls(img, device="cuda")
-            S.use_pdl = pdl
+            S.use_pdl = bool(pdl)
+            S.pdl_refresh_late = (pdl == "late")
             n = 2000 if N <= 128 else (600 if N <= 256 else 200)
             S._advance(n // 4)
             torch.cuda.synchronize()
@@ -62,7 +65,8 @@ def main():
             torch.cuda.synchronize()
             res.setdefault(pdl, []).append(1e3 * e0.elapsed_time(e1) / n)
             del S
-        print(f"{cls.__name__} {N}^3: us/iteration plain {min(res[False]):.2f}  pdl {min(res[True]):.2f}  "
+        late = f"  pdl + late refresh trigger {min(res['late']):.2f}" if "late" in res else ""
+        print(f"{cls.__name__} {N}^3: us/iteration plain {min(res[False]):.2f}  pdl {min(res[True]):.2f}{late}  "
               f"({N ** 3 / min(res[False]) / 1e3:.0f} -> {N ** 3 / min(res[True]) / 1e3:.0f} GLUPS)", flush=True)
     print("ALL BITWISE EQUAL" if ok else "MISMATCH", f"({time.time() - t00:.0f} s)")
     return 0 if ok else 1
