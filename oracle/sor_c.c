@@ -87,6 +87,37 @@ void orc_half_sweep_range(float *f, const float *factor, const float *Dx, const 
     }
 }
 
+/* AnisotropicSolver (taufactor.py:473-478): s = ((x+ + x-) + Ky*(y+ + y-)) + Kz*(z+ + z-), Ky / Kz already
+ * rounded to fp32 (torch multiplies an fp32 tensor by the Python scalar in fp32); update as above, no
+ * periodic variant. */
+void orc_sweeps_aniso(float *f, const float *factor, int bs, int Nx, int Ny, int Nz, float omega, float Ky,
+                      float Kz, long iter0, int n)
+{
+    const size_t PX = Nx + 2, PY = Ny + 2, PZ = Nz + 2;
+    for (int it = 0; it < n; ++it) {
+        const int colour = (int)((iter0 + it) & 1);
+        for (int b = 0; b < bs; ++b)
+            for (int a = 0; a < Nx; ++a)
+                for (int c = 0; c < Ny; ++c) {
+                    const size_t fo = ((size_t)b * Nx + a) * Ny + c;
+                    for (int d = (a + c + colour) & 1; d < Nz; d += 2) {
+                        const size_t p = IDX(b, a + 1, c + 1, d + 1);
+                        float s = f[p + PY * PZ] + f[p - PY * PZ];
+                        float t = f[p + PZ] + f[p - PZ];
+                        t = Ky * t;
+                        s = s + t;
+                        t = f[p + 1] + f[p - 1];
+                        t = Kz * t;
+                        s = s + t;
+                        float inc = s / factor[fo * Nz + d];
+                        inc = inc - f[p];
+                        inc = inc * omega;
+                        f[p] = f[p] + inc;
+                    }
+                }
+    }
+}
+
 /* Per-x-plane sums (fp64): flux_sum[b][i] over faces i|i+1, i = 0..Nx-2, and field_sum[b][i]. */
 void orc_plane_sums(const float *f, const float *factor, const float *Dx, int bs, int Nx, int Ny,
                     int Nz, double *flux_sum, double *field_sum)

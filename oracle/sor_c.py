@@ -32,6 +32,8 @@ def lib():
         _LIB.orc_half_sweep_range.restype = None
         _LIB.orc_refresh_ghosts.argtypes = [fp] + [ctypes.c_int] * 4
         _LIB.orc_refresh_ghosts.restype = None
+        _LIB.orc_sweeps_aniso.argtypes = [fp, fp] + [ctypes.c_int] * 4 + [ctypes.c_float] * 3 + [ctypes.c_long, ctypes.c_int]
+        _LIB.orc_sweeps_aniso.restype = None
         _LIB.orc_plane_sums.argtypes = [fp, fp, fp] + [ctypes.c_int] * 4 + [fp, fp]
         _LIB.orc_plane_sums.restype = None
     return _LIB
@@ -57,6 +59,12 @@ def _arrays(st):
 def sweep(st, n):
     fac, dx, dy, dz = _arrays(st)
     omega32 = np.float32(st["omega"])
+    if st["kind"] == "anisotropic":
+        lib().orc_sweeps_aniso(_p(st["field"]), _p(fac), st["bs"], st["Nx"], st["Ny"], st["Nz"],
+                               ctypes.c_float(float(omega32)), ctypes.c_float(float(np.float32(st["Ky"]))),
+                               ctypes.c_float(float(np.float32(st["Kz"]))), st["iter"], int(n))
+        st["iter"] += int(n)
+        return
     lib().orc_sweeps(_p(st["field"]), _p(fac), _p(dx), _p(dy), _p(dz), st["bs"], st["Nx"], st["Ny"],
                      st["Nz"], int(st["periodic"]), ctypes.c_float(float(omega32)), st["iter"], int(n))
     st["iter"] += int(n)

@@ -39,7 +39,7 @@ def headless(cls_name, st, img):
     return S
 
 
-@pytest.mark.parametrize("name", [n for n in FAST if cases.CASES[n][0] != "AnisotropicSolver"])
+@pytest.mark.parametrize("name", FAST)
 def test_host_check_reproduces_the_reference_solve(name):
     cls, build, _, skw, _ = cases.CASES[name]
     st, _ = build_state(name)

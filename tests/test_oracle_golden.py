@@ -40,7 +40,7 @@ def test_field_trajectory_bitwise(name, engine):
     assert np.array_equal(st["factor"], FIELDS[f"{name}@factor"])
     for k in cases.SNAPSHOT_ITERS:
         while st["iter"] < k:
-            if engine == "numpy" or st["kind"] == "anisotropic":   # the C restatement has no anisotropic loop
+            if engine == "numpy":
                 orc.half_sweep(st)
             else:
                 sor_c.sweep(st, 1)
@@ -59,7 +59,7 @@ FAST = [n for n in cases.CASES if SOLVE[n]["seconds"] < 8]
 def test_solve_matches_reference(name):
     st, skw = build_state(name)
     trace = []
-    orc.solve(st, trace=trace, sweep=None if st["kind"] == "anisotropic" else sor_c.sweep, **skw)
+    orc.solve(st, trace=trace, sweep=sor_c.sweep, **skw)
     g = SOLVE[name]
     assert st["iter"] == g["iter"]
     assert bool(st["converged"]) == g["converged"]
