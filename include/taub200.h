@@ -147,7 +147,8 @@ int taub_half_sweep(const taub_problem *p, int64_t iter, int i_lo, int i_hi, voi
  * blocked, TMA-bulk staged shared-memory tiles, register-rotating plane march.  Binary kind.
  * Returns TAUB_ERR_UNSUPPORTED when the problem does not qualify (see taub_can_fuse). */
 int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, void *stream);
-int taub_can_fuse(const taub_problem *p);
+int taub_can_fuse(const taub_problem *p);   /* periodic problems with odd Ny / Nz: only with the experimental
+                                             * OP kernel variant, environment TAUB_FUSE_ODD_PERIODIC=1 */
 /* The fused kernel divides by the neighbour count with an FMA-corrected reciprocal that equals the
  * IEEE quotient for s == 0 and every |s| >= 2^-100.  This counts the threads that ever saw a
  * non-zero sum below 2^-100 (there the result may differ from IEEE division by one subnormal ulp);

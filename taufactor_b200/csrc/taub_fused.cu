@@ -18,6 +18,8 @@
 // y/z halos are recomputed by the neighbouring tile (overlapped tiling); the source buffer is
 // read-only during the pass (ping-pong), so there is no inter-CTA hazard.  The arithmetic per
 // voxel is the same correctly rounded sequence as the generic kernel: results are bit-identical.
+#include <stdlib.h>
+
 #include <cuda.h>   // CUtensorMap types only; the encoder is fetched through the runtime (no -lcuda)
 
 #include "taub_common.cuh"
@@ -168,7 +170,14 @@ __device__ __forceinline__ float z_neighbour(const bool is_xz, const float4 &v, 
 // y-neighbours stay in registers, only the rows above and below it come from shared memory.  PA0 = parity
 // of the column's first row at step 0 (uniform over the whole grid, chosen by the host), so every step
 // body is branch-free.
-template <int NRW, int PA0, int KIND, int NB>   // KIND: TAUB_BINARY (4-bit codes) or TAUB_MULTIPHASE_CLASS (class ids)
+//
+// OP ("odd periodic", experimental -- see taub_can_fuse): a periodic extent Ny or Nz is odd, so the wrap joins two
+// voxels of the SAME colour and a ghost cell is the image of a voxel whose colour differs from the ghost's own
+// index parity.  The reference reads ghost SNAPSHOTS taken before each iteration (taufactor.py:501-505); with
+// the images loaded once per pass that is reproduced exactly by leaving the ghost ring of the odd axis out of
+// the colour-A step: where the imaged voxel has colour B the snapshot before iteration t+1 equals the loaded
+// value, and where it has colour A no colour-B voxel reads it.
+template <int NRW, int PA0, int KIND, int NB, bool OP = false>   // KIND: TAUB_BINARY (4-bit codes) or TAUB_MULTIPHASE_CLASS (class ids)
 __global__ void __launch_bounds__(F_NT, 2)      // NB: ring depth (planes of the tile resident in shared memory)
 fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tmap,
                     const __grid_constant__ CUtensorMap cmap)
@@ -247,6 +256,22 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     for (int r = 0; r < NRW; ++r)
         if (doit && colB && lr0 + r >= 2 && lr0 + r < LR - 2 && Ra + r >= G && Ra + r < G + g.Ny) canB |= 1u << r;
     const bool all_rows = (canB == (1u << NRW) - 1u);   // interior columns: every row is an output row
+    // OP: ghost rows (odd Ny) keep their snapshot in the colour-A step, and so do the ghost columns k = -1
+    // (.w of group 0) and k = Nz (component Nz % 4 of group (Nz + 4) / 4) for odd Nz
+    unsigned keep_rows = 0;
+    bool keep_lo_w = false, keep_hi_y = false, keep_hi_w = false;
+    if (OP) {
+        if (g.Ny & 1) {
+#pragma unroll
+            for (int r = 0; r < NRW; ++r)
+                if (Ra + r < G || Ra + r >= G + g.Ny) keep_rows |= 1u << r;
+        }
+        if (g.Nz & 1) {
+            keep_lo_w = (Gs == 0);
+            keep_hi_y = (Gs == ((g.Nz + COL0) >> 2)) && ((g.Nz & 3) == 1);
+            keep_hi_w = (Gs == ((g.Nz + COL0) >> 2)) && ((g.Nz & 3) == 3);
+        }
+    }
     const int i0 = lr0 * LG + gg;            // float4 index of row 0 inside a ring slot (row r: + r*LG)
     const int ic0 = (lr0 * LGc + gg) * CPG;  // uint16 index of row 0's code / class ids (row r: + r*LGc*CPG)
     // colour B first writes plane c0 (at step 2)
@@ -321,6 +346,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                         // its neighbours leave unchanged in this step
                         const float4 &dn = (r == 0) ? below : rg[r - 1][iP];
                         const float4 &up = (r == NRW - 1) ? above : rg[r + 1][iP];
+                        const float4 snap = rg[r][iP];
                         if (ANI)
                             row_update_aniso(((PA0 + ss + r) & 1) == 0, rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r],
                                              *reinterpret_cast<const uint2 *>(codP + ic0 + r * LGc * CPG), s_div, Ky, Kz, P.omega, umin);
@@ -330,6 +356,14 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
                         else
                             row_update(((PA0 + ss + r) & 1) == 0, rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r],
                                        cr[r >> 1][iP] >> (16 * (r & 1)), s_div, P.omega, umin);
+                        if (OP) {   // ghost cells of an odd periodic axis keep their snapshot
+                            if (keep_rows & (1u << r)) {
+                                rg[r][iP] = snap;
+                            } else {
+                                if (keep_lo_w || keep_hi_w) rg[r][iP].w = snap.w;
+                                if (keep_hi_y) rg[r][iP].y = snap.y;
+                            }
+                        }
                     }
                     if (keepA) {
                         // other threads read the column's first and last row (their above / below) and,
@@ -557,6 +591,18 @@ static void choose_chunks(int n_planes, int64_t tiles, int capacity, int *chunk_
 
 using namespace taub;
 
+static bool odd_periodic(const taub_geom &g) { return g.periodic && ((g.Ny & 1) || (g.Nz & 1)); }
+
+static bool fuse_odd_periodic_enabled()
+{
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("TAUB_FUSE_ODD_PERIODIC");
+        on = (e && e[0] == '1') ? 1 : 0;
+    }
+    return on == 1;
+}
+
 extern "C" {
 
 unsigned long long taub_inexact_events(void)
@@ -574,8 +620,9 @@ int taub_can_fuse(const taub_problem *p)
     if (p->kind != TAUB_BINARY && !p->lut) return 0;
     const taub_geom &g = p->g;
     // periodic wrap with odd Ny/Nz couples two voxels of the SAME colour (reference reads a ghost
-    // snapshot); the in-place shared-memory colour update cannot express that -> generic path.
-    if (g.periodic && ((g.Ny & 1) || (g.Nz & 1))) return 0;
+    // snapshot): generic path, unless the experimental OP variant of the fused kernel (ghost ring of the odd
+    // axis left out of the colour-A step) is switched on with TAUB_FUSE_ODD_PERIODIC=1.
+    if (odd_periodic(g) && !fuse_odd_periodic_enabled()) return 0;
     if (g.bs > 65535) return 0;
     return choose_tile(g, (p->kind == TAUB_MULTIPHASE_CLASS || p->kind == TAUB_ANISOTROPIC) ? 4 : 1).eff > 0.0 ? 1 : 0;
 }
@@ -631,24 +678,30 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     // Tile row offsets (multiples of the even OR_) and chunk starts (multiples of the even
     // chunk_len) do not change it, so it is one number for the whole grid.
     const int pa0 = (1 - G + g.i_offset + P.colourA + (i_lo - 1)) & 1;   // row lr = 1 is row 0 of a column
-#define TAUB_LAUNCH_FUSED(PA_, KIND_, NB_)                                                                        \
+#define TAUB_LAUNCH_FUSED(PA_, KIND_, NB_, OP_)                                                                   \
     do {                                                                                                          \
         static size_t smem_set[64] = {0};   /* per device: raise the opt-in limit only when it grows */         \
         if (smem > smem_set[dev_ord & 63]) {                                                                      \
-            TAUB_CUDA(cudaFuncSetAttribute(fused_sweep2_kernel<F_NRW, PA_, KIND_, NB_>,                           \
+            TAUB_CUDA(cudaFuncSetAttribute(fused_sweep2_kernel<F_NRW, PA_, KIND_, NB_, OP_>,                      \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
             smem_set[dev_ord & 63] = smem;                                                                        \
         }                                                                                                         \
-        TAUB_CUDA(launch_maybe_pdl(fused_sweep2_kernel<F_NRW, PA_, KIND_, NB_>, grid, dim3(F_NT), smem, s, P, tmap,    \
-                                   cmap));                                                                        \
+        TAUB_CUDA(launch_maybe_pdl(fused_sweep2_kernel<F_NRW, PA_, KIND_, NB_, OP_>, grid, dim3(F_NT), smem, s, P, \
+                                   tmap, cmap));                                                                  \
     } while (0)
+#define TAUB_LAUNCH_FUSED_PA(KIND_, NB_, OP_)                                                                     \
+    do {                                                                                                          \
+        if (pa0 == 0) TAUB_LAUNCH_FUSED(0, KIND_, NB_, OP_); else TAUB_LAUNCH_FUSED(1, KIND_, NB_, OP_);          \
+    } while (0)
+    const bool op = odd_periodic(g);
     if (p->kind == TAUB_MULTIPHASE_CLASS) {
-        if (pa0 == 0) TAUB_LAUNCH_FUSED(0, TAUB_MULTIPHASE_CLASS, F_NB_CLS); else TAUB_LAUNCH_FUSED(1, TAUB_MULTIPHASE_CLASS, F_NB_CLS);
+        if (op) TAUB_LAUNCH_FUSED_PA(TAUB_MULTIPHASE_CLASS, F_NB_CLS, true); else TAUB_LAUNCH_FUSED_PA(TAUB_MULTIPHASE_CLASS, F_NB_CLS, false);
     } else if (p->kind == TAUB_ANISOTROPIC) {
-        if (pa0 == 0) TAUB_LAUNCH_FUSED(0, TAUB_ANISOTROPIC, F_NB_CLS); else TAUB_LAUNCH_FUSED(1, TAUB_ANISOTROPIC, F_NB_CLS);
+        TAUB_LAUNCH_FUSED_PA(TAUB_ANISOTROPIC, F_NB_CLS, false);      // no periodic variant of this solver
     } else {
-        if (pa0 == 0) TAUB_LAUNCH_FUSED(0, TAUB_BINARY, F_NB); else TAUB_LAUNCH_FUSED(1, TAUB_BINARY, F_NB);
+        if (op) TAUB_LAUNCH_FUSED_PA(TAUB_BINARY, F_NB, true); else TAUB_LAUNCH_FUSED_PA(TAUB_BINARY, F_NB, false);
     }
+#undef TAUB_LAUNCH_FUSED_PA
 #undef TAUB_LAUNCH_FUSED
     TAUB_CUDA(cudaGetLastError());
     count_launch();
