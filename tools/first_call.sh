@@ -7,6 +7,10 @@
 set -u
 mkdir -p gpurun_out
 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/gpu_tests.txt 2>&1; echo "gpu tests rc=$?"; tail -3 gpurun_out/gpu_tests.txt
+# experimental switches, each against the whole parity suite (bit-exact goldens): odd periodic shapes on the fused
+# kernel; serial launches
+TAUB_FUSE_ODD_PERIODIC=1 python -m pytest tests/test_gpu_parity.py tests/test_gpu_electrode.py -q -m gpu -p no:cacheprovider > gpurun_out/gpu_tests_fuse_odd.txt 2>&1; echo "fuse-odd tests rc=$?"; tail -3 gpurun_out/gpu_tests_fuse_odd.txt
+TAUB_PDL=0 python -m pytest tests/test_gpu_parity.py -q -m gpu -p no:cacheprovider > gpurun_out/gpu_tests_no_pdl.txt 2>&1; echo "no-pdl tests rc=$?"; tail -3 gpurun_out/gpu_tests_no_pdl.txt
 python tools/pdl_check.py > gpurun_out/pdl_check.txt 2>&1; echo "pdl_check rc=$?"; tail -8 gpurun_out/pdl_check.txt
 python bench.py > gpurun_out/bench_512.json 2> gpurun_out/bench_512.err; echo "bench rc=$?"; cat gpurun_out/bench_512.json
 python tools/perf_matrix.py > gpurun_out/perf_matrix.txt 2>&1; echo "perf_matrix rc=$?"; cat gpurun_out/perf_matrix.txt
