@@ -213,6 +213,9 @@ def _read_page(buf, tags, bo):
     pred = _one(tags, _PREDICTOR, 1)
     dtype, bits = _sample_dtype(tags, bo)
     out_dtype = np.dtype(np.bool_) if bits == 1 else dtype.newbyteorder("=")       # bilevel -> bool like tifffile
+    if min(W, H, spp) < 1 or W * H * spp * max(bits // 8, 1) > 1100 * len(buf) + (1 << 20):
+        # no supported codec expands beyond ~1032 : 1 (Deflate): a damaged header, not an image
+        raise TiffError(f"implausible image size {W} x {H} x {spp} for a file of {len(buf)} bytes")
     page = np.empty((H, W, spp), out_dtype)
     tiled = _TILE_OFFSETS in tags
     if tiled:
@@ -297,8 +300,11 @@ def imread(path):
             # pages of another shape or type (thumbnails, masks) are not part of the volume: tifffile's first series
             pages = [t for t in ifds if key(t) == key(first)]
             stack = np.stack([_read_page(buf, t, bo) for t in pages])
-    except (struct.error, zlib.error) as e:                      # truncated directory / damaged Deflate stream
-        raise TiffError(f"corrupt TIFF file: {e}") from e
+    except TiffError:
+        raise
+    except (struct.error, zlib.error, KeyError, IndexError, TypeError, ValueError, ArithmeticError, MemoryError) as e:
+        # truncated directory, damaged stream, tag of the wrong type / count, zero sizes ...
+        raise TiffError(f"corrupt TIFF file: {type(e).__name__}: {e}") from e
     if stack.shape[-1] == 1:
         stack = stack[..., 0]
     if stack.shape[0] == 1:

@@ -206,6 +206,25 @@ def test_rejects_what_it_does_not_understand():
     assert issubclass(TiffError, ValueError)
 
 
+def test_damaged_files_raise_tifferror_only():
+    """Byte flips and truncation of valid files: the reader either returns an array or raises TiffError."""
+    rng = np.random.default_rng(0)
+    vol = labels((3, 9, 11), seed=11)
+    seeds = [pil_bytes(vol, compression=c) for c in ("raw", "tiff_lzw", "packbits", "tiff_adobe_deflate")]
+    seeds += [build_tiff(list(vol), bo=">", compress=8), build_tiff(list(vol), big=True), build_tiff(list(vol), tile=(16, 16)),
+              imagej_file(vol, "ImageJ=1.53t\nimages=3\n")]
+    for it in range(4000):
+        b = bytearray(seeds[it % len(seeds)])
+        for _ in range(rng.integers(1, 4)):
+            b[rng.integers(0, len(b))] = rng.integers(0, 256)
+        if rng.random() < 0.1:
+            b = b[: rng.integers(0, len(b))]
+        try:
+            imread(bytes(b))
+        except TiffError:
+            pass
+
+
 @pytest.mark.parametrize("name", ["tiny_lzw.tif", "tiny_deflate_be.tif", "tiny_packbits.tif"])
 def test_committed_fixtures(name):
     """Files written once by tests/golden/make_tiff_fixtures.py (Pillow / the writer above) and kept in the repo:
