@@ -127,3 +127,48 @@ def test_python_surface_matches_reference_signatures():
             assert len(got) == len(ref[meth]), (cls, meth)
         names = [b.__name__ for b in C.__mro__[1:-1]]
         assert [n for n in ref["bases"] if n != "ABC"] == names, (cls, names)
+
+
+def test_header_is_c99_and_layout_matches_ctypes(lib, tmp_path):
+    """A plain C99 caller: the header compiles with gcc -std=c99 -pedantic, links against the library, and the C
+    compiler's struct layout (sizeof / offsetof) is the one the ctypes binding assumes."""
+    import ctypes
+    import shutil
+    import subprocess
+    from taufactor_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "caller.c"
+    src.write_text(r'''
+#include <stddef.h>
+#include <stdio.h>
+#include "taub200.h"
+int main(void)
+{
+    taub_geom g;
+    if (taub_abi_version() != TAUB_ABI_VERSION) return 2;
+    if (taub_geom_init(&g, 2, 30, 28, 1, 30, 0, 1) != TAUB_OK) return 3;
+    if (taub_geom_init(&g, 0, 30, 28, 1, 30, 0, 1) != TAUB_ERR_ARG || taub_last_error()[0] == 0) return 4;
+    taub_geom_init(&g, 2, 30, 28, 1, 30, 0, 1);
+    printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(taub_geom), sizeof(taub_problem),
+           offsetof(taub_geom, plane_stride), offsetof(taub_problem, kind), offsetof(taub_problem, field),
+           offsetof(taub_problem, codes), offsetof(taub_problem, lut), offsetof(taub_problem, omega),
+           offsetof(taub_problem, stop), offsetof(taub_problem, peer_lo), offsetof(taub_problem, peer_hi));
+    printf("%d %d %d %lld %lld %zu\n", g.planes, g.rows, g.pitch, (long long)g.plane_stride, (long long)g.image_stride,
+           taub_field_elems(&g));
+    return 0;
+}
+''')
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-l:libtaub200.so", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    P, Gm = _lib.Problem, _lib.Geom
+    expect = [ctypes.sizeof(Gm), ctypes.sizeof(P), Gm.plane_stride.offset, P.kind.offset, P.field.offset, P.codes.offset,
+              P.lut.offset, P.omega.offset, P.stop.offset, P.peer_lo.offset, P.peer_hi.offset]
+    assert [int(x) for x in out[0].split()] == expect
+    g = Gm()
+    assert lib.taub_geom_init(g, 2, 30, 28, 1, 30, 0, 1) == 0
+    assert [int(x) for x in out[1].split()] == [g.planes, g.rows, g.pitch, g.plane_stride, g.image_stride,
+                                                lib.taub_field_elems(g)]
