@@ -10,6 +10,8 @@ python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/gpu_tests.txt 
 # experimental switches, each against the whole parity suite (bit-exact goldens): odd periodic shapes on the fused
 # kernel; serial launches
 TAUB_FUSE_ODD_PERIODIC=1 python -m pytest tests/test_gpu_parity.py tests/test_gpu_electrode.py -q -m gpu -p no:cacheprovider > gpurun_out/gpu_tests_fuse_odd.txt 2>&1; echo "fuse-odd tests rc=$?"; tail -3 gpurun_out/gpu_tests_fuse_odd.txt
+TAUB_REFRESH_V2=1 python -m pytest tests/test_gpu_parity.py tests/test_gpu_electrode.py -q -m gpu -p no:cacheprovider > gpurun_out/gpu_tests_refresh_v2.txt 2>&1; echo "refresh-v2 tests rc=$?"; tail -3 gpurun_out/gpu_tests_refresh_v2.txt
+TAUB_REFRESH_V2=1 python tools/pdl_check.py 256 512 > gpurun_out/pdl_check_refresh_v2.txt 2>&1; echo "refresh-v2 timing rc=$?"; tail -5 gpurun_out/pdl_check_refresh_v2.txt
 TAUB_PDL=0 python -m pytest tests/test_gpu_parity.py -q -m gpu -p no:cacheprovider > gpurun_out/gpu_tests_no_pdl.txt 2>&1; echo "no-pdl tests rc=$?"; tail -3 gpurun_out/gpu_tests_no_pdl.txt
 python tools/pdl_check.py > gpurun_out/pdl_check.txt 2>&1; echo "pdl_check rc=$?"; tail -8 gpurun_out/pdl_check.txt
 python bench.py > gpurun_out/bench_512.json 2> gpurun_out/bench_512.err; echo "bench rc=$?"; cat gpurun_out/bench_512.json
