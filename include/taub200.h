@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TAUB_ABI_VERSION 8
+#define TAUB_ABI_VERSION 9
 #define TAUB_GHOST 2            /* ghost width in x (planes), y (rows) and z (columns) */
 #define TAUB_COL0 4             /* column of interior voxel k = 0 */
 #define TAUB_MAX_LABELS 64      /* dense phase indices 0..L-1, L <= 64; index L = "outside" */
@@ -206,6 +206,13 @@ int taub_stop_rule_async(int bs, int Nx_global, const float *flux_mean, const do
  * = no percolating path. */
 int taub_flood_round(const uint8_t *mask, uint8_t *reach, int bs, int Nx, int Ny, int Nz, int32_t *changed,
                      void *stream);
+
+/* ---- host-side helpers of taufactor_b200.io.imread (no CUDA): decoders of the two byte-oriented TIFF codecs
+ * (TIFF 6.0 sections 9 and 13).  The reference's users read their volumes with tifffile.imread (README.md:51-54,
+ * every notebook); both return the number of bytes written into dst (decoding stops when dst is full or src is
+ * exhausted) or a negative taub_status (corrupt LZW stream: message in taub_last_error()). */
+int64_t taub_unpackbits(const uint8_t *src, size_t n_src, uint8_t *dst, size_t n_dst);
+int64_t taub_unlzw(const uint8_t *src, size_t n_src, uint8_t *dst, size_t n_dst);
 
 #ifdef __cplusplus
 }

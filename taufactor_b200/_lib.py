@@ -56,6 +56,8 @@ SIGNATURES = {
     "taub_check_async": (c_int, [ctypes.POINTER(Problem), c_vp, c_vp, c_vp, c_vp, c_vp, c_float, c_vp, c_vp]),
     "taub_stop_rule_async": (c_int, [c_int, c_int, c_vp, c_vp, c_vp, c_float, c_vp, c_vp, c_vp]),
     "taub_flood_round": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "taub_unpackbits": (c_i64, [c_vp, ctypes.c_size_t, c_vp, ctypes.c_size_t]),
+    "taub_unlzw": (c_i64, [c_vp, ctypes.c_size_t, c_vp, ctypes.c_size_t]),
 }
 
 _lib = None
@@ -77,7 +79,7 @@ def load():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.taub_abi_version() != 8:
+        if lib.taub_abi_version() != 9:
             raise ImportError("libtaub200.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib

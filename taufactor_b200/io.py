@@ -12,7 +12,8 @@ not part of this image, so this module reads the TIFF flavours those volumes com
 * ImageJ hyperstacks whose planes follow the first page contiguously (``images=N`` in the description: how
   ImageJ / Fiji store stacks, and the only form they use above 4 GB).
 
-``imread`` returns what ``tifffile.imread`` returns for these files: ``[pages, height, width]`` (a single
+PackBits and LZW are decoded by the C routines of ``libtaub200.so`` (``csrc/taub_tiff.cu``) when the library is
+built, by the interpreter loops below otherwise.  ``imread`` returns what ``tifffile.imread`` returns for these files: ``[pages, height, width]`` (a single
 page gives ``[height, width]``; several samples per pixel add a trailing axis), in the file's sample type.
 Host-side input decoding only; nothing of it is on the solve path.
 """
@@ -131,7 +132,7 @@ def _unpackbits(data, expected):
         elif c > 128:
             out += data[i:i + 1] * (257 - c)
             i += 1
-    return bytes(out)
+    return bytes(out[:expected])
 
 
 def _unlzw(data, expected):
@@ -151,6 +152,7 @@ def _unlzw(data, expected):
             break
         code = (bitbuf >> (nbits - width)) & ((1 << width) - 1)
         nbits -= width
+        bitbuf &= (1 << nbits) - 1
         if code == 257:
             break
         if code == 256:
@@ -163,8 +165,9 @@ def _unlzw(data, expected):
             entry = table[code]
         elif code < len(table):
             entry = table[code]
-            table.append(prev + entry[:1])
-        elif code == len(table):
+            if len(table) < 4096:
+                table.append(prev + entry[:1])
+        elif code == len(table) and len(table) < 4096:
             entry = prev + prev[:1]
             table.append(entry)
         else:
@@ -173,7 +176,35 @@ def _unlzw(data, expected):
         prev = entry
         if len(table) >= (1 << width) - 1 and width < 12:
             width += 1
-    return bytes(out)
+    return bytes(out[:expected])
+
+
+def _native():
+    """The C decoders of libtaub200.so (csrc/taub_tiff.cu: taub_unpackbits / taub_unlzw, ~100x the interpreter
+    loops below), or None when the library is not built -- reading a file does not need a GPU."""
+    global _NATIVE
+    if _NATIVE is False:
+        try:
+            from . import _lib
+            _NATIVE = _lib.load()
+        except (ImportError, OSError, AttributeError):
+            _NATIVE = None
+    return _NATIVE
+
+
+_NATIVE = False
+USE_NATIVE = True      # False: always use the pure-Python decoders (tests compare the two)
+
+
+def _native_decode(fn_name, data, expected):
+    import ctypes
+    lib = _native()
+    src = np.frombuffer(data, np.uint8)
+    dst = np.empty(expected, np.uint8)
+    n = getattr(lib, fn_name)(src.ctypes.data_as(ctypes.c_void_p), src.size, dst.ctypes.data_as(ctypes.c_void_p), expected)
+    if n < 0:
+        raise TiffError(lib.taub_last_error().decode(errors="replace"))
+    return dst[:n].tobytes() if n < expected else dst.data
 
 
 def _decompress(chunk, compression, expected):
@@ -181,10 +212,11 @@ def _decompress(chunk, compression, expected):
         return chunk
     if compression in (8, 32946):
         return zlib.decompress(chunk)
-    if compression == 32773:
-        return _unpackbits(bytes(chunk), expected)
-    if compression == 5:
-        return _unlzw(bytes(chunk), expected)
+    if compression in (32773, 5):
+        name = "taub_unpackbits" if compression == 32773 else "taub_unlzw"
+        if USE_NATIVE and _native() is not None:
+            return _native_decode(name, bytes(chunk), expected)
+        return (_unpackbits if compression == 32773 else _unlzw)(bytes(chunk), expected)
     raise TiffError(f"unsupported TIFF compression {compression} (supported: none, Deflate, PackBits, LZW)")
 
 

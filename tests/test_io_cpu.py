@@ -231,3 +231,69 @@ def test_committed_fixtures(name):
     the expected volume is regenerated from its seed."""
     vol = labels((4, 9, 11), seed=11)
     assert np.array_equal(imread(os.path.join(GOLDEN, name)), vol)
+
+
+# ----------------------------------------------------------------------------- native decoders (csrc/taub_tiff.cu)
+def _strips(data):
+    """(compressed strip, decoded size) pairs of a TIFF written by the helpers above."""
+    import taufactor_b200.io as tio
+    buf = memoryview(data)
+    ifds, bo = tio._read_ifds(buf)
+    out = []
+    for t in ifds:
+        W, H, rps = t[256][0], t[257][0], t.get(278, (t[257][0],))[0]
+        bps = t[258][0] // 8 * t.get(277, (1,))[0]
+        for k, (off, cnt) in enumerate(zip(t[273], t[279])):
+            rows = min(rps, H - k * rps)
+            out.append((bytes(buf[off:off + cnt]), rows * W * bps))
+    return out
+
+
+@pytest.mark.parametrize("compression,fn,code", [("packbits", "taub_unpackbits", 32773), ("tiff_lzw", "taub_unlzw", 5)])
+def test_native_decoders_equal_the_python_ones(compression, fn, code):
+    import taufactor_b200.io as tio
+    if tio._native() is None:
+        pytest.skip("libtaub200.so not built")
+    rng = np.random.default_rng(4)
+    vols = [labels((3, 40, 50), 2), (rng.random((2, 64, 96)) * 255).astype(np.uint8),          # runs / noise (12-bit codes)
+            np.zeros((1, 300, 300), np.uint8), (rng.random((1, 128, 257)) * 65535).astype(np.uint16)]
+    for v in vols:
+        for strip, n in _strips(pil_bytes(v, compression=compression)):
+            py = (tio._unpackbits if code == 32773 else tio._unlzw)(strip, n)
+            assert tio._native_decode(fn, strip, n) == py and len(py) == n
+            # a destination smaller than the stream: both stop when it is full
+            assert tio._native_decode(fn, strip, n // 3) == py[: n // 3]
+    # end to end through imread, both ways
+    v = vols[1]
+    data = pil_bytes(v, compression=compression)
+    try:
+        tio.USE_NATIVE = False
+        a = imread(data)
+    finally:
+        tio.USE_NATIVE = True
+    assert np.array_equal(a, v) and np.array_equal(imread(data), v)
+
+
+def test_native_decoders_survive_damaged_streams():
+    import taufactor_b200.io as tio
+    if tio._native() is None:
+        pytest.skip("libtaub200.so not built")
+    rng = np.random.default_rng(5)
+    v = (rng.random((1, 64, 96)) * 255).astype(np.uint8)
+    for compression, fn, py in (("packbits", "taub_unpackbits", tio._unpackbits), ("tiff_lzw", "taub_unlzw", tio._unlzw)):
+        strip, n = _strips(pil_bytes(v, compression=compression))[0]
+        for it in range(3000):
+            b = bytearray(strip)
+            for _ in range(rng.integers(1, 6)):
+                b[rng.integers(0, len(b))] = rng.integers(0, 256)
+            if it % 7 == 0:
+                b = b[: rng.integers(0, len(b))]
+            try:
+                got = tio._native_decode(fn, bytes(b), n)
+            except TiffError:
+                got = None
+            try:
+                want = py(bytes(b), n)
+            except TiffError:
+                want = None
+            assert (got is None) == (want is None) and (got is None or bytes(got) == want), (compression, it)
