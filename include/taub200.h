@@ -210,7 +210,7 @@ int taub_flood_round(const uint8_t *mask, uint8_t *reach, int bs, int Nx, int Ny
 /* ---- host-side helpers of taufactor_b200.io.imread (no CUDA): decoders of the two byte-oriented TIFF codecs
  * (TIFF 6.0 sections 9 and 13).  The reference's users read their volumes with tifffile.imread (README.md:51-54,
  * every notebook); both return the number of bytes written into dst (decoding stops when dst is full or src is
- * exhausted) or a negative taub_status (corrupt LZW stream: message in taub_last_error()). */
+ * exhausted) or a negative status code for a corrupt LZW stream, message in taub_last_error(). */
 int64_t taub_unpackbits(const uint8_t *src, size_t n_src, uint8_t *dst, size_t n_dst);
 int64_t taub_unlzw(const uint8_t *src, size_t n_src, uint8_t *dst, size_t n_dst);
 

@@ -11,7 +11,7 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from taufactor_b200.build import NVCC_FLAGS, SOURCES, nvcc  # noqa: E402
+from taufactor_b200.build import NVCC_FLAGS, nvcc  # noqa: E402
 
 
 def kernels(so):
@@ -35,7 +35,7 @@ def build_rev(rev, tmp):
     so = os.path.join(tmp, "rev.so")
     src = os.path.join(tmp, "taufactor_b200", "csrc")
     subprocess.check_call([nvcc()] + NVCC_FLAGS + ["-I", os.path.join(tmp, "include"), "-I", src]
-                          + [os.path.join(src, s) for s in SOURCES] + ["-o", so])
+                          + sorted(os.path.join(src, f) for f in os.listdir(src) if f.endswith(".cu")) + ["-o", so])
     return so
 
 
