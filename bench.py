@@ -4,19 +4,27 @@ time-to-converged tau).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size 512]
 
-A "step" is one pass of the solve loop's unit of work: 100 reference iterations (checkerboard
-half-sweeps over the whole lattice) followed by one flux / convergence check, exactly what
-``Solver.solve()`` executes between two stop-rule evaluations.  LUP = one voxel visited in one
-reference iteration; GLUPS = bs*Nx*Ny*Nz*iterations / seconds / 1e9.
+A "step" is the solve loop's unit of work: 100 reference iterations (checkerboard half-sweeps over the
+whole lattice) followed by one flux / convergence check -- what ``Solver.solve()`` keeps queued on the
+device between two reads of the check records (``SORSolver.run_blocks``: no host synchronisation inside
+the timed region).  LUP = one voxel visited in one reference iteration;
+GLUPS = bs*Nx*Ny*Nz*iterations / seconds / 1e9.
 
-N = 1   workload = BASELINE configs[1]: tau.Solver on the 512^3 synthetic blob microstructure.
-N > 1   workload = the 2048-plane volume tiled from that blob, x-slab partitioned over the N ranks
-        (ghost-plane exchange each pass); ``--workload batch`` runs configs[2] instead (one
-        independent 384^3 image per rank, joint stop rule).
-Prints ONE JSON line (rank 0).  ``--impl reference`` times the reference's CPU algorithm (the
-oracle's PyTorch-eager port; the reference itself is Python and does not travel to the GPU box).
+N = 1   workload = BASELINE configs[1]: tau.Solver on the 512^3 synthetic blob microstructure.  The line also
+        carries ``scale_base`` (the 2048^3 volume of configs[4] on this ONE GPU: the base of the strong-scaling
+        curve) and ``configs`` (configs[0], [2], [3] on this GPU: time-to-converged, tau, GLUPS).
+N > 1   workload = the 2048^3 volume (the periodic 512^3 blob tiled 4x4x4), x-slab partitioned over the N ranks
+        (ghost-plane exchange each pass).  Before anything is timed the ranks check a 512^3 slab solve over the same
+        NCCL / peer-memory path bit for bit against the single-GPU solve (``parity``; the run fails if it differs);
+        rank 0 then measures the same 2048^3 volume on its GPU alone (``scale_base`` -> ``speedup_vs_1gpu_2048``);
+        ``batch`` = configs[2] (one independent 384^3 image per rank, joint stop rule).
+Prints ONE JSON line (rank 0).  ``--impl reference`` times the UNMODIFIED reference package (baseline/_ref, see
+baseline/__init__.py) on the host cores through its own ``Solver(img, device='cpu').solve(...)``; when it is not
+staged, the oracle's PyTorch-eager port of the same loop (``kind: "port"``).
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -32,7 +40,9 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 BYTES_PER_LUP = 8.125      # fp32 field read + write + 1 bit of mask
+BYTES_PER_LUP_MULTI = 9.0  # fp32 field read + write + 1 byte phase label
 ITERS_PER_STEP = 100
+D3 = {0: 0.0, 1: 1.0, 2: 0.3}   # config 4 diffusivities
 
 
 def measured_peak():
@@ -90,214 +100,448 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def blob_image(size, seed=None):
+def images(jobs):
+    """Seeded volumes of SURVEY.md 8(d), generated in parallel child processes and cached under the temp directory."""
     import cases
-    return cases.blobs(size, 0.5, seed=size if seed is None else seed)
+    return cases.generate_parallel(jobs)
+
+
+def blob_image(size, seed=None):
+    return images([("blobs", size, size if seed is None else seed)])[0]
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
-def cpu_reference(img, n_iters, warm=1):
-    """The reference's CPU algorithm (PyTorch-eager port of ref:174-182) on all host threads."""
+class CpuReference:
+    """The reference's own CPU path on all host threads: ``taufactor.Solver(img, device='cpu')`` and its stock
+    ``solve()`` loop (taufactor.py:156-191), advanced a few iterations at a time through ``iter_limit``.  Falls back to
+    the oracle's PyTorch-eager port of that loop when the reference package is not staged."""
+
+    def __init__(self, img):
+        import torch
+        import baseline
+        self.threads = os.cpu_count() or 1
+        torch.set_num_threads(self.threads)
+        self.img = img
+        self.ref = baseline.load_reference()
+        t0 = time.perf_counter()
+        if self.ref is not None:
+            self.kind = "reference"
+            with quiet():
+                self.S = self.ref.Solver(img, device="cpu")
+        else:
+            from oracle import sor_numpy as orc, sor_torch
+            self.kind = "port"
+            self._half_sweep = sor_torch.half_sweep
+            self.S = sor_torch.from_state(orc.build_binary(img))
+        self.ctor_s = time.perf_counter() - t0
+
+    def run(self, n_iters):
+        """n more iterations; returns seconds."""
+        t0 = time.perf_counter()
+        if self.kind == "reference":
+            with quiet():
+                self.S.solve(iter_limit=self.S.iter + n_iters, verbose=False)
+        else:
+            for _ in range(n_iters):
+                self._half_sweep(self.S)
+        return time.perf_counter() - t0
+
+    def describe(self):
+        return ("unmodified reference package (taufactor 1.2.1, baseline/_ref): Solver(img, device='cpu').solve(iter_limit=...)"
+                if self.kind == "reference" else "PyTorch-eager port of the reference loop (oracle/sor_torch.py)")
+
+
+def cpu_time_to_converged(img):
+    """Full reference solve of a small volume on the host (config 1): seconds, tau, iterations."""
+    import baseline
+    ref = baseline.load_reference()
+    if ref is None:
+        return None
     import torch
-    from oracle import sor_numpy as orc, sor_torch
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    st = orc.build_binary(img)
-    t = sor_torch.from_state(st)
-    for _ in range(warm):
-        sor_torch.half_sweep(t)
+    torch.set_num_threads(os.cpu_count() or 1)
     t0 = time.perf_counter()
-    for _ in range(n_iters):
-        sor_torch.half_sweep(t)
-    dt = time.perf_counter() - t0
-    return img.size * n_iters / dt / 1e9, threads, dt
+    with quiet():
+        S = ref.Solver(img, device="cpu")
+        S.solve(verbose=False)
+    return {"time_to_converged_s": time.perf_counter() - t0, "tau": [float(x) for x in S.tau], "iterations": int(S.iter),
+            "cores": os.cpu_count() or 1, "kind": "reference"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base = min(args.size, 512)                    # --size > 512 means the 512^3 blob tiled: one tile is the sample
-    img = blob_image(base)
-    sample = img[: max(8, base // 4)]             # bounded sample: a quarter of the planes
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     n_it = 4
-    vals = []
+    if world > 1 and args.workload == "batch":
+        img = blob_image(384, seed=384)
+        workload = f"batched Solver: {world} x 384^3 independent volumes, one per GPU"
+        sample = f"{n_it} iterations per step of ONE of the {world} 384^3 images (whole image)"
+    elif world > 1 or args.size > 512:
+        # the 2048^3 volume is the 512^3 blob tiled; the reference cannot construct a 2048^3 state (172 GB): one tile
+        img = blob_image(512)
+        side = args.size if args.size > 512 else 2048
+        workload = (f"tau.Solver on {side}^3 volume (512^3 blob tiled {side // 512}x{side // 512}x{side // 512}), "
+                    + ("x-slab partitioned" if world > 1 else "single GPU"))
+        sample = (f"{n_it} iterations per step of ONE 512^3 tile of that volume (whole tile; the reference cannot "
+                  f"build its state at {side}^3)")
+    else:
+        img = blob_image(args.size)
+        workload = f"tau.Solver on {args.size}^3 synthetic blob microstructure (porosity 0.5, seed {args.size})"
+        sample = f"{n_it} iterations per step of the whole {args.size}^3 volume"
+    cpu = CpuReference(img)
     for _ in range(args.warmup):
-        cpu_reference(sample, 1, warm=0)
+        cpu.run(1)
     t_all = 0.0
     for _ in range(args.steps):
-        v, threads, dt = cpu_reference(sample, n_it)
-        vals.append(v); t_all += dt
-    value = float(np.mean(vals))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1 and args.workload == "slab":
-        # the N-GPU arm runs the 512^3 blob tiled to 2048^3: a 128 x 512 x 512 block of one tile is a sample of it
-        side = args.size if args.size > 512 else 2048
-        workload = f"tau.Solver on {side}^3 volume (512^3 blob tiled {side // 512}x{side // 512}x{side // 512}), x-slab partitioned"
-        desc = (f"{n_it} iterations per step on a {sample.shape[0]}x{base}x{base} block of one tile of that volume, "
-                f"PyTorch-eager port of the reference loop on the host cores (rank 0 only)")
-    else:
-        if args.size > 512:
-            workload = f"tau.Solver on {args.size}^3 volume (512^3 blob tiled), single GPU"
-        else:
-            workload = f"tau.Solver on {args.size}^3 synthetic blob microstructure (porosity 0.5, seed {args.size})"
-        desc = (f"{n_it} iterations per step on the first {sample.shape[0]} planes of the {base}^3 blob volume "
-                f"({sample.shape[0]}x{base}x{base}), PyTorch-eager port of the reference loop")
+        t_all += cpu.run(n_it)
+    value = img.size * n_it * args.steps / t_all / 1e9
     line = {"impl": "reference", "metric": "stencil_sweep_throughput", "value": value, "unit": "GLUPS",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_all / max(args.steps, 1), "higher_is_better": True,
             "scaling": "strong" if (world > 1 and args.workload == "slab") else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "l2": "inputs larger than L2"},
-            "cpu_baseline": {"value": value, "unit": "GLUPS", "cores": threads, "kind": "port", "sample": desc},
+            "cpu_baseline": {"value": value, "unit": "GLUPS", "cores": cpu.threads, "kind": cpu.kind,
+                             "sample": f"{sample}; {cpu.describe()}; state build {cpu.ctor_s:.1f} s (not timed)"},
             "e2e": {"value": value, "unit": "GLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
-# ----------------------------------------------------------------------------- multi-GPU workloads
-def make_bench_solver(args, rank, world, dev):
-    """Workloads of ``bench.py --gpus N`` (N > 1)."""
+# ----------------------------------------------------------------------------- helpers of our arm
+class Env:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def sync_all(self):
+        self.torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_true(self, flag):
+        if self.world == 1:
+            return bool(flag)
+        t = self.torch.tensor([1 if flag else 0], device=self.dev, dtype=self.torch.int64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(int(t.item()))
+
+
+def voxels_of(S):
+    return S.global_voxels if hasattr(S, "global_voxels") else int(np.prod(S.cpu_img.shape))
+
+
+def timed_blocks(env, S, steps, warmup):
+    """``steps`` x (100 iterations + device-side check), queued without host synchronisation; CUDA events on the
+    launching stream, max over ranks.  Returns ms for all steps."""
+    torch = env.torch
+    can = hasattr(S, "run_blocks") and S.iter % 100 == 0 and S._can_pipeline() and getattr(S, "pipeline", True)
+
+    def step(n=1):
+        if can:
+            S.run_blocks(n)
+        else:                       # batch-sharded solver: the joint rule needs the host at every check
+            for _ in range(n):
+                S._advance(ITERS_PER_STEP)
+                S._check_only()
+
+    step(max(warmup, 3))
+    env.sync_all()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    step(steps)
+    ev1.record()
+    env.sync_all()
+    return env.max_over_ranks(ev0.elapsed_time(ev1)), can
+
+
+def timed_sweeps(env, S, n_sw=200):
+    """Sweeps only (the dominant kernel): n_sw iterations, CUDA events on the launching stream."""
+    torch = env.torch
+    lib = S._lib if hasattr(S, "_lib") else S.local._lib
+    S._advance(ITERS_PER_STEP)
+    env.sync_all()
+    l0 = lib.taub_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    S._advance(n_sw)
+    ev1.record()
+    env.sync_all()
+    return ev0.elapsed_time(ev1), int(lib.taub_launch_count() - l0)
+
+
+def e2e_run(env, make, iter_limit, **solve_kw):
+    """The user-facing call with HOST buffers: ctor (H2D of the image, state build) + solve() to the reference's
+    stop rule (D2H of the check records).  Returns (solver, seconds total [max over ranks], seconds ctor)."""
+    torch = env.torch
+    env.sync_all()
+    t0 = time.perf_counter()
+    with quiet():
+        S = make()
+        torch.cuda.synchronize(env.dev)
+        t_ctor = time.perf_counter() - t0
+        S.solve(verbose=False, iter_limit=iter_limit, **solve_kw)
+    env.sync_all()
+    return S, env.max_over_ranks(time.perf_counter() - t0), t_ctor
+
+
+def tiled_2048_window(side, lo, hi):
+    """Global planes [lo, hi) of the side^3 volume = the periodic 512^3 blob tiled, as a pinned host array."""
     import torch
-    import cases
-    from taufactor_b200.distributed import BatchShardedSolver, DistributedSolver, image_window, slab_bounds
-    if args.workload == "batch":
-        # BASELINE configs[2]: one independent 384^3 image per GPU
-        imgs = np.zeros((world, 384, 384, 384), np.uint8)      # every rank only fills (and uses) its own image
-        imgs[rank] = cases.blobs(384, 0.5, seed=384 + rank)
-        return (lambda: BatchShardedSolver(imgs, device=dev), f"batched Solver: {world} x 384^3 independent volumes, one per GPU",
-                f"batch sharded, {world} ranks, joint stop rule (2 floats per image all-gathered per check)", imgs[rank])
-    # BASELINE configs[4]: the periodic 512^3 blob tiled to side*side*side, x-slab partitioned
-    side = args.size if args.size > 512 else 2048
     reps = side // 512
-    blob = cases.blobs(512, 0.5, seed=512)
-    lo, hi = slab_bounds(side, world)[rank]
-    w0, w1 = image_window(lo, hi, side)
-    planes = np.arange(w0, w1) % 512
-    window = torch.empty((w1 - w0, side, side), dtype=torch.uint8).pin_memory()
-    window.numpy()[...] = np.tile(blob[planes], (1, reps, reps))
-    host = window.numpy()
-    make = lambda: DistributedSolver(host, device=dev, window=(w0, w1), shape=(side, side, side))
-    return (make, f"tau.Solver on {side}^3 volume (512^3 blob tiled {reps}x{reps}x{reps}), x-slab partitioned",
-            f"{world} x-slabs of {side // world} planes; per fused pass the boundary kernels store 2 ghost planes per "
-            f"neighbour over NVLink peer memory (device-side signals), overlapped with the interior planes", host)
+    blob = blob_image(512)
+    window = torch.empty((hi - lo, side, side), dtype=torch.uint8).pin_memory()
+    window.numpy()[...] = np.tile(blob[np.arange(lo, hi) % 512], (1, reps, reps))
+    return window
+
+
+def scale_base(env, side, steps, converge):
+    """The strong-scaling base: the SAME side^3 volume on ONE GPU (this rank's), same step, same kernels.
+    ``converge``: also run host image -> converged tau (the e2e figure of the N-GPU lines)."""
+    import taufactor_b200 as tau
+    torch = env.torch
+    e1 = Env1(env)
+    t0 = time.perf_counter()
+    win = tiled_2048_window(side, 0, side)
+    host = win.numpy()
+    t_img = time.perf_counter() - t0
+    out = {"workload": f"tau.Solver on {side}^3 volume (512^3 blob tiled), single GPU", "n_gpus": 1, "host_image_s": t_img}
+    if converge:
+        S, t, tc = e2e_run(e1, lambda: tau.Solver(host, device=env.dev), 10000)
+        out.update({"time_to_converged_s": t, "ctor_s": tc, "iterations": int(S.iter), "converged": bool(S.converged),
+                    "tau": [float(x) for x in S.tau], "e2e_value": host.size * S.iter / t / 1e9})
+    else:
+        t0 = time.perf_counter()
+        S = tau.Solver(host, device=env.dev)
+        torch.cuda.synchronize(env.dev)
+        out["ctor_s"] = time.perf_counter() - t0
+    ms, _ = timed_blocks(e1, S, steps, 2)
+    ms_sw, _ = timed_sweeps(e1, S, 100)
+    out.update({"value": host.size * ITERS_PER_STEP * steps / (ms * 1e-3) / 1e9, "unit": "GLUPS", "steps": steps,
+                "ms_per_step": ms / steps, "glups_sweeps_only": host.size * 100 / (ms_sw * 1e-3) / 1e9})
+    del S, win, host
+    torch.cuda.empty_cache()
+    return out
+
+
+class Env1:
+    """Single-rank view of an Env (helpers that must not enter a collective)."""
+    def __init__(self, env):
+        self.torch, self.dev, self.world, self.rank = env.torch, env.dev, 1, 0
+
+    def sync_all(self):
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, x):
+        return float(x)
+
+
+def parity_check(env):
+    """512^3 blob volume: x-slab solve over the NCCL / peer-memory path vs the single-GPU solve on every rank, bit for
+    bit on the field after 200 iterations, and the checks' tau (taufactor.py:156-191)."""
+    import taufactor_b200 as tau
+    from taufactor_b200.distributed import DistributedSolver
+    torch = env.torch
+    img = blob_image(512)
+    out = {}
+    ok_all = True
+    for name, periodic in (("Solver", False), ("PeriodicSolver", True)):
+        with quiet():
+            D = DistributedSolver(img, device=env.dev, periodic=periodic)
+            D.solve(iter_limit=200, verbose=False)
+            M = (tau.PeriodicSolver if periodic else tau.Solver)(img, device=env.dev)
+            M.solve(iter_limit=200, verbose=False)
+        mine = D.field[:, 1:-1, 1:-1, 1:-1]
+        whole = M.field[:, 1 + D.lo:1 + D.hi, 1:-1, 1:-1]
+        same = bool(torch.equal(mine, whole)) and D.iter == M.iter == 200
+        tau_close = bool(np.allclose(np.asarray(D.tau), np.asarray(M.tau), rtol=1e-6, atol=0))
+        ok = env.all_true(same and tau_close)
+        p2p = env.all_true(bool(getattr(D, "p2p_active", False)))
+        out[name] = {"slab_bitwise": ok, "p2p": p2p, "tau": [float(x) for x in np.asarray(M.tau)],
+                     "tau_bitwise": env.all_true(bool(np.array_equal(np.asarray(D.tau), np.asarray(M.tau))))}
+        ok_all = ok_all and ok
+        del D, M
+        torch.cuda.empty_cache()
+    return {"slab_bitwise": ok_all, "p2p": all(v["p2p"] for v in out.values()),
+            "what": "512^3 blobs, 200 iterations + 2 checks, every rank compares its slab with the single-GPU field",
+            "cases": out}
+
+
+# ----------------------------------------------------------------------------- extra configs on one GPU
+def config_results(env, skip):
+    """BASELINE configs[0], [2], [3] on this GPU: time from host image to converged tau, tau, GLUPS."""
+    import cases
+    import taufactor_b200 as tau
+    torch = env.torch
+    e1 = Env1(env)
+    out = {}
+    if "config1" not in skip:
+        img = cases.random_img(100, 0.5, 0)
+        e2e_run(e1, lambda: tau.Solver(img, device=env.dev), 10000)
+        S, t, tc = e2e_run(e1, lambda: tau.Solver(img, device=env.dev), 10000)
+        out["config1"] = {"workload": "tau.Solver on 100^3 random binary microstructure (porosity 0.5, seed 0)",
+                          "time_to_converged_s": t, "ctor_s": tc, "iterations": int(S.iter), "tau": [float(x) for x in S.tau],
+                          "glups_e2e": img.size * S.iter / t / 1e9, "cpu_reference": cpu_time_to_converged(img)}
+        del S
+    jobs = []
+    if "config3" not in skip:
+        jobs += [("blobs", 384, 384 + b) for b in range(8)]
+    if "config4" not in skip:
+        jobs += [("blobs3", 768, 768)]
+    imgs = images(jobs) if jobs else []
+    if "config3" not in skip:
+        batch = np.stack(imgs[:8])
+        S, t, tc = e2e_run(e1, lambda: tau.Solver(batch, device=env.dev), 10000)
+        ms, _ = timed_blocks(e1, S, 5, 3)
+        out["config3_one_gpu"] = {"workload": "batched Solver: 8 x 384^3 independent volumes as ONE batch on this GPU (joint stop rule)",
+                                  "time_to_converged_s": t, "ctor_s": tc, "iterations": int(S.iter),
+                                  "tau": [float(x) for x in S.tau], "value": batch.size * 100 * 5 / (ms * 1e-3) / 1e9,
+                                  "unit": "GLUPS", "ms_per_step": ms / 5}
+        del S, batch
+        torch.cuda.empty_cache()
+    if "config4" not in skip:
+        img3 = imgs[-1]
+        peak, _ = measured_peak()
+        for cls in ("MultiPhaseSolver", "PeriodicMultiPhaseSolver"):
+            S, t, tc = e2e_run(e1, lambda: getattr(tau, cls)(img3, dict(D3), device=env.dev), 10000)
+            its, tau_v = int(S.iter), [float(x) for x in S.tau]
+            ms, _ = timed_blocks(e1, S, 5, 3)
+            ms_sw, _ = timed_sweeps(e1, S, 100)
+            g_sw = img3.size * 100 / (ms_sw * 1e-3) / 1e9
+            out["config4_" + cls] = {"workload": f"{cls} on 768^3 three-phase blobs, D = {D3}",
+                                     "time_to_converged_s": t, "ctor_s": tc, "iterations": its, "tau": tau_v,
+                                     "value": img3.size * 100 * 5 / (ms * 1e-3) / 1e9, "unit": "GLUPS", "ms_per_step": ms / 5,
+                                     "glups_sweeps_only": g_sw, "n_stencil_classes": getattr(S, "n_stencil_classes", None),
+                                     "kernel": S.sweep_kernel_name(),
+                                     "roofline_frac": g_sw * BYTES_PER_LUP_MULTI / peak, "algorithmic_bytes_per_lup": BYTES_PER_LUP_MULTI}
+            del S
+            torch.cuda.empty_cache()
+    return out
 
 
 # ----------------------------------------------------------------------------- our arm
 def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    env = Env()
+    torch, dist, rank, world, dev = env.torch, env.dist, env.rank, env.world, env.dev
     import taufactor_b200 as tau
     from taufactor_b200 import _lib
     lib = _lib.load()
-
-    def sync_all():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize(dev)
+    skip = set(filter(None, args.skip.split(",")))
 
     # warm the context / library with a tiny problem
-    w = tau.Solver(np.ones((16, 16, 16), np.uint8), device=dev)
-    w.solve(iter_limit=100, verbose=False)
+    with quiet():
+        w = tau.Solver(np.ones((16, 16, 16), np.uint8), device=dev)
+        w.solve(iter_limit=100, verbose=False)
     del w
 
+    parity = base = None
+    pageable = None
     if world == 1:
-        if args.size > 512:     # the multi-GPU workload on one GPU (strong-scaling reference point)
-            reps = args.size // 512
-            img = np.tile(blob_image(512), (reps, reps, reps))
-            workload = f"tau.Solver on {512 * reps}^3 volume (512^3 blob tiled {reps}x{reps}x{reps}), single GPU"
+        if args.size > 512:     # the multi-GPU workload on one GPU
+            pinned = tiled_2048_window(args.size, 0, args.size)
+            workload = f"tau.Solver on {args.size}^3 volume (512^3 blob tiled), single GPU"
         else:
             img = blob_image(args.size)
             workload = f"tau.Solver on {args.size}^3 synthetic blob microstructure (porosity 0.5, seed {args.size})"
-        pinned = torch.empty(img.shape, dtype=torch.uint8).pin_memory()
-        pinned.numpy()[...] = img
+            pinned = torch.empty(img.shape, dtype=torch.uint8).pin_memory()
+            pinned.numpy()[...] = img
+            pageable = img
         host_img = pinned.numpy()
-        del img
         make = lambda: tau.Solver(host_img, device=dev)
         parallelism = "single GPU"
     else:
-        make, workload, parallelism, host_img = make_bench_solver(args, rank, world, dev)
+        from taufactor_b200.distributed import BatchShardedSolver, DistributedSolver, image_window, slab_bounds
+        if args.workload == "slab" and "parity" not in skip:
+            parity = parity_check(env)
+            if rank == 0 and not parity["slab_bitwise"]:
+                print(json.dumps({"error": "slab solve differs from the single-GPU solve", "parity": parity}))
+            if not parity["slab_bitwise"]:
+                dist.destroy_process_group()
+                sys.exit(3)
+        side = args.size if args.size > 512 else 2048
+        if args.workload == "slab" and "scale_base" not in skip:
+            if rank == 0:
+                try:
+                    base = scale_base(env, side, 3, False)
+                except Exception as e:      # noqa: BLE001 -- reported in the line, the N-GPU measurement still runs
+                    base = {"error": repr(e)}
+            env.sync_all()
+        if args.workload == "batch":
+            imgs = np.zeros((world, 384, 384, 384), np.uint8)      # every rank only fills (and uses) its own image
+            imgs[rank] = blob_image(384, seed=384 + rank)
+            make = lambda: BatchShardedSolver(imgs, device=dev)
+            workload = f"batched Solver: {world} x 384^3 independent volumes, one per GPU"
+            parallelism = f"batch sharded, {world} ranks, joint stop rule (2 floats per image all-gathered per check)"
+            host_img = imgs[rank]
+        else:
+            lo, hi = slab_bounds(side, world)[rank]
+            w0, w1 = image_window(lo, hi, side)
+            host_img = tiled_2048_window(side, w0, w1).numpy()
+            make = lambda: DistributedSolver(host_img, device=dev, window=(w0, w1), shape=(side, side, side))
+            workload = f"tau.Solver on {side}^3 volume (512^3 blob tiled {side // 512}x{side // 512}x{side // 512}), x-slab partitioned"
+            parallelism = (f"{world} x-slabs of {side // world} planes; per fused pass the boundary kernels store 2 ghost planes "
+                           f"per neighbour over NVLink peer memory (device-side signals), overlapped with the interior planes")
 
-    # ---- e2e: the user-facing call with HOST buffers: ctor (H2D of the pinned image, state build) +
-    #      solve() to the reference's default stop rule (D2H of the flux profiles every check).
-    #      Run twice back to back: the first run also pays one-time process costs (first large
-    #      cudaMalloc of the caching allocator, lazy module loading, pinned-buffer allocation) and is
-    #      reported as "first_run_s"; the headline is the second, steady-state run.
+    # ---- e2e: host image -> converged tau, twice back to back: the first run also pays one-time process costs
+    #      (first large cudaMalloc of the caching allocator, lazy module loading) and is reported as "first_run_s"
     first_run = None
     for attempt in range(2):
         S = None
-        sync_all()
-        t0 = time.perf_counter()
-        S = make()
-        torch.cuda.synchronize(dev)
-        t_ctor = time.perf_counter() - t0
-        S.solve(verbose=False, iter_limit=args.e2e_iter_limit)
-        sync_all()
-        t_e2e = time.perf_counter() - t0
+        S, t_e2e, t_ctor = e2e_run(env, make, args.e2e_iter_limit)
         if attempt == 0:
             first_run = t_e2e
-    if world > 1:
-        tt = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_e2e = float(tt.item())
-    voxels_total = S.global_voxels if hasattr(S, "global_voxels") else int(np.prod(S.cpu_img.shape))
+    voxels_total = voxels_of(S)
     e2e_iters, e2e_tau = S.iter, (None if S.tau is None else [float(x) for x in S.tau])
     e2e_checks = max(S.iter // 100, 1)
     e2e = {"value": voxels_total * e2e_iters / t_e2e / 1e9, "unit": "GLUPS",
            "h2d_bytes_per_step": int(host_img.nbytes // e2e_checks),
-           "d2h_bytes_per_step": int(4 * (2 * S.Nx - 1) * S.batch_size),
-           "time_to_converged_s": t_e2e, "ctor_s": t_ctor, "solve_s": t_e2e - t_ctor, "first_run_s": first_run, "iterations": e2e_iters, "converged": bool(S.converged), "tau": e2e_tau}
+           "d2h_bytes_per_step": int(4 * (2 * S.Nx - 1 + 2 + 2 * S.batch_size) * S.batch_size),
+           "time_to_converged_s": t_e2e, "ctor_s": t_ctor, "solve_s": t_e2e - t_ctor, "first_run_s": first_run,
+           "iterations": e2e_iters, "converged": bool(S.converged), "tau": e2e_tau, "host_image": "pinned"}
+    if pageable is not None:     # what a drop-in user passes: an ordinary (pageable) NumPy array
+        del S
+        S, t_pg, t_ctor_pg = e2e_run(env, lambda: tau.Solver(pageable, device=dev), args.e2e_iter_limit)
+        e2e["pageable"] = {"value": voxels_total * S.iter / t_pg / 1e9, "time_to_converged_s": t_pg, "ctor_s": t_ctor_pg}
 
-    # ---- device-resident throughput: K steps of (100 iterations + flux check), CUDA events
-    def step():
-        S._advance(ITERS_PER_STEP)
-        S._check_only()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    sampler = ClockSampler(local)
+    # ---- device-resident throughput: K steps of (100 iterations + device-side flux check), CUDA events
+    if S.iter % 100:
+        S._advance(100 - S.iter % 100)
+    timed_blocks(env, S, 3, max(args.warmup, 3))
+    sampler = ClockSampler(env.local)
     if rank == 0:
         sampler.start()
         sampler.wait_first()
-    for _ in range(3):      # keep the GPU under the same load while the sampler spins up
-        step()
-    sync_all()
     t_begin = time.perf_counter()
     l0 = lib.taub_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    sync_all()
-    launches = int(lib.taub_launch_count() - l0)
-    ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
+    ms, queued = timed_blocks(env, S, args.steps, 3)
+    launches = int((lib.taub_launch_count() - l0) * args.steps / (args.steps + 3))
     clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
     value = voxels_total * ITERS_PER_STEP * args.steps / (ms * 1e-3) / 1e9
 
     # ---- roofline of the dominant kernel (the sweep): sweeps only, CUDA events on the same stream
     n_sw = 200
-    S._advance(ITERS_PER_STEP)
-    sync_all()
-    l0 = lib.taub_launch_count()
-    ev0.record()
-    S._advance(n_sw)
-    ev1.record()
-    sync_all()
-    sweep_launches = int(lib.taub_launch_count() - l0)
-    ms_sw = ev0.elapsed_time(ev1)
+    ms_sw, sweep_launches = timed_sweeps(env, S, n_sw)
     local_vox = int(np.prod(S.local_shape)) if hasattr(S, "local_shape") else voxels_total
     peak, peak_src = measured_peak()
     glups_sw = local_vox * n_sw / (ms_sw * 1e-3) / 1e9
@@ -316,40 +560,86 @@ def run_ours(args):
             roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full on the "
                                         "512^3 volume (profiles/traffic.json); algorithmic bytes per launch = "
                                         f"{BYTES_PER_LUP} B x LUPs per launch")
+            if isinstance(t, dict) and t.get("bytes_per_launch"):
+                roofline["dram_gbs_physical"] = t["bytes_per_launch"] / (roofline["avg_launch_us"] * 1e-6) / 1e9
+                roofline["dram_frac_of_peak"] = roofline["dram_gbs_physical"] / peak
         except Exception:
             pass
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
     extra_cfg = {}
     if world > 1 and args.workload == "slab":
         extra_cfg = {"halo_exchange": ("one-sided stores over NVLink peer memory" if getattr(S, "p2p_active", False)
                                        else "NCCL send/recv"),
                      "overlap": bool(getattr(S, "_overlap", False)),
-                     "single_gpu_point": "strong-scaling base = `bench.py --size 2048` on 1 GPU (profiles/SCALING.md), "
-                                         "not the default 512^3 N=1 line"}
+                     "p2p_fallback_reason": getattr(S, "_p2p_error", None)}
+    del S
+    torch.cuda.empty_cache()
 
-    # ---- CPU baseline (rank 0, N = 1 only): bounded sample on the host cores
-    cpu = None
-    if world == 1 and not args.no_cpu:
-        sample = np.ascontiguousarray(host_img[: max(8, min(args.size, 512) // 4), :512, :512])
-        _, _, dt4 = cpu_reference(sample, 4)
-        n_cpu = int(min(400, max(8, 12.0 / max(dt4 / 4, 1e-4))))      # about 12 s of CPU work
-        v, threads, dt = cpu_reference(sample, n_cpu)
-        cpu = {"value": v, "unit": "GLUPS", "cores": threads, "kind": "port",
-               "sample": f"{n_cpu} iterations on the first {sample.shape[0]} planes of the workload volume "
-                         f"({sample.shape[0]}x{args.size}x{args.size}), PyTorch-eager port of the reference loop ({dt:.1f} s)"}
+    # ---- N > 1: configs[2] (batch sharding) in the same line
+    batch = None
+    if world > 1 and args.workload == "slab" and "batch" not in skip:
+        try:
+            imgs = np.zeros((world, 384, 384, 384), np.uint8)
+            imgs[rank] = blob_image(384, seed=384 + rank)
+            B, t_b, tc_b = e2e_run(env, lambda: BatchShardedSolver(imgs, device=dev), 10000)
+            ms_b, _ = timed_blocks(env, B, 5, 3)
+            batch = {"workload": f"batched Solver: {world} x 384^3 independent volumes, one per GPU (joint stop rule)",
+                     "value": int(np.prod(imgs.shape)) * 100 * 5 / (ms_b * 1e-3) / 1e9, "unit": "GLUPS", "ms_per_step": ms_b / 5,
+                     "time_to_converged_s": t_b, "ctor_s": tc_b, "iterations": int(B.iter), "tau": [float(x) for x in B.tau],
+                     "scaling": "weak", "step": "100 iterations + host-side joint check (2 floats per image all-gathered)"}
+            del B
+        except Exception as e:      # noqa: BLE001
+            batch = {"error": repr(e)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- rank 0, N = 1: CPU baseline (bounded sample), the strong-scaling base, the other configs
+    cpu = configs = None
+    if world == 1:
+        if not args.no_cpu:
+            cimg = blob_image(min(args.size, 512))
+            c = CpuReference(cimg)
+            dt = c.run(2)
+            n_cpu = int(min(400, max(4, 12.0 / max(dt / 2, 1e-4))))      # about 12 s of CPU work
+            dt = c.run(n_cpu)
+            cpu = {"value": cimg.size * n_cpu / dt / 1e9, "unit": "GLUPS", "cores": c.threads, "kind": c.kind,
+                   "sample": f"{n_cpu} iterations of the whole {cimg.shape[0]}^3 volume ({dt:.1f} s; state build "
+                             f"{c.ctor_s:.1f} s not timed); {c.describe()}"}
+            del c
+        if args.size <= 512 and "scale_base" not in skip:
+            try:
+                base = scale_base(env, 2048, 3, not args.no_base_converge)
+            except Exception as e:      # noqa: BLE001
+                base = {"error": repr(e)}
+        if args.size <= 512:
+            try:
+                configs = config_results(env, skip)
+            except Exception as e:      # noqa: BLE001
+                configs = {"error": repr(e)}
 
     line = {"metric": "stencil_sweep_throughput", "value": value, "unit": "GLUPS", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak" if world == 1 or args.workload == "batch" else "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict({"workload": workload, "parallelism": parallelism, "iterations_per_step": ITERS_PER_STEP,
+                            "step": ("100 iterations + device-side flux check, queued without host synchronisation"
+                                     if queued else "100 iterations + flux check read back by the host"),
                             "l2": "inputs larger than L2 (field >= 0.5 GB per GPU vs 126 MB L2)"}, **extra_cfg),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "true_updates_per_s": value * 1e9 / 2}
+    if parity is not None:
+        line["parity"] = parity
+    if base is not None:
+        line["scale_base"] = base
+        if world > 1 and "value" in base:
+            line["speedup_vs_1gpu_2048"] = value / base["value"]
+            line["speedup_sweeps_only_vs_1gpu_2048"] = glups_sw * world / base["glups_sweeps_only"]
+    if batch is not None:
+        line["batch"] = batch
+    if configs is not None:
+        line["configs"] = configs
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -365,6 +655,9 @@ def main():
     ap.add_argument("--workload", default="slab", choices=["slab", "batch"])
     ap.add_argument("--e2e-iter-limit", type=int, default=10000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-base-converge", action="store_true",
+                    help="N = 1: measure only the steady-state rate of the 2048^3 strong-scaling base (skip its ~1 min solve)")
+    ap.add_argument("--skip", default="", help="comma list of: parity, scale_base, batch, config1, config3, config4")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

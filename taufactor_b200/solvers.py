@@ -320,17 +320,8 @@ class SORSolver:
         lib, dev = self._lib, self.device
         lib.taub_set_device(self._dev_index)
         bs = self.batch_size
-        prof_dev = self._pipeline_profiles()
+        P, prof_dev = self._pipe_state()
         nprof, nrec = prof_dev.numel(), 2 + 2 * bs
-        if getattr(self, "_pipe", None) is None:
-            with torch.cuda.device(dev):
-                self._pipe = dict(
-                    ctl=torch.zeros(1, dtype=torch.int32, device=dev),
-                    old_tau=torch.zeros(bs, dtype=torch.float32, device=dev),
-                    D_mean=torch.from_numpy(np.atleast_1d(np.asarray(self.D_mean, np.float64)).copy()).to(dev),
-                    rec=torch.zeros(nrec, dtype=torch.float32, device=dev),
-                    host=torch.zeros((self.PIPELINE_DEPTH + 1, nprof + nrec), dtype=torch.float32).pin_memory())
-        P = self._pipe
         P["ctl"].zero_()
         P["old_tau"].copy_(torch.from_numpy(np.broadcast_to(np.asarray(self.old_tau, np.float32), (bs,)).copy()))
         self._prob.stop = P["ctl"].data_ptr()
@@ -389,6 +380,41 @@ class SORSolver:
     def _pipeline_profiles(self):
         """Device record [flux (bs x (Nx-1)) | mean (bs x Nx)] of the whole volume that a queued check fills."""
         return self._prof_dev
+
+    def _pipe_state(self):
+        """Device / pinned-host buffers of the queued checks (stop flag, old tau, D_mean, record), made once."""
+        dev, bs = self.device, self.batch_size
+        prof_dev = self._pipeline_profiles()
+        if getattr(self, "_pipe", None) is None:
+            nprof, nrec = prof_dev.numel(), 2 + 2 * bs
+            with torch.cuda.device(dev):
+                self._pipe = dict(
+                    ctl=torch.zeros(1, dtype=torch.int32, device=dev),
+                    old_tau=torch.zeros(bs, dtype=torch.float32, device=dev),
+                    D_mean=torch.from_numpy(np.atleast_1d(np.asarray(self.D_mean, np.float64)).copy()).to(dev),
+                    rec=torch.zeros(nrec, dtype=torch.float32, device=dev),
+                    host=torch.zeros((self.PIPELINE_DEPTH + 1, nprof + nrec), dtype=torch.float32).pin_memory())
+        return self._pipe, prof_dev
+
+    def run_blocks(self, n_blocks, conv_crit=-1.0):
+        """Queue ``n_blocks`` x (100 iterations + the device-side check of taub_check_async) on the current stream
+        with NO host synchronisation -- what ``solve()`` keeps in flight between two reads of the check records.
+        With the default ``conv_crit`` < 0 the stop rule can never fire, so the queued work always runs (steady-state
+        throughput measurements: bench.py, profiling); the last check's record stays on the device.  Needs
+        ``iter % 100 == 0``; advances ``iter``."""
+        if self.iter % 100 != 0 or not self._can_pipeline():
+            raise ValueError("run_blocks needs iter % 100 == 0 and a solver that supports queued checks")
+        self._lib.taub_set_device(self._dev_index)
+        P, _ = self._pipe_state()
+        P["ctl"].zero_()
+        self._prob.stop = P["ctl"].data_ptr()
+        try:
+            flags, stream = self._iterate_flags(), self._stream()
+            for _ in range(int(n_blocks)):
+                self._queue_block(self.iter, flags, conv_crit, P, stream)
+                self.iter += 100
+        finally:
+            self._prob.stop = None
 
     def _queue_block(self, it, flags, conv_crit, P, stream):
         """Queue 100 iterations starting at iteration ``it`` and the device-side check that follows."""

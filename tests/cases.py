@@ -34,6 +34,63 @@ def blobs3(shape, fractions=(0.40, 0.35, 0.25), blobiness=1, seed=0):
     return np.digitize(g, np.quantile(g, np.cumsum(fractions)[:-1])).astype(np.uint8)
 
 
+def generate(job):
+    """(kind, size, seed) -> image; picklable entry point for worker processes that build big volumes."""
+    kind, size, seed = job
+    if kind == "blobs":
+        return blobs(size, 0.5, seed=seed)
+    if kind == "blobs3":
+        return blobs3(size, seed=seed)
+    raise ValueError(kind)
+
+
+def _cache_path(job):
+    import os
+    import tempfile
+    d = os.path.join(tempfile.gettempdir(), "taub_img_cache")
+    os.makedirs(d, exist_ok=True)
+    return os.path.join(d, "{}_{}_{}.npy".format(*job))
+
+
+def generate_parallel(jobs, workers=None, cache=True):
+    """Images of ``jobs`` = [(kind, size, seed), ...], built in parallel child interpreters (``python cases.py kind
+    size seed out.npy``: plain subprocesses, so a CUDA context in the parent does not matter) and kept as .npy files
+    under the system temp directory, so the two arms of bench.py and the tests of one box generate each volume once."""
+    import os
+    import subprocess
+    import sys
+    workers = workers or max(1, min(len(jobs), (os.cpu_count() or 2) - 1))
+    out = [None] * len(jobs)
+    todo, running = [], []
+    for i, job in enumerate(jobs):
+        path = _cache_path(job)
+        if cache and os.path.exists(path):
+            try:
+                out[i] = np.load(path)
+                continue
+            except Exception:
+                os.remove(path)
+        todo.append((i, job, path))
+    if len(todo) == 1 and not cache:
+        i, job, _ = todo.pop()
+        out[i] = generate(job)
+    while todo or running:
+        while todo and len(running) < workers:
+            i, (kind, size, seed), path = todo.pop(0)
+            tmp = path + f".{os.getpid()}.tmp.npy"
+            running.append((i, path, tmp, subprocess.Popen([sys.executable, os.path.abspath(__file__), kind, str(size),
+                                                            str(seed), tmp])))
+        i, path, tmp, proc = running.pop(0)
+        if proc.wait() != 0:
+            raise RuntimeError(f"image generator failed for job {jobs[i]}")
+        out[i] = np.load(tmp)
+        if cache:
+            os.replace(tmp, path)
+        else:
+            os.remove(tmp)
+    return out
+
+
 def uniform_block(shape, zero_row=True):
     img = np.ones(shape)
     if zero_row:
@@ -173,3 +230,8 @@ SNAPSHOT_CASES = ("odd_11_13_9", "odd_11_13_9_per", "odd3_mp", "odd3_pmp", "flat
 
 # fast subset for the GPU parity run through the product API
 GPU_SOLVE_CASES = tuple(CASES)
+
+
+if __name__ == "__main__":      # worker of generate_parallel
+    import sys
+    np.save(sys.argv[4], generate((sys.argv[1], int(sys.argv[2]), int(sys.argv[3]))))

@@ -16,8 +16,18 @@ def run_bench(*args, env=None):
                           env=e, timeout=300)
 
 
-def test_reference_arm_line():
-    r = run_bench("--impl", "reference", "--size", "64", "--steps", "2", "--warmup", "1")
+import pytest
+
+
+@pytest.mark.parametrize("kind", ["reference", "port"])
+def test_reference_arm_line(kind):
+    """kind = reference: the unmodified package staged under baseline/_ref (or /root/reference) runs the steps;
+    kind = port: it is hidden, the oracle's PyTorch-eager port stands in."""
+    import baseline
+    if kind == "reference" and baseline.reference_path() is None:
+        pytest.skip("reference package not staged here")
+    r = run_bench("--impl", "reference", "--size", "64", "--steps", "2", "--warmup", "1",
+                  env={"TAUB_NO_REFERENCE": "1" if kind == "port" else "0"})
     assert r.returncode == 0, r.stderr
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -25,7 +35,7 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and d["metric"] == "stencil_sweep_throughput" and d["unit"] == "GLUPS"
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f32" and d["data"] == "synthetic"
     assert d["value"] > 0 and d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["gpu_launches"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == kind and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "GLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
 
