@@ -229,14 +229,13 @@ __device__ __forceinline__ float sor_multi(float c, float xp, float xm, float yp
 // s as in taufactor.py:606-613 (each product rounded, summed left to right); q = s / b by
 // q0 = RN(s*r), rem = s - q0*b (exact FMA), q = RN(q0 + rem*r): the fast path of IEEE division with the
 // exactly rounded reciprocal (checked against s / b on 6e8 random pairs; same guard word as div_fast).
+// The two half rows wa = {w_x+, w_x-, w_y+, w_y-}, wb = {w_z+, w_z-, b, r} are passed in: the fused kernel reads them
+// from its shared-memory copy of the most frequent classes or, for the rare others, through the read-only path
+// (two half-row arrays: a 32-byte sector holds the halves of two frequency-adjacent classes).
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sor_class(float c, float xp, float xm, float yp, float ym, float zp, float zm,
-                                           unsigned cls, const float4 *__restrict__ tabA, const float4 *__restrict__ tabB,
-                                           float omega, unsigned &umin)
+__device__ __forceinline__ float sor_class_rows(float c, float xp, float xm, float yp, float ym, float zp, float zm,
+                                                const float4 &wa, const float4 &wb, float omega, unsigned &umin)
 {
-    // two half-row arrays: a 32-byte sector holds the halves of two (frequency-adjacent) classes, so a
-    // warp's gather touches fewer sectors than with one 32-byte row per class
-    const float4 wa = __ldg(tabA + cls), wb = __ldg(tabB + cls);
     float s = __fadd_rn(__fmul_rn(xp, wa.x), __fmul_rn(xm, wa.y));
     s = __fadd_rn(s, __fmul_rn(yp, wa.z));
     s = __fadd_rn(s, __fmul_rn(ym, wa.w));

@@ -18,7 +18,18 @@
 // y/z halos are recomputed by the neighbouring tile (overlapped tiling); the source buffer is
 // read-only during the pass (ping-pong), so there is no inter-CTA hazard.  The arithmetic per
 // voxel is the same correctly rounded sequence as the generic kernel: results are bit-identical.
+//
+// Round 2 ("instruction diet"): the step body exists twice -- a FAST instantiation for the steady state of the
+// march (every plane-range flag true, no peer stores: straight-line code, predicated stores only) and the GENERIC
+// one for the first / last few planes of a chunk; ring-slot addresses are rotated incrementally (no `% NB`), every
+// shared-memory access is `thread offset + uniform slot offset + immediate`, the (n, 1/n) look-up is
+// `(code >> k & 0x78) | table base` on a 128-byte aligned table, and threads without a column alias a real one
+// instead of branching.  The stencil-class kinds keep the K most frequent weight rows in shared memory (the sweep's
+// limiter was the L1 gather of those rows) with a warp-uniform vote per step for the rare others.
 #include <stdlib.h>
+
+#include <atomic>
+#include <type_traits>
 
 #include <cuda.h>   // CUtensorMap types only; the encoder is fetched through the runtime (no -lcuda)
 
@@ -26,8 +37,13 @@
 
 namespace taub {
 
-constexpr int F_NT = 256;  // threads per CTA
-constexpr int F_NB = 6;    // ring depth (planes in shared memory) of the binary kind
+constexpr int F_NT = 256;     // threads per CTA
+constexpr int F_NRW = 4;      // rows per thread column
+constexpr int F_NB = 6;       // field ring depth (planes in shared memory) of the binary kind
+constexpr int F_NB_CLS = 4;   // ... of the class kinds (their slots carry 8 more bytes per float4 group)
+constexpr int F_NBC_BIN = 4;  // code ring depth of the binary kind: codes are copied to registers when their plane
+                              // is first read, so only the plane being read + 3 in flight need a slot
+constexpr int F_TABK = 256;   // stencil-class rows kept in shared memory (most frequent classes first)
 
 struct FusedParams {
     taub_geom g;
@@ -50,6 +66,7 @@ struct FusedParams {
     float *peer_hi;    // last G output planes are also stored into its upper / lower ghost planes
     int slot_f4;       // float4 per field ring slot
     int cslot_h;       // uint16 per code ring slot
+    int tab_k;         // class kind: rows of the weight table staged in shared memory (<= F_TABK)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -86,57 +103,108 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         : "memory");
 }
 
-// 128-bit shared load that the compiler cannot split into scalar loads (a scalar load of one
+// Shared-memory accesses through 32-bit shared-window addresses: `thread register + uniform register + immediate`
+// is one LDS / STS operand, so a ring-slot offset (uniform) and a compile-time row offset cost no instruction.
+template <class T>
+__device__ __forceinline__ T ld_sh(uint32_t a)
+{
+    return *reinterpret_cast<const T *>(__cvta_shared_to_generic((size_t)a));
+}
+template <class T>
+__device__ __forceinline__ void st_sh(uint32_t a, const T &v)
+{
+    *reinterpret_cast<T *>(__cvta_shared_to_generic((size_t)a)) = v;
+}
+// 128-bit shared load that neither the compiler nor ptxas can split into scalar loads (a scalar load of one
 // component of consecutive float4 groups is a 4-way bank conflict: same wavefronts, a quarter of the data).
-__device__ __forceinline__ float4 lds128(const float4 *p)
+template <int IMM>
+__device__ __forceinline__ float4 lds128(uint32_t a)
 {
     float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+    asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(a), "n"(IMM));
     return v;
 }
 
-// One row of a column: "xz" rows update components x and z, "yw" rows y and w.  zs is the one z
-// neighbour that lives in the adjacent group (.w of the left group / .x of the right group).
-__device__ __forceinline__ void row_update(const bool is_xz, float4 &c, const float4 &xp, const float4 &xm,
-                                           const float4 &up, const float4 &dn, float zs, unsigned code,
-                                           const float2 *s_div, float omega, unsigned &umin)
+// (n, 1/n) of the 4-bit neighbour count at bit `SH` of `code`, from the 128-byte aligned static table at shared
+// address `base`: the entry's byte offset n * 8 is OR-ed into the base (one shift, one LOP3, one LDS.64; no
+// generic-pointer arithmetic).  Plain asm: the table is written once, before the first barrier of the kernel.
+template <int SH>
+__device__ __forceinline__ float2 div_pair_at(unsigned code, uint32_t base)
 {
-    float n0, n1;
-    if (is_xz) {
-        xz_fast(c, xp, xm, up, dn, zs, code, s_div, omega, n0, n1, umin);
+    const unsigned off = (SH >= 3) ? (code >> (SH - 3)) : (code << (3 - SH));
+    float2 v;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"((off & 0x78u) | base));
+    return v;
+}
+
+// One row of a column, binary kind: "xz" rows update components x and z, "yw" rows y and w.  zs is the one z
+// neighbour that lives in the adjacent group (.w of the left group / .x of the right group).  The row's 16-bit
+// code word sits at bit SH16 (0 or 16) of `codes2`.
+template <bool IS_XZ, int SH16>
+__device__ __forceinline__ void row_update(float4 &c, const float4 &xp, const float4 &xm, const float4 &up, const float4 &dn,
+                                           float zs, unsigned codes2, uint32_t div_base, float omega, unsigned &umin)
+{
+    if (IS_XZ) {
+        const float n0 = sor_fast(c.x, xp.x, xm.x, up.x, dn.x, c.y, zs, div_pair_at<SH16 + 0>(codes2, div_base), omega, umin);
+        const float n1 = sor_fast(c.z, xp.z, xm.z, up.z, dn.z, c.w, c.y, div_pair_at<SH16 + 8>(codes2, div_base), omega, umin);
         c.x = n0;
         c.z = n1;
     } else {
-        yw_fast(c, xp, xm, up, dn, zs, code, s_div, omega, n0, n1, umin);
+        const float n0 = sor_fast(c.y, xp.y, xm.y, up.y, dn.y, c.z, c.x, div_pair_at<SH16 + 4>(codes2, div_base), omega, umin);
+        const float n1 = sor_fast(c.w, xp.w, xm.w, up.w, dn.w, zs, c.z, div_pair_at<SH16 + 12>(codes2, div_base), omega, umin);
         c.y = n0;
         c.w = n1;
     }
 }
 
-// Class kind: cls2 = the row's four uint16 class ids (x | y << 16, z | w << 16).
-__device__ __forceinline__ void row_update_class(const bool is_xz, float4 &c, const float4 &xp, const float4 &xm,
-                                                 const float4 &up, const float4 &dn, float zs, uint2 cls2,
-                                                 const float4 *tab, const float4 *tabB, float omega, unsigned &umin)
+// Weight rows of a stencil class: from the shared-memory copy of the first tab_k rows (SM = true; the caller has
+// checked cls < tab_k for the whole warp) or through the read-only global path.
+template <bool SM>
+__device__ __forceinline__ void class_rows(unsigned cls, const float4 *__restrict__ tabA, const float4 *__restrict__ tabB,
+                                           const float4 *sA, const float4 *sB, float4 &wa, float4 &wb)
 {
-    if (is_xz) {
-        const float n0 = sor_class(c.x, xp.x, xm.x, up.x, dn.x, c.y, zs, cls2.x & 0xffffu, tab, tabB, omega, umin);
-        const float n1 = sor_class(c.z, xp.z, xm.z, up.z, dn.z, c.w, c.y, cls2.y & 0xffffu, tab, tabB, omega, umin);
+    if (SM) {
+        wa = sA[cls];
+        wb = sB[cls];
+    } else {
+        wa = __ldg(tabA + cls);
+        wb = __ldg(tabB + cls);
+    }
+}
+
+// Class kind: cls2 = the row's four uint16 class ids (x | y << 16, z | w << 16).
+template <bool IS_XZ, bool SM>
+__device__ __forceinline__ void row_update_class(float4 &c, const float4 &xp, const float4 &xm, const float4 &up,
+                                                 const float4 &dn, float zs, uint2 cls2, const float4 *tabA, const float4 *tabB,
+                                                 const float4 *sA, const float4 *sB, float omega, unsigned &umin)
+{
+    float4 wa0, wb0, wa1, wb1;
+    if (IS_XZ) {
+        class_rows<SM>(cls2.x & 0xffffu, tabA, tabB, sA, sB, wa0, wb0);
+        class_rows<SM>(cls2.y & 0xffffu, tabA, tabB, sA, sB, wa1, wb1);
+        const float n0 = sor_class_rows(c.x, xp.x, xm.x, up.x, dn.x, c.y, zs, wa0, wb0, omega, umin);
+        const float n1 = sor_class_rows(c.z, xp.z, xm.z, up.z, dn.z, c.w, c.y, wa1, wb1, omega, umin);
         c.x = n0;
         c.z = n1;
     } else {
-        const float n0 = sor_class(c.y, xp.y, xm.y, up.y, dn.y, c.z, c.x, cls2.x >> 16, tab, tabB, omega, umin);
-        const float n1 = sor_class(c.w, xp.w, xm.w, up.w, dn.w, zs, c.z, cls2.y >> 16, tab, tabB, omega, umin);
+        class_rows<SM>(cls2.x >> 16, tabA, tabB, sA, sB, wa0, wb0);
+        class_rows<SM>(cls2.y >> 16, tabA, tabB, sA, sB, wa1, wb1);
+        const float n0 = sor_class_rows(c.y, xp.y, xm.y, up.y, dn.y, c.z, c.x, wa0, wb0, omega, umin);
+        const float n1 = sor_class_rows(c.w, xp.w, xm.w, up.w, dn.w, zs, c.z, wa1, wb1, omega, umin);
         c.y = n0;
         c.w = n1;
     }
 }
 
 // Anisotropic kind: cls2 as above, the (b, 1/b) pair of a class from the static shared table.
-__device__ __forceinline__ void row_update_aniso(const bool is_xz, float4 &c, const float4 &xp, const float4 &xm,
-                                                 const float4 &up, const float4 &dn, float zs, uint2 cls2,
-                                                 const float2 *s_div, float Ky, float Kz, float omega, unsigned &umin)
+template <bool IS_XZ>
+__device__ __forceinline__ void row_update_aniso(float4 &c, const float4 &xp, const float4 &xm, const float4 &up,
+                                                 const float4 &dn, float zs, uint2 cls2, const float2 *s_div, float Ky, float Kz,
+                                                 float omega, unsigned &umin)
 {
-    if (is_xz) {
+    if (IS_XZ) {
         const float n0 = sor_aniso_fast(c.x, xp.x, xm.x, up.x, dn.x, c.y, zs, s_div[cls2.x & 0xffffu], Ky, Kz, omega, umin);
         const float n1 = sor_aniso_fast(c.z, xp.z, xm.z, up.z, dn.z, c.w, c.y, s_div[cls2.y & 0xffffu], Ky, Kz, omega, umin);
         c.x = n0;
@@ -149,21 +217,8 @@ __device__ __forceinline__ void row_update_aniso(const bool is_xz, float4 &c, co
     }
 }
 
-// The z neighbour from the adjacent lane's registers (one crossbar pass instead of a 4-way conflicted
-// shared load); the two lanes at the warp ends read shared memory.  All 32 lanes must call this.
-__device__ __forceinline__ float z_neighbour(const bool is_xz, const float4 &v, const float4 *buf, int i4, int lane,
-                                             bool valid)
-{
-    float zs;
-    if (is_xz) {
-        zs = __shfl_up_sync(0xffffffffu, v.w, 1);
-        if (lane == 0 && valid) zs = reinterpret_cast<const float *>(buf)[4 * i4 - 1];
-    } else {
-        zs = __shfl_down_sync(0xffffffffu, v.x, 1);
-        if (lane == 31 && valid) zs = reinterpret_cast<const float *>(buf)[4 * i4 + 4];
-    }
-    return zs;
-}
+template <int V>
+using IC = std::integral_constant<int, V>;
 
 // Thread work item = a COLUMN of NRW vertically adjacent rows x one float4 group.  In every step the
 // rows of a column alternate between "xz" and "yw" rows and swap roles each step; the column's internal
@@ -171,14 +226,14 @@ __device__ __forceinline__ float z_neighbour(const bool is_xz, const float4 &v, 
 // of the column's first row at step 0 (uniform over the whole grid, chosen by the host), so every step
 // body is branch-free.
 //
-// OP ("odd periodic", experimental -- see taub_can_fuse): a periodic extent Ny or Nz is odd, so the wrap joins two
-// voxels of the SAME colour and a ghost cell is the image of a voxel whose colour differs from the ghost's own
-// index parity.  The reference reads ghost SNAPSHOTS taken before each iteration (taufactor.py:501-505); with
-// the images loaded once per pass that is reproduced exactly by leaving the ghost ring of the odd axis out of
-// the colour-A step: where the imaged voxel has colour B the snapshot before iteration t+1 equals the loaded
-// value, and where it has colour A no colour-B voxel reads it.
-template <int NRW, int PA0, int KIND, int NB, bool OP = false>   // KIND: TAUB_BINARY (4-bit codes) or TAUB_MULTIPHASE_CLASS (class ids)
-__global__ void __launch_bounds__(F_NT, 2)      // NB: ring depth (planes of the tile resident in shared memory)
+// OP ("odd periodic"): a periodic extent Ny or Nz is odd, so the wrap joins two voxels of the SAME colour and a
+// ghost cell is the image of a voxel whose colour differs from the ghost's own index parity.  The reference reads
+// ghost SNAPSHOTS taken before each iteration (taufactor.py:501-505); with the images loaded once per pass that is
+// reproduced exactly by leaving the ghost ring of the odd axis out of the colour-A step: where the imaged voxel has
+// colour B the snapshot before iteration t+1 equals the loaded value, and where it has colour A no colour-B voxel
+// reads it (rule pinned on the CPU by tests/test_fused_odd_periodic_cpu.py, on the GPU by the odd periodic goldens).
+template <int OGT, int PA0, int KIND, bool OP = false>   // OGT: output groups per tile row (compile-time tile width);
+__global__ void __launch_bounds__(F_NT, 2)              // KIND: TAUB_BINARY (4-bit codes) or a class kind (ids)
 fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tmap,
                     const __grid_constant__ CUtensorMap cmap)
 {
@@ -191,17 +246,25 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     unsigned char *smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
     const taub_geom &g = P.g;
     constexpr bool ANI = (KIND == TAUB_ANISOTROPIC);
-    constexpr bool CLS = (KIND == TAUB_MULTIPHASE_CLASS) || ANI;   // one uint16 id per voxel travels with the field
+    constexpr bool MPC = (KIND == TAUB_MULTIPHASE_CLASS);
+    constexpr bool CLS = MPC || ANI;             // one uint16 id per voxel travels with the field
+    constexpr int NRW = F_NRW;                   // rows per thread column
     constexpr int CPG = CLS ? 4 : 1;             // uint16 side-array elements per float4 group
-    const int LR = P.LR, LG = P.LG, LGc = P.LGc;
-    const float4 *tab = reinterpret_cast<const float4 *>(P.table);   // class kind: half rows A, then half rows B
-    const float4 *tabB = tab + P.n_classes;
-    const int plane_f4 = P.slot_f4;              // ring slot size in float4 (>= LR*LG, multiple of 8)
-    const int cslot = P.cslot_h;
-    float4 *planes = reinterpret_cast<float4 *>(smem_raw);
-    uint16_t *cplanes = reinterpret_cast<uint16_t *>(smem_raw + (size_t)NB * plane_f4 * 16);
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(cplanes + (size_t)NB * cslot);
-    __shared__ float2 s_div[ANISO_CLASSES];   // static: constant address, no address arithmetic per lookup
+    constexpr int NB = CLS ? F_NB_CLS : F_NB;    // field ring depth (planes of the tile resident in shared memory)
+    constexpr int NBC = CLS ? NB : F_NBC_BIN;    // code ring depth
+    constexpr int LGt = OGT + 2, LG = OGT + 3, LGc = OGT + 8;   // thread groups per row; box widths (field: odd pitch)
+    constexpr uint32_t ROWB = LG * 16u, CROWB = LGc * CPG * 2u; // bytes per field row / id-code row of a ring slot
+    const int LR = P.LR;
+    const float4 *tabA = reinterpret_cast<const float4 *>(P.table);   // class kind: half rows A, then half rows B
+    const float4 *tabB = tabA + P.n_classes;
+    const uint32_t slotB = (uint32_t)P.slot_f4 * 16u;   // bytes per field ring slot (multiple of 128)
+    const uint32_t cslotB = (uint32_t)P.cslot_h * 2u;   // bytes per code ring slot (multiple of 128)
+    unsigned char *planes = smem_raw;
+    unsigned char *cplanes = smem_raw + (size_t)NB * slotB;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(cplanes + (size_t)NBC * cslotB);
+    const float4 *sA = reinterpret_cast<const float4 *>(mbar + 16);   // class kind: staged weight half rows
+    const float4 *sB = sA + P.tab_k;
+    __shared__ __align__(512) float2 s_div[ANISO_CLASSES];   // static: constant address; aligned for the OR look-up
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int tk = blockIdx.x % P.tiles_k, tj = blockIdx.x / P.tiles_k;
@@ -214,8 +277,9 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     const int64_t ps = g.plane_stride;
 
     if (!ANI && tid < ANISO_CLASSES) s_div[tid] = div_entry(tid);   // binary: (n, 1/n) of the neighbour count
+    const uint32_t mbar_u32 = smem_u32(mbar);
     if (tid == 0) {
-        for (int n = 0; n < NB; ++n) mbar_init(smem_u32(&mbar[n]), 1);
+        for (int n = 0; n < NB; ++n) mbar_init(mbar_u32 + 8u * n, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -224,38 +288,56 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     // (returns at once when this grid was not launched as a programmatic dependent)
     pdl_wait();
     if (P.stop && *P.stop) return;
-    // anisotropic: (b, 1/b) of the prefactor classes; first used after the step loop's first __syncthreads
+    // anisotropic: (b, 1/b) of the prefactor classes; class kind: the first tab_k weight rows.  First used after
+    // the step loop's first __syncthreads
     if (ANI && tid < ANISO_CLASSES) s_div[tid] = reinterpret_cast<const float2 *>(P.table)[tid];
+    if (MPC) {
+        float4 *w = const_cast<float4 *>(sA);
+        for (int t = tid; t < 2 * P.tab_k; t += F_NT) w[t] = (t < P.tab_k) ? __ldg(tabA + t) : __ldg(tabB + (t - P.tab_k));
+    }
     const float Ky = ANI ? P.table[2 * ANISO_CLASSES] : 0.0f, Kz = ANI ? P.table[2 * ANISO_CLASSES + 1] : 0.0f;
+    const uint32_t div_base = smem_u32(s_div);
 
-    // one thread stages plane rel (local plane c0-2+rel) into ring slot rel % NB with one TMA box
-    // (columns 4*G0.., rows R0.., one plane) plus the matching box of neighbour codes; the part of a
-    // box outside the tensor reads as 0
-    auto issue = [&](int rel) {
-        const int slot = rel % NB;
-        const uint32_t bar = smem_u32(&mbar[slot]);
+    // ---- TMA producer (thread 0): plane rel (local plane c0-2+rel) -> field slot rel % NB, code slot rel % NBC,
+    //      one box each; the part of a box outside the tensor reads as 0.  The slot offsets and the plane
+    //      coordinate of the next box are carried along instead of being recomputed from rel.
+    const uint32_t planes_u32 = smem_u32(planes), cplanes_u32 = smem_u32(cplanes);
+    const uint32_t tx_bytes = (uint32_t)LR * (ROWB + CROWB);
+    uint32_t is_f = 0, is_c = 0, is_bar = mbar_u32;   // next issue: field / code slot byte offset, barrier address
+    int is_pl = b * g.planes + (c0 - 2 + G);          // ... and tensor plane coordinate
+    auto issue = [&]() {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, (uint32_t)(LR * (LG * 16 + LGc * CPG * 2)));
-        const int pl = b * g.planes + (c0 - 2 + rel + G);
-        tma_load_3d(smem_u32(planes + (size_t)slot * plane_f4), &tmap, 4 * G0, R0, pl, bar);
-        tma_load_3d(smem_u32(cplanes + (size_t)slot * cslot), &cmap, G0 * CPG, R0, pl, bar);
+        mbar_expect_tx(is_bar, tx_bytes);
+        tma_load_3d(planes_u32 + is_f, &tmap, 4 * G0, R0, is_pl, is_bar);
+        tma_load_3d(cplanes_u32 + is_c, &cmap, G0 * CPG, R0, is_pl, is_bar);
+        ++is_pl;
+        is_f += slotB;
+        is_bar += 8u;
+        if (is_f == NB * slotB) {
+            is_f = 0;
+            is_bar = mbar_u32;
+        }
+        is_c += cslotB;
+        if (is_c == NBC * cslotB) is_c = 0;
     };
     if (tid == 0)
-        for (int rel = 0; rel < min(NB - 1, total_rel); ++rel) issue(rel);
+        for (int rel = 0; rel < min(NB - 1, total_rel); ++rel) issue();
 
-    // ---- this thread's column: rows lr0 .. lr0+NRW-1 of the tile, group gg
+    // ---- this thread's column: rows lr0 .. lr0+NRW-1 of the tile, group gg.  Threads beyond the tile's columns
+    //      (m >= NCT) shadow column 0 of their group: they load and compute like everybody else (no divergence in
+    //      the step body) but never store anything.
     const int NCT = (LR - 2) / NRW;          // columns stacked in the tile
-    const int LGt = P.LGt;
-    const int m = tid / LGt, gg = tid - m * LGt;
+    const int m_raw = tid / LGt, gg = tid - m_raw * LGt;
+    const bool own = m_raw < NCT;            // has cells in the shared-memory tile
+    const int m = own ? m_raw : 0;
     const int lr0 = 1 + NRW * m;
     const int Ra = R0 + lr0, Gs = G0 + gg;
-    const bool doit = (m < NCT) && (Gs < PG) && (Ra < g.rows);
+    const bool doit = own && (Gs < PG) && (Ra < g.rows);
     const bool colB = gg >= 1 && gg < LGt - 1 && Gs >= 1 && Gs < 1 + interior_groups(g.Nz);
     unsigned canB = 0;                       // bit r: row r of the column is an output row
 #pragma unroll
     for (int r = 0; r < NRW; ++r)
         if (doit && colB && lr0 + r >= 2 && lr0 + r < LR - 2 && Ra + r >= G && Ra + r < G + g.Ny) canB |= 1u << r;
-    const bool all_rows = (canB == (1u << NRW) - 1u);   // interior columns: every row is an output row
     // OP: ghost rows (odd Ny) keep their snapshot in the colour-A step, and so do the ghost columns k = -1
     // (.w of group 0) and k = Nz (component Nz % 4 of group (Nz + 4) / 4) for odd Nz
     unsigned keep_rows = 0;
@@ -272,8 +354,13 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
             keep_hi_w = (Gs == ((g.Nz + COL0) >> 2)) && ((g.Nz & 3) == 3);
         }
     }
-    const int i0 = lr0 * LG + gg;            // float4 index of row 0 inside a ring slot (row r: + r*LG)
-    const int ic0 = (lr0 * LGc + gg) * CPG;  // uint16 index of row 0's code / class ids (row r: + r*LGc*CPG)
+    // shared-window addresses of row 0 of the column in field slot 0 / id-code slot 0 (row r: + r * ROWB / CROWB)
+    const uint32_t tbase = planes_u32 + (uint32_t)(lr0 * LG + gg) * 16u;
+    const uint32_t cbase = cplanes_u32 + (uint32_t)((lr0 * LGc + gg) * CPG) * 2u;
+    const bool lane_lo = (lane == 0), lane_hi = (lane == 31);
+    // which of this thread's rows other threads read: the column's first and last row (their above / below) and,
+    // at the two ends of a warp, every row (z_neighbour fall-back of the adjacent warp)
+    const bool st_mid = own && (lane_lo || lane_hi);
     // colour B first writes plane c0 (at step 2)
     float *dst0 = P.dst + (int64_t)b * g.image_stride + 4 * Gs + (int64_t)(c0 + G) * ps + (int64_t)Ra * g.pitch;
 
@@ -281,189 +368,301 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     //      a[p-2] = rg[.][ss], a[p-1] = rg[.][ss+1], raw[p] -> a[p] = rg[.][ss+2], raw[p+1] = rg[.][ss+3]
     float4 rg[NRW][4];
     unsigned cr[NRW / 2][4];   // binary: neighbour codes, two rows per word, same ring positions
-    mbar_wait(smem_u32(&mbar[0]), 0);
-    mbar_wait(smem_u32(&mbar[1 % NB]), 0);
+    mbar_wait(mbar_u32, 0);
+    mbar_wait(mbar_u32 + 8u * (1 % NB), 0);
 #pragma unroll
     for (int r = 0; r < NRW; ++r) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) rg[r][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (doit) {
-            rg[r][1] = planes[i0 + r * LG];
-            rg[r][2] = planes[plane_f4 + i0 + r * LG];
-        }
+        rg[r][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        rg[r][3] = make_float4(0.f, 0.f, 0.f, 0.f);
+        rg[r][1] = ld_sh<float4>(tbase + r * ROWB);
+        rg[r][2] = ld_sh<float4>(tbase + slotB + r * ROWB);
     }
 #pragma unroll
     for (int q = 0; q < NRW / 2; ++q) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) cr[q][k] = 0;
-        if (doit && !CLS)
-            cr[q][2] = (unsigned)cplanes[cslot + ic0 + 2 * q * LGc] | ((unsigned)cplanes[cslot + ic0 + (2 * q + 1) * LGc] << 16);
+        if (!CLS)
+            cr[q][2] = (unsigned)ld_sh<uint16_t>(cbase + cslotB + 2 * q * CROWB) |
+                       ((unsigned)ld_sh<uint16_t>(cbase + cslotB + (2 * q + 1) * CROWB) << 16);
     }
 
     unsigned umin = 0xffffffffu;   // guard word of every neighbour sum this thread divides
     const int n_steps = c1 - c0 + 2;
-    for (int s4 = 0; s4 < n_steps; s4 += 4) {
+
+    // ---- ring state of step s (all warp-uniform): field slots of planes p-1, p, p+1 and the mbarrier of p+1;
+    //      code / id slots of the same planes.  Rotated at the end of every step.
+    uint32_t oM1 = 0, oP = slotB, oP1 = 2u * slotB;               // s % NB, (s+1) % NB, (s+2) % NB at s = 0
+    uint32_t w_bar = mbar_u32 + 16u, w_par = 0;                      // barrier / parity of plane rel = s+2
+    uint32_t kM1 = 0, kP = cslotB, kP1 = 2u * cslotB;                // code / id slots: s % NBC, ... (NBC >= 4)
+
+    // One step of the march.  FAST: every plane-range flag is true and there are no peer stores (steady state).
+    auto step = [&](auto fast_c, auto ss_c, const int s) {
+        constexpr bool FAST = decltype(fast_c)::value != 0;
+        constexpr int ss = decltype(ss_c)::value;
+        constexpr int iM2 = ss & 3, iM1 = (ss + 1) & 3, iP = (ss + 2) & 3, iP1 = (ss + 3) & 3;
+        const int p = c0 - 1 + s;   // plane receiving colour A; colour B goes to plane p-1
+        __syncthreads();            // ring slot of plane p-2 is free; a[p-1] is visible in its slot
+        if (tid == 0 && (FAST || s - 1 + NB < total_rel)) issue();
+        mbar_wait(w_bar, w_par);
+        const uint32_t aM1 = tbase + oM1, aP = tbase + oP, aP1 = tbase + oP1;   // this column in the three slots
+        const bool doA = FAST || ((p >= P.a_lo) && (p < P.a_hi));
+        const bool keepA = FAST || ((p >= c0) && (p < c1));   // a[p] is read by colour B of plane p next step
+        const bool doB = FAST || (s >= 2);
+        // one-sided halo exchange: output plane p-1 is one of the neighbour's ghost planes
+        const bool send_lo = !FAST && P.peer_lo != nullptr && (p - 1) < G;
+        const bool send_hi = !FAST && P.peer_hi != nullptr && (p - 1) >= g.Nx - G;
 #pragma unroll
-        for (int ss = 0; ss < 4; ++ss) {
-            const int s = s4 + ss;
-            if (s >= n_steps) break;
-            const int p = c0 - 1 + s;   // plane receiving colour A; colour B goes to plane p-1
-            const int iM2 = ss & 3, iM1 = (ss + 1) & 3, iP = (ss + 2) & 3, iP1 = (ss + 3) & 3;
-            __syncthreads();            // ring slot of plane p-2 is free; a[p-1] is visible in its slot
-            if (tid == 0 && s - 1 + NB < total_rel) issue(s - 1 + NB);
-            mbar_wait(smem_u32(&mbar[(s + 2) % NB]), (uint32_t)(((s + 2) / NB) & 1));
-            const float4 *bufM1 = planes + (size_t)(s % NB) * plane_f4;
-            float4 *bufP = planes + (size_t)((s + 1) % NB) * plane_f4;
-            const float4 *bufP1 = planes + (size_t)((s + 2) % NB) * plane_f4;
-            const uint16_t *codP1 = cplanes + (size_t)((s + 2) % NB) * cslot;
-            const uint16_t *codP = cplanes + (size_t)((s + 1) % NB) * cslot;    // class kind reads ids in place
-            const uint16_t *codM1 = cplanes + (size_t)(s % NB) * cslot;
-            const bool doA = (p >= P.a_lo) && (p < P.a_hi);
-            const bool keepA = (p >= c0) && (p < c1);   // a[p] is read by colour B of plane p next step
-            const bool doB = (s >= 2);
-            // one-sided halo exchange: output plane p-1 is one of the neighbour's ghost planes
-            const bool send_lo = P.peer_lo != nullptr && (p - 1) < G;
-            const bool send_hi = P.peer_hi != nullptr && (p - 1) >= g.Nx - G;
-            if (doit) {
+        for (int r = 0; r < NRW; ++r) rg[r][iP1] = ld_sh<float4>(aP1 + r * ROWB);
+        if (!CLS) {
 #pragma unroll
-                for (int r = 0; r < NRW; ++r) rg[r][iP1] = bufP1[i0 + r * LG];
-                if (!CLS) {
+            for (int q = 0; q < NRW / 2; ++q)
+                cr[q][iP1] = (unsigned)ld_sh<uint16_t>(cbase + kP1 + 2 * q * CROWB) |
+                             ((unsigned)ld_sh<uint16_t>(cbase + kP1 + (2 * q + 1) * CROWB) << 16);
+        }
+        if (doA) {   // block-uniform
+            // the z neighbour from the adjacent lane's registers (one crossbar pass instead of a 4-way conflicted
+            // shared load); the two lanes at the warp ends read shared memory
+            float zs[NRW];
 #pragma unroll
-                    for (int q = 0; q < NRW / 2; ++q)
-                        cr[q][iP1] = (unsigned)codP1[ic0 + 2 * q * LGc] | ((unsigned)codP1[ic0 + (2 * q + 1) * LGc] << 16);
+            for (int r = 0; r < NRW; ++r) {
+                if (((PA0 + ss + r) & 1) == 0) {
+                    zs[r] = __shfl_up_sync(0xffffffffu, rg[r][iP].w, 1);
+                    if (lane_lo) zs[r] = ld_sh<float>(aP + r * ROWB - 4);
+                } else {
+                    zs[r] = __shfl_down_sync(0xffffffffu, rg[r][iP].x, 1);
+                    if (lane_hi) zs[r] = ld_sh<float>(aP + r * ROWB + 16);
                 }
             }
-            if (doA) {   // block-uniform
-                float zs[NRW];
+            const float4 below = lds128<-(int)ROWB>(aP), above = lds128<(int)(NRW * ROWB)>(aP);
+            uint2 ids[NRW];
+            bool sm_rows = true;
+            if (CLS) {
 #pragma unroll
-                for (int r = 0; r < NRW; ++r)
-                    zs[r] = z_neighbour(((PA0 + ss + r) & 1) == 0, rg[r][iP], bufP, i0 + r * LG, lane, doit);
-                if (doit) {
-                    const float4 below = lds128(bufP + i0 - LG), above = lds128(bufP + i0 + NRW * LG);
+                for (int r = 0; r < NRW; ++r) ids[r] = ld_sh<uint2>(cbase + kP + r * CROWB);
+                if (MPC) {   // all 2 * NRW classes of this step in the shared-memory part of the table, warp-wide?
+                    unsigned mx = 0;
 #pragma unroll
                     for (int r = 0; r < NRW; ++r) {
-                        // neighbours inside the column are registers; each row only reads the components
-                        // its neighbours leave unchanged in this step
-                        const float4 &dn = (r == 0) ? below : rg[r - 1][iP];
-                        const float4 &up = (r == NRW - 1) ? above : rg[r + 1][iP];
-                        const float4 snap = rg[r][iP];
-                        if (ANI)
-                            row_update_aniso(((PA0 + ss + r) & 1) == 0, rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r],
-                                             *reinterpret_cast<const uint2 *>(codP + ic0 + r * LGc * CPG), s_div, Ky, Kz, P.omega, umin);
-                        else if (CLS)
-                            row_update_class(((PA0 + ss + r) & 1) == 0, rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r],
-                                             *reinterpret_cast<const uint2 *>(codP + ic0 + r * LGc * CPG), tab, tabB, P.omega, umin);
-                        else
-                            row_update(((PA0 + ss + r) & 1) == 0, rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r],
-                                       cr[r >> 1][iP] >> (16 * (r & 1)), s_div, P.omega, umin);
-                        if (OP) {   // ghost cells of an odd periodic axis keep their snapshot
-                            if (keep_rows & (1u << r)) {
-                                rg[r][iP] = snap;
-                            } else {
-                                if (keep_lo_w || keep_hi_w) rg[r][iP].w = snap.w;
-                                if (keep_hi_y) rg[r][iP].y = snap.y;
-                            }
-                        }
+                        const bool xz = ((PA0 + ss + r) & 1) == 0;
+                        mx = max(mx, max(xz ? (ids[r].x & 0xffffu) : (ids[r].x >> 16), xz ? (ids[r].y & 0xffffu) : (ids[r].y >> 16)));
                     }
-                    if (keepA) {
-                        // other threads read the column's first and last row (their above / below) and,
-                        // at the two ends of a warp, the neighbour lane's group (z_neighbour fall-back)
-                        const bool edge_lane = (lane == 0) || (lane == 31);
+                    sm_rows = __all_sync(0xffffffffu, mx < (unsigned)P.tab_k);
+                }
+            }
+            float4 snap[NRW];
+            if (OP) {
 #pragma unroll
-                        for (int r = 0; r < NRW; ++r)
-                            if (r == 0 || r == NRW - 1 || edge_lane) bufP[i0 + r * LG] = rg[r][iP];
+                for (int r = 0; r < NRW; ++r) snap[r] = rg[r][iP];
+            }
+            auto phaseA = [&](auto sm_c) {
+                constexpr bool SM = decltype(sm_c)::value != 0;
+#pragma unroll
+                for (int r = 0; r < NRW; ++r) {
+                    // neighbours inside the column are registers; each row only reads the components
+                    // its neighbours leave unchanged in this step
+                    const float4 &dn = (r == 0) ? below : rg[r - 1][iP];
+                    const float4 &up = (r == NRW - 1) ? above : rg[r + 1][iP];
+                    if (((PA0 + ss + r) & 1) == 0) {
+                        if (ANI)
+                            row_update_aniso<true>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], ids[r], s_div, Ky, Kz, P.omega, umin);
+                        else if (CLS)
+                            row_update_class<true, SM>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], ids[r], tabA, tabB, sA, sB, P.omega, umin);
+                        else if (r & 1)
+                            row_update<true, 16>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], cr[r >> 1][iP], div_base, P.omega, umin);
+                        else
+                            row_update<true, 0>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], cr[r >> 1][iP], div_base, P.omega, umin);
+                    } else {
+                        if (ANI)
+                            row_update_aniso<false>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], ids[r], s_div, Ky, Kz, P.omega, umin);
+                        else if (CLS)
+                            row_update_class<false, SM>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], ids[r], tabA, tabB, sA, sB, P.omega, umin);
+                        else if (r & 1)
+                            row_update<false, 16>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], cr[r >> 1][iP], div_base, P.omega, umin);
+                        else
+                            row_update<false, 0>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], cr[r >> 1][iP], div_base, P.omega, umin);
+                    }
+                }
+            };
+            if (!MPC || sm_rows) phaseA(IC<1>{}); else phaseA(IC<0>{});
+            if (OP) {   // ghost cells of an odd periodic axis keep their snapshot
+#pragma unroll
+                for (int r = 0; r < NRW; ++r) {
+                    if (keep_rows & (1u << r)) {
+                        rg[r][iP] = snap[r];
+                    } else {
+                        if (keep_lo_w || keep_hi_w) rg[r][iP].w = snap[r].w;
+                        if (keep_hi_y) rg[r][iP].y = snap[r].y;
                     }
                 }
             }
-            if (doB) {   // block-uniform
-                float zs[NRW];
+            if (keepA) {
+                // other threads read the column's first and last row (their above / below) and, at the two ends
+                // of a warp, the neighbour lane's group (z_neighbour fall-back)
 #pragma unroll
                 for (int r = 0; r < NRW; ++r)
-                    zs[r] = z_neighbour(((PA0 + ss + r) & 1) == 0, rg[r][iM1], bufM1, i0 + r * LG, lane, doit);
-                if (canB) {
-                    const float4 below = lds128(bufM1 + i0 - LG), above = lds128(bufM1 + i0 + NRW * LG);
-#pragma unroll
-                    for (int r = 0; r < NRW; ++r) {
-                        const float4 &dn = (r == 0) ? below : rg[r - 1][iM1];
-                        const float4 &up = (r == NRW - 1) ? above : rg[r + 1][iM1];
-                        float4 out = rg[r][iM1];
-                        if (ANI)
-                            row_update_aniso(((PA0 + ss + r) & 1) == 0, out, rg[r][iP], rg[r][iM2], up, dn, zs[r],
-                                             *reinterpret_cast<const uint2 *>(codM1 + ic0 + r * LGc * CPG), s_div, Ky, Kz, P.omega, umin);
-                        else if (CLS)
-                            row_update_class(((PA0 + ss + r) & 1) == 0, out, rg[r][iP], rg[r][iM2], up, dn, zs[r],
-                                             *reinterpret_cast<const uint2 *>(codM1 + ic0 + r * LGc * CPG), tab, tabB, P.omega, umin);
-                        else
-                            row_update(((PA0 + ss + r) & 1) == 0, out, rg[r][iP], rg[r][iM2], up, dn, zs[r],
-                                       cr[r >> 1][iM1] >> (16 * (r & 1)), s_div, P.omega, umin);
-                        if (all_rows || (canB & (1u << r))) {
-                            float *d = dst0 + (int64_t)r * g.pitch;
-                            *reinterpret_cast<float4 *>(d) = out;
-                            if (send_lo) *reinterpret_cast<float4 *>(P.peer_lo + (d - P.dst) + (int64_t)g.Nx * ps) = out;
-                            if (send_hi) *reinterpret_cast<float4 *>(P.peer_hi + (d - P.dst) - (int64_t)g.Nx * ps) = out;
-                        }
-                    }
-                }
-                dst0 += ps;
+                    if ((r == 0 || r == NRW - 1) ? own : st_mid) st_sh<float4>(aP + r * ROWB, rg[r][iP]);
             }
         }
+        if (doB) {   // block-uniform
+            float zs[NRW];
+#pragma unroll
+            for (int r = 0; r < NRW; ++r) {
+                if (((PA0 + ss + r) & 1) == 0) {
+                    zs[r] = __shfl_up_sync(0xffffffffu, rg[r][iM1].w, 1);
+                    if (lane_lo) zs[r] = ld_sh<float>(aM1 + r * ROWB - 4);
+                } else {
+                    zs[r] = __shfl_down_sync(0xffffffffu, rg[r][iM1].x, 1);
+                    if (lane_hi) zs[r] = ld_sh<float>(aM1 + r * ROWB + 16);
+                }
+            }
+            const float4 below = lds128<-(int)ROWB>(aM1), above = lds128<(int)(NRW * ROWB)>(aM1);
+            uint2 ids[NRW];
+            bool sm_rows = true;
+            if (CLS) {
+#pragma unroll
+                for (int r = 0; r < NRW; ++r) ids[r] = ld_sh<uint2>(cbase + kM1 + r * CROWB);
+                if (MPC) {
+                    unsigned mx = 0;
+#pragma unroll
+                    for (int r = 0; r < NRW; ++r) {
+                        const bool xz = ((PA0 + ss + r) & 1) == 0;
+                        mx = max(mx, max(xz ? (ids[r].x & 0xffffu) : (ids[r].x >> 16), xz ? (ids[r].y & 0xffffu) : (ids[r].y >> 16)));
+                    }
+                    sm_rows = __all_sync(0xffffffffu, mx < (unsigned)P.tab_k);
+                }
+            }
+            float4 out[NRW];
+#pragma unroll
+            for (int r = 0; r < NRW; ++r) out[r] = rg[r][iM1];
+            auto phaseB = [&](auto sm_c) {
+                constexpr bool SM = decltype(sm_c)::value != 0;
+#pragma unroll
+                for (int r = 0; r < NRW; ++r) {
+                    const float4 &dn = (r == 0) ? below : rg[r - 1][iM1];
+                    const float4 &up = (r == NRW - 1) ? above : rg[r + 1][iM1];
+                    if (((PA0 + ss + r) & 1) == 0) {
+                        if (ANI)
+                            row_update_aniso<true>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], ids[r], s_div, Ky, Kz, P.omega, umin);
+                        else if (CLS)
+                            row_update_class<true, SM>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], ids[r], tabA, tabB, sA, sB, P.omega, umin);
+                        else if (r & 1)
+                            row_update<true, 16>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], cr[r >> 1][iM1], div_base, P.omega, umin);
+                        else
+                            row_update<true, 0>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], cr[r >> 1][iM1], div_base, P.omega, umin);
+                    } else {
+                        if (ANI)
+                            row_update_aniso<false>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], ids[r], s_div, Ky, Kz, P.omega, umin);
+                        else if (CLS)
+                            row_update_class<false, SM>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], ids[r], tabA, tabB, sA, sB, P.omega, umin);
+                        else if (r & 1)
+                            row_update<false, 16>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], cr[r >> 1][iM1], div_base, P.omega, umin);
+                        else
+                            row_update<false, 0>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], cr[r >> 1][iM1], div_base, P.omega, umin);
+                    }
+                }
+            };
+            if (!MPC || sm_rows) phaseB(IC<1>{}); else phaseB(IC<0>{});
+#pragma unroll
+            for (int r = 0; r < NRW; ++r) {
+                if (canB & (1u << r)) {
+                    float *d = dst0 + (int64_t)r * g.pitch;
+                    *reinterpret_cast<float4 *>(d) = out[r];
+                    if (send_lo) *reinterpret_cast<float4 *>(P.peer_lo + (d - P.dst) + (int64_t)g.Nx * ps) = out[r];
+                    if (send_hi) *reinterpret_cast<float4 *>(P.peer_hi + (d - P.dst) - (int64_t)g.Nx * ps) = out[r];
+                }
+            }
+            dst0 += ps;
+        }
+        // rotate the ring: plane p becomes p-1, ...; the slot after p+1's is the next to be waited for
+        oM1 = oP;
+        oP = oP1;
+        oP1 += slotB;
+        w_bar += 8u;
+        if (oP1 == NB * slotB) {
+            oP1 = 0;
+            w_bar = mbar_u32;
+            w_par ^= 1u;
+        }
+        kM1 = kP;
+        kP = kP1;
+        kP1 += cslotB;
+        if (kP1 == NBC * cslotB) kP1 = 0;
+    };
+
+    // steps s4 .. s4+3 form a group (the register ring and the row parities have period 4): groups that lie wholly
+    // in the steady state of the march -- colour A and B both active, plane kept, a box left to issue, no peer
+    // stores -- run the FAST body
+    const bool peers = (P.peer_lo != nullptr) || (P.peer_hi != nullptr);
+    for (int s4 = 0; s4 < n_steps; s4 += 4) {
+        // fast: s4 >= 2 (doB); p = c0-1+s in [max(a_lo, c0), min(a_hi, c1)) for s4..s4+3; s+NB-1 < total_rel
+        const int p_first = c0 - 1 + s4, p_last = p_first + 3;
+        bool fast = s4 >= 2 && p_first >= c0 && p_first >= P.a_lo && p_last < c1 && p_last < P.a_hi && s4 + 3 + NB - 1 < total_rel;
+        if (peers && (p_first - 1 < G || p_last - 1 >= g.Nx - G)) fast = false;
+        if (fast) {
+            step(IC<1>{}, IC<0>{}, s4);
+            step(IC<1>{}, IC<1>{}, s4 + 1);
+            step(IC<1>{}, IC<2>{}, s4 + 2);
+            step(IC<1>{}, IC<3>{}, s4 + 3);
+        } else {
+            step(IC<0>{}, IC<0>{}, s4);
+            if (s4 + 1 < n_steps) step(IC<0>{}, IC<1>{}, s4 + 1);
+            if (s4 + 2 < n_steps) step(IC<0>{}, IC<2>{}, s4 + 2);
+            if (s4 + 3 < n_steps) step(IC<0>{}, IC<3>{}, s4 + 3);
+        }
     }
-    // a non-zero sum below 2^-100 went through the fast division: count it (results stay within one
-    // subnormal ulp of the reference there; never observed -- taub_inexact_events() reports it)
-    if (umin < GUARD_T) atomicAdd(&g_inexact_events, 1ULL);
+    // a non-zero sum below 2^-100 went through the fast division: count it (the result may then differ from the
+    // IEEE quotient by one subnormal ulp; never seen in a through-transport solve -- taub_inexact_events() reports it)
+    if (doit && umin < GUARD_T) atomicAdd(&g_inexact_events, 1ULL);
 }
 
-static size_t fused_smem_bytes(int LR, int LG, int LGc, int cpg, int nb)
+static size_t fused_smem_bytes(int LR, int LG, int LGc, int cpg, int nb, int nbc, int tab_k)
 {
     const size_t slot = ((size_t)(LR * LG + 7) / 8) * 8 * 16;               // fp32 box, 128-byte multiple
     const size_t cslot = ((size_t)(LR * LGc * cpg * 2 + 127) / 128) * 128;  // uint16 box (codes / class ids)
-    return nb * (slot + cslot) + nb * 8 + 128;                    // + mbarriers, alignment slack (the division
-                                                                      // table is 128 bytes of static shared memory)
+    return nb * slot + nbc * cslot + 16 * 8 + (size_t)tab_k * 32 + 128;      // + mbarriers (16 slots reserved), staged
+                                                                             // weight rows, alignment slack (the
+                                                                             // division table is static shared memory)
 }
-
-constexpr int F_NRW = 4;   // rows per thread column
 
 struct TileChoice {
     int LR, LG, LGc, LGt, OR_, OG, tiles_j, tiles_k;
     double eff;
 };
 
-// Tile = NCT columns (of F_NRW rows) stacked in y x LG float4 groups (OG = LG - 2 of them are outputs);
-// one thread per (column, group).  TMA wants every box to start on a 16-byte boundary and to be a
-// multiple of 16 bytes wide; for the uint16 code box that means OG (the tile step) is a multiple of 8
-// groups and the code box is LG rounded up to 8.  A box is at most 256 elements wide (LG <= 64).  Pick
-// the shape that wastes the fewest threads while two CTAs still fit in one SM's shared memory.
+// Tile = NCT columns (of F_NRW rows) stacked in y x LG float4 groups (OG of them are outputs, one halo group each
+// side, one more to make the shared-memory row pitch odd: warps that straddle two columns would otherwise
+// bank-conflict); one thread per (column, group).  TMA wants every box to start on a 16-byte boundary and to be a
+// multiple of 16 bytes wide; for the uint16 code box that means OG (the tile step) is a multiple of 8 groups and the
+// code box is OG + 8 wide.  The width is a template parameter of the kernel (row offsets become immediates), compiled
+// for OG = 8, 16 and 32 (OG = 32 is the best shape of every extent that is a multiple of 128; the narrow ones serve
+// 2-D images and small volumes); the height follows from the shared memory two CTAs per SM leave.  Pick the shape that
+// wastes the fewest threads; wider wins a tie (longer rows per TMA box).
 // Ring depth per kind.  The class kind carries 8 more bytes per float4 group in every slot and is bound by
-// the L1 gather of its weight rows, not by HBM latency: a shallower ring (one plane of prefetch) buys
+// its weight-row look-ups, not by HBM latency: a shallower ring (one plane of prefetch) buys
 // ~1.6x larger tiles -> fewer halo re-loads and idle threads (measured: 6 -> 4 slots = +10 % at 384^3 / 512^3).
-constexpr int F_NB_CLS = 4;
 static int ring_depth(int cpg) { return cpg == 1 ? F_NB : F_NB_CLS; }
+static int code_ring_depth(int cpg) { return cpg == 1 ? F_NBC_BIN : F_NB_CLS; }
 
-static TileChoice choose_tile(const taub_geom &g, int cpg)
+static TileChoice choose_tile(const taub_geom &g, int cpg, int tab_k, bool narrow_only)
 {
-    const int nb = ring_depth(cpg);
-    // shared-memory budget per CTA (two CTAs per SM).  The class kind reads its weight rows through L1,
-    // which shares the 256 KB with shared memory: leave it a little more.
-    const size_t budget = (cpg == 1) ? 115000 : 106000;
+    const int nb = ring_depth(cpg), nbc = code_ring_depth(cpg);
+    // shared memory per CTA with two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2, less the 512-byte static
+    // division table
+    const size_t budget = 115712 - 512;
     const int ng = interior_groups(g.Nz);
     TileChoice best{};
     best.eff = -1.0;
-    for (int OG = 8; OG <= 56; OG += 8) {
-        // threads work on LGt = OG + 2 groups per row.  Columns are F_NRW rows apart and 4*LG float4 is
-        // a multiple of 32 banks when LG is even, so warps that straddle two columns bank-conflict; a
-        // box one group wider (odd pitch) avoids that -- taken when it does not cost a column.
-        const int LGt = OG + 2;
+    static const int shapes[3] = {8, 16, 32};
+    for (int si = 0; si < (narrow_only ? 1 : 3); ++si) {
+        const int OG = shapes[si];
+        const int LGt = OG + 2, LG = OG + 3, LGc = OG + 8;
         int NCT = F_NT / LGt;   // columns the CTA's threads can cover
-        while (NCT >= 1 && fused_smem_bytes(F_NRW * NCT + 2, LGt, ((LGt + 7) / 8) * 8, cpg, nb) > budget) --NCT;
+        while (NCT >= 1 && fused_smem_bytes(F_NRW * NCT + 2, LG, LGc, cpg, nb, nbc, tab_k) > budget) --NCT;
         if (NCT < 1) continue;
-        int LG = LGt;
-        if (fused_smem_bytes(F_NRW * NCT + 2, LGt + 1, ((LGt + 8) / 8) * 8, cpg, nb) <= budget) LG = LGt + 1;
-        const int LGc = ((LG + 7) / 8) * 8;
         const int NR = F_NRW * NCT, OR_ = NR - 2, LR = NR + 2;
         const int tj = ceil_div(g.Ny, OR_), tk = ceil_div(ng, OG);
         const double eff = ((double)g.Ny * ng) / ((double)tj * tk * F_NT * F_NRW);
-        if (eff > best.eff + 1e-12) best = TileChoice{LR, LG, LGc, LGt, OR_, OG, tj, tk, eff};
-        if (OG >= ng) break;          // one tile already spans the row
+        if (eff > best.eff - 1e-12) best = TileChoice{LR, LG, LGc, LGt, OR_, OG, tj, tk, eff};
     }
     return best;
 }
@@ -489,10 +688,10 @@ static EncodeTiledFn encode_tiled_fn()
 // combinations thousands of times, so keep the last few maps (per host thread).
 struct MapKey {
     const void *base;
-    int pitch, rows, planes_total, box_w, box_h, elem;
+    int dev, pitch, rows, planes_total, box_w, box_h, elem;
     bool operator==(const MapKey &o) const
     {
-        return base == o.base && pitch == o.pitch && rows == o.rows && planes_total == o.planes_total &&
+        return base == o.base && dev == o.dev && pitch == o.pitch && rows == o.rows && planes_total == o.planes_total &&
                box_w == o.box_w && box_h == o.box_h && elem == o.elem;
     }
 };
@@ -521,9 +720,9 @@ static thread_local MapCache g_maps;
 thread_local bool g_fused_pdl = false;
 
 // 3-D view of one ping-pong buffer: (columns = pitch, rows, bs * planes), fp32, box = LG*4 x LR x 1.
-static int make_field_map(CUtensorMap *map, const taub_geom &g, const float *base, int LR, int LG)
+static int make_field_map(CUtensorMap *map, const taub_geom &g, const float *base, int LR, int LG, int dev)
 {
-    const MapKey key{base, g.pitch, g.rows, g.bs * g.planes, LG * 4, LR, 4};
+    const MapKey key{base, dev, g.pitch, g.rows, g.bs * g.planes, LG * 4, LR, 4};
     if (const CUtensorMap *hit = g_maps.find(key)) {
         *map = *hit;
         return TAUB_OK;
@@ -545,9 +744,9 @@ static int make_field_map(CUtensorMap *map, const taub_geom &g, const float *bas
 
 // Same view of the uint16 side array (cpg elements per float4 group: 1 = neighbour codes, 4 = class ids):
 // (pitch/4 * cpg, rows, bs * planes), box = LGc*cpg x LR x 1.
-static int make_code_map(CUtensorMap *map, const taub_geom &g, const uint16_t *base, int LR, int LGc, int cpg)
+static int make_code_map(CUtensorMap *map, const taub_geom &g, const uint16_t *base, int LR, int LGc, int cpg, int dev)
 {
-    const MapKey key{base, g.pitch * cpg / 4, g.rows, g.bs * g.planes, LGc * cpg, LR, 2};
+    const MapKey key{base, dev, g.pitch * cpg / 4, g.rows, g.bs * g.planes, LGc * cpg, LR, 2};
     if (const CUtensorMap *hit = g_maps.find(key)) {
         *map = *hit;
         return TAUB_OK;
@@ -593,15 +792,7 @@ using namespace taub;
 
 static bool odd_periodic(const taub_geom &g) { return g.periodic && ((g.Ny & 1) || (g.Nz & 1)); }
 
-static bool fuse_odd_periodic_enabled()
-{
-    static int on = -1;
-    if (on < 0) {
-        const char *e = getenv("TAUB_FUSE_ODD_PERIODIC");
-        on = (e && e[0] == '1') ? 1 : 0;
-    }
-    return on == 1;
-}
+static int class_rows_in_smem(const taub_problem *p) { return p->kind == TAUB_MULTIPHASE_CLASS ? min(p->L, F_TABK) : 0; }
 
 extern "C" {
 
@@ -619,12 +810,11 @@ int taub_can_fuse(const taub_problem *p)
         return 0;
     if (p->kind != TAUB_BINARY && !p->lut) return 0;
     const taub_geom &g = p->g;
-    // periodic wrap with odd Ny/Nz couples two voxels of the SAME colour (reference reads a ghost
-    // snapshot): generic path, unless the experimental OP variant of the fused kernel (ghost ring of the odd
-    // axis left out of the colour-A step) is switched on with TAUB_FUSE_ODD_PERIODIC=1.
-    if (odd_periodic(g) && !fuse_odd_periodic_enabled()) return 0;
     if (g.bs > 65535) return 0;
-    return choose_tile(g, (p->kind == TAUB_MULTIPHASE_CLASS || p->kind == TAUB_ANISOTROPIC) ? 4 : 1).eff > 0.0 ? 1 : 0;
+    return choose_tile(g, (p->kind == TAUB_MULTIPHASE_CLASS || p->kind == TAUB_ANISOTROPIC) ? 4 : 1, class_rows_in_smem(p),
+                       odd_periodic(g)).eff > 0.0
+               ? 1
+               : 0;
 }
 
 int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, void *stream)
@@ -636,7 +826,9 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     const taub_geom &g = p->g;
     TAUB_REQUIRE(i_lo >= 0 && i_hi <= g.Nx && i_lo < i_hi, "taub_fused_sweep2: planes [%d, %d) outside the slab", i_lo, i_hi);
     const int cpg = (p->kind == TAUB_MULTIPHASE_CLASS || p->kind == TAUB_ANISOTROPIC) ? 4 : 1;
-    const TileChoice t = choose_tile(g, cpg);
+    const int tab_k = class_rows_in_smem(p);
+    const bool op = odd_periodic(g);   // the odd-periodic variant of the kernel is compiled for the narrow tile only
+    const TileChoice t = choose_tile(g, cpg, tab_k, op);
     FusedParams P;
     P.g = g;
     P.src = p->field[p->cur];
@@ -644,6 +836,7 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     P.codes = p->codes;
     P.table = p->lut;
     P.n_classes = p->L;
+    P.tab_k = tab_k;
     P.omega = p->omega;
     P.stop = p->stop;
     P.peer_lo = p->peer_lo[p->cur ^ 1];
@@ -659,48 +852,56 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     const int64_t tiles = (int64_t)t.tiles_j * t.tiles_k * g.bs;
     int dev_ord = 0;
     TAUB_CUDA(cudaGetDevice(&dev_ord));
-    static int sm_count = 0;
-    if (!sm_count) TAUB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev_ord));
+    static int sm_count[64] = {0};   // per device
+    if (!sm_count[dev_ord & 63])
+        TAUB_CUDA(cudaDeviceGetAttribute(&sm_count[dev_ord & 63], cudaDevAttrMultiProcessorCount, dev_ord));
     int chunk_len, chunks;
-    choose_chunks(n_planes, tiles, 2 * sm_count, &chunk_len, &chunks);
+    choose_chunks(n_planes, tiles, 2 * sm_count[dev_ord & 63], &chunk_len, &chunks);
     P.chunk_len = chunk_len;
     TAUB_REQUIRE(chunks <= 65535, "taub_fused_sweep2: too many plane chunks");
     P.slot_f4 = ((t.LR * t.LG + 7) / 8) * 8;
     P.cslot_h = ((t.LR * t.LGc * cpg * 2 + 127) / 128) * 64;
-    const int nb = ring_depth(cpg);
-    const size_t smem = fused_smem_bytes(t.LR, t.LG, t.LGc, cpg, nb);
+    const size_t smem = fused_smem_bytes(t.LR, t.LG, t.LGc, cpg, ring_depth(cpg), code_ring_depth(cpg), tab_k);
     dim3 grid(t.tiles_j * t.tiles_k, chunks, g.bs);
     cudaStream_t s = (cudaStream_t)stream;
     CUtensorMap tmap, cmap;
-    if (int rc = make_field_map(&tmap, g, P.src, t.LR, t.LG)) return rc;
-    if (int rc = make_code_map(&cmap, g, P.codes, t.LR, t.LGc, cpg)) return rc;
+    if (int rc = make_field_map(&tmap, g, P.src, t.LR, t.LG, dev_ord)) return rc;
+    if (int rc = make_code_map(&cmap, g, P.codes, t.LR, t.LGc, cpg, dev_ord)) return rc;
     // parity of loaded row 1 (row a of every pair) at step 0, i.e. at plane c0-1: 0 -> x,z active.
     // Tile row offsets (multiples of the even OR_) and chunk starts (multiples of the even
     // chunk_len) do not change it, so it is one number for the whole grid.
     const int pa0 = (1 - G + g.i_offset + P.colourA + (i_lo - 1)) & 1;   // row lr = 1 is row 0 of a column
-#define TAUB_LAUNCH_FUSED(PA_, KIND_, NB_, OP_)                                                                   \
+    // the opt-in shared-memory limit of a kernel is per device and only ever raised: set it on every launch that
+    // needs more than the largest value requested so far (a relaxed atomic per instantiation and device)
+#define TAUB_LAUNCH_FUSED(OG_, PA_, KIND_, OP_)                                                                   \
     do {                                                                                                          \
-        static size_t smem_set[64] = {0};   /* per device: raise the opt-in limit only when it grows */         \
-        if (smem > smem_set[dev_ord & 63]) {                                                                      \
-            TAUB_CUDA(cudaFuncSetAttribute(fused_sweep2_kernel<F_NRW, PA_, KIND_, NB_, OP_>,                      \
+        static std::atomic<size_t> smem_set[64];                                                                  \
+        if (smem > smem_set[dev_ord & 63].load(std::memory_order_relaxed)) {                                      \
+            TAUB_CUDA(cudaFuncSetAttribute(fused_sweep2_kernel<OG_, PA_, KIND_, OP_>,                             \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
-            smem_set[dev_ord & 63] = smem;                                                                        \
+            smem_set[dev_ord & 63].store(smem, std::memory_order_relaxed);                                        \
         }                                                                                                         \
-        TAUB_CUDA(launch_maybe_pdl(fused_sweep2_kernel<F_NRW, PA_, KIND_, NB_, OP_>, grid, dim3(F_NT), smem, s, P, \
-                                   tmap, cmap));                                                                  \
+        TAUB_CUDA(launch_maybe_pdl(fused_sweep2_kernel<OG_, PA_, KIND_, OP_>, grid, dim3(F_NT), smem, s, P, tmap,  \
+                                   cmap));                                                                        \
     } while (0)
-#define TAUB_LAUNCH_FUSED_PA(KIND_, NB_, OP_)                                                                     \
+#define TAUB_LAUNCH_FUSED_PA(OG_, KIND_, OP_)                                                                     \
     do {                                                                                                          \
-        if (pa0 == 0) TAUB_LAUNCH_FUSED(0, KIND_, NB_, OP_); else TAUB_LAUNCH_FUSED(1, KIND_, NB_, OP_);          \
+        if (pa0 == 0) TAUB_LAUNCH_FUSED(OG_, 0, KIND_, OP_); else TAUB_LAUNCH_FUSED(OG_, 1, KIND_, OP_);          \
     } while (0)
-    const bool op = odd_periodic(g);
+#define TAUB_LAUNCH_FUSED_OG(KIND_)                                                                               \
+    do {                                                                                                          \
+        if (t.OG == 8) TAUB_LAUNCH_FUSED_PA(8, KIND_, false);                                                     \
+        else if (t.OG == 16) TAUB_LAUNCH_FUSED_PA(16, KIND_, false);                                              \
+        else TAUB_LAUNCH_FUSED_PA(32, KIND_, false);                                                              \
+    } while (0)
     if (p->kind == TAUB_MULTIPHASE_CLASS) {
-        if (op) TAUB_LAUNCH_FUSED_PA(TAUB_MULTIPHASE_CLASS, F_NB_CLS, true); else TAUB_LAUNCH_FUSED_PA(TAUB_MULTIPHASE_CLASS, F_NB_CLS, false);
+        if (op) TAUB_LAUNCH_FUSED_PA(8, TAUB_MULTIPHASE_CLASS, true); else TAUB_LAUNCH_FUSED_OG(TAUB_MULTIPHASE_CLASS);
     } else if (p->kind == TAUB_ANISOTROPIC) {
-        TAUB_LAUNCH_FUSED_PA(TAUB_ANISOTROPIC, F_NB_CLS, false);      // no periodic variant of this solver
+        TAUB_LAUNCH_FUSED_OG(TAUB_ANISOTROPIC);      // no periodic variant of this solver
     } else {
-        if (op) TAUB_LAUNCH_FUSED_PA(TAUB_BINARY, F_NB, true); else TAUB_LAUNCH_FUSED_PA(TAUB_BINARY, F_NB, false);
+        if (op) TAUB_LAUNCH_FUSED_PA(8, TAUB_BINARY, true); else TAUB_LAUNCH_FUSED_OG(TAUB_BINARY);
     }
+#undef TAUB_LAUNCH_FUSED_OG
 #undef TAUB_LAUNCH_FUSED_PA
 #undef TAUB_LAUNCH_FUSED
     TAUB_CUDA(cudaGetLastError());

@@ -11,7 +11,6 @@
 #include <stdlib.h>
 
 #include "taub_common.cuh"
-#include "taub_refresh.cuh"
 
 namespace taub {
 
@@ -61,30 +60,6 @@ refresh_ghosts_kernel(taub_geom g, float *__restrict__ f, int p_lo, const int *_
             row[c + 1] = v1;
         }
     }
-}
-
-// v2 (experimental, TAUB_REFRESH_V2=1): one CTA (pair) per plane runs taub_refresh.cuh's plane routine -- no
-// integer division per item, float4 copies inside the interior columns, a single wave of CTAs.
-constexpr int REFRESH_V2_THREADS = 128;
-
-__global__ void __launch_bounds__(REFRESH_V2_THREADS)
-refresh_ghosts_v2_kernel(taub_geom g, float *__restrict__ f, int p_lo, const int *__restrict__ stop, int early_trigger)
-{
-    if (early_trigger) pdl_trigger();
-    pdl_wait();      // before the first global read and before any thread exits (see launch_maybe_pdl)
-    if (stop && *stop) return;
-    float *plane = f + (int64_t)blockIdx.z * g.image_stride + (int64_t)(p_lo + blockIdx.y) * g.plane_stride;
-    refresh_plane_v2(g, plane, blockIdx.x * REFRESH_V2_THREADS + threadIdx.x, gridDim.x * REFRESH_V2_THREADS);
-}
-
-static bool refresh_v2_enabled()
-{
-    static int on = -1;
-    if (on < 0) {
-        const char *e = getenv("TAUB_REFRESH_V2");
-        on = (e && e[0] == '1') ? 1 : 0;
-    }
-    return on == 1;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -236,13 +211,6 @@ static int refresh_ghosts(const taub_geom *g, float *field, int p_lo, int p_hi, 
     TAUB_REQUIRE(p_lo >= 0 && p_hi <= g->planes && p_lo < p_hi, "taub_refresh_ghosts: planes [%d, %d) invalid", p_lo, p_hi);
     const int total = 2 * G * (g->pitch >> 2) + 2 * g->Ny;
     for (int b0 = 0; b0 < g->bs; b0 += 65535) {
-        if (refresh_v2_enabled()) {
-            // about 6 items per thread: 1..4 CTAs per plane, all planes resident in one wave
-            dim3 grid2(min(4, max(1, ceil_div(total, 6 * REFRESH_V2_THREADS))), p_hi - p_lo, min(g->bs - b0, 65535));
-            TAUB_CUDA(launch_maybe_pdl(refresh_ghosts_v2_kernel, grid2, dim3(REFRESH_V2_THREADS), 0, (cudaStream_t)stream, *g,
-                                       field + (int64_t)b0 * g->image_stride, p_lo, stop, g_refresh_late_trigger ? 0 : 1));
-            continue;
-        }
         dim3 grid(ceil_div(total, 256), p_hi - p_lo, min(g->bs - b0, 65535));
         TAUB_CUDA(launch_maybe_pdl(refresh_ghosts_kernel, grid, dim3(256), 0, (cudaStream_t)stream, *g,
                                    field + (int64_t)b0 * g->image_stride, p_lo, stop, g_refresh_late_trigger ? 0 : 1));

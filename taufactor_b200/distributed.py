@@ -17,6 +17,7 @@ voxel does not depend on the order in which voxels are visited (tests/test_gpu_s
 from __future__ import annotations
 
 import math
+import warnings
 from timeit import default_timer as timer
 
 import numpy as np
@@ -194,16 +195,34 @@ class DistributedSolver(Solver):
             self._symm = None
             equal_slabs = len({h - l for l, h in self.bounds}) == 1
             if p2p and self.world > 1 and equal_slabs and dist.get_backend(group) == "nccl":
-                try:      # peer-addressable field buffers (same size on every rank)
+                # peer-addressable field buffers (same size on every rank).  Allocation can fail per rank (no P2P /
+                # fabric support); the rendezvous is a collective, so the ranks first agree that everybody got its
+                # buffers and only then enter it -- and agree again on its outcome: one-sided stores on some ranks and
+                # NCCL messages on others would hang or leave stale ghost planes.
+                bufs, err = None, None
+                try:
                     import torch.distributed._symmetric_memory as symm
                     grp = group if group is not None else dist.group.WORLD
                     if not symm.is_symm_mem_enabled_for_group(grp.group_name):
                         symm.enable_symm_mem_for_group(grp.group_name)
                     bufs = [symm.empty(n, dtype=torch.float32, device=dev) for _ in range(2)]
-                    self._symm = [symm.rendezvous(b, grp) for b in bufs]
+                except Exception as e:
+                    err = repr(e)
+                if self._all_ranks_ok(err is None, dev, group):
+                    try:
+                        self._symm = [symm.rendezvous(b, grp) for b in bufs]
+                    except Exception as e:
+                        err, self._symm = repr(e), None
+                    if not self._all_ranks_ok(self._symm is not None, dev, group):
+                        self._symm = None
+                if self._symm is not None:
                     self._bufs = bufs
-                except Exception as e:   # no P2P / fabric support here: fall back to NCCL messages
-                    self._symm, self._p2p_error = None, repr(e)
+                else:
+                    self._p2p_error = err or "symmetric memory unavailable on another rank"
+                    if self.rank == 0:
+                        warnings.warn("DistributedSolver: NVLink peer memory (torch symmetric memory) is unavailable "
+                                      f"({self._p2p_error}); ghost planes travel as NCCL send/recv messages instead",
+                                      RuntimeWarning)
             if self._symm is None:
                 self._bufs = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(2)]
             # only the planes this rank needs travel to the device
@@ -228,6 +247,16 @@ class DistributedSolver(Solver):
             counts = torch.zeros(self.batch_size * g.Nx, dtype=torch.int64, device=dev)
             sel = torch.zeros(256, dtype=torch.uint8, device=dev)
             if not self._multi:
+                # label check of ref:387-397 on the device (the host check above only covers small, whole images):
+                # histogram of this rank's planes, summed over the ranks; every rank raises together
+                hist = torch.zeros(self.batch_size * 256, dtype=torch.int64, device=dev)
+                self._call(self._lib.taub_plane_counts(g, img_dev.data_ptr(), need[0], need[1] - need[0], sel.data_ptr(),
+                                                       counts.data_ptr(), hist.data_ptr(), self._stream()), "taub_plane_counts")
+                if self.world > 1:
+                    dist.all_reduce(hist, group=group)
+                present = np.flatnonzero(hist.cpu().numpy().reshape(self.batch_size, 256).sum(axis=0))
+                if present.size and present.max() > 1:
+                    self._raise_not_binary(present)
                 codes = torch.empty(self._lib.taub_codes_elems(g), dtype=torch.int16, device=dev)
                 p.codes = codes.data_ptr()
                 self._call(self._lib.taub_init_binary(p, img_dev.data_ptr(), need[0], need[1] - need[0],
@@ -307,6 +336,13 @@ class DistributedSolver(Solver):
         self._fuse = None
         self.overlap = overlap
         self._report = (self.rank == 0)
+
+    @staticmethod
+    def _all_ranks_ok(ok, dev, group):
+        """True when ``ok`` holds on every rank of the group (one tiny all-reduce)."""
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        return bool(int(flag.item()))
 
     # pipeline = True (inherited): the stop rule runs on the device of every rank, on the all-gathered
     # profiles, so the next block of sweeps is queued before the check is read back

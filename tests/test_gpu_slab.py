@@ -174,3 +174,38 @@ def test_multiphase_slabs_equal_single_gpu(tmp_path, shape, periodic, world, mod
     assert np.array_equal(B.flux_1d, got["flux"])
     assert np.array_equal(B.D_mean, got["D_mean"]) and np.array_equal(B.vol_x, got["vol_x"])
     assert np.array_equal(B.tau, got["tau"]) and np.array_equal(B.D_eff, got["D_eff"])
+
+
+def _label_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.cuda.set_device(0)
+        from taufactor_b200.distributed import DistributedSolver, image_window, slab_bounds
+        shape = (40, 24, 20)
+        img = cases.random_img(shape, 0.7, seed=5)
+        img[33, 3, 4] = 2                       # one stray label, in the LAST rank's slab only
+        lo, hi = slab_bounds(shape[0], world)[rank]
+        w = image_window(lo, hi, shape[0])
+        msg = ""
+        try:
+            DistributedSolver(img[w[0]:w[1]], device="cuda:0", window=w, shape=shape)
+        except ValueError as e:
+            msg = str(e)
+        with open(f"{out}.{rank}", "w") as fh:
+            fh.write(msg)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_windowed_slabs_reject_non_binary_labels_on_every_rank(tmp_path):
+    """ref:387-397 -- a segmentation with labels other than 0/1 must raise, also when every rank only sees a window of
+    the volume (no host-side check possible): the device histograms are summed over the ranks."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "labels")
+    mp.spawn(_label_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    for r in range(2):
+        msg = open(f"{out}.{r}").read()
+        assert "Input image must only contain 0s and 1s" in msg and "[0 1 2]" in msg, (r, msg)
