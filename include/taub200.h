@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TAUB_ABI_VERSION 9
+#define TAUB_ABI_VERSION 10
 #define TAUB_GHOST 2            /* ghost width in x (planes), y (rows) and z (columns) */
 #define TAUB_COL0 4             /* column of interior voxel k = 0 */
 #define TAUB_MAX_LABELS 64      /* dense phase indices 0..L-1, L <= 64; index L = "outside" */
@@ -49,10 +49,11 @@ typedef enum taub_kind {
                             * class id (< 64) per storage voxel, lut = device float[130]: {b, RN(1/b)} per class
                             * (b = weighted neighbour count :462-467; b = 1/b = 0 where it is infinite), then Ky, Kz */
     TAUB_MULTIPHASE_CLASS = 3  /* multi-phase through a stencil-class table: codes = one uint16 class id per
-                                * storage voxel, lut = device float[2][L][4]: half rows {w_x+, w_x-, w_y+, w_y-}
-                                * of all L classes, then half rows {w_z+, w_z-, b, RN(1/b)} with b = prefactor
-                                * (b = 1/b = 0 where it is infinite), L = number of classes (see
-                                * taub_multiphase_keys) */
+                                * storage voxel, lut = device float[L][8]: one 32-byte row
+                                * {w_x+, w_x-, w_y+, w_y-, w_z+, w_z-, b, RN(1/b)} per class with b = prefactor
+                                * (b = 1/b = 0 where it is infinite), most frequent classes first (the fused
+                                * kernel keeps the first 256 rows in shared memory), L = number of classes
+                                * (see taub_multiphase_keys) */
 } taub_kind;
 
 /* Geometry of one rank's slab.  Filled by taub_geom_init. */

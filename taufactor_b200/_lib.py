@@ -79,7 +79,7 @@ def load():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.taub_abi_version() != 9:
+        if lib.taub_abi_version() != 10:
             raise ImportError("libtaub200.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib

@@ -50,7 +50,7 @@ struct FusedParams {
     const float *src;
     float *dst;
     const uint16_t *codes;   // binary: one uint16 (four 4-bit counts) per group; class kind: one uint16 per voxel
-    const float *table;      // class kind: [2][n_classes][4] weight half-rows
+    const float *table;      // class kind: [n_classes][8] weight rows
     int n_classes;
     float omega;
     int colourA;
@@ -67,6 +67,7 @@ struct FusedParams {
     int slot_f4;       // float4 per field ring slot
     int cslot_h;       // uint16 per code ring slot
     int tab_k;         // class kind: rows of the weight table staged in shared memory (<= F_TABK)
+    int write_solid;   // binary kind: 1 = also store float4 groups whose four voxels are all non-conductive
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -159,38 +160,44 @@ __device__ __forceinline__ void row_update(float4 &c, const float4 &xp, const fl
     }
 }
 
-// Weight rows of a stencil class: from the shared-memory copy of the first tab_k rows (SM = true; the caller has
-// checked cls < tab_k for the whole warp) or through the read-only global path.
-template <bool SM>
-__device__ __forceinline__ void class_rows(unsigned cls, const float4 *__restrict__ tabA, const float4 *__restrict__ tabB,
-                                           const float4 *sA, const float4 *sB, float4 &wa, float4 &wb)
+// Weight row of a stencil class (two float4: {w_x+, w_x-, w_y+, w_y-}, {w_z+, w_z-, b, 1/b}): from the shared-memory
+// copy of the tab_k most frequent rows or -- for the lanes whose class is a rare one -- through the read-only global
+// path.  The compiler turns the two sides into complementary predicated loads: no divergence, and a predicated-off
+// load costs an issue slot but no memory transaction.
+struct ClassTab {
+    const float4 *g;   // global table, two float4 per class
+    uint32_t s;        // shared-window address of the staged copy of the first k rows
+    unsigned k;        // rows staged
+};
+
+__device__ __forceinline__ void class_row(unsigned cls, const ClassTab &T, float4 &wa, float4 &wb)
 {
-    if (SM) {
-        wa = sA[cls];
-        wb = sB[cls];
+    if (cls < T.k) {
+        wa = ld_sh<float4>(T.s + cls * 32u);
+        wb = ld_sh<float4>(T.s + cls * 32u + 16u);
     } else {
-        wa = __ldg(tabA + cls);
-        wb = __ldg(tabB + cls);
+        const float4 *row = T.g + 2 * cls;
+        wa = __ldg(row);
+        wb = __ldg(row + 1);
     }
 }
 
 // Class kind: cls2 = the row's four uint16 class ids (x | y << 16, z | w << 16).
-template <bool IS_XZ, bool SM>
+template <bool IS_XZ>
 __device__ __forceinline__ void row_update_class(float4 &c, const float4 &xp, const float4 &xm, const float4 &up,
-                                                 const float4 &dn, float zs, uint2 cls2, const float4 *tabA, const float4 *tabB,
-                                                 const float4 *sA, const float4 *sB, float omega, unsigned &umin)
+                                                 const float4 &dn, float zs, uint2 cls2, const ClassTab &T, float omega,
+                                                 unsigned &umin)
 {
+    const unsigned c0 = IS_XZ ? (cls2.x & 0xffffu) : (cls2.x >> 16), c1 = IS_XZ ? (cls2.y & 0xffffu) : (cls2.y >> 16);
     float4 wa0, wb0, wa1, wb1;
+    class_row(c0, T, wa0, wb0);
+    class_row(c1, T, wa1, wb1);
     if (IS_XZ) {
-        class_rows<SM>(cls2.x & 0xffffu, tabA, tabB, sA, sB, wa0, wb0);
-        class_rows<SM>(cls2.y & 0xffffu, tabA, tabB, sA, sB, wa1, wb1);
         const float n0 = sor_class_rows(c.x, xp.x, xm.x, up.x, dn.x, c.y, zs, wa0, wb0, omega, umin);
         const float n1 = sor_class_rows(c.z, xp.z, xm.z, up.z, dn.z, c.w, c.y, wa1, wb1, omega, umin);
         c.x = n0;
         c.z = n1;
     } else {
-        class_rows<SM>(cls2.x >> 16, tabA, tabB, sA, sB, wa0, wb0);
-        class_rows<SM>(cls2.y >> 16, tabA, tabB, sA, sB, wa1, wb1);
         const float n0 = sor_class_rows(c.y, xp.y, xm.y, up.y, dn.y, c.z, c.x, wa0, wb0, omega, umin);
         const float n1 = sor_class_rows(c.w, xp.w, xm.w, up.w, dn.w, zs, c.z, wa1, wb1, omega, umin);
         c.y = n0;
@@ -255,15 +262,13 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     constexpr int LGt = OGT + 2, LG = OGT + 3, LGc = OGT + 8;   // thread groups per row; box widths (field: odd pitch)
     constexpr uint32_t ROWB = LG * 16u, CROWB = LGc * CPG * 2u; // bytes per field row / id-code row of a ring slot
     const int LR = P.LR;
-    const float4 *tabA = reinterpret_cast<const float4 *>(P.table);   // class kind: half rows A, then half rows B
-    const float4 *tabB = tabA + P.n_classes;
+    const float4 *tab4 = reinterpret_cast<const float4 *>(P.table);   // class kind: two float4 per class
     const uint32_t slotB = (uint32_t)P.slot_f4 * 16u;   // bytes per field ring slot (multiple of 128)
     const uint32_t cslotB = (uint32_t)P.cslot_h * 2u;   // bytes per code ring slot (multiple of 128)
     unsigned char *planes = smem_raw;
     unsigned char *cplanes = smem_raw + (size_t)NB * slotB;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(cplanes + (size_t)NBC * cslotB);
-    const float4 *sA = reinterpret_cast<const float4 *>(mbar + 16);   // class kind: staged weight half rows
-    const float4 *sB = sA + P.tab_k;
+    float4 *s_tab = reinterpret_cast<float4 *>(mbar + 16);   // class kind: staged weight rows
     __shared__ __align__(512) float2 s_div[ANISO_CLASSES];   // static: constant address; aligned for the OR look-up
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -291,10 +296,9 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     // anisotropic: (b, 1/b) of the prefactor classes; class kind: the first tab_k weight rows.  First used after
     // the step loop's first __syncthreads
     if (ANI && tid < ANISO_CLASSES) s_div[tid] = reinterpret_cast<const float2 *>(P.table)[tid];
-    if (MPC) {
-        float4 *w = const_cast<float4 *>(sA);
-        for (int t = tid; t < 2 * P.tab_k; t += F_NT) w[t] = (t < P.tab_k) ? __ldg(tabA + t) : __ldg(tabB + (t - P.tab_k));
-    }
+    if (MPC)
+        for (int t = tid; t < 2 * P.tab_k; t += F_NT) s_tab[t] = __ldg(tab4 + t);
+    const ClassTab ctab{tab4, smem_u32(s_tab), (unsigned)P.tab_k};
     const float Ky = ANI ? P.table[2 * ANISO_CLASSES] : 0.0f, Kz = ANI ? P.table[2 * ANISO_CLASSES + 1] : 0.0f;
     const uint32_t div_base = smem_u32(s_div);
 
@@ -305,11 +309,14 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     const uint32_t tx_bytes = (uint32_t)LR * (ROWB + CROWB);
     uint32_t is_f = 0, is_c = 0, is_bar = mbar_u32;   // next issue: field / code slot byte offset, barrier address
     int is_pl = b * g.planes + (c0 - 2 + G);          // ... and tensor plane coordinate
-    auto issue = [&]() {
+    // with_codes = false: plane c0-2 (rel 0) is only ever an x- neighbour, nothing on it is updated, so its codes / ids
+    // are never read -- and must not be loaded: the binary kind's code ring has fewer slots (4) than the prologue has
+    // boxes in flight (5), and two boxes in flight into the same slot (rel 0 and rel 4) may land in either order
+    auto issue = [&](const bool with_codes) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(is_bar, tx_bytes);
+        mbar_expect_tx(is_bar, with_codes ? tx_bytes : (uint32_t)LR * ROWB);
         tma_load_3d(planes_u32 + is_f, &tmap, 4 * G0, R0, is_pl, is_bar);
-        tma_load_3d(cplanes_u32 + is_c, &cmap, G0 * CPG, R0, is_pl, is_bar);
+        if (with_codes) tma_load_3d(cplanes_u32 + is_c, &cmap, G0 * CPG, R0, is_pl, is_bar);
         ++is_pl;
         is_f += slotB;
         is_bar += 8u;
@@ -321,7 +328,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
         if (is_c == NBC * cslotB) is_c = 0;
     };
     if (tid == 0)
-        for (int rel = 0; rel < min(NB - 1, total_rel); ++rel) issue();
+        for (int rel = 0; rel < min(NB - 1, total_rel); ++rel) issue(rel > 0);
 
     // ---- this thread's column: rows lr0 .. lr0+NRW-1 of the tile, group gg.  Threads beyond the tile's columns
     //      (m >= NCT) shadow column 0 of their group: they load and compute like everybody else (no divergence in
@@ -402,7 +409,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
         constexpr int iM2 = ss & 3, iM1 = (ss + 1) & 3, iP = (ss + 2) & 3, iP1 = (ss + 3) & 3;
         const int p = c0 - 1 + s;   // plane receiving colour A; colour B goes to plane p-1
         __syncthreads();            // ring slot of plane p-2 is free; a[p-1] is visible in its slot
-        if (tid == 0 && (FAST || s - 1 + NB < total_rel)) issue();
+        if (tid == 0 && (FAST || s - 1 + NB < total_rel)) issue(true);
         mbar_wait(w_bar, w_par);
         const uint32_t aM1 = tbase + oM1, aP = tbase + oP, aP1 = tbase + oP1;   // this column in the three slots
         const bool doA = FAST || ((p >= P.a_lo) && (p < P.a_hi));
@@ -435,55 +442,41 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
             }
             const float4 below = lds128<-(int)ROWB>(aP), above = lds128<(int)(NRW * ROWB)>(aP);
             uint2 ids[NRW];
-            bool sm_rows = true;
             if (CLS) {
 #pragma unroll
                 for (int r = 0; r < NRW; ++r) ids[r] = ld_sh<uint2>(cbase + kP + r * CROWB);
-                if (MPC) {   // all 2 * NRW classes of this step in the shared-memory part of the table, warp-wide?
-                    unsigned mx = 0;
-#pragma unroll
-                    for (int r = 0; r < NRW; ++r) {
-                        const bool xz = ((PA0 + ss + r) & 1) == 0;
-                        mx = max(mx, max(xz ? (ids[r].x & 0xffffu) : (ids[r].x >> 16), xz ? (ids[r].y & 0xffffu) : (ids[r].y >> 16)));
-                    }
-                    sm_rows = __all_sync(0xffffffffu, mx < (unsigned)P.tab_k);
-                }
             }
             float4 snap[NRW];
             if (OP) {
 #pragma unroll
                 for (int r = 0; r < NRW; ++r) snap[r] = rg[r][iP];
             }
-            auto phaseA = [&](auto sm_c) {
-                constexpr bool SM = decltype(sm_c)::value != 0;
 #pragma unroll
-                for (int r = 0; r < NRW; ++r) {
-                    // neighbours inside the column are registers; each row only reads the components
-                    // its neighbours leave unchanged in this step
-                    const float4 &dn = (r == 0) ? below : rg[r - 1][iP];
-                    const float4 &up = (r == NRW - 1) ? above : rg[r + 1][iP];
-                    if (((PA0 + ss + r) & 1) == 0) {
-                        if (ANI)
-                            row_update_aniso<true>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], ids[r], s_div, Ky, Kz, P.omega, umin);
-                        else if (CLS)
-                            row_update_class<true, SM>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], ids[r], tabA, tabB, sA, sB, P.omega, umin);
-                        else if (r & 1)
-                            row_update<true, 16>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], cr[r >> 1][iP], div_base, P.omega, umin);
-                        else
-                            row_update<true, 0>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], cr[r >> 1][iP], div_base, P.omega, umin);
-                    } else {
-                        if (ANI)
-                            row_update_aniso<false>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], ids[r], s_div, Ky, Kz, P.omega, umin);
-                        else if (CLS)
-                            row_update_class<false, SM>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], ids[r], tabA, tabB, sA, sB, P.omega, umin);
-                        else if (r & 1)
-                            row_update<false, 16>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], cr[r >> 1][iP], div_base, P.omega, umin);
-                        else
-                            row_update<false, 0>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], cr[r >> 1][iP], div_base, P.omega, umin);
-                    }
+            for (int r = 0; r < NRW; ++r) {
+                // neighbours inside the column are registers; each row only reads the components
+                // its neighbours leave unchanged in this step
+                const float4 &dn = (r == 0) ? below : rg[r - 1][iP];
+                const float4 &up = (r == NRW - 1) ? above : rg[r + 1][iP];
+                if (((PA0 + ss + r) & 1) == 0) {
+                    if (ANI)
+                        row_update_aniso<true>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], ids[r], s_div, Ky, Kz, P.omega, umin);
+                    else if (CLS)
+                        row_update_class<true>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], ids[r], ctab, P.omega, umin);
+                    else if (r & 1)
+                        row_update<true, 16>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], cr[r >> 1][iP], div_base, P.omega, umin);
+                    else
+                        row_update<true, 0>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], cr[r >> 1][iP], div_base, P.omega, umin);
+                } else {
+                    if (ANI)
+                        row_update_aniso<false>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], ids[r], s_div, Ky, Kz, P.omega, umin);
+                    else if (CLS)
+                        row_update_class<false>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], ids[r], ctab, P.omega, umin);
+                    else if (r & 1)
+                        row_update<false, 16>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], cr[r >> 1][iP], div_base, P.omega, umin);
+                    else
+                        row_update<false, 0>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], cr[r >> 1][iP], div_base, P.omega, umin);
                 }
-            };
-            if (!MPC || sm_rows) phaseA(IC<1>{}); else phaseA(IC<0>{});
+            }
             if (OP) {   // ghost cells of an odd periodic axis keep their snapshot
 #pragma unroll
                 for (int r = 0; r < NRW; ++r) {
@@ -517,54 +510,42 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
             }
             const float4 below = lds128<-(int)ROWB>(aM1), above = lds128<(int)(NRW * ROWB)>(aM1);
             uint2 ids[NRW];
-            bool sm_rows = true;
             if (CLS) {
 #pragma unroll
                 for (int r = 0; r < NRW; ++r) ids[r] = ld_sh<uint2>(cbase + kM1 + r * CROWB);
-                if (MPC) {
-                    unsigned mx = 0;
-#pragma unroll
-                    for (int r = 0; r < NRW; ++r) {
-                        const bool xz = ((PA0 + ss + r) & 1) == 0;
-                        mx = max(mx, max(xz ? (ids[r].x & 0xffffu) : (ids[r].x >> 16), xz ? (ids[r].y & 0xffffu) : (ids[r].y >> 16)));
-                    }
-                    sm_rows = __all_sync(0xffffffffu, mx < (unsigned)P.tab_k);
-                }
             }
             float4 out[NRW];
 #pragma unroll
-            for (int r = 0; r < NRW; ++r) out[r] = rg[r][iM1];
-            auto phaseB = [&](auto sm_c) {
-                constexpr bool SM = decltype(sm_c)::value != 0;
-#pragma unroll
-                for (int r = 0; r < NRW; ++r) {
-                    const float4 &dn = (r == 0) ? below : rg[r - 1][iM1];
-                    const float4 &up = (r == NRW - 1) ? above : rg[r + 1][iM1];
-                    if (((PA0 + ss + r) & 1) == 0) {
-                        if (ANI)
-                            row_update_aniso<true>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], ids[r], s_div, Ky, Kz, P.omega, umin);
-                        else if (CLS)
-                            row_update_class<true, SM>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], ids[r], tabA, tabB, sA, sB, P.omega, umin);
-                        else if (r & 1)
-                            row_update<true, 16>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], cr[r >> 1][iM1], div_base, P.omega, umin);
-                        else
-                            row_update<true, 0>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], cr[r >> 1][iM1], div_base, P.omega, umin);
-                    } else {
-                        if (ANI)
-                            row_update_aniso<false>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], ids[r], s_div, Ky, Kz, P.omega, umin);
-                        else if (CLS)
-                            row_update_class<false, SM>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], ids[r], tabA, tabB, sA, sB, P.omega, umin);
-                        else if (r & 1)
-                            row_update<false, 16>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], cr[r >> 1][iM1], div_base, P.omega, umin);
-                        else
-                            row_update<false, 0>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], cr[r >> 1][iM1], div_base, P.omega, umin);
-                    }
+            for (int r = 0; r < NRW; ++r) {
+                out[r] = rg[r][iM1];
+                const float4 &dn = (r == 0) ? below : rg[r - 1][iM1];
+                const float4 &up = (r == NRW - 1) ? above : rg[r + 1][iM1];
+                if (((PA0 + ss + r) & 1) == 0) {
+                    if (ANI)
+                        row_update_aniso<true>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], ids[r], s_div, Ky, Kz, P.omega, umin);
+                    else if (CLS)
+                        row_update_class<true>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], ids[r], ctab, P.omega, umin);
+                    else if (r & 1)
+                        row_update<true, 16>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], cr[r >> 1][iM1], div_base, P.omega, umin);
+                    else
+                        row_update<true, 0>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], cr[r >> 1][iM1], div_base, P.omega, umin);
+                } else {
+                    if (ANI)
+                        row_update_aniso<false>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], ids[r], s_div, Ky, Kz, P.omega, umin);
+                    else if (CLS)
+                        row_update_class<false>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], ids[r], ctab, P.omega, umin);
+                    else if (r & 1)
+                        row_update<false, 16>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], cr[r >> 1][iM1], div_base, P.omega, umin);
+                    else
+                        row_update<false, 0>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], cr[r >> 1][iM1], div_base, P.omega, umin);
                 }
-            };
-            if (!MPC || sm_rows) phaseB(IC<1>{}); else phaseB(IC<0>{});
+            }
 #pragma unroll
             for (int r = 0; r < NRW; ++r) {
-                if (canB & (1u << r)) {
+                // binary kind: a float4 group whose four voxels are all non-conductive (code word 0) holds zeros in both
+                // ping-pong buffers since the state build and for ever after -- there is nothing to write
+                const bool live = CLS || P.write_solid || ((cr[r >> 1][iM1] >> (16 * (r & 1))) & 0xffffu) != 0u;
+                if ((canB & (1u << r)) && live) {
                     float *d = dst0 + (int64_t)r * g.pitch;
                     *reinterpret_cast<float4 *>(d) = out[r];
                     if (send_lo) *reinterpret_cast<float4 *>(P.peer_lo + (d - P.dst) + (int64_t)g.Nx * ps) = out[r];
@@ -792,7 +773,18 @@ using namespace taub;
 
 static bool odd_periodic(const taub_geom &g) { return g.periodic && ((g.Ny & 1) || (g.Nz & 1)); }
 
-static int class_rows_in_smem(const taub_problem *p) { return p->kind == TAUB_MULTIPHASE_CLASS ? min(p->L, F_TABK) : 0; }
+// Tuning switches (read once): TAUB_TABK = stencil-class rows staged in shared memory (default 256, 0 = none);
+// TAUB_WRITE_SOLID=1 = store all-solid float4 groups too (the plain behaviour, for A/B measurements).
+static int env_int(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+static int class_rows_in_smem(const taub_problem *p)
+{
+    static const int tabk = max(0, min(env_int("TAUB_TABK", F_TABK), 2048));
+    return p->kind == TAUB_MULTIPHASE_CLASS ? min(p->L, tabk) : 0;
+}
 
 extern "C" {
 
@@ -837,6 +829,8 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     P.table = p->lut;
     P.n_classes = p->L;
     P.tab_k = tab_k;
+    static const int write_solid = env_int("TAUB_WRITE_SOLID", 0);
+    P.write_solid = write_solid;
     P.omega = p->omega;
     P.stop = p->stop;
     P.peer_lo = p->peer_lo[p->cur ^ 1];

@@ -71,7 +71,7 @@ plane_sums_kernel(taub_geom g, const float *__restrict__ f, const uint16_t *__re
                         v = open ? v : 0.0f;
                     } else if (KIND == TAUB_MULTIPHASE_CLASS) {
                         // D_x face conductance towards plane i+1 = first entry of the voxel's class row
-                        v = __fmul_rn(__ldg(lut + 4 * (int)codes[o + q]), v);
+                        v = __fmul_rn(__ldg(lut + 8 * (int)codes[o + q]), v);
                     } else if (KIND == TAUB_ANISOTROPIC) {
                         // the reference's factor > 8 test (:417-418) on the weighted prefactors of both voxels
                         // (b = 0 encodes inf); the prefactor may legitimately exceed 8 here

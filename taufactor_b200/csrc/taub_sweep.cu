@@ -116,13 +116,13 @@ half_sweep_kernel(taub_geom g, const float *__restrict__ src, float *__restrict_
             else
                 update_yw(c4, xp4, xm4, yp4, ym4, src[o + 4], code, s_div, omega);
         } else if (KIND == TAUB_MULTIPHASE_CLASS) {
-            // codes: one uint16 class id per voxel; lut = half rows {w_x+, w_x-, w_y+, w_y-}[L], {w_z+, w_z-, b, 1/b}[L]
+            // codes: one uint16 class id per voxel; lut = one 8-float row {w_x+, w_x-, w_y+, w_y-, w_z+, w_z-, b, 1/b} per class
             // (b = 0 stands for an infinite prefactor); true IEEE division here, the fused kernel uses 1/b
             const uint2 cw = *reinterpret_cast<const uint2 *>(codes + o);
             const float4 *tab = reinterpret_cast<const float4 *>(lut);
 #define TAUB_CLASS_Q(CLS, CEN, XP, XM, YP, YM, ZP, ZM)                                                     \
     {                                                                                                      \
-        const float4 wa = __ldg(tab + (CLS)), wb = __ldg(tab + L + (CLS));                                   \
+        const float4 wa = __ldg(tab + 2 * (CLS)), wb = __ldg(tab + 2 * (CLS) + 1);                                   \
         float s = __fadd_rn(__fmul_rn(XP, wa.x), __fmul_rn(XM, wa.y));                                       \
         s = __fadd_rn(s, __fmul_rn(YP, wa.z));                                                              \
         s = __fadd_rn(s, __fmul_rn(YM, wa.w));                                                              \

@@ -155,8 +155,8 @@ class DistributedSolver(Solver):
                 raise ValueError("the distributed multi-phase solver needs integer labels in 0..255")
             if D_scaling is not None:
                 D_0 = D_scaling
-        else:
-            self._check_binary_labels(img4)
+        elif dist.get_world_size(group) == 1:
+            self._check_binary_labels(img4)      # several ranks: checked collectively from the device histograms below
         if window is None:
             window = (0, img4.shape[1])
             Nx_g, Ny, Nz = img4.shape[1:]
@@ -230,8 +230,9 @@ class DistributedSolver(Solver):
             img_dev = None if sub is None else torch.from_numpy(np.ascontiguousarray(sub)).to(dev)
             sh = 1 / (2 * Nx_g)
             vec = torch.linspace(TOP_BC + sh, BOT_BC - sh, Nx_g, dtype=torch.float32).to(dev)
-            if sub is None:
-                raise ValueError("the distributed multi-phase solver needs integer labels in 0..255")
+            if not self._all_ranks_ok(sub is not None, dev, group):     # every rank raises, none is left in a collective
+                raise ValueError("the distributed solvers need integer labels in 0..255 "
+                                 "(binary images: 0 / 1, see Solver)")
             p = Problem()
             p.g = g
             p.kind = _lib.MULTIPHASE if self._multi else _lib.BINARY

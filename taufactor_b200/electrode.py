@@ -143,7 +143,7 @@ class ElectrodeSolver(SORSolver):
             rows.append(np.stack([xp_i.astype(np.float32), one, one, one, one, one, fac, rcp], axis=-1).reshape(-1, 8))
         table = np.concatenate(rows + [np.zeros((1, 8), np.float32)])         # last row: inert (non-conductive)
         inert = len(table) - 1
-        table_dev = torch.from_numpy(np.ascontiguousarray(np.concatenate([table[:, :4], table[:, 4:]]))).to(dev)
+        table_dev = torch.from_numpy(np.ascontiguousarray(table)).to(dev)
         xp = shift_zero(cond, 1, -1)
         ids = ((cond_nn.to(torch.int32) * _N_REAC + reac_nn.to(torch.int32)) * 2 + xp.to(torch.int32))
         ids += (torch.arange(bs, device=dev, dtype=torch.int32) * n_img).view(bs, 1, 1, 1)
@@ -210,8 +210,7 @@ class ElectrodeSolver(SORSolver):
         g = self._geom
         G, C0 = _lib.GHOST, _lib.COL0
         classes, table_dev, _ = self._keep
-        L = table_dev.shape[0] // 2
-        b = table_dev[L:, 2]                                   # second half rows: {w_z+, w_z-, b, 1/b}
+        b = table_dev[:, 6]                                    # rows {w_x+, w_x-, w_y+, w_y-, w_z+, w_z-, b, 1/b}
         ids = classes.view(self.batch_size, g.planes, g.rows, g.pitch)[:, G:G + self.Nx, G:G + self.Ny, C0:C0 + self.Nz]
         fac = b[ids.to(torch.int64) & 0xffff]
         return torch.where(fac > 0, fac, torch.full_like(fac, float("inf")))

@@ -857,8 +857,8 @@ def build_class_table(lib, p, dense_D, periodic, dev, stream, i_lo, i_hi):
     # the volume: ghost frame of the no-flux solvers, Dirichlet planes, row padding
     inert = len(k)
     table = np.concatenate([table, np.zeros((1, 8), np.float32)])
-    # device layout: the first halves of all rows, then the second halves (float[2][L][4])
-    table_dev = torch.from_numpy(np.ascontiguousarray(np.concatenate([table[:, :4], table[:, 4:]]))).to(dev)
+    # device layout: one 32-byte row per class (float[L][8])
+    table_dev = torch.from_numpy(np.ascontiguousarray(table)).to(dev)
     classes = torch.full((lib.taub_field_elems(g),), inert, dtype=torch.int32, device=dev).to(torch.int16)
     G, C0 = _lib.GHOST, _lib.COL0
     cv = classes.view(g.bs, g.planes, g.rows, g.pitch)
