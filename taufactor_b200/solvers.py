@@ -751,12 +751,61 @@ class MultiPhaseSolver(ThroughTransportSolver):
 
     use_class_table = True   # False: recompute the face conductances from the labels in the kernel
 
+    # ------------------------------------------------------------------ the reference's state tensors, on demand
+    def _face_conductances(self):
+        """``D_x [bs,Nx+1,Ny,Nz]``, ``D_y [bs,Nx,Ny+1,Nz]``, ``D_z [bs,Nx,Ny,Nz+1]`` and ``factor [bs,Nx,Ny,Nz]`` as the
+        reference holds them (ref:585-604, periodic ref:626-650), rebuilt from the image with the reference's fp32
+        operations the first time one of them is read.  Inspection only: the kernels work from stencil classes (or
+        labels + the harmonic-mean table) and never touch these 16 B/voxel."""
+        cached = self.__dict__.get("_face_state")
+        if cached is None:
+            with torch.cuda.device(self.device):
+                cached = self._face_state = face_conductance_tensors(self.cpu_img, self.Ds, self._periodic, self.device)
+        return cached
+
+    D_x = property(lambda self: self._face_conductances()[0], doc="face conductances between x planes (ref:594)")
+    D_y = property(lambda self: self._face_conductances()[1], doc="face conductances between y rows (ref:595)")
+    D_z = property(lambda self: self._face_conductances()[2], doc="face conductances between z columns (ref:596)")
+    factor = property(lambda self: self._face_conductances()[3], doc="sum of the six face conductances (ref:598-604)")
+
     def _build_class_table(self, p):
         out = build_class_table(self._lib, p, self._dense_D, self._periodic, self.device, self._stream(), 0, p.g.Nx)
         if out:
             self.n_stencil_classes = out[2]
             return out[:2]
         return ()
+
+
+def face_conductance_tensors(img4, Ds, periodic, device):
+    """(D_x, D_y, D_z, factor) of a labelled image [bs,Nx,Ny,Nz] with the reference's fp32 operations (ref:585-604,
+    periodic y/z: ref:626-650)."""
+    raw = torch.from_numpy(np.ascontiguousarray(img4)).to(device)
+    d = torch.zeros(raw.shape, dtype=torch.float32, device=device)
+    for label, D_p in Ds.items():
+        d[raw == label] = float(D_p)
+    del raw
+    bs, Nx, Ny, Nz = d.shape
+    pad = torch.zeros((bs, Nx + 2, Ny + 2, Nz + 2), dtype=torch.float32, device=device)
+    pad[:, 1:-1, 1:-1, 1:-1] = d
+    del d
+    pad[:, 0], pad[:, -1] = pad[:, 1].clone(), pad[:, -2].clone()    # the Dirichlet face sees its own phase
+    if periodic:
+        pad[:, :, 0], pad[:, :, -1] = pad[:, :, -2].clone(), pad[:, :, 1].clone()
+        pad[:, :, :, 0], pad[:, :, :, -1] = pad[:, :, :, -2].clone(), pad[:, :, :, 1].clone()
+
+    def hm(a, b):                                  # ref:577-583: ((2 a) b) / (a + b), 0 where a + b == 0
+        s = a + b
+        return torch.where(s > 0, 2 * a * b / s, torch.zeros_like(s))
+
+    core = pad[:, :, 1:-1, 1:-1]
+    D_x = hm(core[:, :-1], core[:, 1:])
+    D_y = hm(pad[:, 1:-1, :-1, 1:-1], pad[:, 1:-1, 1:, 1:-1])
+    D_z = hm(pad[:, 1:-1, 1:-1, :-1], pad[:, 1:-1, 1:-1, 1:])
+    f = D_x[:, :-1] + D_x[:, 1:] + D_y[:, :, :-1] + D_y[:, :, 1:] + D_z[..., :-1] + D_z[..., 1:]
+    f[:, 0] += D_x[:, 0]
+    f[:, -1] += D_x[:, -1]
+    f[f == 0] = torch.inf
+    return D_x, D_y, D_z, f
 
 
 def ctypes_copy(dst, src):

@@ -232,13 +232,30 @@ def api_goldens():
         E = tau.ElectrodeSolver(cases.random_img((24, 20, 16), 0.7, 11), device="cpu")
         E.solve(verbose=False)
     api["solved_attributes_electrode"] = sorted(a for a in vars(E) if not a.startswith("_"))
+    M = run_case("odd3_mp")[1]
+    api["solved_attributes_multiphase"] = sorted(a for a in vars(M) if not a.startswith("_"))
     with open(os.path.join(HERE, "api.json"), "w") as fh:
         json.dump(api, fh, indent=1)
+
+
+MULTIPHASE_STATE_CASES = ("odd3_mp", "odd3_pmp", "ref_mp_batched", "ref_pmp_slanted_odd")
+
+
+def multiphase_state_goldens():
+    """tests/golden/multiphase_state.npz: the reference's D_x / D_y / D_z / factor tensors (taufactor.py:594-604)."""
+    out = {}
+    for name in MULTIPHASE_STATE_CASES:
+        S, _ = make_solver(name)
+        for a in ("D_x", "D_y", "D_z", "factor"):
+            out[f"{name}@{a}"] = getattr(S, a).numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "multiphase_state.npz"), **out)
 
 
 def main():
     if "--api-only" in sys.argv:
         return api_goldens()
+    if "--multiphase-state-only" in sys.argv:
+        return multiphase_state_goldens()
     if "--benchmark-only" in sys.argv:
         return benchmark_goldens()
     if "--electrode-only" in sys.argv:
@@ -260,6 +277,7 @@ def main():
                 assert S2.iter == k or S2.converged
                 fields[f"{name}@{k}"] = S2.field.numpy().copy()
     api_goldens()
+    multiphase_state_goldens()
     with open(os.path.join(HERE, "solve.json"), "w") as fh:
         json.dump(solve, fh, indent=1)
     np.savez_compressed(os.path.join(HERE, "fields.npz"), **fields)

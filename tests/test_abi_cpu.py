@@ -104,6 +104,19 @@ def test_harmonic_table_matches_oracle():
     assert np.array_equal(t, ref) and np.array_equal(t, t.T)
 
 
+def test_face_conductance_tensors_equal_the_reference_state():
+    """MultiPhaseSolver.D_x / D_y / D_z / factor (rebuilt on demand) against the tensors of the unmodified reference
+    (tests/golden/multiphase_state.npz, taufactor.py:585-604 and :626-650), bit for bit -- the host logic on CPU tensors."""
+    import cases
+    from taufactor_b200.solvers import face_conductance_tensors, _expand_to_4d
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "multiphase_state.npz"))
+    for name in ("odd3_mp", "odd3_pmp", "ref_mp_batched", "ref_pmp_slanted_odd"):
+        cls, build, ckw, _, _ = cases.CASES[name]
+        got = face_conductance_tensors(_expand_to_4d(build()), ckw["diffusivities"], cls.startswith("Periodic"), "cpu")
+        for a, t in zip(("D_x", "D_y", "D_z", "factor"), got):
+            assert np.array_equal(t.numpy(), gold[f"{name}@{a}"]), (name, a)
+
+
 def test_python_surface_matches_reference_signatures():
     """Drop-in check against tests/golden/api.json (generated from the unmodified reference by
     tests/golden/make_golden.py): same constructor / solve() parameter names, order and defaults, same

@@ -142,6 +142,22 @@ def test_solve_matches_reference(tau, name):
     assert S.tau_x.shape == (S.batch_size, S.Nx - 1) and S.c_x.shape == (S.batch_size, S.Nx)
 
 
+@pytest.mark.parametrize("name", ["odd3_mp", "odd3_pmp", "ref_mp_batched", "ref_pmp_slanted_odd"])
+def test_multiphase_object_carries_the_reference_state_tensors(tau, name):
+    """ref:594-604: D_x / D_y / D_z / factor exist on a multi-phase solver (rebuilt on demand) and equal the
+    reference's tensors bit for bit; every public attribute of a solved reference MultiPhaseSolver exists."""
+    api = json.load(open(os.path.join(HERE, "golden", "api.json")))
+    gold = np.load(os.path.join(HERE, "golden", "multiphase_state.npz"))
+    S, skw = make(tau, name)
+    for a in ("D_x", "D_y", "D_z", "factor"):
+        got = getattr(S, a)
+        assert got.is_cuda and str(got.dtype) == "torch.float32"
+        assert np.array_equal(got.cpu().numpy(), gold[f"{name}@{a}"]), (name, a)
+    S.solve(verbose=False, **skw)
+    missing = [a for a in api["solved_attributes_multiphase"] if not hasattr(S, a)]
+    assert not missing, missing
+
+
 def test_solved_object_carries_the_reference_attributes(tau):
     """Every public attribute a solved reference object has (tests/golden/api.json) exists here too."""
     api = json.load(open(os.path.join(HERE, "golden", "api.json")))

@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+# Round-2 (re-entry) first call: tests incl. the staged reference, sweeps-only throughput, both bench arms, ncu.
+set -u
+mkdir -p gpurun_out
+ls -d /root/reference baseline/_ref 2>&1; nvidia-smi -L; nproc
+SECONDS=0
+python -m pytest tests -q -m gpu -p no:cacheprovider --ignore=tests/test_gpu_zz_reference.py > gpurun_out/gpu_tests.txt 2>&1; echo "gpu tests rc=$? in ${SECONDS}s"; tail -12 gpurun_out/gpu_tests.txt
+python tools/perf_quick.py > gpurun_out/perf_quick.txt 2>&1; cat gpurun_out/perf_quick.txt
+SECONDS=0
+python bench.py --steps 20 --warmup 5 > gpurun_out/bench_512.json 2> gpurun_out/bench_512.err; echo "bench rc=$? in ${SECONDS}s"; cat gpurun_out/bench_512.json; tail -5 gpurun_out/bench_512.err
+SECONDS=0
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "bench ref rc=$? in ${SECONDS}s"; cat gpurun_out/bench_ref.json; tail -3 gpurun_out/bench_ref.err
+ncu --set full --clock-control none --import-source on -k regex:fused_sweep2 -s 4 -c 1 -o gpurun_out/r2_fused_bin -f \
+    python tools/profile_target.py 512 fused 12 > gpurun_out/ncu_bin.log 2>&1; echo "ncu bin rc=$?"
+python tools/ncu_summary.py gpurun_out/r2_fused_bin.ncu-rep > gpurun_out/r2_fused_bin_ncu.txt 2>&1; tail -42 gpurun_out/r2_fused_bin_ncu.txt
+ncu --set full --clock-control none --import-source on -k regex:fused_sweep2 -s 2 -c 1 -o gpurun_out/r2_fused_cls -f \
+    python tools/profile_multi.py > gpurun_out/ncu_cls.log 2>&1; echo "ncu cls rc=$?"
+python tools/ncu_summary.py gpurun_out/r2_fused_cls.ncu-rep > gpurun_out/r2_fused_cls_ncu.txt 2>&1; tail -42 gpurun_out/r2_fused_cls_ncu.txt
+SECONDS=0
+python -m pytest tests/test_gpu_zz_reference.py -q -s -m gpu -p no:cacheprovider > gpurun_out/gpu_tests_reference.txt 2>&1; echo "reference tests rc=$? in ${SECONDS}s"; grep -E "^\[|passed|failed|Error" gpurun_out/gpu_tests_reference.txt | tail -20
