@@ -163,7 +163,8 @@ class DistributedSolver(Solver):
             self.cpu_img = img4
         else:
             Nx_g, Ny, Nz = shape
-            self.cpu_img = None          # no full image on this rank (percolation fallback unavailable)
+            self.cpu_img = None          # no full image on this rank: the percolation check floods slab by slab
+        self._window_img, self._window = img4, window
         self.batch_size = img4.shape[0]
         self.Nx, self.Ny, self.Nz = Nx_g, Ny, Nz
         self.bounds = slab_bounds(Nx_g, self.world)
@@ -502,11 +503,65 @@ class DistributedSolver(Solver):
             parts.append((allr[r, 0, :, :nf], allr[r, 1, :, : h - l]))
         return assemble_profiles(parts, self.bounds, bs)
 
-    def _host_conductive_mask(self, b):
-        if self.cpu_img is None:
-            raise RuntimeError("a slice flux is exactly 0 and the percolation check (ref:318-327) needs the whole "
-                               "image on the host; construct DistributedSolver from the full image")
-        return super()._host_conductive_mask(b)
+    def _no_percolating_path(self, b):
+        """ref:318-327 on a partitioned volume.  With the whole image on every rank each rank answers for itself
+        (identical answers, no collective).  With windowed images the flood fill of taub_flood_round runs slab by
+        slab: every rank fills its own planes to a local fixed point, neighbours swap the "reached" state of their
+        boundary planes, and the ranks repeat until nobody's boundary changes or the last plane is reached.
+        Collective: every rank sees the same profiles, so every rank gets here at the same check."""
+        if self.cpu_img is not None:
+            return super()._no_percolating_path(b)
+        cache = self.__dict__.setdefault("_percolation_cache", {})
+        if b not in cache:
+            cache[b] = self._slab_no_percolating_path(b)
+        return cache[b]
+
+    def _slab_no_percolating_path(self, b):
+        dev, lib, group = self.device, self._lib, self.group
+        w0 = self._window[0]
+        labels = self.conductive_labels
+        with torch.cuda.device(dev):
+            own = np.isin(self._window_img[b, self.lo - w0: self.hi - w0], labels)
+            m = torch.from_numpy(np.ascontiguousarray(own, dtype=np.uint8)).to(dev)
+            n, Ny, Nz = m.shape
+            reach = torch.zeros_like(m)
+            if self.rank == 0:
+                reach[0] = m[0]
+            flag = torch.zeros(1, dtype=torch.int32, device=dev)
+            edge = torch.zeros((2, Ny, Nz), dtype=torch.uint8, device=dev)
+            edges = torch.zeros((self.world, 2, Ny, Nz), dtype=torch.uint8, device=dev)
+            state = torch.zeros(2, dtype=torch.int64, device=dev)
+            for _ in range(self.MAX_FLOOD_ROUNDS):
+                for _ in range(self.MAX_FLOOD_ROUNDS):           # local fixed point
+                    self._call(lib.taub_flood_round(m.data_ptr(), reach.data_ptr(), 1, n, Ny, Nz, flag.data_ptr(),
+                                                    self._stream()), "taub_flood_round")
+                    if int(flag.item()) == 0:
+                        break
+                edge[0], edge[1] = reach[0], reach[-1]
+                all_gather_flat(edges.view(-1), edge.view(-1), group)
+                changed = False
+                if self.rank > 0:                                # the lower neighbour's last plane touches my first
+                    new = reach[0] | (edges[self.rank - 1, 1] & m[0])
+                    changed |= bool((new != reach[0]).any())
+                    reach[0] = new
+                if self.rank < self.world - 1:
+                    new = reach[-1] | (edges[self.rank + 1, 0] & m[-1])
+                    changed |= bool((new != reach[-1]).any())
+                    reach[-1] = new
+                state[0] = int(changed)
+                state[1] = int(self.rank == self.world - 1 and bool(reach[-1].any()))
+                if dist.get_backend(group) == "gloo":
+                    host = state.cpu()
+                    dist.all_reduce(host, op=dist.ReduceOp.MAX, group=group)
+                    any_changed, spanned = int(host[0]), int(host[1])
+                else:
+                    dist.all_reduce(state, op=dist.ReduceOp.MAX, group=group)
+                    any_changed, spanned = (int(v) for v in state.cpu())
+                if spanned:
+                    return False
+                if not any_changed:
+                    return True
+        raise RuntimeError("percolation flood fill did not converge")
 
     @property
     def field(self):

@@ -258,12 +258,19 @@ class SORSolver:
             reach[0] = m[0]
             flag = torch.zeros(1, dtype=torch.int32, device=dev)
             Nx, Ny, Nz = m.shape
-            for _ in range(self.MAX_FLOOD_ROUNDS):
-                self._call(self._lib.taub_flood_round(m.data_ptr(), reach.data_ptr(), 1, Nx, Ny, Nz, flag.data_ptr(),
-                                                      self._stream()), "taub_flood_round")
-                if bool(reach[-1].any()):
+            rounds, batch = 0, 1
+            while rounds < self.MAX_FLOOD_ROUNDS:
+                # `batch` rounds per host read (1, 2, 4, 8, 8, ...): a round past the fixed point changes nothing, and
+                # the flag of the last round of a batch says whether the fill is still moving
+                for _ in range(batch):
+                    self._call(self._lib.taub_flood_round(m.data_ptr(), reach.data_ptr(), 1, Nx, Ny, Nz, flag.data_ptr(),
+                                                          self._stream()), "taub_flood_round")
+                rounds += batch
+                batch = min(2 * batch, 8)
+                state = torch.stack([reach[-1].any().to(torch.int32), flag[0]]).cpu()
+                if int(state[0]):
                     return False                      # spanning cluster found: no need to finish the fill
-                if int(flag.item()) == 0:
+                if int(state[1]) == 0:
                     return True
         raise RuntimeError("percolation flood fill did not converge")
 

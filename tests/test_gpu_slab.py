@@ -209,3 +209,60 @@ def test_windowed_slabs_reject_non_binary_labels_on_every_rank(tmp_path):
     for r in range(2):
         msg = open(f"{out}.{r}").read()
         assert "Input image must only contain 0s and 1s" in msg and "[0 1 2]" in msg, (r, msg)
+
+
+def _percolation_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.cuda.set_device(0)
+        from taufactor_b200.distributed import DistributedSolver, image_window, slab_bounds
+        from test_gpu_percolation import serpentine
+        answers = []
+        imgs = [serpentine()[0], None, cases.random_img((45, 20, 24), 0.31, seed=3), cases.random_img((45, 20, 24), 0.36, seed=1),
+                cases.deadend()]
+        imgs[1] = imgs[0].copy()
+        imgs[1][24] = 0                                        # sever every x run of the channel
+        for img in imgs:
+            shape = img.shape
+            lo, hi = slab_bounds(shape[0], world)[rank]
+            w = image_window(lo, hi, shape[0])
+            S = DistributedSolver(img[w[0]:w[1]], device="cuda:0", window=w, shape=shape)
+            assert S.cpu_img is None
+            answers.append(bool(S._no_percolating_path(0)))
+        # a whole solve of a non-percolating volume from windowed images: tau = inf like the reference (ref:318-327, :152)
+        img = cases.deadend()
+        lo, hi = slab_bounds(img.shape[0], world)[rank]
+        w = image_window(lo, hi, img.shape[0])
+        S = DistributedSolver(img[w[0]:w[1]], device="cuda:0", window=w, shape=img.shape)
+        S.solve(verbose=False)
+        np.savez(f"{out}.{rank}.npz", answers=np.array(answers), tau=S.tau, D_eff=S.D_eff, iters=S.iter)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_windowed_slabs_run_the_percolation_check_across_slabs(tmp_path, world):
+    """ref:318-327: a zero-flux slice triggers the spanning-cluster check.  Ranks that only hold their window of
+    the image flood-fill slab by slab (boundary planes exchanged) and must agree with the labelling of the whole
+    volume; a non-percolating volume then solves to tau = inf, D_eff = 0 on every rank."""
+    import torch.multiprocessing as mp
+    import taufactor_b200 as tau
+    from oracle import sor_numpy as on
+    from test_gpu_percolation import serpentine
+    out = str(tmp_path / "perc")
+    mp.spawn(_percolation_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    imgs = [serpentine()[0], None, cases.random_img((45, 20, 24), 0.31, seed=3), cases.random_img((45, 20, 24), 0.36, seed=1),
+            cases.deadend()]
+    imgs[1] = imgs[0].copy()
+    imgs[1][24] = 0
+    want = [bool(on.through_fraction_is_zero(np.asarray(i) == 1)) for i in imgs]
+    assert want[0] is False and want[1] is True and want[4] is True
+    B = tau.Solver(cases.deadend(), device="cuda")
+    B.solve(verbose=False)
+    for r in range(world):
+        got = np.load(f"{out}.{r}.npz")
+        assert list(got["answers"]) == want, (r, list(got["answers"]), want)
+        assert np.isinf(got["tau"]).all() and np.array_equal(got["D_eff"], B.D_eff) and int(got["iters"]) == B.iter
