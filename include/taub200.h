@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TAUB_ABI_VERSION 10
+#define TAUB_ABI_VERSION 11
 #define TAUB_GHOST 2            /* ghost width in x (planes), y (rows) and z (columns) */
 #define TAUB_COL0 4             /* column of interior voxel k = 0 */
 #define TAUB_MAX_LABELS 64      /* dense phase indices 0..L-1, L <= 64; index L = "outside" */
@@ -91,6 +91,10 @@ typedef struct taub_problem {
                                  * kernel then stores its first / last TAUB_GHOST output planes straight into
                                  * the neighbour's ghost planes of the destination buffer (one-sided halo
                                  * exchange; the caller orders passes with device-side signals). */
+    int32_t *sync_ws;           /* optional: taub_sync_ws_ints() device int32 counters, zeroed once by the caller, for
+                                 * the shared-memory resident path of small volumes (taub_resident_pairs); NULL =
+                                 * that path is never taken */
+    int32_t sync_epoch;         /* host-side: pairs run on sync_ws so far (maintained by taub_resident_pairs) */
 } taub_problem;
 
 /* -- library ------------------------------------------------------------------------------ */
@@ -162,8 +166,20 @@ unsigned long long taub_inexact_events(void);
  * (cudaLaunchAttributeProgrammaticStreamSerialization) -- the next pass's launch and shared-memory
  * prologue overlap the tail of the previous one; its first read waits for the previous grid to
  * complete (griddepcontrol.wait), so results are unchanged.  bit 2 (with bit 1, periodic solvers): the ghost
- * refresh releases the sweep behind it when it has finished, not when it starts. */
+ * refresh releases the sweep behind it when it has finished, not when it starts.  bit 3: never take the
+ * shared-memory resident path (taub_resident_pairs). */
 int taub_iterate(taub_problem *p, int64_t iter, int n, int flags, void *stream);
+/* Small whole volumes (binary kind, Nz >= 8, periodic only with even Ny and Nz, bricks of <= 227 KB): n_pairs x two
+ * reference iterations (iter, iter+1, ...) in ONE cooperative launch with the field resident in shared memory --
+ * one (x, y) brick per CTA, neighbours exchange their 2-wide faces through the ping-pong buffers with
+ * release / acquire counters in p->sync_ws (no grid barrier, no relaunch, no pipeline fill per pass).  Same
+ * arithmetic, bit-identical field.  Flips p->cur when n_pairs is odd.  taub_iterate takes this path by itself
+ * when taub_can_reside(p) == 1 (flags bit 3 or TAUB_RESIDENT=0: never). */
+int taub_can_reside(const taub_problem *p);
+int taub_resident_pairs(taub_problem *p, int64_t iter, int n_pairs, void *stream);
+size_t taub_sync_ws_ints(void);                 /* int32 counters p->sync_ws must hold */
+unsigned long long taub_resident_timeouts(void); /* waits on a neighbour's counter that gave up after ~2 s (0 in
+                                                  * every correct run; a non-zero value voids the result) */
 
 /* -- the check (replaces vertical_flux :412-419 / :615-620 and the two torch.mean reductions in
  *    compute_metrics :296, :307) --------------------------------------------------------------- */

@@ -28,7 +28,7 @@ class Problem(ctypes.Structure):
     _fields_ = [("g", Geom), ("kind", ctypes.c_int32), ("L", ctypes.c_int32),
                 ("field", c_vp * 2), ("codes", c_vp), ("labels", c_vp), ("lut", c_vp),
                 ("omega", ctypes.c_float), ("cur", ctypes.c_int32), ("stop", c_vp),
-                ("peer_lo", c_vp * 2), ("peer_hi", c_vp * 2)]
+                ("peer_lo", c_vp * 2), ("peer_hi", c_vp * 2), ("sync_ws", c_vp), ("sync_epoch", ctypes.c_int32)]
 
 
 # name -> (restype, argtypes); must list every symbol include/taub200.h declares
@@ -52,6 +52,10 @@ SIGNATURES = {
     "taub_inexact_events": (ctypes.c_ulonglong, []),
     "taub_can_fuse": (c_int, [ctypes.POINTER(Problem)]),
     "taub_iterate": (c_int, [ctypes.POINTER(Problem), c_i64, c_int, c_int, c_vp]),
+    "taub_can_reside": (c_int, [ctypes.POINTER(Problem)]),
+    "taub_resident_pairs": (c_int, [ctypes.POINTER(Problem), c_i64, c_int, c_vp]),
+    "taub_sync_ws_ints": (ctypes.c_size_t, []),
+    "taub_resident_timeouts": (ctypes.c_ulonglong, []),
     "taub_plane_means": (c_int, [ctypes.POINTER(Problem), c_vp, c_vp, c_vp, c_vp]),
     "taub_check_async": (c_int, [ctypes.POINTER(Problem), c_vp, c_vp, c_vp, c_vp, c_vp, c_float, c_vp, c_vp]),
     "taub_stop_rule_async": (c_int, [c_int, c_int, c_vp, c_vp, c_vp, c_float, c_vp, c_vp, c_vp]),
@@ -79,7 +83,7 @@ def load():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.taub_abi_version() != 10:
+        if lib.taub_abi_version() != 11:
             raise ImportError("libtaub200.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libtaub200.so")
-SOURCES = ["taub_core.cu", "taub_init.cu", "taub_sweep.cu", "taub_fused.cu", "taub_metrics.cu", "taub_percolate.cu",
+SOURCES = ["taub_core.cu", "taub_init.cu", "taub_sweep.cu", "taub_fused.cu", "taub_resident.cu", "taub_metrics.cu", "taub_percolate.cu",
            "taub_tiff.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

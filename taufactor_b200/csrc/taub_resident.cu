@@ -1,0 +1,429 @@
+// taub_resident.cu -- small volumes: the field stays RESIDENT in shared memory for a whole block of iterations.
+//
+// The marching kernel of taub_fused.cu pays a pipeline fill of four planes per CTA and one launch per pass; below
+// ~150^3 voxels that overhead is most of the time (100^3: 3.7 us per iteration however it is tiled).  Here ONE
+// cooperative launch runs any number of iteration pairs of taufactor.py:174-182:
+//   * the volume is cut into (x, y) bricks, one CTA per brick (<= one per SM), whole z rows; a brick and a 2-wide
+//     frame of its neighbours' voxels live in shared memory for the whole launch;
+//   * a pair = iteration t (colour A) on the brick plus the first ring of the frame, then iteration t+1 (colour B) on
+//     the brick -- the same overlapped scheme as the fused kernel, so ONE exchange feeds TWO iterations;
+//   * exchange through the two ping-pong field buffers in global memory (L2): after a pair a CTA stores the voxels
+//     within 2 of its brick faces into the buffer of that pair and publishes a counter (release); before the next pair
+//     it waits for its <= 8 neighbours' counters (acquire) and re-reads its frame.  Point-to-point, no grid barrier;
+//     alternating buffers make the scheme race free (a CTA can run at most one pair ahead of a neighbour);
+//   * shared-memory rows are stored COLOUR-SPLIT: the even columns of a row, then the odd ones.  The voxels one
+//     iteration updates in a row are then contiguous: a work item is one float4 of four ACTIVE voxels, its x/y
+//     neighbours are aligned float4s of the same half row, its z neighbours one float4 + one scalar of the other half.
+//     No lane computes an inactive voxel, and E/O rows run the same instruction stream (selects, no branch).
+// The arithmetic per voxel is the correctly rounded sequence of taub_common.cuh (reference order, no FMA, exact
+// division: the fast path plus a per-item IEEE re-computation when a sum is a non-zero value below 2^-100), so the
+// field is bit-identical to the other kernels and to the reference at every iteration.
+//
+// Not handled here (the marching kernels take over): periodic volumes with an odd Ny or Nz (a wrap that joins two
+// voxels of one colour needs the snapshot rule of the fused kernel's OP variant), Nz < 8, slabs of a partitioned
+// volume, bricks that do not fit 227 KB of shared memory.
+#include <stdlib.h>
+
+#include "taub_common.cuh"
+
+namespace taub {
+
+constexpr int R_NT = 512;            // threads per CTA
+constexpr int R_WARPS = R_NT / 32;
+constexpr size_t R_SMEM_MAX = 232448 - 1024;   // opt-in dynamic shared memory per CTA (227 KB) less the static part
+
+struct ResParams {
+    taub_geom g;
+    float *buf[2];           // [0]: the current field at launch, [1]: the other ping-pong buffer
+    const uint16_t *codes;   // binary kind: four 4-bit neighbour counts per float4 group
+    float omega;
+    int colour0;             // colour (iter & 1) of the first iteration
+    int n_pairs;
+    int nbx, nby;            // bricks per image along x and y
+    int BX, BY;              // largest brick extents (shared-memory pitches)
+    int ZS;                  // floats per shared-memory row: round_up(Nz + 8, 8); first half even, second half odd columns
+    int *flags;              // one counter per brick (device, persistent): pairs completed, on top of epoch0
+    int epoch0;
+    const int *stop;
+};
+
+__device__ unsigned long long g_resident_timeouts = 0ULL;
+
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Brick extents: balanced cuts, sizes differ by at most one.
+__host__ __device__ __forceinline__ int cut(int n, int parts, int i) { return (int)(((int64_t)n * i) / parts); }
+
+struct Brick {
+    int b, bi, bj;          // image, brick coordinates
+    int x0, x1, y0, y1;     // owned voxels [x0, x1) x [y0, y1)
+    int bx, by;
+};
+
+// ------------------------------------------------------------------------------------------------------
+// Global <-> shared rows.  Shared row (li, lj) holds global x = x0 - 2 + li, y = y0 - 2 + lj (y wrapped for the
+// periodic solvers), storage columns [0, ZS): half row E = even columns, half row O = odd columns.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ const float *global_row(const ResParams &P, const Brick &K, const float *base, int li, int lj)
+{
+    const taub_geom &g = P.g;
+    const int gx = K.x0 - 2 + li, gy = K.y0 - 2 + lj;
+    const int sr = g.periodic ? G + wrap(gy, g.Ny) : G + gy;
+    return base + (int64_t)K.b * g.image_stride + (int64_t)(gx + G) * g.plane_stride + (int64_t)sr * g.pitch;
+}
+
+__device__ __forceinline__ void load_row(float *srow, const float *grow, int ZS, int lane)
+{
+    const int ZH = ZS >> 1;
+    for (int g4 = lane; g4 < (ZS >> 2); g4 += 32) {
+        const float4 v = __ldcg(reinterpret_cast<const float4 *>(grow) + g4);
+        *reinterpret_cast<float2 *>(srow + 2 * g4) = make_float2(v.x, v.z);
+        *reinterpret_cast<float2 *>(srow + ZH + 2 * g4) = make_float2(v.y, v.w);
+    }
+}
+
+__device__ __forceinline__ void store_row(float *grow, const float *srow, int ZS, int Nz, int lane)
+{
+    const int ZH = ZS >> 1;
+    // interior columns [4, Nz + 4): groups 1 .. (Nz + 3) / 4; a partial last group is stored voxel by voxel
+    const int g_end = (Nz + COL0 + 3) >> 2;
+    for (int g4 = 1 + lane; g4 < g_end; g4 += 32) {
+        const float2 e = *reinterpret_cast<const float2 *>(srow + 2 * g4);
+        const float2 o = *reinterpret_cast<const float2 *>(srow + ZH + 2 * g4);
+        if (4 * g4 + 3 < Nz + COL0) {
+            __stcg(reinterpret_cast<float4 *>(grow) + g4, make_float4(e.x, o.x, e.y, o.y));
+        } else {
+            const float v[4] = {e.x, o.x, e.y, o.y};
+            for (int q = 0; q < 4; ++q)
+                if (4 * g4 + q < Nz + COL0) __stcg(grow + 4 * g4 + q, v[q]);
+        }
+    }
+}
+
+// One colour step on shared rows li in [li0, li1), lj in [lj0, lj1) (in place: an active voxel only reads voxels of
+// the other colour).  Thread = (row slot, float4 group of the active half row).
+__device__ __forceinline__ void colour_step(const ResParams &P, const Brick &K, float *fld, const uint16_t *cod,
+                                            const float2 *s_div, int colour, int li0, int li1, int lj0, int lj1,
+                                            int my_r, int my_q, int rows_per_round)
+{
+    const int ZS = P.ZS, ZH = ZS >> 1, RY = P.BY + 4, CY = P.BY + 2, CG = ZS >> 2;
+    const int nj = lj1 - lj0, nrows = (li1 - li0) * nj;
+    if (nj <= 0 || my_r >= rows_per_round) return;
+    const float omega = P.omega;
+    for (int r = my_r; r < nrows; r += rows_per_round) {
+        const int di = r / nj;
+        const int li = li0 + di, lj = lj0 + (r - di * nj);
+        // voxel (i, j, k) is active when (i + j + k) % 2 == colour; k and the storage column have the same parity
+        const int par = (K.x0 + li + K.y0 + lj + colour) & 1;      // 0: even columns (E) active, 1: odd columns (O)
+        float *row = fld + (size_t)(li * RY + lj) * ZS;
+        float *act = row + (par ? ZH : 0) + 4 * my_q;
+        const float *oth = row + (par ? 0 : ZH) + 4 * my_q;
+        float4 c = *reinterpret_cast<const float4 *>(act);
+        const float4 xp = *reinterpret_cast<const float4 *>(act + (size_t)RY * ZS);
+        const float4 xm = *reinterpret_cast<const float4 *>(act - (size_t)RY * ZS);
+        const float4 yp = *reinterpret_cast<const float4 *>(act + ZS);
+        const float4 ym = *reinterpret_cast<const float4 *>(act - ZS);
+        const float4 z4 = *reinterpret_cast<const float4 *>(oth);
+        const float ze = par ? oth[4] : oth[-1];
+        // E active: z+ = O[m], z- = O[m-1];  O active: z- = E[m], z+ = E[m+1]
+        const float4 zp = par ? make_float4(z4.y, z4.z, z4.w, ze) : z4;
+        const float4 zm = par ? z4 : make_float4(ze, z4.x, z4.y, z4.z);
+        // neighbour counts: code words of storage groups 2q, 2q+1; E voxels are nibbles 0 and 2, O voxels 1 and 3
+        const unsigned cw = *reinterpret_cast<const unsigned *>(cod + (size_t)((li - 1) * CY + (lj - 1)) * CG + 2 * my_q) >>
+                            (par ? 4 : 0);
+        const float2 d0 = s_div[cw & 15u], d1 = s_div[(cw >> 8) & 15u], d2 = s_div[(cw >> 16) & 15u],
+                     d3 = s_div[(cw >> 24) & 15u];
+        unsigned um = 0xffffffffu;
+        float n0 = sor_fast(c.x, xp.x, xm.x, yp.x, ym.x, zp.x, zm.x, d0, omega, um);
+        float n1 = sor_fast(c.y, xp.y, xm.y, yp.y, ym.y, zp.y, zm.y, d1, omega, um);
+        float n2 = sor_fast(c.z, xp.z, xm.z, yp.z, ym.z, zp.z, zm.z, d2, omega, um);
+        float n3 = sor_fast(c.w, xp.w, xm.w, yp.w, ym.w, zp.w, zm.w, d3, omega, um);
+        if (um < GUARD_T) {   // a non-zero sum below 2^-100: IEEE division (taufactor.py:177), never the fast path
+            n0 = sor_exact(c.x, xp.x, xm.x, yp.x, ym.x, zp.x, zm.x, d0.x, omega);
+            n1 = sor_exact(c.y, xp.y, xm.y, yp.y, ym.y, zp.y, zm.y, d1.x, omega);
+            n2 = sor_exact(c.z, xp.z, xm.z, yp.z, ym.z, zp.z, zm.z, d2.x, omega);
+            n3 = sor_exact(c.w, xp.w, xm.w, yp.w, ym.w, zp.w, zm.w, d3.x, omega);
+        }
+        *reinterpret_cast<float4 *>(act) = make_float4(n0, n1, n2, n3);
+    }
+}
+
+__global__ void __launch_bounds__(R_NT, 1)
+resident_kernel(const ResParams P)
+{
+    extern __shared__ __align__(16) unsigned char r_smem[];
+    __shared__ __align__(128) float2 s_div[16];
+    const taub_geom &g = P.g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (P.stop && *P.stop) return;      // uniform over the grid: set by a check queued before this launch
+    if (tid < 16) s_div[tid] = div_entry(tid);
+
+    Brick K;
+    {
+        int id = blockIdx.x;
+        K.bj = id % P.nby;
+        id /= P.nby;
+        K.bi = id % P.nbx;
+        K.b = id / P.nbx;
+        K.x0 = cut(g.Nx, P.nbx, K.bi);
+        K.x1 = cut(g.Nx, P.nbx, K.bi + 1);
+        K.y0 = cut(g.Ny, P.nby, K.bj);
+        K.y1 = cut(g.Ny, P.nby, K.bj + 1);
+        K.bx = K.x1 - K.x0;
+        K.by = K.y1 - K.y0;
+    }
+    const int ZS = P.ZS, ZH = ZS >> 1, RY = P.BY + 4, CY = P.BY + 2, CG = ZS >> 2;
+    float *fld = reinterpret_cast<float *>(r_smem);                                 // [BX+4][BY+4][ZS]
+    uint16_t *cod = reinterpret_cast<uint16_t *>(fld + (size_t)(P.BX + 4) * RY * ZS);  // [BX+2][BY+2][ZS/4]
+    const int LX = K.bx + 4, LY = K.by + 4;     // rows held: the brick and its 2-wide frame
+
+    // ---- start: the brick and its frame from the current field, neighbour codes of the brick and its first ring
+    for (int r = warp; r < LX * LY; r += R_WARPS) {
+        const int li = r / LY, lj = r - li * LY;
+        load_row(fld + (size_t)(li * RY + lj) * ZS, global_row(P, K, P.buf[0], li, lj), ZS, lane);
+    }
+    for (int r = warp; r < (LX - 2) * (LY - 2); r += R_WARPS) {
+        const int ci = r / (LY - 2), cj = r - ci * (LY - 2);
+        const int gx = K.x0 - 1 + ci, gy = K.y0 - 1 + cj;
+        const bool inside = gx >= 0 && gx < g.Nx && (g.periodic || (gy >= 0 && gy < g.Ny));
+        const int sr = g.periodic ? G + wrap(gy, g.Ny) : G + gy;
+        const uint16_t *grow = P.codes + ((int64_t)K.b * g.planes + (gx + G)) * g.rows * (g.pitch >> 2) + (int64_t)sr * (g.pitch >> 2);
+        for (int g4 = lane; g4 < CG; g4 += 32) {
+            unsigned w = inside ? (unsigned)__ldg(grow + g4) : 0u;
+            // only interior columns [4, Nz + 4) are ever updated: ghost / padding columns get count 0
+            unsigned keep = 0;
+            for (int q = 0; q < 4; ++q)
+                if (4 * g4 + q >= COL0 && 4 * g4 + q < g.Nz + COL0) keep |= 0xfu << (4 * q);
+            cod[(size_t)(ci * CY + cj) * CG + g4] = (uint16_t)(w & keep);
+        }
+    }
+
+    // ---- geometry of the steps (shared-row indices)
+    const bool per = g.periodic != 0;
+    const int a_li0 = (K.x0 == 0) ? 2 : 1, a_li1 = (K.x1 == g.Nx) ? K.bx + 2 : K.bx + 3;   // never a Dirichlet plane
+    const int a_lj0 = (!per && K.y0 == 0) ? 2 : 1, a_lj1 = (!per && K.y1 == g.Ny) ? K.by + 2 : K.by + 3;
+    const int QN = ZS >> 3;                         // float4 groups per half row
+    const int rows_per_round = R_NT / QN;
+    const int my_r = tid / QN, my_q = tid - my_r * QN;
+
+    // neighbour bricks whose counters gate this brick's frame (threads 0..8, centre excluded)
+    int nb_flag = -1;
+    if (tid < 9 && tid != 4) {
+        const int nbi = K.bi + tid / 3 - 1;
+        int nbj = K.bj + tid % 3 - 1;
+        bool ok = nbi >= 0 && nbi < P.nbx;
+        if (per)
+            nbj = wrap(nbj, P.nby);
+        else
+            ok = ok && nbj >= 0 && nbj < P.nby;
+        if (ok && !(nbi == K.bi && nbj == K.bj)) nb_flag = (K.b * P.nbx + nbi) * P.nby + nbj;
+    }
+    // periodic z: ghost column 3 := column Nz + 3 (odd), ghost column Nz + 4 := column 4 (even); Nz is even here
+    auto z_ghosts = [&]() {
+        const int nj = a_lj1 - a_lj0, nrows = (a_li1 - a_li0) * nj;
+        for (int r = tid; r < nrows; r += R_NT) {
+            const int di = r / nj;
+            float *row = fld + (size_t)((a_li0 + di) * RY + a_lj0 + (r - di * nj)) * ZS;
+            row[ZH + 1] = row[ZH + ((g.Nz + 3) >> 1)];
+            row[(g.Nz + COL0) >> 1] = row[COL0 >> 1];
+        }
+    };
+
+    for (int n = 0; n < P.n_pairs; ++n) {
+        float *wbuf = P.buf[(n & 1) ^ 1];            // pair n publishes into buf[1], buf[0], buf[1], ...
+        if (n > 0) {
+            // ---- wait for the neighbours' pair n-1, then re-read the frame from the buffer they wrote
+            if (nb_flag >= 0) {
+                const int target = P.epoch0 + n;
+                const long long t0 = clock64();
+                while (ld_acquire(P.flags + nb_flag) - target < 0) {
+                    if (clock64() - t0 > 4000000000LL) {     // ~2 s: never in a correct run; do not hang the device
+                        atomicAdd(&g_resident_timeouts, 1ULL);
+                        break;
+                    }
+                }
+                __threadfence();
+            }
+            __syncthreads();
+            const float *rbuf = P.buf[((n - 1) & 1) ^ 1];
+            for (int r = warp; r < LX * LY; r += R_WARPS) {
+                const int li = r / LY, lj = r - li * LY;
+                const bool frame = li < 2 || li >= K.bx + 2 || lj < 2 || lj >= K.by + 2;
+                const int gx = K.x0 - 2 + li, gy = K.y0 - 2 + lj;
+                const bool moving = gx >= 0 && gx < g.Nx && (per || (gy >= 0 && gy < g.Ny));   // else constants
+                if (frame && moving) load_row(fld + (size_t)(li * RY + lj) * ZS, global_row(P, K, rbuf, li, lj), ZS, lane);
+            }
+        }
+        __syncthreads();
+        if (per) {
+            z_ghosts();
+            __syncthreads();
+        }
+        colour_step(P, K, fld, cod, s_div, P.colour0, a_li0, a_li1, a_lj0, a_lj1, my_r, my_q, rows_per_round);
+        __syncthreads();
+        if (per) {
+            z_ghosts();
+            __syncthreads();
+        }
+        colour_step(P, K, fld, cod, s_div, P.colour0 ^ 1, 2, K.bx + 2, 2, K.by + 2, my_r, my_q, rows_per_round);
+        __syncthreads();
+        // ---- publish: the voxels the neighbours' frames cover (everything after the last pair)
+        const bool last = (n == P.n_pairs - 1);
+        for (int r = warp; r < K.bx * K.by; r += R_WARPS) {
+            const int oi = r / K.by, oj = r - oi * K.by;
+            if (last || oi < 2 || oi >= K.bx - 2 || oj < 2 || oj >= K.by - 2) {
+                float *grow = wbuf + (int64_t)K.b * g.image_stride + (int64_t)(K.x0 + oi + G) * g.plane_stride +
+                              (int64_t)(K.y0 + oj + G) * g.pitch;
+                store_row(grow, fld + (size_t)((oi + 2) * RY + oj + 2) * ZS, ZS, g.Nz, lane);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            st_release(P.flags + blockIdx.x, P.epoch0 + n + 1);
+        }
+    }
+}
+
+struct ResChoice {
+    bool ok;
+    int nbx, nby, BX, BY, ZS;
+    size_t smem;
+};
+
+static size_t resident_smem(int BX, int BY, int ZS)
+{
+    return (size_t)(BX + 4) * (BY + 4) * ZS * 4 + (size_t)(BX + 2) * (BY + 2) * (ZS / 4) * 2 + 16;
+}
+
+// Bricks: at most one per SM; smallest colour-A region ((BX + 2) x (BY + 2) rows per CTA), then the fewest frame rows.
+static ResChoice choose_bricks(const taub_geom &g, int sms)
+{
+    ResChoice best{};
+    best.ok = false;
+    const int ZS = ((g.Nz + 8 + 7) / 8) * 8;
+    long best_cost = -1;
+    for (int nbx = 1; nbx <= g.Nx / 2 && nbx * g.bs <= sms; ++nbx) {
+        for (int nby = 1; nby <= g.Ny / 2 && (int64_t)nbx * nby * g.bs <= sms; ++nby) {
+            const int BX = ceil_div(g.Nx, nbx), BY = ceil_div(g.Ny, nby);
+            const size_t smem = resident_smem(BX, BY, ZS);
+            if (smem > R_SMEM_MAX) continue;
+            const long cost = (long)(BX + 2) * (BY + 2) * 64 + (BX + BY);
+            if (best_cost < 0 || cost < best_cost) {
+                best_cost = cost;
+                best = ResChoice{true, nbx, nby, BX, BY, ZS, smem};
+            }
+        }
+    }
+    return best;
+}
+
+static int resident_env()
+{
+    static const int on = [] {
+        const char *e = getenv("TAUB_RESIDENT");
+        return (e && *e) ? atoi(e) : 1;
+    }();
+    return on;
+}
+
+}  // namespace taub
+
+using namespace taub;
+
+extern "C" {
+
+unsigned long long taub_resident_timeouts(void)
+{
+    unsigned long long v = 0;
+    if (cudaMemcpyFromSymbol(&v, g_resident_timeouts, sizeof(v)) != cudaSuccess) return ~0ULL;
+    return v;
+}
+
+size_t taub_sync_ws_ints(void) { return 1024; }
+
+static int device_sms(int *sms, int *coop)
+{
+    int dev = 0;
+    TAUB_CUDA(cudaGetDevice(&dev));
+    static int s_sms[64] = {0}, s_coop[64] = {0};
+    if (!s_sms[dev & 63]) {
+        TAUB_CUDA(cudaDeviceGetAttribute(&s_coop[dev & 63], cudaDevAttrCooperativeLaunch, dev));
+        TAUB_CUDA(cudaDeviceGetAttribute(&s_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+    }
+    *sms = s_sms[dev & 63];
+    *coop = s_coop[dev & 63];
+    return TAUB_OK;
+}
+
+int taub_can_reside(const taub_problem *p)
+{
+    if (!p || p->kind != TAUB_BINARY || !p->codes || !p->field[0] || !p->field[1] || !p->sync_ws) return 0;
+    if (!resident_env()) return 0;
+    const taub_geom &g = p->g;
+    if (g.i_offset != 0 || g.Nx != g.Nx_global) return 0;          // whole volumes only
+    if (g.Nx < 2 || g.Ny < 2 || g.Nz < 8) return 0;
+    if (g.periodic && ((g.Ny & 1) || (g.Nz & 1))) return 0;        // snapshot rule of the odd wrap: marching kernels
+    if (p->peer_lo[0] || p->peer_hi[0] || p->peer_lo[1] || p->peer_hi[1]) return 0;
+    int sms = 0, coop = 0;
+    if (device_sms(&sms, &coop) != TAUB_OK || !coop) return 0;
+    if ((int64_t)g.bs > sms) return 0;
+    return choose_bricks(g, sms).ok ? 1 : 0;
+}
+
+int taub_resident_pairs(taub_problem *p, int64_t iter, int n_pairs, void *stream)
+{
+    TAUB_REQUIRE(p && n_pairs >= 1, "taub_resident_pairs: bad arguments");
+    if (taub_can_reside(p) != 1) {
+        set_error("taub_resident_pairs: problem does not qualify for the shared-memory resident path");
+        return TAUB_ERR_UNSUPPORTED;
+    }
+    const taub_geom &g = p->g;
+    int sms = 0, coop = 0;
+    if (int rc = device_sms(&sms, &coop)) return rc;
+    const ResChoice c = choose_bricks(g, sms);
+    const int bricks = g.bs * c.nbx * c.nby;
+    TAUB_REQUIRE(bricks <= (int)taub_sync_ws_ints(), "taub_resident_pairs: more bricks than counters");
+    ResParams P;
+    P.g = g;
+    P.buf[0] = p->field[p->cur];
+    P.buf[1] = p->field[p->cur ^ 1];
+    P.codes = p->codes;
+    P.omega = p->omega;
+    P.colour0 = (int)(iter & 1);
+    P.n_pairs = n_pairs;
+    P.nbx = c.nbx;
+    P.nby = c.nby;
+    P.BX = c.BX;
+    P.BY = c.BY;
+    P.ZS = c.ZS;
+    P.flags = p->sync_ws;
+    P.epoch0 = p->sync_epoch;
+    P.stop = p->stop;
+    int dev = 0;
+    TAUB_CUDA(cudaGetDevice(&dev));
+    static size_t smem_set[64] = {0};
+    if (c.smem > smem_set[dev & 63]) {
+        TAUB_CUDA(cudaFuncSetAttribute(resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM_MAX));
+        smem_set[dev & 63] = R_SMEM_MAX;
+    }
+    void *args[] = {(void *)&P};
+    TAUB_CUDA(cudaLaunchCooperativeKernel((const void *)resident_kernel, dim3(bricks), dim3(R_NT), args, c.smem,
+                                          (cudaStream_t)stream));
+    count_launch();
+    p->sync_epoch += n_pairs;
+    // the last pair stored the whole field into its buffer: buf[1] after an odd number of pairs, buf[0] otherwise
+    if (n_pairs & 1) p->cur ^= 1;
+    return TAUB_OK;
+}
+
+}  // extern "C"

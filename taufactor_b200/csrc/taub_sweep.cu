@@ -279,8 +279,16 @@ int taub_iterate(taub_problem *p, int64_t iter, int n, int flags, void *stream)
         explicit LateScope(bool on) : saved(g_refresh_late_trigger) { g_refresh_late_trigger = on; }
         ~LateScope() { g_refresh_late_trigger = saved; }
     } late_scope((flags & 4) != 0);
+    const bool reside_ok = !(flags & (1 | 8)) && taub_can_reside(p) == 1;
     int done = 0;
     while (done < n) {
+        if (reside_ok && n - done >= 2) {
+            // small volume: every remaining pair in one cooperative launch, field resident in shared memory
+            const int pairs = (n - done) / 2;
+            if (int rc = taub_resident_pairs(p, iter + done, pairs, stream)) return rc;
+            done += 2 * pairs;
+            continue;
+        }
         if (g.periodic) {
             if (int rc = refresh_ghosts(&g, p->field[p->cur], 0, g.planes, p->stop, stream)) return rc;
         }

@@ -96,6 +96,9 @@ class SORSolver:
             p.field[0], p.field[1] = self._bufs[0].data_ptr(), self._bufs[1].data_ptr()
             p.omega = float(np.float32(omega))          # rounded once to fp32, ref:224
             p.cur = 0
+            # counters of the shared-memory resident path for small volumes (taub_resident_pairs), zeroed once
+            self._sync_ws = torch.zeros(int(self._lib.taub_sync_ws_ints()), dtype=torch.int32, device=dev)
+            p.sync_ws, p.sync_epoch = self._sync_ws.data_ptr(), 0
             self._prob = p
             # label histogram (ref:564-567) -> which phases exist; then the per-slice volume
             # fraction numerators of the conductive phases (ref:42)
@@ -462,9 +465,12 @@ class SORSolver:
 
     pdl_refresh_late = False    # experimental (flags bit 2): the periodic ghost refresh releases the next sweep late
 
+    use_resident = True         # small volumes: whole blocks of iterations in one launch, field in shared memory
+
     def _iterate_flags(self):
         pdl = self._pdl_on()
-        return (1 if self.force_generic else 0) | (2 if pdl else 0) | (4 if pdl and self.pdl_refresh_late else 0)
+        return ((1 if self.force_generic else 0) | (2 if pdl else 0) | (4 if pdl and self.pdl_refresh_late else 0)
+                | (0 if self.use_resident else 8))
 
     def _check_only(self):
         """The reduction + device->host read of one convergence check, without the stop rule."""
@@ -478,6 +484,8 @@ class SORSolver:
         return int(self._lib.taub_inexact_events())
 
     def sweep_kernel_name(self):
+        if self.use_resident and not self.force_generic and self._lib.taub_can_reside(self._prob) == 1:
+            return "resident_kernel"
         fused = (not self.force_generic) and self._lib.taub_can_fuse(self._prob) == 1
         return "fused_sweep2_kernel" if fused else "half_sweep_kernel"
 

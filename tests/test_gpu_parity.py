@@ -62,10 +62,15 @@ def used_part(f):
 
 
 # ------------------------------------------------------------------ bit-exact trajectories
+KERNELS = {"generic": dict(force_generic=True), "marching": dict(use_resident=False), "auto": {}}
+
+
 @pytest.mark.parametrize("name", cases.SNAPSHOT_CASES)
-@pytest.mark.parametrize("generic", [True, False])
-def test_field_bitwise_vs_reference_goldens(tau, name, generic):
-    S, _ = make(tau, name, force_generic=generic)
+@pytest.mark.parametrize("kernel", list(KERNELS))
+def test_field_bitwise_vs_reference_goldens(tau, name, kernel):
+    """generic = one iteration per pass; marching = the fused two-iteration TMA kernel where it applies; auto = what a
+    user gets (small binary volumes: the shared-memory resident kernel)."""
+    S, _ = make(tau, name, **KERNELS[kernel])
     f0 = S.field.cpu().numpy()
     assert np.array_equal(f0[:, 1:-1, 1:-1, 1:-1], FIELDS[f"{name}@0"][:, 1:-1, 1:-1, 1:-1])
     if hasattr(S, "factor"):
@@ -82,10 +87,10 @@ def test_field_bitwise_vs_reference_goldens(tau, name, generic):
 
 @pytest.mark.parametrize("name", ["rand40", "blobs64_per", "blobs3_48_mp", "blobs3_48_pmp", "batch3_blobs48",
                                   "flat2d_per_batch", "omega_custom"])
-@pytest.mark.parametrize("generic", [True, False])
-def test_field_bitwise_vs_oracle_after_57_iterations(tau, name, generic):
+@pytest.mark.parametrize("kernel", list(KERNELS))
+def test_field_bitwise_vs_oracle_after_57_iterations(tau, name, kernel):
     from oracle import sor_c
-    S, _ = make(tau, name, force_generic=generic)
+    S, _ = make(tau, name, **KERNELS[kernel])
     st = oracle_state(name)
     S.solve(iter_limit=57, verbose=False)
     sor_c.sweep(st, 57)
@@ -101,6 +106,7 @@ def test_periodic_fused_vs_generic_small_and_odd_group_shapes(tau, shape):
     import torch
     img = cases.random_img(shape, 0.75, seed=sum(shape))
     A = tau.PeriodicSolver(img, device="cuda")
+    A.use_resident = False
     B = tau.PeriodicSolver(img, device="cuda")
     B.force_generic = True
     assert A.sweep_kernel_name() == "fused_sweep2_kernel"
@@ -388,7 +394,7 @@ _EVENTS0 = []
 def test_zz_fused_fast_division_was_exact_everywhere(tau):
     """Runs last in this file: no thread of the fused kernel divided a sub-2^-100 sum on the fast path in any
     through-transport test above, so every fused trajectory was bit-identical to IEEE division."""
-    S, _ = make(tau, "rand40")
+    S, _ = make(tau, "rand40", use_resident=False)
     S.solve(iter_limit=100, verbose=False)
     assert S.sweep_kernel_name() == "fused_sweep2_kernel"
     assert S.inexact_events == _EVENTS0[0]
@@ -413,8 +419,8 @@ def test_programmatic_dependent_launch_changes_nothing(cls, shape, kw):
     out = {}
     for pdl in (False, True):
         S = getattr(tau, cls)(img, device="cuda", **kw)
-        S.use_pdl = pdl
-        assert S._iterate_flags() == (2 if pdl else 0)
+        S.use_pdl, S.use_resident = pdl, False
+        assert S._iterate_flags() == (2 if pdl else 0) | 8
         fields = []
         for n in (1, 2, 98):
             S._advance(n)
@@ -439,7 +445,55 @@ def test_dependent_launch_default(monkeypatch):
     assert A._pdl_on() and B._pdl_on()
     B.PDL_PERIODIC_MAX_VOXELS = 100
     assert not B._pdl_on() and B._iterate_flags() == 0
+    B.use_resident = False
+    assert B._iterate_flags() == 8
     monkeypatch.setenv("TAUB_PDL", "0")
     assert not A._pdl_on()
     A.use_pdl = True
     assert A._pdl_on() and A._iterate_flags() == 2
+
+
+# ------------------------------------------------------------------ shared-memory resident kernel (small volumes)
+RESIDENT_SHAPES = [
+    ("Solver", (100, 100, 100), 0.5), ("Solver", (64, 48, 40), 0.6), ("Solver", (33, 17, 9), 0.7),
+    ("Solver", (2, 2, 8), 1.0), ("Solver", (5, 64, 130), 0.55), ("Solver", (3, 48, 40, 44), 0.6),
+    ("Solver", (128, 128, 128), 0.45), ("Solver", (150, 20, 250), 0.5), ("PeriodicSolver", (20, 22, 30), 0.6),
+    ("PeriodicSolver", (64, 64, 64), 0.5), ("PeriodicSolver", (40, 2, 8), 0.8), ("PeriodicSolver", (2, 30, 16, 12), 0.6),
+    ("PeriodicSolver", (96, 100, 104), 0.5),
+]
+
+
+@pytest.mark.parametrize("cls,shape,p", RESIDENT_SHAPES)
+def test_resident_kernel_equals_the_marching_kernels(tau, cls, shape, p):
+    """taub_resident_pairs (one cooperative launch, bricks resident in shared memory, neighbour exchange through
+    release / acquire counters) against the fused / generic kernels: bit-identical fields after 2, 5, 42 and 142
+    iterations, odd totals included (the last iteration then runs on the generic kernel), no counter wait timed out."""
+    img = cases.random_img(shape, p, seed=sum(shape))
+    A = getattr(tau, cls)(img, device="cuda")
+    B = getattr(tau, cls)(img, device="cuda")
+    B.use_resident = False
+    assert A.sweep_kernel_name() == "resident_kernel" and B.sweep_kernel_name() != "resident_kernel"
+    for n in (2, 3, 37, 100):
+        A._advance(n)
+        B._advance(n)
+        assert torch_equal(A.field, B.field), (cls, shape, n)
+    A.solve(verbose=False, iter_limit=600)
+    B.solve(verbose=False, iter_limit=600)
+    assert A.iter == B.iter and np.array_equal(A.tau, B.tau) and torch_equal(A.field, B.field)
+    assert A._lib.taub_resident_timeouts() == 0
+
+
+def torch_equal(a, b):
+    import torch
+    return bool(torch.equal(a[:, 1:-1, 1:-1, 1:-1], b[:, 1:-1, 1:-1, 1:-1]))
+
+
+def test_resident_kernel_is_not_taken_where_it_does_not_apply(tau):
+    """Odd periodic extents (snapshot rule of the wrap), thin z, volumes whose bricks exceed shared memory, the
+    multi-phase kinds: the marching kernels run."""
+    for cls, shape in (("PeriodicSolver", (20, 21, 20)), ("PeriodicSolver", (20, 20, 21)), ("Solver", (30, 30, 6)),
+                       ("Solver", (256, 256, 256))):
+        S = getattr(tau, cls)(cases.random_img(shape, 0.6, seed=1), device="cuda")
+        assert S.sweep_kernel_name() != "resident_kernel", (cls, shape)
+    S = tau.MultiPhaseSolver(cases.blobs3((32, 32, 32), seed=1), {0: 0.0, 1: 1.0, 2: 0.3}, device="cuda")
+    assert S.sweep_kernel_name() != "resident_kernel"
