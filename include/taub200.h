@@ -134,6 +134,30 @@ int taub_init_multiphase(const taub_problem *p, const uint8_t *img, int img_i0, 
  * Voxels with equal keys have identical face conductances and prefactor, so the caller can replace the
  * labels by the index into the table of distinct keys (TAUB_MULTIPHASE_CLASS). */
 int taub_multiphase_keys(const taub_problem *p, int i_lo, int i_hi, int32_t *keys, void *stream);
+/* The same classification without a per-voxel key array (what MultiPhaseSolver uses): taub_class_count fills a
+ * device hash table with the distinct stencil keys of planes [i_lo, i_hi) and their voxel counts -- workspace of
+ * taub_class_ws_bytes() bytes: int32 header[4] = {distinct keys, overflow flag (more than 65534 keys), capacity, 0},
+ * int32 keys[capacity] (-1 = empty slot), uint64 counts[capacity].  The caller ranks the keys (most frequent first),
+ * builds the weight rows (taufactor.py:594-603 in fp32) and passes slot_class[capacity] (uint16, device: class id of
+ * the key in each slot); taub_class_assign then writes the class id of EVERY storage voxel into classes (uint16 per
+ * storage voxel): voxels of planes [i_lo, i_hi) and, for the periodic solvers, their images in the y/z ghost frame
+ * get their class, everything else `inert`. */
+size_t taub_class_ws_bytes(void);
+int taub_class_count(const taub_problem *p, int i_lo, int i_hi, void *ws, void *stream);
+int taub_class_assign(const taub_problem *p, int i_lo, int i_hi, const void *ws, const uint16_t *slot_class, int inert,
+                      uint16_t *classes, void *stream);
+/* AnisotropicSolver state (taufactor.py:436-471): start field as taub_init_binary + one prefactor-class id per
+ * storage voxel in p->codes: (nx * 3 + ny) * 3 + nz with nx = conductive x neighbours (the Dirichlet planes count 2:
+ * 0..4), ny, nz in 0..2; 63 = non-conductive / outside.  p->kind == TAUB_ANISOTROPIC. */
+int taub_init_anisotropic(const taub_problem *p, const uint8_t *img, int img_i0, int img_n, const float *vec, void *stream);
+/* ElectrodeSolver / PeriodicElectrodeSolver state (electrode.py:39-64, :136-150; taufactor.py:47-56) of a whole volume:
+ * class id per storage voxel in p->codes = b * 112 + (cond_nn * 7 + reac_nn) * 2 + [x+ neighbour conducts] for the
+ * voxels of phase cond_label (cond_nn counts the left Dirichlet plane twice, the right end is closed; reac_nn =
+ * neighbours of phase reac_label), bs * 112 elsewhere; start field vec[i] on the conductive phase, 2 (= 2 * left_bc)
+ * on the left ghost plane; reac_sums[b][i] (int64, device) = sum of reac_nn over the conductive voxels of plane i.
+ * img: device uint8 [bs][Nx][Ny][Nz]; p->kind == TAUB_MULTIPHASE_CLASS; a label of -1 matches nothing. */
+int taub_init_electrode(const taub_problem *p, const uint8_t *img, int cond_label, int reac_label, const float *vec,
+                        int64_t *reac_sums, void *stream);
 /* counts[b][i] (int64, device) = voxels of local plane i whose raw label has sel256[label] != 0
  * (numerator of vol_x, taufactor.py:42); hist[b][256] (int64, device, may be NULL) = label
  * histogram (numerators of VF, taufactor.py:564-567). */

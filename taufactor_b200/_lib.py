@@ -45,6 +45,11 @@ SIGNATURES = {
     "taub_init_binary": (c_int, [ctypes.POINTER(Problem), c_vp, c_int, c_int, c_vp, c_vp]),
     "taub_init_multiphase": (c_int, [ctypes.POINTER(Problem), c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "taub_multiphase_keys": (c_int, [ctypes.POINTER(Problem), c_int, c_int, c_vp, c_vp]),
+    "taub_class_ws_bytes": (ctypes.c_size_t, []),
+    "taub_class_count": (c_int, [ctypes.POINTER(Problem), c_int, c_int, c_vp, c_vp]),
+    "taub_class_assign": (c_int, [ctypes.POINTER(Problem), c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp]),
+    "taub_init_anisotropic": (c_int, [ctypes.POINTER(Problem), c_vp, c_int, c_int, c_vp, c_vp]),
+    "taub_init_electrode": (c_int, [ctypes.POINTER(Problem), c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
     "taub_plane_counts": (c_int, [ctypes.POINTER(Geom), c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "taub_refresh_ghosts": (c_int, [ctypes.POINTER(Geom), c_vp, c_int, c_int, c_vp]),
     "taub_half_sweep": (c_int, [ctypes.POINTER(Problem), c_i64, c_int, c_int, c_vp]),

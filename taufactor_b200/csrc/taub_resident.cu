@@ -81,13 +81,40 @@ __device__ __forceinline__ const float *global_row(const ResParams &P, const Bri
     return base + (int64_t)K.b * g.image_stride + (int64_t)(gx + G) * g.plane_stride + (int64_t)sr * g.pitch;
 }
 
-__device__ __forceinline__ void load_row(float *srow, const float *grow, int ZS, int lane)
+// Rows f = warp, warp + R_WARPS, ... of a list of n rows (row_of(f, li, lj) -> false: skip) from global memory into
+// their shared rows.  A warp first issues the loads of up to R_BATCH rows, then stores them: the global-memory latency
+// is paid once per batch, not once per row (the exchange of a pair is latency bound).
+constexpr int R_BATCH = 8;
+
+template <class RowOf>
+__device__ __forceinline__ void load_rows(const ResParams &P, const Brick &K, float *fld, const float *base, int n, int warp,
+                                          int lane, RowOf row_of)
 {
-    const int ZH = ZS >> 1;
-    for (int g4 = lane; g4 < (ZS >> 2); g4 += 32) {
-        const float4 v = __ldcg(reinterpret_cast<const float4 *>(grow) + g4);
-        *reinterpret_cast<float2 *>(srow + 2 * g4) = make_float2(v.x, v.z);
-        *reinterpret_cast<float2 *>(srow + ZH + 2 * g4) = make_float2(v.y, v.w);
+    const int ZS = P.ZS, ZH = ZS >> 1, RY = P.BY + 4, CG = ZS >> 2;
+    for (int f0 = warp; f0 < n; f0 += R_WARPS * R_BATCH) {
+        for (int g0 = 0; g0 < CG; g0 += 32) {
+            const int g4 = g0 + lane;
+            float4 v[R_BATCH];
+            int dst[R_BATCH];
+#pragma unroll
+            for (int u = 0; u < R_BATCH; ++u) {
+                const int f = f0 + u * R_WARPS;
+                int li = 0, lj = 0;
+                dst[u] = -1;
+                if (f < n && g4 < CG && row_of(f, li, lj)) {
+                    dst[u] = (li * RY + lj) * ZS;
+                    v[u] = __ldcg(reinterpret_cast<const float4 *>(global_row(P, K, base, li, lj)) + g4);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < R_BATCH; ++u) {
+                if (dst[u] >= 0) {
+                    float *srow = fld + dst[u];
+                    *reinterpret_cast<float2 *>(srow + 2 * g4) = make_float2(v[u].x, v[u].z);
+                    *reinterpret_cast<float2 *>(srow + ZH + 2 * g4) = make_float2(v[u].y, v[u].w);
+                }
+            }
+        }
     }
 }
 
@@ -187,10 +214,11 @@ resident_kernel(const ResParams P)
     const int LX = K.bx + 4, LY = K.by + 4;     // rows held: the brick and its 2-wide frame
 
     // ---- start: the brick and its frame from the current field, neighbour codes of the brick and its first ring
-    for (int r = warp; r < LX * LY; r += R_WARPS) {
-        const int li = r / LY, lj = r - li * LY;
-        load_row(fld + (size_t)(li * RY + lj) * ZS, global_row(P, K, P.buf[0], li, lj), ZS, lane);
-    }
+    load_rows(P, K, fld, P.buf[0], LX * LY, warp, lane, [&](int f, int &li, int &lj) {
+        li = f / LY;
+        lj = f - li * LY;
+        return true;
+    });
     for (int r = warp; r < (LX - 2) * (LY - 2); r += R_WARPS) {
         const int ci = r / (LY - 2), cj = r - ci * (LY - 2);
         const int gx = K.x0 - 1 + ci, gy = K.y0 - 1 + cj;
@@ -251,17 +279,22 @@ resident_kernel(const ResParams P)
                         break;
                     }
                 }
-                __threadfence();
             }
             __syncthreads();
-            const float *rbuf = P.buf[((n - 1) & 1) ^ 1];
-            for (int r = warp; r < LX * LY; r += R_WARPS) {
-                const int li = r / LY, lj = r - li * LY;
-                const bool frame = li < 2 || li >= K.bx + 2 || lj < 2 || lj >= K.by + 2;
+            // the frame: two bands of 2 x LY rows below / above the brick, then 4 rows beside each of its bx planes
+            load_rows(P, K, fld, P.buf[((n - 1) & 1) ^ 1], 4 * LY + 4 * K.bx, warp, lane, [&](int f, int &li, int &lj) {
+                if (f < 4 * LY) {
+                    const int band = f / LY;                  // 0, 1: planes 0, 1; 2, 3: planes bx+2, bx+3
+                    li = band < 2 ? band : K.bx + band;
+                    lj = f - band * LY;
+                } else {
+                    const int e = f - 4 * LY, c = e & 3;
+                    li = 2 + (e >> 2);
+                    lj = c < 2 ? c : K.by + c;
+                }
                 const int gx = K.x0 - 2 + li, gy = K.y0 - 2 + lj;
-                const bool moving = gx >= 0 && gx < g.Nx && (per || (gy >= 0 && gy < g.Ny));   // else constants
-                if (frame && moving) load_row(fld + (size_t)(li * RY + lj) * ZS, global_row(P, K, rbuf, li, lj), ZS, lane);
-            }
+                return gx >= 0 && gx < g.Nx && (per || (gy >= 0 && gy < g.Ny));   // outside: constants, loaded once
+            });
         }
         __syncthreads();
         if (per) {
@@ -287,10 +320,9 @@ resident_kernel(const ResParams P)
             }
         }
         __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            st_release(P.flags + blockIdx.x, P.epoch0 + n + 1);
-        }
+        // bar.sync orders the CTA's stores before thread 0's release, which is cumulative: a neighbour that acquires
+        // the counter sees every row published above
+        if (tid == 0) st_release(P.flags + blockIdx.x, P.epoch0 + n + 1);
     }
 }
 

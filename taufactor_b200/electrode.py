@@ -19,8 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .solvers import (SORSolver, _as_uint8_labels, _expand_to_4d, fill_periodic_frame, neighbour_count_axis,
-                      shift_zero)
+from .solvers import SORSolver, _as_uint8_labels, _expand_to_4d
 
 __all__ = ["ElectrodeSolver", "PeriodicElectrodeSolver", "compute_impedance", "compute_impedance_batched"]
 
@@ -98,37 +97,34 @@ class ElectrodeSolver(SORSolver):
         self._setup(img4, omega, device, u8, prepare, self._init_electrode)
         self.c_x = 0
 
-    # ------------------------------------------------------------------ state build (device tensor ops)
-    def _neighbour_count(self, a, left_ghost):
-        """Number of set 6-neighbours of every voxel of ``a`` (int8 0/1, [bs,Nx,Ny,Nz]); the left x ghost
-        plane counts ``left_ghost``, the right one 0; y/z ghosts 0, or the periodic image
-        (ref electrode.py:48-64 / :136-150 with taufactor.py:228-253)."""
-        n = neighbour_count_axis(a, 1, False)
-        n[:, 0] += left_ghost
-        for dim in (2, 3):
-            n += neighbour_count_axis(a, dim, self._periodic)
-        return n
-
+    # ------------------------------------------------------------------ state build (one kernel)
     def _init_electrode(self, p, img_dev, vec_unused):
+        """taub_init_electrode: class ids (image, cond_nn, reac_nn, x+ neighbour conducts), the cosh start field and
+        the per-slice reactive-neighbour sums in one pass over the label image; the class table follows on the host
+        once the reaction constant k_0 is known (ref electrode.py:39-64, taufactor.py:47-56)."""
         lib, dev, g = self._lib, self.device, p.g
         bs, Nx, Ny, Nz = self.batch_size, self.Nx, self.Ny, self.Nz
-        G, C0 = _lib.GHOST, _lib.COL0
-        cond = (img_dev == self._cond_u8).to(torch.int8)
-        reac = (img_dev == self._reac_u8).to(torch.int8)
-        cond_nn = self._neighbour_count(cond, 2)
-        reac_nn = self._neighbour_count(reac, 0) * cond                   # 0 off the conductive phase
-        del reac
+        n_img = _N_COND * _N_REAC * 2
+        if bs * n_img > 65534:
+            raise ValueError(f"batch of {bs} images needs more than 65534 stencil classes")
+        # initial field (ref electrode.py:39-46): the ideal cosh profile on the conductive phase; left
+        # ghost plane 2 * left_bc (the Dirichlet plane counts twice), right ghost plane 0 (closed end)
+        x = np.arange(Nx) + 0.5
+        c_init = self.electrode_bc + (self.left_bc - self.electrode_bc) * np.cosh(1 - x / Nx) / np.cosh(1)
+        vec = torch.tensor(c_init, dtype=torch.float32, device=dev)
+        classes = torch.empty(lib.taub_field_elems(g), dtype=torch.int16, device=dev)
+        reac = torch.zeros(bs * Nx, dtype=torch.int64, device=dev)
+        p.codes = classes.data_ptr()
+        self._call(lib.taub_init_electrode(p, img_dev.data_ptr(), int(self._cond_u8), int(self._reac_u8), vec.data_ptr(),
+                                           reac.data_ptr(), self._stream()), "taub_init_electrode")
         # surface area per slice and the reaction prefactor -- the reference's fp32 tensor expressions
         # (taufactor.py:48-51) on the exact per-slice integer sums, evaluated with the same torch CPU ops
-        reac_sum = reac_nn.sum(dim=(2, 3), dtype=torch.int64).cpu().to(torch.float32)
+        reac_sum = reac.view(bs, Nx).cpu().to(torch.float32)
         vol_x = torch.from_numpy(self.vol_x)
         a_x = reac_sum / (Ny * Nz * self.dx)
         k_0 = torch.mean(vol_x, 1) / torch.mean(a_x * self.dx, 1) / Nx ** 2
         self.a_x, self.k_0 = a_x.numpy(), k_0.numpy()
         # stencil classes: (image, cond_nn, reac_nn, x+ neighbour conductive) -> prefactor and unit weights
-        n_img = _N_COND * _N_REAC * 2
-        if bs * n_img > 65534:
-            raise ValueError(f"batch of {bs} images needs more than 65534 stencil classes")
         c_i, r_i, xp_i = np.meshgrid(np.arange(_N_COND), np.arange(_N_REAC), np.arange(2), indexing="ij")
         rows = []
         for b in range(bs):
@@ -142,33 +138,8 @@ class ElectrodeSolver(SORSolver):
             # a non-conductive (value 0) neighbour leaves the neighbour sum unchanged
             rows.append(np.stack([xp_i.astype(np.float32), one, one, one, one, one, fac, rcp], axis=-1).reshape(-1, 8))
         table = np.concatenate(rows + [np.zeros((1, 8), np.float32)])         # last row: inert (non-conductive)
-        inert = len(table) - 1
         table_dev = torch.from_numpy(np.ascontiguousarray(table)).to(dev)
-        xp = shift_zero(cond, 1, -1)
-        ids = ((cond_nn.to(torch.int32) * _N_REAC + reac_nn.to(torch.int32)) * 2 + xp.to(torch.int32))
-        ids += (torch.arange(bs, device=dev, dtype=torch.int32) * n_img).view(bs, 1, 1, 1)
-        ids = torch.where(cond.bool(), ids, torch.full_like(ids, inert)).to(torch.int16)
-        del cond_nn, reac_nn, xp
-        classes = torch.full((lib.taub_field_elems(g),), inert, dtype=torch.int32, device=dev).to(torch.int16)
-        cv = classes.view(bs, g.planes, g.rows, g.pitch)
-        cv[:, G:G + Nx, G:G + Ny, C0:C0 + Nz] = ids
-        del ids
-        if self._periodic:
-            fill_periodic_frame(cv[:, G:G + Nx], g)
-        p.codes, p.lut, p.L = classes.data_ptr(), table_dev.data_ptr(), int(len(table))
-        # initial field (ref electrode.py:39-46): the ideal cosh profile on the conductive phase; left
-        # ghost plane 2 * left_bc (the Dirichlet plane counts twice), right ghost plane 0 (closed end)
-        x = np.arange(Nx) + 0.5
-        c_init = self.electrode_bc + (self.left_bc - self.electrode_bc) * np.cosh(1 - x / Nx) / np.cosh(1)
-        vec = torch.tensor(c_init, dtype=torch.float32, device=dev)
-        f0 = self._bufs[0].view(bs, g.planes, g.rows, g.pitch)
-        f0.zero_()
-        f0[:, G:G + Nx, G:G + Ny, C0:C0 + Nz] = cond.to(torch.float32) * vec.view(1, Nx, 1, 1)
-        if self._periodic:      # ghost-frame voxels are updated like their periodic images and read x-1 too
-            f0[:, G - 1, :, C0 - G:C0 + Nz + G] = self.left_bc * 2
-        else:
-            f0[:, G - 1, G:G + Ny, C0:C0 + Nz] = self.left_bc * 2
-        self._bufs[1].copy_(self._bufs[0])
+        p.lut, p.L = table_dev.data_ptr(), int(len(table))
         return classes, table_dev, vec
 
     # ------------------------------------------------------------------ metrics (ref electrode.py:69-105)

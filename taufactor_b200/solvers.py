@@ -616,32 +616,15 @@ class AnisotropicSolver(Solver):
     _INERT = 63             # non-conductive voxels and everything outside the volume
 
     def _init_binary(self, p, img_dev, vec):
-        """State = the binary solver's start field + one prefactor-class id per voxel.  The weighted
-        neighbour count (ref:459-471) depends only on the number of conductive neighbours per axis
-        (x: 0..4 with the Dirichlet planes counting 2; y, z: 0..2), so it is a 45-entry table of
-        (b, RN(1/b)) pairs built here in the reference's fp32 accumulation order."""
+        """State = the binary solver's start field + one prefactor-class id per voxel, both from one kernel
+        (taub_init_anisotropic).  The weighted neighbour count (ref:459-471) depends only on the number of
+        conductive neighbours per axis (x: 0..4 with the Dirichlet planes counting 2; y, z: 0..2), so it is a
+        45-entry table of (b, RN(1/b)) pairs built here in the reference's fp32 accumulation order."""
         lib, dev, g = self._lib, self.device, p.g
-        G, C0 = _lib.GHOST, _lib.COL0
-        # start field through the binary state build (its neighbour codes are not kept)
-        tmp = Problem()
-        ctypes_copy(tmp, p)
-        tmp.kind = _lib.BINARY
-        scratch = torch.empty(lib.taub_codes_elems(g), dtype=torch.int16, device=dev)
-        tmp.codes = scratch.data_ptr()
-        self._call(lib.taub_init_binary(tmp, img_dev.data_ptr(), 0, self.Nx, vec.data_ptr(), self._stream()),
-                   "taub_init_binary")
-        cond = (img_dev == 1).to(torch.int8)
-        nx = neighbour_count_axis(cond, 1, False)
-        nx[:, 0] += 2
-        nx[:, -1] += 2
-        ny = neighbour_count_axis(cond, 2, False)
-        nz = neighbour_count_axis(cond, 3, False)
-        ids = ((nx.to(torch.int16) * 3 + ny) * 3 + nz)
-        ids = torch.where(cond.bool(), ids, torch.full_like(ids, self._INERT))
-        del nx, ny, nz, cond
-        classes = torch.full((lib.taub_field_elems(g),), self._INERT, dtype=torch.int16, device=dev)
-        classes.view(g.bs, g.planes, g.rows, g.pitch)[:, G:G + self.Nx, G:G + self.Ny, C0:C0 + self.Nz] = ids
-        del ids, scratch
+        classes = torch.empty(lib.taub_field_elems(g), dtype=torch.int16, device=dev)
+        p.codes = classes.data_ptr()
+        self._call(lib.taub_init_anisotropic(p, img_dev.data_ptr(), 0, self.Nx, vec.data_ptr(), self._stream()),
+                   "taub_init_anisotropic")
         Ky, Kz = np.float32(self.Ky), np.float32(self.Kz)       # rounded to fp32 like torch's tensor * scalar
         lut = np.zeros(2 * self.N_CLASSES + 2, np.float32)
         for cx in range(5):
@@ -656,7 +639,7 @@ class AnisotropicSolver(Solver):
                         lut[2 * i], lut[2 * i + 1] = b, np.float32(1.0 / np.float64(b))
         lut[2 * self.N_CLASSES], lut[2 * self.N_CLASSES + 1] = Ky, Kz
         table = torch.from_numpy(lut).to(dev)
-        p.codes, p.lut, p.L = classes.data_ptr(), table.data_ptr(), self.N_CLASSES
+        p.lut, p.L = table.data_ptr(), self.N_CLASSES
         return (classes, vec, table)
 
     @property
@@ -823,45 +806,6 @@ def face_conductance_tensors(img4, Ds, periodic, device):
     return D_x, D_y, D_z, f
 
 
-def ctypes_copy(dst, src):
-    """Field-by-field copy of a ctypes structure."""
-    import ctypes
-    ctypes.memmove(ctypes.byref(dst), ctypes.byref(src), ctypes.sizeof(src))
-
-
-def shift_zero(a, dim, step):
-    """``a`` moved by ``step`` along ``dim`` with zeros entering (the reference's zero padding, ref:228-238)."""
-    out = torch.zeros_like(a)
-    n = a.shape[dim]
-    if abs(step) < n:
-        src = [slice(None)] * a.dim()
-        dst = [slice(None)] * a.dim()
-        src[dim] = slice(0, n - step) if step > 0 else slice(-step, n)
-        dst[dim] = slice(step, n) if step > 0 else slice(0, n + step)
-        out[tuple(dst)] = a[tuple(src)]
-    return out
-
-
-def neighbour_count_axis(a, dim, periodic):
-    """Number of set neighbours along one axis of a 0/1 int8 tensor [bs,Nx,Ny,Nz] (zero or periodic ends)."""
-    if periodic:
-        return torch.roll(a, 1, dim) + torch.roll(a, -1, dim)
-    return shift_zero(a, dim, 1) + shift_zero(a, dim, -1)
-
-
-def fill_periodic_frame(planes, g):
-    """y/z ghost frame (width G, corners included) of storage planes [bs, n, rows, pitch] := periodic image
-    of the interior -- rows first, then columns over all rows.  The fused kernel applies colour A on the
-    first ghost ring too, so per-voxel side arrays (class ids) need their periodic images there."""
-    G, C0 = _lib.GHOST, _lib.COL0
-    for w in range(G):
-        planes[:, :, G - 1 - w] = planes[:, :, G + g.Ny - 1 - (w % g.Ny)]
-        planes[:, :, G + g.Ny + w] = planes[:, :, G + (w % g.Ny)]
-    for w in range(G):
-        planes[:, :, :, C0 - 1 - w] = planes[:, :, :, C0 + g.Nz - 1 - (w % g.Nz)]
-        planes[:, :, :, C0 + g.Nz + w] = planes[:, :, :, C0 + (w % g.Nz)]
-
-
 def validated_diffusivities(diffusivities):
     """Argument checks of ref:524-545 (MultiPhaseSolver.__init__)."""
     if diffusivities is None:
@@ -886,22 +830,29 @@ def build_class_table(lib, p, dense_D, periodic, dev, stream, i_lo, i_hi):
     combinations that occur are few (<= 3 * L^7, in practice hundreds): each becomes a class with one
     8-float row {w_x+, w_x-, w_y+, w_y-, w_z+, w_z-, prefactor, 1/prefactor}, computed here in the
     reference's fp32 op order; the sweep then reads one uint16 class id per voxel and one row instead of
-    seven labels and six table look-ups.  Returns (classes, table, n_classes) or None (too many classes)."""
+    seven labels and six table look-ups.
+
+    The classification runs on the device without any per-voxel temporary: ``taub_class_count`` hashes the
+    stencil keys into a table of distinct keys + voxel counts, the host ranks the <= 65534 keys (most frequent
+    first; ties by key) and builds the rows, ``taub_class_assign`` writes the class id of every storage voxel
+    (periodic ghost frame included; everything outside the volume gets the inert class).
+    Returns (classes, table, n_classes) or None (too many classes)."""
     g = p.g
-    n_i = i_hi - i_lo
-    keys = torch.empty(g.bs * n_i * g.Ny * g.Nz, dtype=torch.int32, device=dev)
-    check(lib.taub_multiphase_keys(p, i_lo, i_hi, keys.data_ptr(), stream), "taub_multiphase_keys")
-    uniq, inv, counts = torch.unique(keys, return_inverse=True, return_counts=True)
-    del keys
-    if uniq.numel() > 65534:
+    ws = torch.empty(int(lib.taub_class_ws_bytes()), dtype=torch.uint8, device=dev)
+    check(lib.taub_class_count(p, i_lo, i_hi, ws.data_ptr(), stream), "taub_class_count")
+    host = ws.cpu().numpy()
+    n_distinct, overflow, cap = (int(v) for v in host[:12].view(np.int32))
+    if overflow or n_distinct > 65534:
         return None
-    # most frequent classes first: the handful of "uniform interior" stencils that cover most voxels
-    # then share one or two cache lines of the weight table
-    order = torch.argsort(counts, descending=True, stable=True)
-    rank = torch.empty_like(order)
-    rank[order] = torch.arange(order.numel(), device=dev)
-    inv = rank[inv]
-    k = uniq[order].cpu().numpy().astype(np.int64)
+    slot_keys = host[16:16 + 4 * cap].view(np.int32)
+    slot_counts = host[16 + 4 * cap:16 + 12 * cap].view(np.uint64)
+    slots = np.flatnonzero(slot_keys >= 0)
+    assert len(slots) == n_distinct
+    # most frequent classes first: the handful of "uniform interior" stencils that cover most voxels then
+    # sit at the front of the table (the fused kernel stages the first rows in shared memory)
+    order = np.lexsort((slot_keys[slots], -slot_counts[slots].astype(np.int64)))
+    slots = slots[order]
+    k = slot_keys[slots].astype(np.int64)
     lut = MultiPhaseSolver.harmonic_table(dense_D)
     own = k & 15
     wxm, wxp = lut[own, (k >> 4) & 15], lut[own, (k >> 8) & 15]
@@ -923,13 +874,13 @@ def build_class_table(lib, p, dense_D, periodic, dev, stream, i_lo, i_hi):
     table = np.concatenate([table, np.zeros((1, 8), np.float32)])
     # device layout: one 32-byte row per class (float[L][8])
     table_dev = torch.from_numpy(np.ascontiguousarray(table)).to(dev)
-    classes = torch.full((lib.taub_field_elems(g),), inert, dtype=torch.int32, device=dev).to(torch.int16)
-    G, C0 = _lib.GHOST, _lib.COL0
-    cv = classes.view(g.bs, g.planes, g.rows, g.pitch)
-    cv[:, G + i_lo:G + i_hi, G:G + g.Ny, C0:C0 + g.Nz] = inv.view(g.bs, n_i, g.Ny, g.Nz).to(torch.int16)
-    del inv
-    if periodic:
-        fill_periodic_frame(cv[:, G + i_lo:G + i_hi], g)
+    slot_class = np.full(cap, inert, np.uint16)
+    slot_class[slots] = np.arange(len(slots), dtype=np.uint16)
+    slot_class_dev = torch.from_numpy(slot_class.view(np.int16)).to(dev)
+    classes = torch.empty(lib.taub_field_elems(g), dtype=torch.int16, device=dev)
+    check(lib.taub_class_assign(p, i_lo, i_hi, ws.data_ptr(), slot_class_dev.data_ptr(), inert, classes.data_ptr(), stream),
+          "taub_class_assign")
+    torch.cuda.current_stream(dev).synchronize()      # ws / slot_class_dev are released when this returns
     p.kind, p.codes, p.lut, p.L = _lib.MULTIPHASE_CLASS, classes.data_ptr(), table_dev.data_ptr(), int(len(table))
     return classes, table_dev, int(len(k))
 

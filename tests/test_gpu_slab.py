@@ -211,6 +211,18 @@ def test_windowed_slabs_reject_non_binary_labels_on_every_rank(tmp_path):
         assert "Input image must only contain 0s and 1s" in msg and "[0 1 2]" in msg, (r, msg)
 
 
+def _percolation_images():
+    """A long channel that snakes through every slab several times (open / severed), random media either side of the
+    percolation threshold, the reference's dead-end case."""
+    from test_gpu_percolation import serpentine
+    snake, last_y = serpentine()
+    snake[-1, last_y:last_y + 2, 1:3] = 1                      # open the channel's end onto the last plane
+    cut = snake.copy()
+    cut[24] = 0                                                # sever every x run of the channel
+    return [snake, cut, cases.random_img((45, 20, 24), 0.31, seed=3), cases.random_img((45, 20, 24), 0.36, seed=1),
+            cases.deadend()]
+
+
 def _percolation_worker(rank, world, port, out):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -219,13 +231,8 @@ def _percolation_worker(rank, world, port, out):
     try:
         torch.cuda.set_device(0)
         from taufactor_b200.distributed import DistributedSolver, image_window, slab_bounds
-        from test_gpu_percolation import serpentine
         answers = []
-        imgs = [serpentine()[0], None, cases.random_img((45, 20, 24), 0.31, seed=3), cases.random_img((45, 20, 24), 0.36, seed=1),
-                cases.deadend()]
-        imgs[1] = imgs[0].copy()
-        imgs[1][24] = 0                                        # sever every x run of the channel
-        for img in imgs:
+        for img in _percolation_images():
             shape = img.shape
             lo, hi = slab_bounds(shape[0], world)[rank]
             w = image_window(lo, hi, shape[0])
@@ -251,14 +258,9 @@ def test_windowed_slabs_run_the_percolation_check_across_slabs(tmp_path, world):
     import torch.multiprocessing as mp
     import taufactor_b200 as tau
     from oracle import sor_numpy as on
-    from test_gpu_percolation import serpentine
     out = str(tmp_path / "perc")
     mp.spawn(_percolation_worker, args=(world, _free_port(), out), nprocs=world, join=True)
-    imgs = [serpentine()[0], None, cases.random_img((45, 20, 24), 0.31, seed=3), cases.random_img((45, 20, 24), 0.36, seed=1),
-            cases.deadend()]
-    imgs[1] = imgs[0].copy()
-    imgs[1][24] = 0
-    want = [bool(on.through_fraction_is_zero(np.asarray(i) == 1)) for i in imgs]
+    want = [bool(on.through_fraction_is_zero(np.asarray(i) == 1)) for i in _percolation_images()]
     assert want[0] is False and want[1] is True and want[4] is True
     B = tau.Solver(cases.deadend(), device="cuda")
     B.solve(verbose=False)
