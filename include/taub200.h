@@ -178,11 +178,13 @@ int taub_half_sweep(const taub_problem *p, int64_t iter, int i_lo, int i_hi, voi
 int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, void *stream);
 int taub_can_fuse(const taub_problem *p);   /* periodic problems with odd Ny / Nz: only with the experimental
                                              * OP kernel variant, environment TAUB_FUSE_ODD_PERIODIC=1 */
-/* The fused kernel divides by the neighbour count with an FMA-corrected reciprocal that equals the
- * IEEE quotient for s == 0 and every |s| >= 2^-100.  This counts the threads that ever saw a
- * non-zero sum below 2^-100 (there the result may differ from IEEE division by one subnormal ulp);
- * 0 -- the only value ever observed -- certifies the fused trajectory bit-identical to the generic
- * kernel and the reference.  Synchronises the device. */
+/* The fused kernel divides by the neighbour count / prefactor with an FMA-corrected reciprocal that equals the IEEE
+ * quotient for s == 0 and every |s| >= 2^-100.  A CTA whose threads saw a non-zero sum below 2^-100 (where that
+ * sequence may be one subnormal ulp off) redoes its whole chunk with IEEE division before it exits -- the source
+ * buffer of a pass is read-only, so the second run simply overwrites the first -- hence the fused trajectory equals
+ * the generic kernel's and the reference's for every finite input.  This returns how many chunks were redone since
+ * the library was loaded: 0 in every through-transport solve observed; the electrode solvers get there when a
+ * cluster cut off from the inlet decays towards 0.  Synchronises the device. */
 unsigned long long taub_inexact_events(void);
 /* n iterations starting at iter on the whole local slab (single-rank use): refreshes periodic
  * ghosts, picks fused pairs where possible, flips p->cur.  flags bit 0: force the generic path;
@@ -202,6 +204,10 @@ int taub_iterate(taub_problem *p, int64_t iter, int n, int flags, void *stream);
 int taub_can_reside(const taub_problem *p);
 int taub_resident_pairs(taub_problem *p, int64_t iter, int n_pairs, void *stream);
 size_t taub_sync_ws_ints(void);                 /* int32 counters p->sync_ws must hold */
+/* Cycle counts of the phases of a pair, summed over the pairs that thread 0 of the middle brick has run since the last
+ * reset: [0] wait for the neighbours' counters, [1] frame reload, [2] colour A, [3] colour B, [4] publish stores,
+ * [5] fence + counter store, [6] number of pairs, [7] cycles of whole launches.  Synchronises the device. */
+int taub_resident_profile(unsigned long long out[8], int reset);
 unsigned long long taub_resident_timeouts(void); /* waits on a neighbour's counter that gave up after ~2 s (0 in
                                                   * every correct run; a non-zero value voids the result) */
 

@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtaub200.so")
+# TAUB200_LIB: another build of the same ABI (A/B timing of two revisions on one box, tools/perf_quick.py)
+LIB_PATH = os.environ.get("TAUB200_LIB") or os.path.join(_HERE, "libtaub200.so")
 
 c_int, c_i64, c_vp, c_float = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_float
 
@@ -61,6 +62,7 @@ SIGNATURES = {
     "taub_resident_pairs": (c_int, [ctypes.POINTER(Problem), c_i64, c_int, c_vp]),
     "taub_sync_ws_ints": (ctypes.c_size_t, []),
     "taub_resident_timeouts": (ctypes.c_ulonglong, []),
+    "taub_resident_profile": (c_int, [ctypes.POINTER(ctypes.c_ulonglong), c_int]),
     "taub_plane_means": (c_int, [ctypes.POINTER(Problem), c_vp, c_vp, c_vp, c_vp]),
     "taub_check_async": (c_int, [ctypes.POINTER(Problem), c_vp, c_vp, c_vp, c_vp, c_vp, c_float, c_vp, c_vp]),
     "taub_stop_rule_async": (c_int, [c_int, c_int, c_vp, c_vp, c_vp, c_float, c_vp, c_vp, c_vp]),

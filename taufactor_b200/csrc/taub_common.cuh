@@ -100,8 +100,12 @@ __device__ __forceinline__ float2 div_pair(unsigned nib, const float2 *s_div)
 // u = 2*bits(s) - 1 drops the sign and wraps +-0 to the top, so "0 < |s| < 2^-100" <=> u < GUARD_T.
 constexpr unsigned GUARD_T = (27u << 24) - 1u;
 
+// EXACT = true: the IEEE quotient itself (cr.x == 0 stands for an infinite divisor) -- the fused kernel re-runs a
+// chunk this way when one of its sums was a non-zero value below 2^-100, so its results equal IEEE division always.
+template <bool EXACT = false>
 __device__ __forceinline__ float div_fast(float s, float2 cr, unsigned &umin)
 {
+    if (EXACT) return __fdiv_rn(s, cr.x != 0.0f ? cr.x : __int_as_float(0x7f800000));
     const float q0 = __fmul_rn(s, cr.y);
     const float rem = __fmaf_rn(-q0, cr.x, s);
     umin = min(umin, __float_as_uint(s) * 2u - 1u);
@@ -125,10 +129,11 @@ __device__ __forceinline__ float relax(float c, float q, float omega)
 }
 
 // One binary-solver voxel update on the fast path; the caller checks umin once per group of updates.
+template <bool EXACT = false>
 __device__ __forceinline__ float sor_fast(float c, float xp, float xm, float yp, float ym, float zp, float zm,
                                           float2 cr, float omega, unsigned &umin)
 {
-    return relax(c, div_fast(nbr_sum(xp, xm, yp, ym, zp, zm), cr, umin), omega);
+    return relax(c, div_fast<EXACT>(nbr_sum(xp, xm, yp, ym, zp, zm), cr, umin), omega);
 }
 
 // The same update with a true IEEE division: taken only when some sum in the group is a non-zero
@@ -233,6 +238,7 @@ __device__ __forceinline__ float sor_multi(float c, float xp, float xm, float yp
 // from its shared-memory copy of the most frequent classes or, for the rare others, through the read-only path
 // (two half-row arrays: a 32-byte sector holds the halves of two frequency-adjacent classes).
 // ------------------------------------------------------------------------------------------
+template <bool EXACT = false>
 __device__ __forceinline__ float sor_class_rows(float c, float xp, float xm, float yp, float ym, float zp, float zm,
                                                 const float4 &wa, const float4 &wb, float omega, unsigned &umin)
 {
@@ -241,7 +247,7 @@ __device__ __forceinline__ float sor_class_rows(float c, float xp, float xm, flo
     s = __fadd_rn(s, __fmul_rn(ym, wa.w));
     s = __fadd_rn(s, __fmul_rn(zp, wb.x));
     s = __fadd_rn(s, __fmul_rn(zm, wb.y));
-    return relax(c, div_fast(s, make_float2(wb.z, wb.w), umin), omega);
+    return relax(c, div_fast<EXACT>(s, make_float2(wb.z, wb.w), umin), omega);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -270,10 +276,11 @@ __device__ __forceinline__ float sor_aniso(float c, float xp, float xm, float yp
 }
 
 // fused kernel: the exactly rounded reciprocal + one FMA correction (same fast path as div_fast)
+template <bool EXACT = false>
 __device__ __forceinline__ float sor_aniso_fast(float c, float xp, float xm, float yp, float ym, float zp, float zm,
                                                 float2 br, float Ky, float Kz, float omega, unsigned &umin)
 {
-    return relax(c, div_fast(aniso_sum(xp, xm, yp, ym, zp, zm, Ky, Kz), br, umin), omega);
+    return relax(c, div_fast<EXACT>(aniso_sum(xp, xm, yp, ym, zp, zm, Ky, Kz), br, umin), omega);
 }
 
 __device__ __forceinline__ int wrap(int a, int n)

@@ -49,16 +49,24 @@ struct ResParams {
 
 __device__ unsigned long long g_resident_timeouts = 0ULL;
 
-__device__ __forceinline__ int ld_acquire(const int *p)
+// Counter protocol: the writer's bar.sync orders the CTA's stores before thread 0's fence + relaxed store; a reader
+// polls with relaxed loads (no fence per poll) and fences once after it has seen the value.
+__device__ __forceinline__ int ld_relaxed(const int *p)
 {
     int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release(int *p, int v)
+__device__ __forceinline__ void st_relaxed(int *p, int v)
 {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+// Cycle counts of the phases of a pair, summed over the pairs of the middle brick's thread 0 (taub_resident_profile):
+// [0] wait for the neighbours' counters, [1] frame reload, [2] colour A, [3] colour B, [4] publish stores,
+// [5] fence + counter store, [6] pairs, [7] whole launch.
+__device__ unsigned long long g_resident_prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
 // Brick extents: balanced cuts, sizes differ by at most one.
 __host__ __device__ __forceinline__ int cut(int n, int parts, int i) { return (int)(((int64_t)n * i) / parts); }
@@ -266,21 +274,33 @@ resident_kernel(const ResParams P)
         }
     };
 
+    const bool prof = (tid == 0 && blockIdx.x == gridDim.x / 2);
+    const long long t_launch = clock64();
+    long long t_prev = t_launch;
+#define PROF(slot)                                                                         \
+    if (prof) {                                                                            \
+        const long long t_now = clock64();                                                 \
+        atomicAdd(&g_resident_prof[slot], (unsigned long long)(t_now - t_prev));           \
+        t_prev = t_now;                                                                    \
+    }
     for (int n = 0; n < P.n_pairs; ++n) {
         float *wbuf = P.buf[(n & 1) ^ 1];            // pair n publishes into buf[1], buf[0], buf[1], ...
+        if (prof) t_prev = clock64();
         if (n > 0) {
             // ---- wait for the neighbours' pair n-1, then re-read the frame from the buffer they wrote
             if (nb_flag >= 0) {
                 const int target = P.epoch0 + n;
                 const long long t0 = clock64();
-                while (ld_acquire(P.flags + nb_flag) - target < 0) {
+                while (ld_relaxed(P.flags + nb_flag) - target < 0) {
                     if (clock64() - t0 > 4000000000LL) {     // ~2 s: never in a correct run; do not hang the device
                         atomicAdd(&g_resident_timeouts, 1ULL);
                         break;
                     }
                 }
+                fence_gpu();
             }
             __syncthreads();
+            PROF(0);
             // the frame: two bands of 2 x LY rows below / above the brick, then 4 rows beside each of its bx planes
             load_rows(P, K, fld, P.buf[((n - 1) & 1) ^ 1], 4 * LY + 4 * K.bx, warp, lane, [&](int f, int &li, int &lj) {
                 if (f < 4 * LY) {
@@ -297,18 +317,21 @@ resident_kernel(const ResParams P)
             });
         }
         __syncthreads();
+        PROF(1);
         if (per) {
             z_ghosts();
             __syncthreads();
         }
         colour_step(P, K, fld, cod, s_div, P.colour0, a_li0, a_li1, a_lj0, a_lj1, my_r, my_q, rows_per_round);
         __syncthreads();
+        PROF(2);
         if (per) {
             z_ghosts();
             __syncthreads();
         }
         colour_step(P, K, fld, cod, s_div, P.colour0 ^ 1, 2, K.bx + 2, 2, K.by + 2, my_r, my_q, rows_per_round);
         __syncthreads();
+        PROF(3);
         // ---- publish: the voxels the neighbours' frames cover (everything after the last pair)
         const bool last = (n == P.n_pairs - 1);
         for (int r = warp; r < K.bx * K.by; r += R_WARPS) {
@@ -320,10 +343,20 @@ resident_kernel(const ResParams P)
             }
         }
         __syncthreads();
-        // bar.sync orders the CTA's stores before thread 0's release, which is cumulative: a neighbour that acquires
-        // the counter sees every row published above
-        if (tid == 0) st_release(P.flags + blockIdx.x, P.epoch0 + n + 1);
+        PROF(4);
+        // bar.sync orders the CTA's stores before thread 0's fence, which is cumulative: a neighbour that reads the
+        // counter and fences sees every row published above
+        if (tid == 0) {
+            fence_gpu();
+            st_relaxed(P.flags + blockIdx.x, P.epoch0 + n + 1);
+        }
+        PROF(5);
     }
+    if (prof) {
+        atomicAdd(&g_resident_prof[6], (unsigned long long)P.n_pairs);
+        atomicAdd(&g_resident_prof[7], (unsigned long long)(clock64() - t_launch));
+    }
+#undef PROF
 }
 
 struct ResChoice {
@@ -382,6 +415,17 @@ unsigned long long taub_resident_timeouts(void)
 }
 
 size_t taub_sync_ws_ints(void) { return 1024; }
+
+int taub_resident_profile(unsigned long long out[8], int reset)
+{
+    TAUB_REQUIRE(out != nullptr, "taub_resident_profile: null pointer");
+    TAUB_CUDA(cudaMemcpyFromSymbol(out, g_resident_prof, 8 * sizeof(unsigned long long)));
+    if (reset) {
+        const unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        TAUB_CUDA(cudaMemcpyToSymbol(g_resident_prof, zero, sizeof(zero)));
+    }
+    return TAUB_OK;
+}
 
 static int device_sms(int *sms, int *coop)
 {

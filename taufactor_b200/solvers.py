@@ -478,8 +478,8 @@ class SORSolver:
 
     @property
     def inexact_events(self):
-        """Process-wide count of fused-kernel threads that divided a non-zero neighbour sum below
-        2^-100 on the fast path (0 certifies bit-identity with the reference; see taub200.h)."""
+        """Process-wide count of fused-kernel chunks that were redone with IEEE division because a thread met a
+        non-zero neighbour sum below 2^-100 (the fast division is exact everywhere else; see taub200.h)."""
         self._lib.taub_set_device(self._dev_index)
         return int(self._lib.taub_inexact_events())
 

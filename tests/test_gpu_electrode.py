@@ -52,7 +52,7 @@ def test_solve_matches_reference(name, capsys):
     out = S.solve(verbose=False, **skw)
     if S.inexact_events != e0:       # sub-2^-100 neighbour sums: clusters cut off from the inlet decay to 0
         with capsys.disabled():
-            print(f"\n[{name}: {S.inexact_events - e0} fused-kernel threads saw a neighbour sum below 2^-100]")
+            print(f"\n[{name}: {S.inexact_events - e0} fused-kernel chunks were redone with IEEE division (sums below 2^-100)]")
     g = GOLD[name]
     assert S.iter == g["iter"] and bool(S.converged) == g["converged"]
     assert out is S.tau_x
@@ -66,6 +66,22 @@ def test_solve_matches_reference(name, capsys):
         assert np.allclose(S.tau_x, ARR[f"{name}@tau_x"], rtol=5e-3, atol=5e-3, equal_nan=True)
         assert np.allclose(S.k_x, ARR[f"{name}@k_x"], rtol=5e-3, atol=5e-3)
     assert np.allclose(S.Z_sim, ARR[f"{name}@Z_sim"], rtol=1e-5)
+
+
+def test_fused_kernel_redoes_chunks_with_ieee_division_when_a_sum_is_tiny():
+    """el_labels_per holds clusters cut off from the inlet: their values decay geometrically and their neighbour sums
+    fall below 2^-100, where the fused kernel's reciprocal-based division may be one subnormal ulp off.  The kernel
+    then redoes the affected chunks with IEEE division (taub_inexact_events counts them): the field stays bit-identical
+    to the generic kernel (plain __fdiv_rn) all the way."""
+    A, skw = make("el_labels_per")
+    B, _ = make("el_labels_per")
+    B.force_generic = True
+    e0 = A.inexact_events
+    A.solve(verbose=False, **skw)
+    B.solve(verbose=False, **skw)
+    assert A.inexact_events > e0, "this case is here because it reaches sub-2^-100 sums"
+    assert A.iter == B.iter and torch.equal(A.field, B.field)
+    assert np.array_equal(A.tau, B.tau)
 
 
 @pytest.mark.parametrize("periodic", [False, True])

@@ -20,15 +20,23 @@ def timed(S, n):
 for cls in ("Solver", "PeriodicSolver"):
     for N in sizes:
         img = cases.random_img((N, N, N), 0.5, 0)
-        row = []
+        row, prof = [], ""
         for resident in (True, False):
             S = getattr(tau, cls)(img, device="cuda")
             S.use_resident = resident
             n = 1000
             ms = min(timed(S, n) for _ in range(3))
             row.append((S.sweep_kernel_name(), ms / n * 1e3, img.size * n / ms / 1e6, float(S.field.double().sum())))
+            if resident and hasattr(S._lib, "taub_resident_profile"):
+                import ctypes
+                out = (ctypes.c_ulonglong * 8)()
+                S._lib.taub_resident_profile(out, 1)
+                pairs = max(int(out[6]), 1)
+                prof = "  phases (cycles / pair: wait, frame, A, B, publish, flag | launch): " + " ".join(
+                    f"{int(out[i]) / pairs:6.0f}" for i in range(6)) + f" | {int(out[7]) / pairs:6.0f}"
             del S
         same = row[0][3] == row[1][3]
         print(f"{cls:15s} {N:4d}^3  " + "  |  ".join(f"{k:20s} {us:7.2f} us/iter {gl:7.1f} GLUPS" for k, us, gl, _ in row)
               + f"  | checksums equal: {same}", flush=True)
+        print(prof, flush=True)
 print("resident timeouts:", tau._lib.load().taub_resident_timeouts())
