@@ -31,6 +31,8 @@ namespace taub {
 constexpr int R_NT = 512;            // threads per CTA
 constexpr int R_WARPS = R_NT / 32;
 constexpr size_t R_SMEM_MAX = 232448 - 1024;   // opt-in dynamic shared memory per CTA (227 KB) less the static part
+constexpr int R_FLAG_STRIDE = 32;    // ints between two bricks' counters: one 128-byte line each
+constexpr int R_MAX_BRICKS = 256;
 
 struct ResParams {
     taub_geom g;
@@ -44,6 +46,7 @@ struct ResParams {
     int ZS;                  // floats per shared-memory row: round_up(Nz + 8, 8); first half even, second half odd columns
     int *flags;              // one counter per brick (device, persistent): pairs completed, on top of epoch0
     int epoch0;
+    int prof;                // accumulate the phase profile (TAUB_RESIDENT_PROF=1)
     const int *stop;
 };
 
@@ -89,16 +92,22 @@ __device__ __forceinline__ const float *global_row(const ResParams &P, const Bri
     return base + (int64_t)K.b * g.image_stride + (int64_t)(gx + G) * g.plane_stride + (int64_t)sr * g.pitch;
 }
 
-// Rows f = warp, warp + R_WARPS, ... of a list of n rows (row_of(f, li, lj) -> false: skip) from global memory into
-// their shared rows.  A warp first issues the loads of up to R_BATCH rows, then stores them: the global-memory latency
-// is paid once per batch, not once per row (the exchange of a pair is latency bound).
-constexpr int R_BATCH = 8;
+// Row tables (shared memory, built once per launch): everything a pair needs to know about a row is one 8-byte
+// entry, so the steps of a pair do no index arithmetic (a pair is latency bound: ~1000 instructions per thread).
+//   frame / publish rows: .x = float offset of the row in a field buffer (global), .y = float offset of the shared row
+//                         (-1: skip -- a frame row outside the volume holds constants; publish: see RowTab::bnd)
+//   colour-step rows:     .x = float offset of the shared row, .y = uint16 offset of its code row | parity << 30
+struct RowTab {
+    int2 *frame, *pub, *a, *b;
+    int n_frame, n_pub, n_a, n_b;
+};
+constexpr int R_BATCH = 8;      // global loads a warp keeps in flight while it reloads the frame
 
-template <class RowOf>
-__device__ __forceinline__ void load_rows(const ResParams &P, const Brick &K, float *fld, const float *base, int n, int warp,
-                                          int lane, RowOf row_of)
+// Rows f = warp, warp + R_WARPS, ... of a table from global memory into shared memory.  A warp first issues the loads
+// of up to R_BATCH rows, then stores them: the latency is paid once per batch, not once per row.
+__device__ __forceinline__ void load_rows(const int2 *tab, int n, float *fld, const float *base, int ZS, int warp, int lane)
 {
-    const int ZS = P.ZS, ZH = ZS >> 1, RY = P.BY + 4, CG = ZS >> 2;
+    const int ZH = ZS >> 1, CG = ZS >> 2;
     for (int f0 = warp; f0 < n; f0 += R_WARPS * R_BATCH) {
         for (int g0 = 0; g0 < CG; g0 += 32) {
             const int g4 = g0 + lane;
@@ -107,11 +116,11 @@ __device__ __forceinline__ void load_rows(const ResParams &P, const Brick &K, fl
 #pragma unroll
             for (int u = 0; u < R_BATCH; ++u) {
                 const int f = f0 + u * R_WARPS;
-                int li = 0, lj = 0;
                 dst[u] = -1;
-                if (f < n && g4 < CG && row_of(f, li, lj)) {
-                    dst[u] = (li * RY + lj) * ZS;
-                    v[u] = __ldcg(reinterpret_cast<const float4 *>(global_row(P, K, base, li, lj)) + g4);
+                if (f < n && g4 < CG) {
+                    const int2 d = tab[f];
+                    dst[u] = d.y;
+                    if (d.y >= 0) v[u] = __ldcg(reinterpret_cast<const float4 *>(base + d.x) + g4);
                 }
             }
 #pragma unroll
@@ -144,27 +153,24 @@ __device__ __forceinline__ void store_row(float *grow, const float *srow, int ZS
     }
 }
 
-// One colour step on shared rows li in [li0, li1), lj in [lj0, lj1) (in place: an active voxel only reads voxels of
-// the other colour).  Thread = (row slot, float4 group of the active half row).
-__device__ __forceinline__ void colour_step(const ResParams &P, const Brick &K, float *fld, const uint16_t *cod,
-                                            const float2 *s_div, int colour, int li0, int li1, int lj0, int lj1,
-                                            int my_r, int my_q, int rows_per_round)
+// One colour step on the rows of a table (in place: an active voxel only reads voxels of the other colour).
+// Thread = (row slot, float4 group of the active half row).
+__device__ __forceinline__ void colour_step(const int2 *tab, int nrows, float *fld, const uint16_t *cod, const float2 *s_div,
+                                            int colour, int ZS, int row_stride, float omega, int my_r, int my_q,
+                                            int rows_per_round)
 {
-    const int ZS = P.ZS, ZH = ZS >> 1, RY = P.BY + 4, CY = P.BY + 2, CG = ZS >> 2;
-    const int nj = lj1 - lj0, nrows = (li1 - li0) * nj;
-    if (nj <= 0 || my_r >= rows_per_round) return;
-    const float omega = P.omega;
+    const int ZH = ZS >> 1;
+    if (my_r >= rows_per_round) return;
     for (int r = my_r; r < nrows; r += rows_per_round) {
-        const int di = r / nj;
-        const int li = li0 + di, lj = lj0 + (r - di * nj);
+        const int2 d = tab[r];
         // voxel (i, j, k) is active when (i + j + k) % 2 == colour; k and the storage column have the same parity
-        const int par = (K.x0 + li + K.y0 + lj + colour) & 1;      // 0: even columns (E) active, 1: odd columns (O)
-        float *row = fld + (size_t)(li * RY + lj) * ZS;
+        const int par = ((d.y >> 30) ^ colour) & 1;                 // 0: even columns (E) active, 1: odd columns (O)
+        float *row = fld + d.x;
         float *act = row + (par ? ZH : 0) + 4 * my_q;
         const float *oth = row + (par ? 0 : ZH) + 4 * my_q;
         float4 c = *reinterpret_cast<const float4 *>(act);
-        const float4 xp = *reinterpret_cast<const float4 *>(act + (size_t)RY * ZS);
-        const float4 xm = *reinterpret_cast<const float4 *>(act - (size_t)RY * ZS);
+        const float4 xp = *reinterpret_cast<const float4 *>(act + row_stride);
+        const float4 xm = *reinterpret_cast<const float4 *>(act - row_stride);
         const float4 yp = *reinterpret_cast<const float4 *>(act + ZS);
         const float4 ym = *reinterpret_cast<const float4 *>(act - ZS);
         const float4 z4 = *reinterpret_cast<const float4 *>(oth);
@@ -173,8 +179,7 @@ __device__ __forceinline__ void colour_step(const ResParams &P, const Brick &K, 
         const float4 zp = par ? make_float4(z4.y, z4.z, z4.w, ze) : z4;
         const float4 zm = par ? z4 : make_float4(ze, z4.x, z4.y, z4.z);
         // neighbour counts: code words of storage groups 2q, 2q+1; E voxels are nibbles 0 and 2, O voxels 1 and 3
-        const unsigned cw = *reinterpret_cast<const unsigned *>(cod + (size_t)((li - 1) * CY + (lj - 1)) * CG + 2 * my_q) >>
-                            (par ? 4 : 0);
+        const unsigned cw = *reinterpret_cast<const unsigned *>(cod + (d.y & 0x3fffffff) + 2 * my_q) >> (par ? 4 : 0);
         const float2 d0 = s_div[cw & 15u], d1 = s_div[(cw >> 8) & 15u], d2 = s_div[(cw >> 16) & 15u],
                      d3 = s_div[(cw >> 24) & 15u];
         unsigned um = 0xffffffffu;
@@ -216,22 +221,75 @@ resident_kernel(const ResParams P)
         K.bx = K.x1 - K.x0;
         K.by = K.y1 - K.y0;
     }
+    const bool per = g.periodic != 0;
     const int ZS = P.ZS, ZH = ZS >> 1, RY = P.BY + 4, CY = P.BY + 2, CG = ZS >> 2;
+    const int LX = K.bx + 4, LY = K.by + 4;     // rows held: the brick and its 2-wide frame
     float *fld = reinterpret_cast<float *>(r_smem);                                 // [BX+4][BY+4][ZS]
     uint16_t *cod = reinterpret_cast<uint16_t *>(fld + (size_t)(P.BX + 4) * RY * ZS);  // [BX+2][BY+2][ZS/4]
-    const int LX = K.bx + 4, LY = K.by + 4;     // rows held: the brick and its 2-wide frame
+    RowTab T;
+    T.frame = reinterpret_cast<int2 *>(cod + (((size_t)(P.BX + 2) * CY * CG + 3) & ~(size_t)3));   // 8-byte aligned
+    T.pub = T.frame + 4 * (P.BY + 4) + 4 * P.BX;
+    T.a = T.pub + P.BX * P.BY;
+    T.b = T.a + (P.BX + 2) * (P.BY + 2);
+    // the steps never touch a Dirichlet plane, nor (no-flux solvers) a row outside the volume
+    const int a_li0 = (K.x0 == 0) ? 2 : 1, a_li1 = (K.x1 == g.Nx) ? K.bx + 2 : K.bx + 3;
+    const int a_lj0 = (!per && K.y0 == 0) ? 2 : 1, a_lj1 = (!per && K.y1 == g.Ny) ? K.by + 2 : K.by + 3;
+    T.n_frame = 4 * LY + 4 * K.bx;
+    T.n_pub = K.bx * K.by;
+    T.n_a = (a_li1 - a_li0) * (a_lj1 - a_lj0);
+    T.n_b = K.bx * K.by;
+    // global float offset of shared row (li, lj): x = x0 - 2 + li, y = y0 - 2 + lj (wrapped for the periodic solvers)
+    auto goff = [&](int li, int lj) {
+        const int gx = K.x0 - 2 + li, gy = K.y0 - 2 + lj;
+        const int sr = per ? G + wrap(gy, g.Ny) : G + gy;
+        return (int)((int64_t)K.b * g.image_stride + (int64_t)(gx + G) * g.plane_stride + (int64_t)sr * g.pitch);
+    };
+    auto soff = [&](int li, int lj) { return (li * RY + lj) * ZS; };
+    for (int f = tid; f < T.n_frame; f += R_NT) {
+        // the frame: two bands of 2 x LY rows below / above the brick, then 4 rows beside each of its bx planes
+        int li, lj;
+        if (f < 4 * LY) {
+            const int band = f / LY;                  // 0, 1: planes 0, 1; 2, 3: planes bx+2, bx+3
+            li = band < 2 ? band : K.bx + band;
+            lj = f - band * LY;
+        } else {
+            const int e = f - 4 * LY, c = e & 3;
+            li = 2 + (e >> 2);
+            lj = c < 2 ? c : K.by + c;
+        }
+        const int gx = K.x0 - 2 + li, gy = K.y0 - 2 + lj;
+        const bool moving = gx >= 0 && gx < g.Nx && (per || (gy >= 0 && gy < g.Ny));   // outside: constants, loaded once
+        T.frame[f] = make_int2(goff(li, lj), moving ? soff(li, lj) : -1);
+    }
+    for (int r = tid; r < T.n_pub; r += R_NT) {
+        const int oi = r / K.by, oj = r - oi * K.by;
+        const bool bnd = oi < 2 || oi >= K.bx - 2 || oj < 2 || oj >= K.by - 2;   // a neighbour's frame covers this row
+        // .y: shared offset, bit 30 = interior row (published after the last pair only)
+        T.pub[r] = make_int2(goff(oi + 2, oj + 2), soff(oi + 2, oj + 2) | (bnd ? 0 : 1 << 30));
+        T.b[r] = make_int2(soff(oi + 2, oj + 2), (((oi + 1) * CY + oj + 1) * CG) | (((K.x0 + oi + K.y0 + oj) & 1) << 30));
+    }
+    for (int r = tid; r < T.n_a; r += R_NT) {
+        const int nj = a_lj1 - a_lj0, di = r / nj;
+        const int li = a_li0 + di, lj = a_lj0 + (r - di * nj);
+        T.a[r] = make_int2(soff(li, lj), (((li - 1) * CY + lj - 1) * CG) | (((K.x0 + li + K.y0 + lj) & 1) << 30));
+    }
 
     // ---- start: the brick and its frame from the current field, neighbour codes of the brick and its first ring
-    load_rows(P, K, fld, P.buf[0], LX * LY, warp, lane, [&](int f, int &li, int &lj) {
-        li = f / LY;
-        lj = f - li * LY;
-        return true;
-    });
+    for (int r = warp; r < LX * LY; r += R_WARPS) {
+        const int li = r / LY, lj = r - li * LY;
+        const float *grow = P.buf[0] + goff(li, lj);
+        float *srow = fld + soff(li, lj);
+        for (int g4 = lane; g4 < CG; g4 += 32) {
+            const float4 v = __ldcg(reinterpret_cast<const float4 *>(grow) + g4);
+            *reinterpret_cast<float2 *>(srow + 2 * g4) = make_float2(v.x, v.z);
+            *reinterpret_cast<float2 *>(srow + ZH + 2 * g4) = make_float2(v.y, v.w);
+        }
+    }
     for (int r = warp; r < (LX - 2) * (LY - 2); r += R_WARPS) {
         const int ci = r / (LY - 2), cj = r - ci * (LY - 2);
         const int gx = K.x0 - 1 + ci, gy = K.y0 - 1 + cj;
-        const bool inside = gx >= 0 && gx < g.Nx && (g.periodic || (gy >= 0 && gy < g.Ny));
-        const int sr = g.periodic ? G + wrap(gy, g.Ny) : G + gy;
+        const bool inside = gx >= 0 && gx < g.Nx && (per || (gy >= 0 && gy < g.Ny));
+        const int sr = per ? G + wrap(gy, g.Ny) : G + gy;
         const uint16_t *grow = P.codes + ((int64_t)K.b * g.planes + (gx + G)) * g.rows * (g.pitch >> 2) + (int64_t)sr * (g.pitch >> 2);
         for (int g4 = lane; g4 < CG; g4 += 32) {
             unsigned w = inside ? (unsigned)__ldg(grow + g4) : 0u;
@@ -243,15 +301,13 @@ resident_kernel(const ResParams P)
         }
     }
 
-    // ---- geometry of the steps (shared-row indices)
-    const bool per = g.periodic != 0;
-    const int a_li0 = (K.x0 == 0) ? 2 : 1, a_li1 = (K.x1 == g.Nx) ? K.bx + 2 : K.bx + 3;   // never a Dirichlet plane
-    const int a_lj0 = (!per && K.y0 == 0) ? 2 : 1, a_lj1 = (!per && K.y1 == g.Ny) ? K.by + 2 : K.by + 3;
     const int QN = ZS >> 3;                         // float4 groups per half row
     const int rows_per_round = R_NT / QN;
     const int my_r = tid / QN, my_q = tid - my_r * QN;
+    const int row_stride = RY * ZS;
 
-    // neighbour bricks whose counters gate this brick's frame (threads 0..8, centre excluded)
+    // neighbour bricks whose counters gate this brick's frame (threads 0..8, centre excluded); every counter has a
+    // 128-byte line of its own: hundreds of pollers on one line would delay the very store they are waiting for
     int nb_flag = -1;
     if (tid < 9 && tid != 4) {
         const int nbi = K.bi + tid / 3 - 1;
@@ -261,20 +317,18 @@ resident_kernel(const ResParams P)
             nbj = wrap(nbj, P.nby);
         else
             ok = ok && nbj >= 0 && nbj < P.nby;
-        if (ok && !(nbi == K.bi && nbj == K.bj)) nb_flag = (K.b * P.nbx + nbi) * P.nby + nbj;
+        if (ok && !(nbi == K.bi && nbj == K.bj)) nb_flag = ((K.b * P.nbx + nbi) * P.nby + nbj) * R_FLAG_STRIDE;
     }
     // periodic z: ghost column 3 := column Nz + 3 (odd), ghost column Nz + 4 := column 4 (even); Nz is even here
     auto z_ghosts = [&]() {
-        const int nj = a_lj1 - a_lj0, nrows = (a_li1 - a_li0) * nj;
-        for (int r = tid; r < nrows; r += R_NT) {
-            const int di = r / nj;
-            float *row = fld + (size_t)((a_li0 + di) * RY + a_lj0 + (r - di * nj)) * ZS;
+        for (int r = tid; r < T.n_a; r += R_NT) {
+            float *row = fld + T.a[r].x;
             row[ZH + 1] = row[ZH + ((g.Nz + 3) >> 1)];
             row[(g.Nz + COL0) >> 1] = row[COL0 >> 1];
         }
     };
 
-    const bool prof = (tid == 0 && blockIdx.x == gridDim.x / 2);
+    const bool prof = (P.prof != 0 && tid == 0 && blockIdx.x == gridDim.x / 2);
     const long long t_launch = clock64();
     long long t_prev = t_launch;
 #define PROF(slot)                                                                         \
@@ -292,6 +346,7 @@ resident_kernel(const ResParams P)
                 const int target = P.epoch0 + n;
                 const long long t0 = clock64();
                 while (ld_relaxed(P.flags + nb_flag) - target < 0) {
+                    __nanosleep(20);
                     if (clock64() - t0 > 4000000000LL) {     // ~2 s: never in a correct run; do not hang the device
                         atomicAdd(&g_resident_timeouts, 1ULL);
                         break;
@@ -301,20 +356,7 @@ resident_kernel(const ResParams P)
             }
             __syncthreads();
             PROF(0);
-            // the frame: two bands of 2 x LY rows below / above the brick, then 4 rows beside each of its bx planes
-            load_rows(P, K, fld, P.buf[((n - 1) & 1) ^ 1], 4 * LY + 4 * K.bx, warp, lane, [&](int f, int &li, int &lj) {
-                if (f < 4 * LY) {
-                    const int band = f / LY;                  // 0, 1: planes 0, 1; 2, 3: planes bx+2, bx+3
-                    li = band < 2 ? band : K.bx + band;
-                    lj = f - band * LY;
-                } else {
-                    const int e = f - 4 * LY, c = e & 3;
-                    li = 2 + (e >> 2);
-                    lj = c < 2 ? c : K.by + c;
-                }
-                const int gx = K.x0 - 2 + li, gy = K.y0 - 2 + lj;
-                return gx >= 0 && gx < g.Nx && (per || (gy >= 0 && gy < g.Ny));   // outside: constants, loaded once
-            });
+            load_rows(T.frame, T.n_frame, fld, P.buf[((n - 1) & 1) ^ 1], ZS, warp, lane);
         }
         __syncthreads();
         PROF(1);
@@ -322,25 +364,21 @@ resident_kernel(const ResParams P)
             z_ghosts();
             __syncthreads();
         }
-        colour_step(P, K, fld, cod, s_div, P.colour0, a_li0, a_li1, a_lj0, a_lj1, my_r, my_q, rows_per_round);
+        colour_step(T.a, T.n_a, fld, cod, s_div, P.colour0, ZS, row_stride, P.omega, my_r, my_q, rows_per_round);
         __syncthreads();
         PROF(2);
         if (per) {
             z_ghosts();
             __syncthreads();
         }
-        colour_step(P, K, fld, cod, s_div, P.colour0 ^ 1, 2, K.bx + 2, 2, K.by + 2, my_r, my_q, rows_per_round);
+        colour_step(T.b, T.n_b, fld, cod, s_div, P.colour0 ^ 1, ZS, row_stride, P.omega, my_r, my_q, rows_per_round);
         __syncthreads();
         PROF(3);
         // ---- publish: the voxels the neighbours' frames cover (everything after the last pair)
-        const bool last = (n == P.n_pairs - 1);
-        for (int r = warp; r < K.bx * K.by; r += R_WARPS) {
-            const int oi = r / K.by, oj = r - oi * K.by;
-            if (last || oi < 2 || oi >= K.bx - 2 || oj < 2 || oj >= K.by - 2) {
-                float *grow = wbuf + (int64_t)K.b * g.image_stride + (int64_t)(K.x0 + oi + G) * g.plane_stride +
-                              (int64_t)(K.y0 + oj + G) * g.pitch;
-                store_row(grow, fld + (size_t)((oi + 2) * RY + oj + 2) * ZS, ZS, g.Nz, lane);
-            }
+        const int skip_mask = (n == P.n_pairs - 1) ? 0 : 1 << 30;
+        for (int r = warp; r < T.n_pub; r += R_WARPS) {
+            const int2 d = T.pub[r];
+            if (!(d.y & skip_mask)) store_row(wbuf + d.x, fld + (d.y & 0x3fffffff), ZS, g.Nz, lane);
         }
         __syncthreads();
         PROF(4);
@@ -348,7 +386,7 @@ resident_kernel(const ResParams P)
         // counter and fences sees every row published above
         if (tid == 0) {
             fence_gpu();
-            st_relaxed(P.flags + blockIdx.x, P.epoch0 + n + 1);
+            st_relaxed(P.flags + blockIdx.x * R_FLAG_STRIDE, P.epoch0 + n + 1);
         }
         PROF(5);
     }
@@ -367,7 +405,8 @@ struct ResChoice {
 
 static size_t resident_smem(int BX, int BY, int ZS)
 {
-    return (size_t)(BX + 4) * (BY + 4) * ZS * 4 + (size_t)(BX + 2) * (BY + 2) * (ZS / 4) * 2 + 16;
+    const size_t tables = (size_t)(4 * (BY + 4) + 4 * BX) + 2 * (size_t)BX * BY + (size_t)(BX + 2) * (BY + 2);   // int2 entries
+    return (size_t)(BX + 4) * (BY + 4) * ZS * 4 + (size_t)(BX + 2) * (BY + 2) * (ZS / 4) * 2 + tables * 8 + 16;
 }
 
 // Bricks: at most one per SM; smallest colour-A region ((BX + 2) x (BY + 2) rows per CTA), then the fewest frame rows.
@@ -414,7 +453,7 @@ unsigned long long taub_resident_timeouts(void)
     return v;
 }
 
-size_t taub_sync_ws_ints(void) { return 1024; }
+size_t taub_sync_ws_ints(void) { return (size_t)R_MAX_BRICKS * R_FLAG_STRIDE; }
 
 int taub_resident_profile(unsigned long long out[8], int reset)
 {
@@ -468,7 +507,7 @@ int taub_resident_pairs(taub_problem *p, int64_t iter, int n_pairs, void *stream
     if (int rc = device_sms(&sms, &coop)) return rc;
     const ResChoice c = choose_bricks(g, sms);
     const int bricks = g.bs * c.nbx * c.nby;
-    TAUB_REQUIRE(bricks <= (int)taub_sync_ws_ints(), "taub_resident_pairs: more bricks than counters");
+    TAUB_REQUIRE(bricks <= R_MAX_BRICKS, "taub_resident_pairs: more bricks than counters");
     ResParams P;
     P.g = g;
     P.buf[0] = p->field[p->cur];
@@ -485,6 +524,11 @@ int taub_resident_pairs(taub_problem *p, int64_t iter, int n_pairs, void *stream
     P.flags = p->sync_ws;
     P.epoch0 = p->sync_epoch;
     P.stop = p->stop;
+    static const int prof_on = [] {
+        const char *e = getenv("TAUB_RESIDENT_PROF");
+        return (e && *e) ? atoi(e) : 0;
+    }();
+    P.prof = prof_on;
     int dev = 0;
     TAUB_CUDA(cudaGetDevice(&dev));
     static size_t smem_set[64] = {0};
