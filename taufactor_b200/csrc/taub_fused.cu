@@ -227,30 +227,16 @@ __device__ __forceinline__ void row_update_aniso(float4 &c, const float4 &xp, co
 template <int V>
 using IC = std::integral_constant<int, V>;
 
-// Thread work item = a COLUMN of NRW vertically adjacent rows x one float4 group.  In every step the
-// rows of a column alternate between "xz" and "yw" rows and swap roles each step; the column's internal
-// y-neighbours stay in registers, only the rows above and below it come from shared memory.  PA0 = parity
-// of the column's first row at step 0 (uniform over the whole grid, chosen by the host), so every step
-// body is branch-free.
-//
-// OP ("odd periodic"): a periodic extent Ny or Nz is odd, so the wrap joins two voxels of the SAME colour and a
-// ghost cell is the image of a voxel whose colour differs from the ghost's own index parity.  The reference reads
-// ghost SNAPSHOTS taken before each iteration (taufactor.py:501-505); with the images loaded once per pass that is
-// reproduced exactly by leaving the ghost ring of the odd axis out of the colour-A step: where the imaged voxel has
-// colour B the snapshot before iteration t+1 equals the loaded value, and where it has colour A no colour-B voxel
-// reads it (rule pinned on the CPU by tests/test_fused_odd_periodic_cpu.py, on the GPU by the odd periodic goldens).
-template <int OGT, int PA0, int KIND, bool OP = false>   // OGT: output groups per tile row (compile-time tile width);
-__global__ void __launch_bounds__(F_NT, 2)              // KIND: TAUB_BINARY (4-bit codes) or a class kind (ids)
-fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tmap,
-                    const __grid_constant__ CUtensorMap cmap)
+// The march of one CTA over its chunk of planes (the whole kernel but its one-time set-up).  EXACT = false: the fast
+// exact-reciprocal division; returns whether this thread met a non-zero neighbour sum below 2^-100, where that division
+// may be off by one subnormal ulp.  EXACT = true: IEEE division -- the kernel calls it (fused_march_exact, a separate
+// out-of-line copy of the code with its own registers, so the common case pays nothing) to redo the chunk of a CTA
+// that reported such a sum: the source buffer is read-only during the pass, so the second run simply overwrites the
+// first one's output.  The fused kernel therefore equals IEEE division for every finite input.
+template <int OGT, int PA0, int KIND, bool OP, bool EXACT>
+__device__ __forceinline__ bool fused_march(const FusedParams &P, const CUtensorMap *tmap_p, const CUtensorMap *cmap_p,
+                                            unsigned char *smem_raw, const float2 *s_div)
 {
-    // Programmatic dependent launch (opt-in, taub_iterate flags bit 1): let the next pass of the stream be
-    // scheduled as soon as every CTA of this one has started, so that its launch latency and shared-memory
-    // prologue overlap this pass's tail.  A no-op for an ordinary launch.
-    pdl_trigger();
-    extern __shared__ unsigned char smem_dyn[];
-    // TMA destinations need 128-byte alignment: align the base, slots are multiples of 128 B
-    unsigned char *smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
     const taub_geom &g = P.g;
     constexpr bool ANI = (KIND == TAUB_ANISOTROPIC);
     constexpr bool MPC = (KIND == TAUB_MULTIPHASE_CLASS);
@@ -269,7 +255,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     unsigned char *cplanes = smem_raw + (size_t)NB * slotB;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(cplanes + (size_t)NBC * cslotB);
     float4 *s_tab = reinterpret_cast<float4 *>(mbar + 16);   // class kind: staged weight rows
-    __shared__ __align__(512) float2 s_div[ANISO_CLASSES];   // static: constant address; aligned for the OR look-up
+    const uint32_t mbar_u32 = smem_u32(mbar);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int tk = blockIdx.x % P.tiles_k, tj = blockIdx.x / P.tiles_k;
@@ -280,6 +266,354 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     const int PG = g.pitch >> 2;
     const int total_rel = c1 - c0 + 4;           // planes c0-2 .. c1+1
     const int64_t ps = g.plane_stride;
+    const ClassTab ctab{tab4, smem_u32(s_tab), (unsigned)P.tab_k};
+    const float Ky = ANI ? P.table[2 * ANISO_CLASSES] : 0.0f, Kz = ANI ? P.table[2 * ANISO_CLASSES + 1] : 0.0f;
+    const uint32_t div_base = smem_u32(s_div);
+    unsigned umin = 0xffffffffu;   // guard word of every neighbour sum this thread divides
+
+    // ---- TMA producer (thread 0): plane rel (local plane c0-2+rel) -> field slot rel % NB, code slot rel % NBC,
+    //      one box each; the part of a box outside the tensor reads as 0.  The slot offsets and the plane
+    //      coordinate of the next box are carried along instead of being recomputed from rel.
+    const uint32_t planes_u32 = smem_u32(planes), cplanes_u32 = smem_u32(cplanes);
+    const uint32_t tx_bytes = (uint32_t)LR * (ROWB + CROWB);
+    uint32_t is_f = 0, is_c = 0, is_bar = mbar_u32;   // next issue: field / code slot byte offset, barrier address
+    int is_pl = b * g.planes + (c0 - 2 + G);          // ... and tensor plane coordinate
+    // with_codes = false: plane c0-2 (rel 0) is only ever an x- neighbour, nothing on it is updated, so its codes / ids
+    // are never read -- and must not be loaded: the binary kind's code ring has fewer slots (4) than the prologue has
+    // boxes in flight (5), and two boxes in flight into the same slot (rel 0 and rel 4) may land in either order
+    auto issue = [&](const bool with_codes) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(is_bar, with_codes ? tx_bytes : (uint32_t)LR * ROWB);
+        tma_load_3d(planes_u32 + is_f, tmap_p, 4 * G0, R0, is_pl, is_bar);
+        if (with_codes) tma_load_3d(cplanes_u32 + is_c, cmap_p, G0 * CPG, R0, is_pl, is_bar);
+        ++is_pl;
+        is_f += slotB;
+        is_bar += 8u;
+        if (is_f == NB * slotB) {
+            is_f = 0;
+            is_bar = mbar_u32;
+        }
+        is_c += cslotB;
+        if (is_c == NBC * cslotB) is_c = 0;
+    };
+    if (tid == 0)
+        for (int rel = 0; rel < min(NB - 1, total_rel); ++rel) issue(rel > 0);
+
+    // ---- this thread's column: rows lr0 .. lr0+NRW-1 of the tile, group gg.  Threads beyond the tile's columns
+    //      (m >= NCT) shadow column 0 of their group: they load and compute like everybody else (no divergence in
+    //      the step body) but never store anything.
+    const int NCT = (LR - 2) / NRW;          // columns stacked in the tile
+    const int m_raw = tid / LGt, gg = tid - m_raw * LGt;
+    const bool own = m_raw < NCT;            // has cells in the shared-memory tile
+    const int m = own ? m_raw : 0;
+    const int lr0 = 1 + NRW * m;
+    const int Ra = R0 + lr0, Gs = G0 + gg;
+    const bool doit = own && (Gs < PG) && (Ra < g.rows);
+    const bool colB = gg >= 1 && gg < LGt - 1 && Gs >= 1 && Gs < 1 + interior_groups(g.Nz);
+    unsigned canB = 0;                       // bit r: row r of the column is an output row
+#pragma unroll
+    for (int r = 0; r < NRW; ++r)
+        if (doit && colB && lr0 + r >= 2 && lr0 + r < LR - 2 && Ra + r >= G && Ra + r < G + g.Ny) canB |= 1u << r;
+    // OP: ghost rows (odd Ny) keep their snapshot in the colour-A step, and so do the ghost columns k = -1
+    // (.w of group 0) and k = Nz (component Nz % 4 of group (Nz + 4) / 4) for odd Nz
+    unsigned keep_rows = 0;
+    bool keep_lo_w = false, keep_hi_y = false, keep_hi_w = false;
+    if (OP) {
+        if (g.Ny & 1) {
+#pragma unroll
+            for (int r = 0; r < NRW; ++r)
+                if (Ra + r < G || Ra + r >= G + g.Ny) keep_rows |= 1u << r;
+        }
+        if (g.Nz & 1) {
+            keep_lo_w = (Gs == 0);
+            keep_hi_y = (Gs == ((g.Nz + COL0) >> 2)) && ((g.Nz & 3) == 1);
+            keep_hi_w = (Gs == ((g.Nz + COL0) >> 2)) && ((g.Nz & 3) == 3);
+        }
+    }
+    // shared-window addresses of row 0 of the column in field slot 0 / id-code slot 0 (row r: + r * ROWB / CROWB)
+    const uint32_t tbase = planes_u32 + (uint32_t)(lr0 * LG + gg) * 16u;
+    const uint32_t cbase = cplanes_u32 + (uint32_t)((lr0 * LGc + gg) * CPG) * 2u;
+    const bool lane_lo = (lane == 0), lane_hi = (lane == 31);
+    // which of this thread's rows other threads read: the column's first and last row (their above / below) and,
+    // at the two ends of a warp, every row (z_neighbour fall-back of the adjacent warp)
+    const bool st_mid = own && (lane_lo || lane_hi);
+    // colour B first writes plane c0 (at step 2)
+    float *dst0 = P.dst + (int64_t)b * g.image_stride + 4 * Gs + (int64_t)(c0 + G) * ps + (int64_t)Ra * g.pitch;
+
+    // ---- register ring: rg[r][k] holds plane (c0-3+k+4j) of row r; at step s = 4j+ss:
+    //      a[p-2] = rg[.][ss], a[p-1] = rg[.][ss+1], raw[p] -> a[p] = rg[.][ss+2], raw[p+1] = rg[.][ss+3]
+    float4 rg[NRW][4];
+    unsigned cr[NRW / 2][4];   // binary: neighbour codes, two rows per word, same ring positions
+    mbar_wait(mbar_u32, 0);
+    mbar_wait(mbar_u32 + 8u * (1 % NB), 0);
+#pragma unroll
+    for (int r = 0; r < NRW; ++r) {
+        rg[r][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        rg[r][3] = make_float4(0.f, 0.f, 0.f, 0.f);
+        rg[r][1] = ld_sh<float4>(tbase + r * ROWB);
+        rg[r][2] = ld_sh<float4>(tbase + slotB + r * ROWB);
+    }
+#pragma unroll
+    for (int q = 0; q < NRW / 2; ++q) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cr[q][k] = 0;
+        if (!CLS)
+            cr[q][2] = (unsigned)ld_sh<uint16_t>(cbase + cslotB + 2 * q * CROWB) |
+                       ((unsigned)ld_sh<uint16_t>(cbase + cslotB + (2 * q + 1) * CROWB) << 16);
+    }
+
+    const int n_steps = c1 - c0 + 2;
+
+    // ---- ring state of step s (all warp-uniform): field slots of planes p-1, p, p+1 and the mbarrier of p+1;
+    //      code / id slots of the same planes.  Rotated at the end of every step.
+    uint32_t oM1 = 0, oP = slotB, oP1 = 2u * slotB;               // s % NB, (s+1) % NB, (s+2) % NB at s = 0
+    uint32_t w_bar = mbar_u32 + 16u, w_par = 0;                      // barrier / parity of plane rel = s+2
+    uint32_t kM1 = 0, kP = cslotB, kP1 = 2u * cslotB;                // code / id slots: s % NBC, ... (NBC >= 4)
+
+    // One step of the march.  FAST: every plane-range flag is true and there are no peer stores (steady state).
+    auto step = [&](auto fast_c, auto ss_c, const int s) {
+        constexpr bool FAST = decltype(fast_c)::value != 0;
+                constexpr int ss = decltype(ss_c)::value;
+        constexpr int iM2 = ss & 3, iM1 = (ss + 1) & 3, iP = (ss + 2) & 3, iP1 = (ss + 3) & 3;
+        const int p = c0 - 1 + s;   // plane receiving colour A; colour B goes to plane p-1
+        __syncthreads();            // ring slot of plane p-2 is free; a[p-1] is visible in its slot
+        if (tid == 0 && (FAST || s - 1 + NB < total_rel)) issue(true);
+        mbar_wait(w_bar, w_par);
+        const uint32_t aM1 = tbase + oM1, aP = tbase + oP, aP1 = tbase + oP1;   // this column in the three slots
+        const bool doA = FAST || ((p >= P.a_lo) && (p < P.a_hi));
+        const bool keepA = FAST || ((p >= c0) && (p < c1));   // a[p] is read by colour B of plane p next step
+        const bool doB = FAST || (s >= 2);
+        // one-sided halo exchange: output plane p-1 is one of the neighbour's ghost planes
+        const bool send_lo = !FAST && P.peer_lo != nullptr && (p - 1) < G;
+        const bool send_hi = !FAST && P.peer_hi != nullptr && (p - 1) >= g.Nx - G;
+#pragma unroll
+        for (int r = 0; r < NRW; ++r) rg[r][iP1] = ld_sh<float4>(aP1 + r * ROWB);
+        if (!CLS) {
+#pragma unroll
+            for (int q = 0; q < NRW / 2; ++q)
+                cr[q][iP1] = (unsigned)ld_sh<uint16_t>(cbase + kP1 + 2 * q * CROWB) |
+                             ((unsigned)ld_sh<uint16_t>(cbase + kP1 + (2 * q + 1) * CROWB) << 16);
+        }
+        if (doA) {   // block-uniform
+            // the z neighbour from the adjacent lane's registers (one crossbar pass instead of a 4-way conflicted
+            // shared load); the two lanes at the warp ends read shared memory
+            float zs[NRW];
+#pragma unroll
+            for (int r = 0; r < NRW; ++r) {
+                if (((PA0 + ss + r) & 1) == 0) {
+                    zs[r] = __shfl_up_sync(0xffffffffu, rg[r][iP].w, 1);
+                    if (lane_lo) zs[r] = ld_sh<float>(aP + r * ROWB - 4);
+                } else {
+                    zs[r] = __shfl_down_sync(0xffffffffu, rg[r][iP].x, 1);
+                    if (lane_hi) zs[r] = ld_sh<float>(aP + r * ROWB + 16);
+                }
+            }
+            const float4 below = lds128<-(int)ROWB>(aP), above = lds128<(int)(NRW * ROWB)>(aP);
+            uint2 ids[NRW];
+            if (CLS) {
+#pragma unroll
+                for (int r = 0; r < NRW; ++r) ids[r] = ld_sh<uint2>(cbase + kP + r * CROWB);
+            }
+            float4 snap[NRW];
+            if (OP) {
+#pragma unroll
+                for (int r = 0; r < NRW; ++r) snap[r] = rg[r][iP];
+            }
+#pragma unroll
+            for (int r = 0; r < NRW; ++r) {
+                // neighbours inside the column are registers; each row only reads the components
+                // its neighbours leave unchanged in this step
+                const float4 &dn = (r == 0) ? below : rg[r - 1][iP];
+                const float4 &up = (r == NRW - 1) ? above : rg[r + 1][iP];
+                if (((PA0 + ss + r) & 1) == 0) {
+                    if (ANI)
+                        row_update_aniso<true, EXACT>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], ids[r], s_div, Ky, Kz, P.omega, umin);
+                    else if (CLS)
+                        row_update_class<true, EXACT>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], ids[r], ctab, P.omega, umin);
+                    else if (r & 1)
+                        row_update<true, 16, EXACT>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], cr[r >> 1][iP], div_base, P.omega, umin);
+                    else
+                        row_update<true, 0, EXACT>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], cr[r >> 1][iP], div_base, P.omega, umin);
+                } else {
+                    if (ANI)
+                        row_update_aniso<false, EXACT>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], ids[r], s_div, Ky, Kz, P.omega, umin);
+                    else if (CLS)
+                        row_update_class<false, EXACT>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], ids[r], ctab, P.omega, umin);
+                    else if (r & 1)
+                        row_update<false, 16, EXACT>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], cr[r >> 1][iP], div_base, P.omega, umin);
+                    else
+                        row_update<false, 0, EXACT>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], cr[r >> 1][iP], div_base, P.omega, umin);
+                }
+            }
+            if (OP) {   // ghost cells of an odd periodic axis keep their snapshot
+#pragma unroll
+                for (int r = 0; r < NRW; ++r) {
+                    if (keep_rows & (1u << r)) {
+                        rg[r][iP] = snap[r];
+                    } else {
+                        if (keep_lo_w || keep_hi_w) rg[r][iP].w = snap[r].w;
+                        if (keep_hi_y) rg[r][iP].y = snap[r].y;
+                    }
+                }
+            }
+            if (keepA) {
+                // other threads read the column's first and last row (their above / below) and, at the two ends
+                // of a warp, the neighbour lane's group (z_neighbour fall-back)
+#pragma unroll
+                for (int r = 0; r < NRW; ++r)
+                    if ((r == 0 || r == NRW - 1) ? own : st_mid) st_sh<float4>(aP + r * ROWB, rg[r][iP]);
+            }
+        }
+        if (doB) {   // block-uniform
+            float zs[NRW];
+#pragma unroll
+            for (int r = 0; r < NRW; ++r) {
+                if (((PA0 + ss + r) & 1) == 0) {
+                    zs[r] = __shfl_up_sync(0xffffffffu, rg[r][iM1].w, 1);
+                    if (lane_lo) zs[r] = ld_sh<float>(aM1 + r * ROWB - 4);
+                } else {
+                    zs[r] = __shfl_down_sync(0xffffffffu, rg[r][iM1].x, 1);
+                    if (lane_hi) zs[r] = ld_sh<float>(aM1 + r * ROWB + 16);
+                }
+            }
+            const float4 below = lds128<-(int)ROWB>(aM1), above = lds128<(int)(NRW * ROWB)>(aM1);
+            uint2 ids[NRW];
+            if (CLS) {
+#pragma unroll
+                for (int r = 0; r < NRW; ++r) ids[r] = ld_sh<uint2>(cbase + kM1 + r * CROWB);
+            }
+            float4 out[NRW];
+#pragma unroll
+            for (int r = 0; r < NRW; ++r) {
+                out[r] = rg[r][iM1];
+                const float4 &dn = (r == 0) ? below : rg[r - 1][iM1];
+                const float4 &up = (r == NRW - 1) ? above : rg[r + 1][iM1];
+                if (((PA0 + ss + r) & 1) == 0) {
+                    if (ANI)
+                        row_update_aniso<true, EXACT>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], ids[r], s_div, Ky, Kz, P.omega, umin);
+                    else if (CLS)
+                        row_update_class<true, EXACT>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], ids[r], ctab, P.omega, umin);
+                    else if (r & 1)
+                        row_update<true, 16, EXACT>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], cr[r >> 1][iM1], div_base, P.omega, umin);
+                    else
+                        row_update<true, 0, EXACT>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], cr[r >> 1][iM1], div_base, P.omega, umin);
+                } else {
+                    if (ANI)
+                        row_update_aniso<false, EXACT>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], ids[r], s_div, Ky, Kz, P.omega, umin);
+                    else if (CLS)
+                        row_update_class<false, EXACT>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], ids[r], ctab, P.omega, umin);
+                    else if (r & 1)
+                        row_update<false, 16, EXACT>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], cr[r >> 1][iM1], div_base, P.omega, umin);
+                    else
+                        row_update<false, 0, EXACT>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], cr[r >> 1][iM1], div_base, P.omega, umin);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < NRW; ++r) {
+                // binary kind: a float4 group whose four voxels are all non-conductive (code word 0) holds zeros in both
+                // ping-pong buffers since the state build and for ever after -- there is nothing to write
+                const bool live = CLS || P.write_solid || ((cr[r >> 1][iM1] >> (16 * (r & 1))) & 0xffffu) != 0u;
+                if ((canB & (1u << r)) && live) {
+                    float *d = dst0 + (int64_t)r * g.pitch;
+                    *reinterpret_cast<float4 *>(d) = out[r];
+                    if (send_lo) *reinterpret_cast<float4 *>(P.peer_lo + (d - P.dst) + (int64_t)g.Nx * ps) = out[r];
+                    if (send_hi) *reinterpret_cast<float4 *>(P.peer_hi + (d - P.dst) - (int64_t)g.Nx * ps) = out[r];
+                }
+            }
+            dst0 += ps;
+        }
+        // rotate the ring: plane p becomes p-1, ...; the slot after p+1's is the next to be waited for
+        oM1 = oP;
+        oP = oP1;
+        oP1 += slotB;
+        w_bar += 8u;
+        if (oP1 == NB * slotB) {
+            oP1 = 0;
+            w_bar = mbar_u32;
+            w_par ^= 1u;
+        }
+        kM1 = kP;
+        kP = kP1;
+        kP1 += cslotB;
+        if (kP1 == NBC * cslotB) kP1 = 0;
+    };
+
+    // steps s4 .. s4+3 form a group (the register ring and the row parities have period 4): groups that lie wholly
+    // in the steady state of the march -- colour A and B both active, plane kept, a box left to issue, no peer
+    // stores -- run the FAST body
+    const bool peers = (P.peer_lo != nullptr) || (P.peer_hi != nullptr);
+    for (int s4 = 0; s4 < n_steps; s4 += 4) {
+        // fast: s4 >= 2 (doB); p = c0-1+s in [max(a_lo, c0), min(a_hi, c1)) for s4..s4+3; s+NB-1 < total_rel
+        const int p_first = c0 - 1 + s4, p_last = p_first + 3;
+        bool fast = s4 >= 2 && p_first >= c0 && p_first >= P.a_lo && p_last < c1 && p_last < P.a_hi && s4 + 3 + NB - 1 < total_rel;
+        if (peers && (p_first - 1 < G || p_last - 1 >= g.Nx - G)) fast = false;
+        if (fast) {
+            step(IC<1>{}, IC<0>{}, s4);
+            step(IC<1>{}, IC<1>{}, s4 + 1);
+            step(IC<1>{}, IC<2>{}, s4 + 2);
+            step(IC<1>{}, IC<3>{}, s4 + 3);
+        } else {
+            step(IC<0>{}, IC<0>{}, s4);
+            if (s4 + 1 < n_steps) step(IC<0>{}, IC<1>{}, s4 + 1);
+            if (s4 + 2 < n_steps) step(IC<0>{}, IC<2>{}, s4 + 2);
+            if (s4 + 3 < n_steps) step(IC<0>{}, IC<3>{}, s4 + 3);
+        }
+    }
+    return !EXACT && doit && umin < GUARD_T;
+}
+
+// The re-run with IEEE division, out of line: re-arms the ring's barriers (every box of the first run has been consumed).
+template <int OGT, int PA0, int KIND, bool OP>
+__device__ __noinline__ void fused_march_exact(const FusedParams *P, const CUtensorMap *tmap_p, const CUtensorMap *cmap_p,
+                                               unsigned char *smem_raw, const float2 *s_div)
+{
+    constexpr bool CLS = (KIND == TAUB_MULTIPHASE_CLASS) || (KIND == TAUB_ANISOTROPIC);
+    constexpr int NB = CLS ? F_NB_CLS : F_NB, NBC = CLS ? NB : F_NBC_BIN;
+    const uint32_t mbar_u32 = smem_u32(smem_raw + (size_t)NB * P->slot_f4 * 16u + (size_t)NBC * P->cslot_h * 2u);
+    if (threadIdx.x == 0) {
+        for (int n = 0; n < NB; ++n) {
+            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mbar_u32 + 8u * n) : "memory");
+            mbar_init(mbar_u32 + 8u * n, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        atomicAdd(&g_inexact_events, 1ULL);      // chunks redone with IEEE division (taub_inexact_events)
+    }
+    __syncthreads();
+    fused_march<OGT, PA0, KIND, OP, true>(*P, tmap_p, cmap_p, smem_raw, s_div);
+}
+
+// Thread work item = a COLUMN of NRW vertically adjacent rows x one float4 group.  In every step the
+// rows of a column alternate between "xz" and "yw" rows and swap roles each step; the column's internal
+// y-neighbours stay in registers, only the rows above and below it come from shared memory.  PA0 = parity
+// of the column's first row at step 0 (uniform over the whole grid, chosen by the host), so every step
+// body is branch-free.
+//
+// OP ("odd periodic"): a periodic extent Ny or Nz is odd, so the wrap joins two voxels of the SAME colour and a
+// ghost cell is the image of a voxel whose colour differs from the ghost's own index parity.  The reference reads
+// ghost SNAPSHOTS taken before each iteration (taufactor.py:501-505); with the images loaded once per pass that is
+// reproduced exactly by leaving the ghost ring of the odd axis out of the colour-A step: where the imaged voxel has
+// colour B the snapshot before iteration t+1 equals the loaded value, and where it has colour A no colour-B voxel
+// reads it (rule pinned on the CPU by tests/test_fused_odd_periodic_cpu.py, on the GPU by the odd periodic goldens).
+template <int OGT, int PA0, int KIND, bool OP = false>   // OGT: output groups per tile row (compile-time tile width);
+__global__ void __launch_bounds__(F_NT, 2)              // KIND: TAUB_BINARY (4-bit codes) or a class kind (ids)
+fused_sweep2_kernel(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap tmap,
+                    const __grid_constant__ CUtensorMap cmap)
+{
+    // Programmatic dependent launch (opt-in, taub_iterate flags bit 1): let the next pass of the stream be
+    // scheduled as soon as every CTA of this one has started, so that its launch latency and shared-memory
+    // prologue overlap this pass's tail.  A no-op for an ordinary launch.
+    pdl_trigger();
+    extern __shared__ unsigned char smem_dyn[];
+    // TMA destinations need 128-byte alignment: align the base, slots are multiples of 128 B
+    unsigned char *smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
+    constexpr bool ANI = (KIND == TAUB_ANISOTROPIC);
+    constexpr bool MPC = (KIND == TAUB_MULTIPHASE_CLASS);
+    constexpr bool CLS = MPC || ANI;
+    constexpr int NB = CLS ? F_NB_CLS : F_NB, NBC = CLS ? NB : F_NBC_BIN;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NB * P.slot_f4 * 16u + (size_t)NBC * P.cslot_h * 2u);
+    float4 *s_tab = reinterpret_cast<float4 *>(mbar + 16);   // class kind: staged weight rows
+    __shared__ __align__(512) float2 s_div[ANISO_CLASSES];   // static: constant address; aligned for the OR look-up
+    const int tid = threadIdx.x;
 
     if (!ANI && tid < ANISO_CLASSES) s_div[tid] = div_entry(tid);   // binary: (n, 1/n) of the neighbour count
     const uint32_t mbar_u32 = smem_u32(mbar);
@@ -296,324 +630,12 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     // anisotropic: (b, 1/b) of the prefactor classes; class kind: the first tab_k weight rows.  First used after
     // the step loop's first __syncthreads
     if (ANI && tid < ANISO_CLASSES) s_div[tid] = reinterpret_cast<const float2 *>(P.table)[tid];
-    if (MPC)
+    if (MPC) {
+        const float4 *tab4 = reinterpret_cast<const float4 *>(P.table);
         for (int t = tid; t < 2 * P.tab_k; t += F_NT) s_tab[t] = __ldg(tab4 + t);
-    const ClassTab ctab{tab4, smem_u32(s_tab), (unsigned)P.tab_k};
-    const float Ky = ANI ? P.table[2 * ANISO_CLASSES] : 0.0f, Kz = ANI ? P.table[2 * ANISO_CLASSES + 1] : 0.0f;
-    const uint32_t div_base = smem_u32(s_div);
-
-    // The march over this CTA's chunk.  It runs once with the fast exact-reciprocal division; only if some thread
-    // of the CTA then reports a non-zero neighbour sum below 2^-100 (where that division may be off by one subnormal
-    // ulp) the whole chunk is redone with IEEE division (EXACT): the source buffer is read-only during the pass, so
-    // the second run simply overwrites the first one's output.  The fused kernel therefore equals IEEE division for
-    // every finite input; the re-run is a separate copy of the code and costs the common case nothing.
-    unsigned umin = 0xffffffffu;   // guard word of every neighbour sum this thread divides
-    bool tiny = false;
-    auto run = [&](auto exact_c) {
-        // ---- TMA producer (thread 0): plane rel (local plane c0-2+rel) -> field slot rel % NB, code slot rel % NBC,
-        //      one box each; the part of a box outside the tensor reads as 0.  The slot offsets and the plane
-        //      coordinate of the next box are carried along instead of being recomputed from rel.
-        const uint32_t planes_u32 = smem_u32(planes), cplanes_u32 = smem_u32(cplanes);
-        const uint32_t tx_bytes = (uint32_t)LR * (ROWB + CROWB);
-        uint32_t is_f = 0, is_c = 0, is_bar = mbar_u32;   // next issue: field / code slot byte offset, barrier address
-        int is_pl = b * g.planes + (c0 - 2 + G);          // ... and tensor plane coordinate
-        // with_codes = false: plane c0-2 (rel 0) is only ever an x- neighbour, nothing on it is updated, so its codes / ids
-        // are never read -- and must not be loaded: the binary kind's code ring has fewer slots (4) than the prologue has
-        // boxes in flight (5), and two boxes in flight into the same slot (rel 0 and rel 4) may land in either order
-        auto issue = [&](const bool with_codes) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(is_bar, with_codes ? tx_bytes : (uint32_t)LR * ROWB);
-            tma_load_3d(planes_u32 + is_f, &tmap, 4 * G0, R0, is_pl, is_bar);
-            if (with_codes) tma_load_3d(cplanes_u32 + is_c, &cmap, G0 * CPG, R0, is_pl, is_bar);
-            ++is_pl;
-            is_f += slotB;
-            is_bar += 8u;
-            if (is_f == NB * slotB) {
-                is_f = 0;
-                is_bar = mbar_u32;
-            }
-            is_c += cslotB;
-            if (is_c == NBC * cslotB) is_c = 0;
-        };
-        if (tid == 0)
-            for (int rel = 0; rel < min(NB - 1, total_rel); ++rel) issue(rel > 0);
-
-        // ---- this thread's column: rows lr0 .. lr0+NRW-1 of the tile, group gg.  Threads beyond the tile's columns
-        //      (m >= NCT) shadow column 0 of their group: they load and compute like everybody else (no divergence in
-        //      the step body) but never store anything.
-        const int NCT = (LR - 2) / NRW;          // columns stacked in the tile
-        const int m_raw = tid / LGt, gg = tid - m_raw * LGt;
-        const bool own = m_raw < NCT;            // has cells in the shared-memory tile
-        const int m = own ? m_raw : 0;
-        const int lr0 = 1 + NRW * m;
-        const int Ra = R0 + lr0, Gs = G0 + gg;
-        const bool doit = own && (Gs < PG) && (Ra < g.rows);
-        const bool colB = gg >= 1 && gg < LGt - 1 && Gs >= 1 && Gs < 1 + interior_groups(g.Nz);
-        unsigned canB = 0;                       // bit r: row r of the column is an output row
-    #pragma unroll
-        for (int r = 0; r < NRW; ++r)
-            if (doit && colB && lr0 + r >= 2 && lr0 + r < LR - 2 && Ra + r >= G && Ra + r < G + g.Ny) canB |= 1u << r;
-        // OP: ghost rows (odd Ny) keep their snapshot in the colour-A step, and so do the ghost columns k = -1
-        // (.w of group 0) and k = Nz (component Nz % 4 of group (Nz + 4) / 4) for odd Nz
-        unsigned keep_rows = 0;
-        bool keep_lo_w = false, keep_hi_y = false, keep_hi_w = false;
-        if (OP) {
-            if (g.Ny & 1) {
-    #pragma unroll
-                for (int r = 0; r < NRW; ++r)
-                    if (Ra + r < G || Ra + r >= G + g.Ny) keep_rows |= 1u << r;
-            }
-            if (g.Nz & 1) {
-                keep_lo_w = (Gs == 0);
-                keep_hi_y = (Gs == ((g.Nz + COL0) >> 2)) && ((g.Nz & 3) == 1);
-                keep_hi_w = (Gs == ((g.Nz + COL0) >> 2)) && ((g.Nz & 3) == 3);
-            }
-        }
-        // shared-window addresses of row 0 of the column in field slot 0 / id-code slot 0 (row r: + r * ROWB / CROWB)
-        const uint32_t tbase = planes_u32 + (uint32_t)(lr0 * LG + gg) * 16u;
-        const uint32_t cbase = cplanes_u32 + (uint32_t)((lr0 * LGc + gg) * CPG) * 2u;
-        const bool lane_lo = (lane == 0), lane_hi = (lane == 31);
-        // which of this thread's rows other threads read: the column's first and last row (their above / below) and,
-        // at the two ends of a warp, every row (z_neighbour fall-back of the adjacent warp)
-        const bool st_mid = own && (lane_lo || lane_hi);
-        // colour B first writes plane c0 (at step 2)
-        float *dst0 = P.dst + (int64_t)b * g.image_stride + 4 * Gs + (int64_t)(c0 + G) * ps + (int64_t)Ra * g.pitch;
-
-        // ---- register ring: rg[r][k] holds plane (c0-3+k+4j) of row r; at step s = 4j+ss:
-        //      a[p-2] = rg[.][ss], a[p-1] = rg[.][ss+1], raw[p] -> a[p] = rg[.][ss+2], raw[p+1] = rg[.][ss+3]
-        float4 rg[NRW][4];
-        unsigned cr[NRW / 2][4];   // binary: neighbour codes, two rows per word, same ring positions
-        mbar_wait(mbar_u32, 0);
-        mbar_wait(mbar_u32 + 8u * (1 % NB), 0);
-    #pragma unroll
-        for (int r = 0; r < NRW; ++r) {
-            rg[r][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-            rg[r][3] = make_float4(0.f, 0.f, 0.f, 0.f);
-            rg[r][1] = ld_sh<float4>(tbase + r * ROWB);
-            rg[r][2] = ld_sh<float4>(tbase + slotB + r * ROWB);
-        }
-    #pragma unroll
-        for (int q = 0; q < NRW / 2; ++q) {
-    #pragma unroll
-            for (int k = 0; k < 4; ++k) cr[q][k] = 0;
-            if (!CLS)
-                cr[q][2] = (unsigned)ld_sh<uint16_t>(cbase + cslotB + 2 * q * CROWB) |
-                           ((unsigned)ld_sh<uint16_t>(cbase + cslotB + (2 * q + 1) * CROWB) << 16);
-        }
-
-        const int n_steps = c1 - c0 + 2;
-
-        // ---- ring state of step s (all warp-uniform): field slots of planes p-1, p, p+1 and the mbarrier of p+1;
-        //      code / id slots of the same planes.  Rotated at the end of every step.
-        uint32_t oM1 = 0, oP = slotB, oP1 = 2u * slotB;               // s % NB, (s+1) % NB, (s+2) % NB at s = 0
-        uint32_t w_bar = mbar_u32 + 16u, w_par = 0;                      // barrier / parity of plane rel = s+2
-        uint32_t kM1 = 0, kP = cslotB, kP1 = 2u * cslotB;                // code / id slots: s % NBC, ... (NBC >= 4)
-
-        // One step of the march.  FAST: every plane-range flag is true and there are no peer stores (steady state).
-        auto step = [&](auto fast_c, auto ss_c, const int s) {
-            constexpr bool FAST = decltype(fast_c)::value != 0;
-            constexpr bool EXACT = decltype(exact_c)::value != 0;
-            constexpr int ss = decltype(ss_c)::value;
-            constexpr int iM2 = ss & 3, iM1 = (ss + 1) & 3, iP = (ss + 2) & 3, iP1 = (ss + 3) & 3;
-            const int p = c0 - 1 + s;   // plane receiving colour A; colour B goes to plane p-1
-            __syncthreads();            // ring slot of plane p-2 is free; a[p-1] is visible in its slot
-            if (tid == 0 && (FAST || s - 1 + NB < total_rel)) issue(true);
-            mbar_wait(w_bar, w_par);
-            const uint32_t aM1 = tbase + oM1, aP = tbase + oP, aP1 = tbase + oP1;   // this column in the three slots
-            const bool doA = FAST || ((p >= P.a_lo) && (p < P.a_hi));
-            const bool keepA = FAST || ((p >= c0) && (p < c1));   // a[p] is read by colour B of plane p next step
-            const bool doB = FAST || (s >= 2);
-            // one-sided halo exchange: output plane p-1 is one of the neighbour's ghost planes
-            const bool send_lo = !FAST && P.peer_lo != nullptr && (p - 1) < G;
-            const bool send_hi = !FAST && P.peer_hi != nullptr && (p - 1) >= g.Nx - G;
-    #pragma unroll
-            for (int r = 0; r < NRW; ++r) rg[r][iP1] = ld_sh<float4>(aP1 + r * ROWB);
-            if (!CLS) {
-    #pragma unroll
-                for (int q = 0; q < NRW / 2; ++q)
-                    cr[q][iP1] = (unsigned)ld_sh<uint16_t>(cbase + kP1 + 2 * q * CROWB) |
-                                 ((unsigned)ld_sh<uint16_t>(cbase + kP1 + (2 * q + 1) * CROWB) << 16);
-            }
-            if (doA) {   // block-uniform
-                // the z neighbour from the adjacent lane's registers (one crossbar pass instead of a 4-way conflicted
-                // shared load); the two lanes at the warp ends read shared memory
-                float zs[NRW];
-    #pragma unroll
-                for (int r = 0; r < NRW; ++r) {
-                    if (((PA0 + ss + r) & 1) == 0) {
-                        zs[r] = __shfl_up_sync(0xffffffffu, rg[r][iP].w, 1);
-                        if (lane_lo) zs[r] = ld_sh<float>(aP + r * ROWB - 4);
-                    } else {
-                        zs[r] = __shfl_down_sync(0xffffffffu, rg[r][iP].x, 1);
-                        if (lane_hi) zs[r] = ld_sh<float>(aP + r * ROWB + 16);
-                    }
-                }
-                const float4 below = lds128<-(int)ROWB>(aP), above = lds128<(int)(NRW * ROWB)>(aP);
-                uint2 ids[NRW];
-                if (CLS) {
-    #pragma unroll
-                    for (int r = 0; r < NRW; ++r) ids[r] = ld_sh<uint2>(cbase + kP + r * CROWB);
-                }
-                float4 snap[NRW];
-                if (OP) {
-    #pragma unroll
-                    for (int r = 0; r < NRW; ++r) snap[r] = rg[r][iP];
-                }
-    #pragma unroll
-                for (int r = 0; r < NRW; ++r) {
-                    // neighbours inside the column are registers; each row only reads the components
-                    // its neighbours leave unchanged in this step
-                    const float4 &dn = (r == 0) ? below : rg[r - 1][iP];
-                    const float4 &up = (r == NRW - 1) ? above : rg[r + 1][iP];
-                    if (((PA0 + ss + r) & 1) == 0) {
-                        if (ANI)
-                            row_update_aniso<true, EXACT>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], ids[r], s_div, Ky, Kz, P.omega, umin);
-                        else if (CLS)
-                            row_update_class<true, EXACT>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], ids[r], ctab, P.omega, umin);
-                        else if (r & 1)
-                            row_update<true, 16, EXACT>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], cr[r >> 1][iP], div_base, P.omega, umin);
-                        else
-                            row_update<true, 0, EXACT>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], cr[r >> 1][iP], div_base, P.omega, umin);
-                    } else {
-                        if (ANI)
-                            row_update_aniso<false, EXACT>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], ids[r], s_div, Ky, Kz, P.omega, umin);
-                        else if (CLS)
-                            row_update_class<false, EXACT>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], ids[r], ctab, P.omega, umin);
-                        else if (r & 1)
-                            row_update<false, 16, EXACT>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], cr[r >> 1][iP], div_base, P.omega, umin);
-                        else
-                            row_update<false, 0, EXACT>(rg[r][iP], rg[r][iP1], rg[r][iM1], up, dn, zs[r], cr[r >> 1][iP], div_base, P.omega, umin);
-                    }
-                }
-                if (OP) {   // ghost cells of an odd periodic axis keep their snapshot
-    #pragma unroll
-                    for (int r = 0; r < NRW; ++r) {
-                        if (keep_rows & (1u << r)) {
-                            rg[r][iP] = snap[r];
-                        } else {
-                            if (keep_lo_w || keep_hi_w) rg[r][iP].w = snap[r].w;
-                            if (keep_hi_y) rg[r][iP].y = snap[r].y;
-                        }
-                    }
-                }
-                if (keepA) {
-                    // other threads read the column's first and last row (their above / below) and, at the two ends
-                    // of a warp, the neighbour lane's group (z_neighbour fall-back)
-    #pragma unroll
-                    for (int r = 0; r < NRW; ++r)
-                        if ((r == 0 || r == NRW - 1) ? own : st_mid) st_sh<float4>(aP + r * ROWB, rg[r][iP]);
-                }
-            }
-            if (doB) {   // block-uniform
-                float zs[NRW];
-    #pragma unroll
-                for (int r = 0; r < NRW; ++r) {
-                    if (((PA0 + ss + r) & 1) == 0) {
-                        zs[r] = __shfl_up_sync(0xffffffffu, rg[r][iM1].w, 1);
-                        if (lane_lo) zs[r] = ld_sh<float>(aM1 + r * ROWB - 4);
-                    } else {
-                        zs[r] = __shfl_down_sync(0xffffffffu, rg[r][iM1].x, 1);
-                        if (lane_hi) zs[r] = ld_sh<float>(aM1 + r * ROWB + 16);
-                    }
-                }
-                const float4 below = lds128<-(int)ROWB>(aM1), above = lds128<(int)(NRW * ROWB)>(aM1);
-                uint2 ids[NRW];
-                if (CLS) {
-    #pragma unroll
-                    for (int r = 0; r < NRW; ++r) ids[r] = ld_sh<uint2>(cbase + kM1 + r * CROWB);
-                }
-                float4 out[NRW];
-    #pragma unroll
-                for (int r = 0; r < NRW; ++r) {
-                    out[r] = rg[r][iM1];
-                    const float4 &dn = (r == 0) ? below : rg[r - 1][iM1];
-                    const float4 &up = (r == NRW - 1) ? above : rg[r + 1][iM1];
-                    if (((PA0 + ss + r) & 1) == 0) {
-                        if (ANI)
-                            row_update_aniso<true, EXACT>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], ids[r], s_div, Ky, Kz, P.omega, umin);
-                        else if (CLS)
-                            row_update_class<true, EXACT>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], ids[r], ctab, P.omega, umin);
-                        else if (r & 1)
-                            row_update<true, 16, EXACT>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], cr[r >> 1][iM1], div_base, P.omega, umin);
-                        else
-                            row_update<true, 0, EXACT>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], cr[r >> 1][iM1], div_base, P.omega, umin);
-                    } else {
-                        if (ANI)
-                            row_update_aniso<false, EXACT>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], ids[r], s_div, Ky, Kz, P.omega, umin);
-                        else if (CLS)
-                            row_update_class<false, EXACT>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], ids[r], ctab, P.omega, umin);
-                        else if (r & 1)
-                            row_update<false, 16, EXACT>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], cr[r >> 1][iM1], div_base, P.omega, umin);
-                        else
-                            row_update<false, 0, EXACT>(out[r], rg[r][iP], rg[r][iM2], up, dn, zs[r], cr[r >> 1][iM1], div_base, P.omega, umin);
-                    }
-                }
-    #pragma unroll
-                for (int r = 0; r < NRW; ++r) {
-                    // binary kind: a float4 group whose four voxels are all non-conductive (code word 0) holds zeros in both
-                    // ping-pong buffers since the state build and for ever after -- there is nothing to write
-                    const bool live = CLS || P.write_solid || ((cr[r >> 1][iM1] >> (16 * (r & 1))) & 0xffffu) != 0u;
-                    if ((canB & (1u << r)) && live) {
-                        float *d = dst0 + (int64_t)r * g.pitch;
-                        *reinterpret_cast<float4 *>(d) = out[r];
-                        if (send_lo) *reinterpret_cast<float4 *>(P.peer_lo + (d - P.dst) + (int64_t)g.Nx * ps) = out[r];
-                        if (send_hi) *reinterpret_cast<float4 *>(P.peer_hi + (d - P.dst) - (int64_t)g.Nx * ps) = out[r];
-                    }
-                }
-                dst0 += ps;
-            }
-            // rotate the ring: plane p becomes p-1, ...; the slot after p+1's is the next to be waited for
-            oM1 = oP;
-            oP = oP1;
-            oP1 += slotB;
-            w_bar += 8u;
-            if (oP1 == NB * slotB) {
-                oP1 = 0;
-                w_bar = mbar_u32;
-                w_par ^= 1u;
-            }
-            kM1 = kP;
-            kP = kP1;
-            kP1 += cslotB;
-            if (kP1 == NBC * cslotB) kP1 = 0;
-        };
-
-        // steps s4 .. s4+3 form a group (the register ring and the row parities have period 4): groups that lie wholly
-        // in the steady state of the march -- colour A and B both active, plane kept, a box left to issue, no peer
-        // stores -- run the FAST body
-        const bool peers = (P.peer_lo != nullptr) || (P.peer_hi != nullptr);
-        for (int s4 = 0; s4 < n_steps; s4 += 4) {
-            // fast: s4 >= 2 (doB); p = c0-1+s in [max(a_lo, c0), min(a_hi, c1)) for s4..s4+3; s+NB-1 < total_rel
-            const int p_first = c0 - 1 + s4, p_last = p_first + 3;
-            bool fast = s4 >= 2 && p_first >= c0 && p_first >= P.a_lo && p_last < c1 && p_last < P.a_hi && s4 + 3 + NB - 1 < total_rel;
-            if (peers && (p_first - 1 < G || p_last - 1 >= g.Nx - G)) fast = false;
-            if (fast) {
-                step(IC<1>{}, IC<0>{}, s4);
-                step(IC<1>{}, IC<1>{}, s4 + 1);
-                step(IC<1>{}, IC<2>{}, s4 + 2);
-                step(IC<1>{}, IC<3>{}, s4 + 3);
-            } else {
-                step(IC<0>{}, IC<0>{}, s4);
-                if (s4 + 1 < n_steps) step(IC<0>{}, IC<1>{}, s4 + 1);
-                if (s4 + 2 < n_steps) step(IC<0>{}, IC<2>{}, s4 + 2);
-                if (s4 + 3 < n_steps) step(IC<0>{}, IC<3>{}, s4 + 3);
-            }
-        }
-        if (!decltype(exact_c)::value) tiny = doit && umin < GUARD_T;
-    };
-    run(IC<0>{});
-    if (__syncthreads_or(tiny)) {
-        if (tid == 0) {
-            for (int n = 0; n < NB; ++n) {
-                asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mbar_u32 + 8u * n) : "memory");
-                mbar_init(mbar_u32 + 8u * n, 1);
-            }
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            atomicAdd(&g_inexact_events, 1ULL);      // chunks redone with IEEE division (taub_inexact_events)
-        }
-        __syncthreads();
-        run(IC<1>{});
     }
+    const bool tiny = fused_march<OGT, PA0, KIND, OP, false>(P, &tmap, &cmap, smem_raw, s_div);
+    if (__syncthreads_or(tiny)) fused_march_exact<OGT, PA0, KIND, OP>(&P, &tmap, &cmap, smem_raw, s_div);
 }
 
 static size_t fused_smem_bytes(int LR, int LG, int LGc, int cpg, int nb, int nbc, int tab_k)

@@ -211,7 +211,13 @@ def _decompress(chunk, compression, expected):
     if compression == 1:
         return chunk
     if compression in (8, 32946):
-        return zlib.decompress(chunk)
+        # bounded inflate: a strip may expand to its declared size and no further (a crafted strip could otherwise
+        # allocate ~1000x its size before any length check sees it)
+        d = zlib.decompressobj()
+        out = d.decompress(bytes(chunk), max(int(expected), 1))
+        if d.unconsumed_tail:
+            raise TiffError("Deflate strip expands beyond its declared size")
+        return out
     if compression in (32773, 5):
         name = "taub_unpackbits" if compression == 32773 else "taub_unlzw"
         if USE_NATIVE and _native() is not None:

@@ -666,6 +666,10 @@ class MultiPhaseSolver(ThroughTransportSolver):
         img: labelled image.
         diffusivities: dict label -> diffusivity (>= 0); labels left out are isolating (warns).
         D_scaling: reference diffusivity D_0.
+
+    Limits the reference does not have: at most 64 distinct phases per image (``TAUB_MAX_LABELS``; up to 15 of them
+    run the fused stencil-class kernel, more the one-iteration label kernel) and at most 255 distinct raw label
+    values; beyond that construction raises ``ValueError`` -- use the reference package for such images.
     """
     _kind = _lib.MULTIPHASE
 
@@ -677,7 +681,8 @@ class MultiPhaseSolver(ThroughTransportSolver):
             # labels outside 0..255: remap to dense indices on the host
             present, inv = np.unique(img4, return_inverse=True)
             if len(present) > 255:
-                raise ValueError("more than 255 distinct phase labels")
+                raise ValueError("more than 255 distinct phase labels (limit of taufactor_b200; the reference package "
+                                 "taufactor has none)")
             u8 = inv.reshape(img4.shape).astype(np.uint8)
             raw_of_u8 = list(present)
         else:
@@ -709,7 +714,8 @@ class MultiPhaseSolver(ThroughTransportSolver):
         self.conductive_labels = [lbl for lbl, D_p in self.Ds.items() if D_p > 0]   # ref:560
         L = len(present_u8)
         if L > _lib.MAX_LABELS:
-            raise ValueError(f"at most {_lib.MAX_LABELS} distinct phases are supported, got {L}")
+            raise ValueError(f"at most {_lib.MAX_LABELS} distinct phases are supported by taufactor_b200, got {L}; "
+                             "the reference package (taufactor) has no such limit")
         D = np.zeros(L + 1, np.float32)
         map256 = np.full(256, L, np.uint8)
         sel = np.zeros(256, np.uint8)
