@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TAUB_ABI_VERSION 11
+#define TAUB_ABI_VERSION 12
 #define TAUB_GHOST 2            /* ghost width in x (planes), y (rows) and z (columns) */
 #define TAUB_COL0 4             /* column of interior voxel k = 0 */
 #define TAUB_MAX_LABELS 64      /* dense phase indices 0..L-1, L <= 64; index L = "outside" */
@@ -95,6 +95,9 @@ typedef struct taub_problem {
                                  * the shared-memory resident path of small volumes (taub_resident_pairs); NULL =
                                  * that path is never taken */
     int32_t sync_epoch;         /* host-side: pairs run on sync_ws so far (maintained by taub_resident_pairs) */
+    int32_t *redo_ws;           /* optional: taub_redo_ws_ints() device int32, zeroed once by the caller: lists of the
+                                 * chunks a fused pass must redo with IEEE division (see taub_inexact_events); NULL =
+                                 * such chunks are only counted */
 } taub_problem;
 
 /* -- library ------------------------------------------------------------------------------ */
@@ -179,13 +182,15 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
 int taub_can_fuse(const taub_problem *p);   /* periodic problems with odd Ny / Nz: only with the experimental
                                              * OP kernel variant, environment TAUB_FUSE_ODD_PERIODIC=1 */
 /* The fused kernel divides by the neighbour count / prefactor with an FMA-corrected reciprocal that equals the IEEE
- * quotient for s == 0 and every |s| >= 2^-100.  A CTA whose threads saw a non-zero sum below 2^-100 (where that
- * sequence may be one subnormal ulp off) redoes its whole chunk with IEEE division before it exits -- the source
- * buffer of a pass is read-only, so the second run simply overwrites the first -- hence the fused trajectory equals
- * the generic kernel's and the reference's for every finite input.  This returns how many chunks were redone since
- * the library was loaded: 0 in every through-transport solve observed; the electrode solvers get there when a
- * cluster cut off from the inlet decays towards 0.  Synchronises the device. */
+ * quotient for s == 0 and every |s| >= 2^-100.  A CTA whose threads met a non-zero value below 2^-100 (where that
+ * sequence may be one subnormal ulp off) puts its chunk on a list in p->redo_ws, and a second kernel launched behind
+ * every fused pass redoes the listed chunks with IEEE division -- the source buffer of a pass is read-only, so the
+ * re-run simply overwrites the first run's output -- hence the fused trajectory equals the generic kernel's and the
+ * reference's for every finite input.  (Environment TAUB_EXACT_REDO=0 or p->redo_ws == NULL: count only.)  This returns
+ * how many chunks were listed since the library was loaded: 0 in the through-transport solves; the electrode solvers
+ * get there when a cluster cut off from the inlet decays towards 0.  Synchronises the device. */
 unsigned long long taub_inexact_events(void);
+size_t taub_redo_ws_ints(void);                  /* int32 elements p->redo_ws must hold */
 /* n iterations starting at iter on the whole local slab (single-rank use): refreshes periodic
  * ghosts, picks fused pairs where possible, flips p->cur.  flags bit 0: force the generic path;
  * bit 1: launch the queued kernels (fused / generic sweeps, ghost refresh) with programmatic dependent launch

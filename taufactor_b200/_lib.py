@@ -29,7 +29,8 @@ class Problem(ctypes.Structure):
     _fields_ = [("g", Geom), ("kind", ctypes.c_int32), ("L", ctypes.c_int32),
                 ("field", c_vp * 2), ("codes", c_vp), ("labels", c_vp), ("lut", c_vp),
                 ("omega", ctypes.c_float), ("cur", ctypes.c_int32), ("stop", c_vp),
-                ("peer_lo", c_vp * 2), ("peer_hi", c_vp * 2), ("sync_ws", c_vp), ("sync_epoch", ctypes.c_int32)]
+                ("peer_lo", c_vp * 2), ("peer_hi", c_vp * 2), ("sync_ws", c_vp), ("sync_epoch", ctypes.c_int32),
+                ("redo_ws", c_vp)]
 
 
 # name -> (restype, argtypes); must list every symbol include/taub200.h declares
@@ -56,6 +57,7 @@ SIGNATURES = {
     "taub_half_sweep": (c_int, [ctypes.POINTER(Problem), c_i64, c_int, c_int, c_vp]),
     "taub_fused_sweep2": (c_int, [ctypes.POINTER(Problem), c_i64, c_int, c_int, c_vp]),
     "taub_inexact_events": (ctypes.c_ulonglong, []),
+    "taub_redo_ws_ints": (ctypes.c_size_t, []),
     "taub_can_fuse": (c_int, [ctypes.POINTER(Problem)]),
     "taub_iterate": (c_int, [ctypes.POINTER(Problem), c_i64, c_int, c_int, c_vp]),
     "taub_can_reside": (c_int, [ctypes.POINTER(Problem)]),
@@ -89,10 +91,12 @@ def load():
         lib = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             if os.environ.get("TAUB200_LIB") and not hasattr(lib, name):
-                continue            # an older build under A/B timing may lack the newest diagnostics
+                if name.endswith("_ws_ints"):      # an older build under A/B timing: a workspace it never touches
+                    setattr(lib, name, lambda: 4096)
+                continue            # ... and it may lack the newest diagnostics
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.taub_abi_version() != 11:
+        if lib.taub_abi_version() != 12 and not os.environ.get("TAUB200_LIB"):
             raise ImportError("libtaub200.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib

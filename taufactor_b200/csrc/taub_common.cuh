@@ -100,15 +100,19 @@ __device__ __forceinline__ float2 div_pair(unsigned nib, const float2 *s_div)
 // u = 2*bits(s) - 1 drops the sign and wraps +-0 to the top, so "0 < |s| < 2^-100" <=> u < GUARD_T.
 constexpr unsigned GUARD_T = (27u << 24) - 1u;
 
-// EXACT = true: the IEEE quotient itself (cr.x == 0 stands for an infinite divisor) -- the fused kernel re-runs a
+// EXACT = true: the IEEE quotient itself (cr.x == 0 stands for an infinite divisor) -- a fused pass re-runs a
 // chunk this way when one of its sums was a non-zero value below 2^-100, so its results equal IEEE division always.
-template <bool EXACT = false>
+// GUARD_Q (divisors 1..8 only, i.e. the binary kind): the guard word is taken from q0 = RN(s / c) instead of s.
+// |q0| >= 2^-100 implies |s| >= 2^-100 (c >= 1), and q0 == 0 means s == 0, an infinite divisor (table entry (0, 0):
+// the quotient is exactly 0 whatever s is) or a quotient that rounds to 0 either way -- so nothing is lost, and the
+// non-conductive neighbours of a decaying isolated voxel (tiny sum, infinite divisor, exact result) raise no alarm.
+template <bool EXACT = false, bool GUARD_Q = false>
 __device__ __forceinline__ float div_fast(float s, float2 cr, unsigned &umin)
 {
     if (EXACT) return __fdiv_rn(s, cr.x != 0.0f ? cr.x : __int_as_float(0x7f800000));
     const float q0 = __fmul_rn(s, cr.y);
     const float rem = __fmaf_rn(-q0, cr.x, s);
-    umin = min(umin, __float_as_uint(s) * 2u - 1u);
+    umin = min(umin, __float_as_uint(GUARD_Q ? q0 : s) * 2u - 1u);
     return __fmaf_rn(rem, cr.y, q0);
 }
 
@@ -133,7 +137,7 @@ template <bool EXACT = false>
 __device__ __forceinline__ float sor_fast(float c, float xp, float xm, float yp, float ym, float zp, float zm,
                                           float2 cr, float omega, unsigned &umin)
 {
-    return relax(c, div_fast<EXACT>(nbr_sum(xp, xm, yp, ym, zp, zm), cr, umin), omega);
+    return relax(c, div_fast<EXACT, true>(nbr_sum(xp, xm, yp, ym, zp, zm), cr, umin), omega);
 }
 
 // The same update with a true IEEE division: taken only when some sum in the group is a non-zero

@@ -44,6 +44,8 @@ constexpr int F_NB_CLS = 4;   // ... of the class kinds (their slots carry 8 mor
 constexpr int F_NBC_BIN = 4;  // code ring depth of the binary kind: codes are copied to registers when their plane
                               // is first read, so only the plane being read + 3 in flight need a slot
 constexpr int F_TABK = 256;   // stencil-class rows kept in shared memory (most frequent classes first)
+constexpr int REDO_CAP = 1022;  // chunks a redo list holds (2 header ints + REDO_CAP ids = 1024 ints); more: redo all
+constexpr int REDO_LISTS = 4;   // lists per problem: passes on [0, Nx), [0, a), [b, Nx), [a, b) may be in flight together
 
 struct FusedParams {
     taub_geom g;
@@ -68,6 +70,8 @@ struct FusedParams {
     int cslot_h;       // uint16 per code ring slot
     int tab_k;         // class kind: rows of the weight table staged in shared memory (<= F_TABK)
     int write_solid;   // binary kind: 1 = also store float4 groups whose four voxels are all non-conductive
+    int *redo;         // optional: redo list of this launch (see fused_redo_kernel)
+    int force_redo;    // testing (TAUB_FORCE_REDO=1): list every chunk, i.e. the whole pass is redone with IEEE division
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -228,14 +232,14 @@ template <int V>
 using IC = std::integral_constant<int, V>;
 
 // The march of one CTA over its chunk of planes (the whole kernel but its one-time set-up).  EXACT = false: the fast
-// exact-reciprocal division; returns whether this thread met a non-zero neighbour sum below 2^-100, where that division
-// may be off by one subnormal ulp.  EXACT = true: IEEE division -- the kernel calls it (fused_march_exact, a separate
-// out-of-line copy of the code with its own registers, so the common case pays nothing) to redo the chunk of a CTA
-// that reported such a sum: the source buffer is read-only during the pass, so the second run simply overwrites the
-// first one's output.  The fused kernel therefore equals IEEE division for every finite input.
+// exact-reciprocal division; returns whether this thread met a non-zero value below 2^-100 where that division may be
+// off by one subnormal ulp.  EXACT = true: IEEE division -- fused_redo_kernel re-runs the chunks of the CTAs that
+// reported such a value (a kernel of its own, so the hot kernel's registers and instruction stream are untouched):
+// the source buffer is read-only during a pass, so the re-run simply overwrites the first run's output.  The fused
+// pass therefore equals IEEE division for every finite input.
 template <int OGT, int PA0, int KIND, bool OP, bool EXACT>
 __device__ __forceinline__ bool fused_march(const FusedParams &P, const CUtensorMap *tmap_p, const CUtensorMap *cmap_p,
-                                            unsigned char *smem_raw, const float2 *s_div)
+                                            unsigned char *smem_raw, const float2 *s_div, int cta_x, int cta_y, int cta_z)
 {
     const taub_geom &g = P.g;
     constexpr bool ANI = (KIND == TAUB_ANISOTROPIC);
@@ -258,9 +262,9 @@ __device__ __forceinline__ bool fused_march(const FusedParams &P, const CUtensor
     const uint32_t mbar_u32 = smem_u32(mbar);
 
     const int tid = threadIdx.x, lane = tid & 31;
-    const int tk = blockIdx.x % P.tiles_k, tj = blockIdx.x / P.tiles_k;
-    const int b = blockIdx.z;
-    const int c0 = P.i_lo + blockIdx.y * P.chunk_len;
+    const int tk = cta_x % P.tiles_k, tj = cta_x / P.tiles_k;     // (cta_x, cta_y, cta_z): tile, plane chunk, image
+    const int b = cta_z;
+    const int c0 = P.i_lo + cta_y * P.chunk_len;
     const int c1 = min(c0 + P.chunk_len, P.i_hi);
     const int R0 = tj * P.OR_, G0 = tk * P.OG;   // storage row / group of loaded (0, 0)
     const int PG = g.pitch >> 2;
@@ -562,26 +566,6 @@ __device__ __forceinline__ bool fused_march(const FusedParams &P, const CUtensor
     return !EXACT && doit && umin < GUARD_T;
 }
 
-// The re-run with IEEE division, out of line: re-arms the ring's barriers (every box of the first run has been consumed).
-template <int OGT, int PA0, int KIND, bool OP>
-__device__ __noinline__ void fused_march_exact(const FusedParams *P, const CUtensorMap *tmap_p, const CUtensorMap *cmap_p,
-                                               unsigned char *smem_raw, const float2 *s_div)
-{
-    constexpr bool CLS = (KIND == TAUB_MULTIPHASE_CLASS) || (KIND == TAUB_ANISOTROPIC);
-    constexpr int NB = CLS ? F_NB_CLS : F_NB, NBC = CLS ? NB : F_NBC_BIN;
-    const uint32_t mbar_u32 = smem_u32(smem_raw + (size_t)NB * P->slot_f4 * 16u + (size_t)NBC * P->cslot_h * 2u);
-    if (threadIdx.x == 0) {
-        for (int n = 0; n < NB; ++n) {
-            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mbar_u32 + 8u * n) : "memory");
-            mbar_init(mbar_u32 + 8u * n, 1);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        atomicAdd(&g_inexact_events, 1ULL);      // chunks redone with IEEE division (taub_inexact_events)
-    }
-    __syncthreads();
-    fused_march<OGT, PA0, KIND, OP, true>(*P, tmap_p, cmap_p, smem_raw, s_div);
-}
-
 // Thread work item = a COLUMN of NRW vertically adjacent rows x one float4 group.  In every step the
 // rows of a column alternate between "xz" and "yw" rows and swap roles each step; the column's internal
 // y-neighbours stay in registers, only the rows above and below it come from shared memory.  PA0 = parity
@@ -596,7 +580,7 @@ __device__ __noinline__ void fused_march_exact(const FusedParams *P, const CUten
 // reads it (rule pinned on the CPU by tests/test_fused_odd_periodic_cpu.py, on the GPU by the odd periodic goldens).
 template <int OGT, int PA0, int KIND, bool OP = false>   // OGT: output groups per tile row (compile-time tile width);
 __global__ void __launch_bounds__(F_NT, 2)              // KIND: TAUB_BINARY (4-bit codes) or a class kind (ids)
-fused_sweep2_kernel(const __grid_constant__ FusedParams P, const __grid_constant__ CUtensorMap tmap,
+fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tmap,
                     const __grid_constant__ CUtensorMap cmap)
 {
     // Programmatic dependent launch (opt-in, taub_iterate flags bit 1): let the next pass of the stream be
@@ -634,8 +618,73 @@ fused_sweep2_kernel(const __grid_constant__ FusedParams P, const __grid_constant
         const float4 *tab4 = reinterpret_cast<const float4 *>(P.table);
         for (int t = tid; t < 2 * P.tab_k; t += F_NT) s_tab[t] = __ldg(tab4 + t);
     }
-    const bool tiny = fused_march<OGT, PA0, KIND, OP, false>(P, &tmap, &cmap, smem_raw, s_div);
-    if (__syncthreads_or(tiny)) fused_march_exact<OGT, PA0, KIND, OP>(&P, &tmap, &cmap, smem_raw, s_div);
+    const bool tiny = fused_march<OGT, PA0, KIND, OP, false>(P, &tmap, &cmap, smem_raw, s_div, blockIdx.x, blockIdx.y, blockIdx.z);
+    // a value below 2^-100 went through the fast division: put this chunk on the list fused_redo_kernel works off
+    if (__syncthreads_or(tiny || P.force_redo) && tid == 0) {
+        if (P.redo) {
+            const int k = atomicAdd(P.redo, 1);
+            if (k < REDO_CAP) P.redo[2 + k] = (int)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+        }
+        atomicAdd(&g_inexact_events, 1ULL);
+    }
+}
+
+// Re-runs, with IEEE division, the chunks that the pass before it put on the redo list (P.redo: [0] = chunks listed,
+// [1] = CTAs of this kernel that are done, [2..] = linear CTA ids of the pass; more than REDO_CAP entries = redo
+// every chunk).  Launched behind every fused pass; all but never has anything to do (one load per CTA).
+template <int OGT, int PA0, int KIND, bool OP = false>
+__global__ void __launch_bounds__(F_NT, 1)
+fused_redo_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap cmap,
+                  int grid_x, int grid_y, int grid_z)
+{
+    pdl_trigger();
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);
+    constexpr bool ANI = (KIND == TAUB_ANISOTROPIC);
+    constexpr bool MPC = (KIND == TAUB_MULTIPHASE_CLASS);
+    constexpr bool CLS = MPC || ANI;
+    constexpr int NB = CLS ? F_NB_CLS : F_NB, NBC = CLS ? NB : F_NBC_BIN;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NB * P.slot_f4 * 16u + (size_t)NBC * P.cslot_h * 2u);
+    float4 *s_tab = reinterpret_cast<float4 *>(mbar + 16);
+    __shared__ __align__(512) float2 s_div[ANISO_CLASSES];
+    const int tid = threadIdx.x;
+    pdl_wait();
+    const int listed = *reinterpret_cast<volatile int *>(P.redo);
+    if (listed == 0) return;                      // the common case
+    if (!ANI && tid < ANISO_CLASSES) s_div[tid] = div_entry(tid);
+    if (ANI && tid < ANISO_CLASSES) s_div[tid] = reinterpret_cast<const float2 *>(P.table)[tid];
+    if (MPC) {
+        const float4 *tab4 = reinterpret_cast<const float4 *>(P.table);
+        for (int t = tid; t < 2 * P.tab_k; t += F_NT) s_tab[t] = __ldg(tab4 + t);
+    }
+    const uint32_t mbar_u32 = smem_u32(mbar);
+    const int n = listed <= REDO_CAP ? listed : grid_x * grid_y * grid_z;
+    bool armed = false;
+    for (int k = blockIdx.x; k < n; k += gridDim.x) {
+        const int id = listed <= REDO_CAP ? P.redo[2 + k] : k;
+        __syncthreads();                          // every box of the previous chunk has been consumed
+        if (tid == 0) {
+            for (int m = 0; m < NB; ++m) {
+                if (armed) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mbar_u32 + 8u * m) : "memory");
+                mbar_init(mbar_u32 + 8u * m, 1);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        armed = true;
+        __syncthreads();
+        fused_march<OGT, PA0, KIND, OP, true>(P, &tmap, &cmap, smem_raw, s_div, id % grid_x, (id / grid_x) % grid_y,
+                                              id / (grid_x * grid_y));
+    }
+    // the last CTA to get here clears the list for the next pass
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(P.redo + 1, 1) == (int)gridDim.x - 1) {
+            P.redo[1] = 0;
+            __threadfence();
+            P.redo[0] = 0;
+        }
+    }
 }
 
 static size_t fused_smem_bytes(int LR, int LG, int LGc, int cpg, int nb, int nbc, int tab_k)
@@ -837,6 +886,8 @@ unsigned long long taub_inexact_events(void)
     return v;
 }
 
+size_t taub_redo_ws_ints(void) { return (size_t)REDO_LISTS * (REDO_CAP + 2); }
+
 int taub_can_fuse(const taub_problem *p)
 {
     if (!p || (p->kind != TAUB_BINARY && p->kind != TAUB_MULTIPHASE_CLASS && p->kind != TAUB_ANISOTROPIC) || !p->codes ||
@@ -875,6 +926,16 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     P.write_solid = write_solid;
     P.omega = p->omega;
     P.stop = p->stop;
+    // redo list of this launch: passes on the whole slab, its lower / upper boundary planes and its interior may be
+    // in flight together (slab solver: boundary planes on a side stream), each kind on one stream at a time
+    static const int exact_redo = env_int("TAUB_EXACT_REDO", 1);
+    P.redo = (p->redo_ws && exact_redo)
+                 ? p->redo_ws + (REDO_CAP + 2) * ((i_lo == 0 ? 0 : 2) + (i_hi == g.Nx ? 0 : 1))
+                 : nullptr;
+    {
+        const char *e = getenv("TAUB_FORCE_REDO");      // read per launch: the tests switch it on and off
+        P.force_redo = (e && *e && P.redo) ? atoi(e) : 0;
+    }
     P.peer_lo = p->peer_lo[p->cur ^ 1];
     P.peer_hi = p->peer_hi[p->cur ^ 1];
     P.colourA = (int)(iter & 1);
@@ -919,6 +980,19 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
         }                                                                                                         \
         TAUB_CUDA(launch_maybe_pdl(fused_sweep2_kernel<OG_, PA_, KIND_, OP_>, grid, dim3(F_NT), smem, s, P, tmap,  \
                                    cmap));                                                                        \
+        if (P.redo) {                                                                                             \
+            static std::atomic<size_t> smem_set_r[64];                                                            \
+            if (smem > smem_set_r[dev_ord & 63].load(std::memory_order_relaxed)) {                                \
+                TAUB_CUDA(cudaFuncSetAttribute(fused_redo_kernel<OG_, PA_, KIND_, OP_>,                           \
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+                smem_set_r[dev_ord & 63].store(smem, std::memory_order_relaxed);                                  \
+            }                                                                                                     \
+            /* an ordinary launch: as a programmatic dependent its CTAs (one per SM, a whole tile of shared memory  \
+               each) would sit on the SMs while the pass is still running and take a slot from its later CTAs */   \
+            fused_redo_kernel<OG_, PA_, KIND_, OP_><<<dim3(sm_count[dev_ord & 63]), dim3(F_NT), smem, s>>>(         \
+                P, tmap, cmap, (int)grid.x, (int)grid.y, (int)grid.z);                                            \
+            count_launch();                                                                                       \
+        }                                                                                                         \
     } while (0)
 #define TAUB_LAUNCH_FUSED_PA(OG_, KIND_, OP_)                                                                     \
     do {                                                                                                          \

@@ -240,6 +240,8 @@ class DistributedSolver(Solver):
             p.field[0], p.field[1] = self._bufs[0].data_ptr(), self._bufs[1].data_ptr()
             p.omega = float(np.float32(omega))
             p.cur = 0
+            self._redo_ws = torch.zeros(int(self._lib.taub_redo_ws_ints()), dtype=torch.int32, device=dev)
+            p.redo_ws = self._redo_ws.data_ptr() if self._exact_redo_on() else None
             if self._symm is not None:
                 for i, h in enumerate(self._symm):
                     ptrs = list(h.buffer_ptrs)
@@ -424,6 +426,7 @@ class DistributedSolver(Solver):
                 for i in range(2):
                     p.peer_lo[i] = None
                     p.peer_hi[i] = None
+        self._bind_exact_redo()
         done = 0
         main = torch.cuda.current_stream(self.device)
         while done < n:

@@ -69,6 +69,7 @@ class ElectrodeSolver(SORSolver):
     _kind = _lib.MULTIPHASE_CLASS
     _periodic = False
     pipeline = False     # the stop rule needs the host-side impedance recursion at every check
+    exact_redo = True    # clusters cut off from the inlet decay to sub-2^-100 values: redo such chunks with IEEE division
 
     def __init__(self, img, conductive_label=1, reactive_label=0, omega=None, spacing=None, device='cuda'):
         self.left_bc = 1.0

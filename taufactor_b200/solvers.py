@@ -99,6 +99,9 @@ class SORSolver:
             # counters of the shared-memory resident path for small volumes (taub_resident_pairs), zeroed once
             self._sync_ws = torch.zeros(int(self._lib.taub_sync_ws_ints()), dtype=torch.int32, device=dev)
             p.sync_ws, p.sync_epoch = self._sync_ws.data_ptr(), 0
+            # redo lists of the fused passes (chunks to be redone with IEEE division, see taub200.h), zeroed once
+            self._redo_ws = torch.zeros(int(self._lib.taub_redo_ws_ints()), dtype=torch.int32, device=dev)
+            p.redo_ws = self._redo_ws.data_ptr() if self._exact_redo_on() else None
             self._prob = p
             # label histogram (ref:564-567) -> which phases exist; then the per-slice volume
             # fraction numerators of the conductive phases (ref:42)
@@ -297,6 +300,7 @@ class SORSolver:
             verbose = 'per_iter'
         if verbose:
             torch.cuda.reset_peak_memory_stats(device=self.device)
+        events0 = None if self._exact_redo_on() else self.inexact_events
         start = timer()
         if self.pipeline and self._can_pipeline():
             self._solve_pipelined(iter_limit, verbose, conv_crit, plot_interval)
@@ -306,6 +310,11 @@ class SORSolver:
                 self.converged = self.check_convergence(verbose, conv_crit, plot_interval)
         torch.cuda.synchronize(self.device)
         self.walltime = timer() - start
+        if events0 is not None and self.inexact_events != events0:
+            warnings.warn(f"{self.inexact_events - events0} chunks of the fused sweep divided a non-zero neighbour sum "
+                          "below 2^-100 on the fast path: the field may differ from IEEE division (the reference) by one "
+                          "subnormal ulp at such voxels.  Set `solver.exact_redo = True` before solve() for the exact "
+                          "re-run.", RuntimeWarning)
         self._end_simulation(self.iter, verbose)
         if self.tau_x is None:
             return self.tau
@@ -467,7 +476,22 @@ class SORSolver:
 
     use_resident = True         # small volumes: whole blocks of iterations in one launch, field in shared memory
 
+    # Exactness of the fused kernel's division (taub200.h, taub_inexact_events): its reciprocal-based quotient equals
+    # IEEE division except, possibly by one subnormal ulp, for a non-zero neighbour sum below 2^-100.  Chunks that meet
+    # such a sum are counted; with ``exact_redo`` a second kernel behind every fused pass redoes them with IEEE
+    # division (bit-identical to the reference for every finite input, ~2 % slower).  Default: on for the
+    # electrode solvers, whose cut-off clusters decay towards 0 and do get there; off for the through-transport
+    # solvers, where no solve has ever met such a sum -- ``solve()`` checks the counter and warns if one did.
+    exact_redo = False
+
+    def _exact_redo_on(self):
+        return bool(self.exact_redo)
+
+    def _bind_exact_redo(self):
+        self._prob.redo_ws = self._redo_ws.data_ptr() if (self._exact_redo_on() and getattr(self, "_redo_ws", None) is not None) else None
+
     def _iterate_flags(self):
+        self._bind_exact_redo()
         pdl = self._pdl_on()
         return ((1 if self.force_generic else 0) | (2 if pdl else 0) | (4 if pdl and self.pdl_refresh_late else 0)
                 | (0 if self.use_resident else 8))

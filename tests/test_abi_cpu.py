@@ -24,7 +24,7 @@ def test_header_symbols_exported(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in taub200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes prototype"
-    assert lib.taub_abi_version() == 11
+    assert lib.taub_abi_version() == 12
 
 
 def test_struct_layout_matches_header(lib):
@@ -32,9 +32,10 @@ def test_struct_layout_matches_header(lib):
     from taufactor_b200 import _lib
     assert ctypes.sizeof(_lib.Geom) == 10 * 4 + 2 * 8
     assert _lib.Problem.field.offset == ctypes.sizeof(_lib.Geom) + 8
-    assert ctypes.sizeof(_lib.Problem) == ctypes.sizeof(_lib.Geom) + 8 + 5 * 8 + 8 + 8 + 4 * 8 + 8 + 8
-    assert _lib.Problem.stop.offset == ctypes.sizeof(_lib.Problem) - 7 * 8
-    assert _lib.Problem.sync_ws.offset == ctypes.sizeof(_lib.Problem) - 2 * 8
+    assert ctypes.sizeof(_lib.Problem) == ctypes.sizeof(_lib.Geom) + 8 + 5 * 8 + 8 + 8 + 4 * 8 + 8 + 8 + 8
+    assert _lib.Problem.stop.offset == ctypes.sizeof(_lib.Problem) - 8 * 8
+    assert _lib.Problem.sync_ws.offset == ctypes.sizeof(_lib.Problem) - 3 * 8
+    assert _lib.Problem.redo_ws.offset == ctypes.sizeof(_lib.Problem) - 8
 
 
 @pytest.mark.parametrize("shape", [(1, 512, 512, 512), (3, 11, 13, 9), (2, 30, 28, 1), (1, 8, 8, 2049)])
@@ -164,11 +165,11 @@ int main(void)
     if (taub_geom_init(&g, 2, 30, 28, 1, 30, 0, 1) != TAUB_OK) return 3;
     if (taub_geom_init(&g, 0, 30, 28, 1, 30, 0, 1) != TAUB_ERR_ARG || taub_last_error()[0] == 0) return 4;
     taub_geom_init(&g, 2, 30, 28, 1, 30, 0, 1);
-    printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(taub_geom), sizeof(taub_problem),
+    printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(taub_geom), sizeof(taub_problem),
            offsetof(taub_geom, plane_stride), offsetof(taub_problem, kind), offsetof(taub_problem, field),
            offsetof(taub_problem, codes), offsetof(taub_problem, lut), offsetof(taub_problem, omega),
            offsetof(taub_problem, stop), offsetof(taub_problem, peer_lo), offsetof(taub_problem, peer_hi),
-           offsetof(taub_problem, sync_ws), offsetof(taub_problem, sync_epoch));
+           offsetof(taub_problem, sync_ws), offsetof(taub_problem, sync_epoch), offsetof(taub_problem, redo_ws));
     printf("%d %d %d %lld %lld %zu\n", g.planes, g.rows, g.pitch, (long long)g.plane_stride, (long long)g.image_stride,
            taub_field_elems(&g));
     return 0;
@@ -182,7 +183,7 @@ int main(void)
     P, Gm = _lib.Problem, _lib.Geom
     expect = [ctypes.sizeof(Gm), ctypes.sizeof(P), Gm.plane_stride.offset, P.kind.offset, P.field.offset, P.codes.offset,
               P.lut.offset, P.omega.offset, P.stop.offset, P.peer_lo.offset, P.peer_hi.offset, P.sync_ws.offset,
-              P.sync_epoch.offset]
+              P.sync_epoch.offset, P.redo_ws.offset]
     assert [int(x) for x in out[0].split()] == expect
     g = Gm()
     assert lib.taub_geom_init(g, 2, 30, 28, 1, 30, 0, 1) == 0

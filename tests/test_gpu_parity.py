@@ -497,3 +497,41 @@ def test_resident_kernel_is_not_taken_where_it_does_not_apply(tau):
         assert S.sweep_kernel_name() != "resident_kernel", (cls, shape)
     S = tau.MultiPhaseSolver(cases.blobs3((32, 32, 32), seed=1), {0: 0.0, 1: 1.0, 2: 0.3}, device="cuda")
     assert S.sweep_kernel_name() != "resident_kernel"
+
+
+# ------------------------------------------------------------------ exact re-run of fused chunks (fused_redo_kernel)
+@pytest.mark.parametrize("cls,shape,kw", [
+    ("Solver", (48, 40, 36), {}), ("Solver", (5, 64, 130), {}), ("Solver", (70, 130, 260), {}),
+    ("PeriodicSolver", (48, 40, 36), {}), ("PeriodicSolver", (21, 13, 9), {}),
+    ("MultiPhaseSolver", (40, 44, 36), {"diffusivities": {0: 0.0, 1: 1.0, 2: 0.3}}),
+    ("PeriodicMultiPhaseSolver", (19, 15, 11), {"diffusivities": {0: 0.0, 1: 1.0, 2: 0.3}}),
+    ("AnisotropicSolver", (48, 40, 36), {"spacing": (1.0, 2.0, 0.5)})])
+def test_redo_kernel_reproduces_the_pass_with_ieee_division(tau, monkeypatch, cls, shape, kw):
+    """`exact_redo`: chunks whose threads met a sub-2^-100 sum are redone by fused_redo_kernel with IEEE division.
+    No through-transport volume gets there by itself, so TAUB_FORCE_REDO=1 lists EVERY chunk: the whole pass is then
+    computed twice, the second time by the redo kernel with __fdiv_rn -- the field must equal the generic kernel's
+    (plain IEEE division) and the ordinary fused pass's, for every kernel variant."""
+    import torch
+    if "MultiPhase" in cls:
+        img = np.random.default_rng(3).integers(0, 3, size=shape).astype(np.uint8)
+    else:
+        img = cases.random_img(shape, 0.8 if min(shape) < 16 else 0.62, seed=1)
+    mk = lambda: getattr(tau, cls)(img, device="cuda", **kw)
+    A, B, C = mk(), mk(), mk()
+    A.use_resident = B.use_resident = False
+    A.exact_redo = True
+    C.force_generic = True
+    e0 = A.inexact_events
+    monkeypatch.setenv("TAUB_FORCE_REDO", "1")
+    for n in (2, 3, 58):
+        A._advance(n)
+    monkeypatch.delenv("TAUB_FORCE_REDO")
+    assert A.inexact_events > e0 and A.sweep_kernel_name() == "fused_sweep2_kernel"
+    for n in (2, 3, 58):
+        B._advance(n)
+        C._advance(n)
+    assert torch.equal(A.field, C.field) and torch.equal(A.field, B.field)
+    # the lists are empty again: an ordinary pass lists nothing
+    e1 = A.inexact_events
+    A._advance(10); B._advance(10)
+    assert A.inexact_events == e1 and torch.equal(A.field, B.field)
