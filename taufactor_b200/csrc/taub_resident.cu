@@ -28,8 +28,8 @@
 
 namespace taub {
 
-constexpr int R_NT = 512;            // threads per CTA
-constexpr int R_WARPS = R_NT / 32;
+// threads per CTA: a template parameter of the kernel (512 or 1024; the steps of a pair are latency bound, so the
+// second variant trades registers -- 64 per thread, smaller load batches -- for twice the warps)
 constexpr size_t R_SMEM_MAX = 232448 - 1024;   // opt-in dynamic shared memory per CTA (227 KB) less the static part
 constexpr int R_FLAG_STRIDE = 32;    // ints between two bricks' counters: one 128-byte line each
 constexpr int R_MAX_BRICKS = 256;
@@ -98,13 +98,13 @@ __device__ __forceinline__ const float *global_row(const ResParams &P, const Bri
 //                         (-1: skip -- a frame row outside the volume holds constants; publish: see RowTab::bnd)
 //   colour-step rows:     .x = float offset of the shared row, .y = uint16 offset of its code row | parity << 30
 struct RowTab {
-    int2 *frame, *pub, *a, *b;
-    int n_frame, n_pub, n_a, n_b;
+    int2 *frame, *pub, *a_in, *a_out, *b;      // colour A: rows that read brick rows only / rows that need the frame
+    int n_frame, n_pub, n_a_in, n_a_out, n_b;
 };
-constexpr int R_BATCH = 8;      // global loads a warp keeps in flight while it reloads the frame
 
 // Rows f = warp, warp + R_WARPS, ... of a table from global memory into shared memory.  A warp first issues the loads
 // of up to R_BATCH rows, then stores them: the latency is paid once per batch, not once per row.
+template <int R_WARPS, int R_BATCH>      // R_BATCH: global loads a warp keeps in flight
 __device__ __forceinline__ void load_rows(const int2 *tab, int n, float *fld, const float *base, int ZS, int warp, int lane)
 {
     const int ZH = ZS >> 1, CG = ZS >> 2;
@@ -197,9 +197,11 @@ __device__ __forceinline__ void colour_step(const int2 *tab, int nrows, float *f
     }
 }
 
+template <int R_NT, int R_BATCH>
 __global__ void __launch_bounds__(R_NT, 1)
 resident_kernel(const ResParams P)
 {
+    constexpr int R_WARPS = R_NT / 32;
     extern __shared__ __align__(16) unsigned char r_smem[];
     __shared__ __align__(128) float2 s_div[16];
     const taub_geom &g = P.g;
@@ -229,14 +231,18 @@ resident_kernel(const ResParams P)
     RowTab T;
     T.frame = reinterpret_cast<int2 *>(cod + (((size_t)(P.BX + 2) * CY * CG + 3) & ~(size_t)3));   // 8-byte aligned
     T.pub = T.frame + 4 * (P.BY + 4) + 4 * P.BX;
-    T.a = T.pub + P.BX * P.BY;
-    T.b = T.a + (P.BX + 2) * (P.BY + 2);
+    T.a_out = T.pub + P.BX * P.BY;
+    T.b = T.a_out + (P.BX + 2) * (P.BY + 2);
+    T.a_in = T.b + P.BX * P.BY;
     // the steps never touch a Dirichlet plane, nor (no-flux solvers) a row outside the volume
     const int a_li0 = (K.x0 == 0) ? 2 : 1, a_li1 = (K.x1 == g.Nx) ? K.bx + 2 : K.bx + 3;
     const int a_lj0 = (!per && K.y0 == 0) ? 2 : 1, a_lj1 = (!per && K.y1 == g.Ny) ? K.by + 2 : K.by + 3;
     T.n_frame = 4 * LY + 4 * K.bx;
     T.n_pub = K.bx * K.by;
-    T.n_a = (a_li1 - a_li0) * (a_lj1 - a_lj0);
+    // colour A on a brick row at least one row inside the brick reads brick rows only: it does not wait for the frame
+    const int in_x = max(K.bx - 2, 0), in_y = max(K.by - 2, 0);
+    T.n_a_in = in_x * in_y;
+    T.n_a_out = (a_li1 - a_li0) * (a_lj1 - a_lj0) - T.n_a_in;
     T.n_b = K.bx * K.by;
     // global float offset of shared row (li, lj): x = x0 - 2 + li, y = y0 - 2 + lj (wrapped for the periodic solvers)
     auto goff = [&](int li, int lj) {
@@ -268,10 +274,15 @@ resident_kernel(const ResParams P)
         T.pub[r] = make_int2(goff(oi + 2, oj + 2), soff(oi + 2, oj + 2) | (bnd ? 0 : 1 << 30));
         T.b[r] = make_int2(soff(oi + 2, oj + 2), (((oi + 1) * CY + oj + 1) * CG) | (((K.x0 + oi + K.y0 + oj) & 1) << 30));
     }
-    for (int r = tid; r < T.n_a; r += R_NT) {
-        const int nj = a_lj1 - a_lj0, di = r / nj;
-        const int li = a_li0 + di, lj = a_lj0 + (r - di * nj);
-        T.a[r] = make_int2(soff(li, lj), (((li - 1) * CY + lj - 1) * CG) | (((K.x0 + li + K.y0 + lj) & 1) << 30));
+    auto a_entry = [&](int li, int lj) {
+        return make_int2(soff(li, lj), (((li - 1) * CY + lj - 1) * CG) | (((K.x0 + li + K.y0 + lj) & 1) << 30));
+    };
+    for (int r = tid; r < T.n_a_in; r += R_NT) T.a_in[r] = a_entry(3 + r / in_y, 3 + r % in_y);
+    if (tid == 0) {          // the rest of the colour-A region, in order (a few hundred rows, once per launch)
+        int m = 0;
+        for (int li = a_li0; li < a_li1; ++li)
+            for (int lj = a_lj0; lj < a_lj1; ++lj)
+                if (!(li >= 3 && li < K.bx + 1 && lj >= 3 && lj < K.by + 1)) T.a_out[m++] = a_entry(li, lj);
     }
 
     // ---- start: the brick and its frame from the current field, neighbour codes of the brick and its first ring
@@ -320,13 +331,18 @@ resident_kernel(const ResParams P)
         if (ok && !(nbi == K.bi && nbj == K.bj)) nb_flag = ((K.b * P.nbx + nbi) * P.nby + nbj) * R_FLAG_STRIDE;
     }
     // periodic z: ghost column 3 := column Nz + 3 (odd), ghost column Nz + 4 := column 4 (even); Nz is even here
-    auto z_ghosts = [&]() {
-        for (int r = tid; r < T.n_a; r += R_NT) {
-            float *row = fld + T.a[r].x;
+    auto z_ghosts = [&](const int2 *tab, int n) {
+        for (int r = tid; r < n; r += R_NT) {
+            float *row = fld + tab[r].x;
             row[ZH + 1] = row[ZH + ((g.Nz + 3) >> 1)];
             row[(g.Nz + COL0) >> 1] = row[COL0 >> 1];
         }
     };
+    // colour A on the inner rows runs on warps 1.. while warp 0 polls the neighbours' counters
+    const int rows_per_round_w = (R_NT - 32) / QN;
+    const int my_r_w = tid >= 32 ? (tid - 32) / QN : rows_per_round_w, my_q_w = tid >= 32 ? (tid - 32) % QN : 0;
+    if (per) z_ghosts(T.b, T.n_b);      // (the brick's own rows; visible after the first barrier of the pair loop)
+    __syncthreads();
 
     const bool prof = (P.prof != 0 && tid == 0 && blockIdx.x == gridDim.x / 2);
     const long long t_launch = clock64();
@@ -340,6 +356,8 @@ resident_kernel(const ResParams P)
     for (int n = 0; n < P.n_pairs; ++n) {
         float *wbuf = P.buf[(n & 1) ^ 1];            // pair n publishes into buf[1], buf[0], buf[1], ...
         if (prof) t_prev = clock64();
+        // ---- colour A on the rows that do not need the frame (warps 1..), under the wait for the neighbours
+        colour_step(T.a_in, T.n_a_in, fld, cod, s_div, P.colour0, ZS, row_stride, P.omega, my_r_w, my_q_w, rows_per_round_w);
         if (n > 0) {
             // ---- wait for the neighbours' pair n-1, then re-read the frame from the buffer they wrote
             if (nb_flag >= 0) {
@@ -356,23 +374,24 @@ resident_kernel(const ResParams P)
             }
             __syncthreads();
             PROF(0);
-            load_rows(T.frame, T.n_frame, fld, P.buf[((n - 1) & 1) ^ 1], ZS, warp, lane);
+            load_rows<R_WARPS, R_BATCH>(T.frame, T.n_frame, fld, P.buf[((n - 1) & 1) ^ 1], ZS, warp, lane);
         }
         __syncthreads();
         PROF(1);
         if (per) {
-            z_ghosts();
+            z_ghosts(T.a_out, T.n_a_out);      // ring rows just loaded (and, again, the brick's edge rows)
             __syncthreads();
         }
-        colour_step(T.a, T.n_a, fld, cod, s_div, P.colour0, ZS, row_stride, P.omega, my_r, my_q, rows_per_round);
+        colour_step(T.a_out, T.n_a_out, fld, cod, s_div, P.colour0, ZS, row_stride, P.omega, my_r, my_q, rows_per_round);
         __syncthreads();
         PROF(2);
         if (per) {
-            z_ghosts();
+            z_ghosts(T.b, T.n_b);
             __syncthreads();
         }
         colour_step(T.b, T.n_b, fld, cod, s_div, P.colour0 ^ 1, ZS, row_stride, P.omega, my_r, my_q, rows_per_round);
         __syncthreads();
+        if (per) z_ghosts(T.b, T.n_b);          // for the next pair's early colour-A rows (barriers below come first)
         PROF(3);
         // ---- publish: the voxels the neighbours' frames cover (everything after the last pair)
         const int skip_mask = (n == P.n_pairs - 1) ? 0 : 1 << 30;
@@ -405,7 +424,7 @@ struct ResChoice {
 
 static size_t resident_smem(int BX, int BY, int ZS)
 {
-    const size_t tables = (size_t)(4 * (BY + 4) + 4 * BX) + 2 * (size_t)BX * BY + (size_t)(BX + 2) * (BY + 2);   // int2 entries
+    const size_t tables = (size_t)(4 * (BY + 4) + 4 * BX) + 3 * (size_t)BX * BY + (size_t)(BX + 2) * (BY + 2);   // int2 entries
     return (size_t)(BX + 4) * (BY + 4) * ZS * 4 + (size_t)(BX + 2) * (BY + 2) * (ZS / 4) * 2 + tables * 8 + 16;
 }
 
@@ -531,14 +550,27 @@ int taub_resident_pairs(taub_problem *p, int64_t iter, int n_pairs, void *stream
     P.prof = prof_on;
     int dev = 0;
     TAUB_CUDA(cudaGetDevice(&dev));
-    static size_t smem_set[64] = {0};
-    if (c.smem > smem_set[dev & 63]) {
-        TAUB_CUDA(cudaFuncSetAttribute(resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM_MAX));
-        smem_set[dev & 63] = R_SMEM_MAX;
-    }
+    static const int nt = [] {
+        const char *e = getenv("TAUB_RESIDENT_NT");
+        return (e && atoi(e) == 1024) ? 1024 : 512;      // measured: 512 is 2-10 % faster at every size (32^3 .. 150^3)
+    }();
     void *args[] = {(void *)&P};
-    TAUB_CUDA(cudaLaunchCooperativeKernel((const void *)resident_kernel, dim3(bricks), dim3(R_NT), args, c.smem,
-                                          (cudaStream_t)stream));
+    static bool attr_set[2][64] = {};
+    if (nt == 512) {
+        if (!attr_set[0][dev & 63]) {
+            TAUB_CUDA(cudaFuncSetAttribute(resident_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM_MAX));
+            attr_set[0][dev & 63] = true;
+        }
+        TAUB_CUDA(cudaLaunchCooperativeKernel((const void *)resident_kernel<512, 8>, dim3(bricks), dim3(512), args, c.smem,
+                                              (cudaStream_t)stream));
+    } else {
+        if (!attr_set[1][dev & 63]) {
+            TAUB_CUDA(cudaFuncSetAttribute(resident_kernel<1024, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM_MAX));
+            attr_set[1][dev & 63] = true;
+        }
+        TAUB_CUDA(cudaLaunchCooperativeKernel((const void *)resident_kernel<1024, 4>, dim3(bricks), dim3(1024), args, c.smem,
+                                              (cudaStream_t)stream));
+    }
     count_launch();
     p->sync_epoch += n_pairs;
     // the last pair stored the whole field into its buffer: buf[1] after an odd number of pairs, buf[0] otherwise
