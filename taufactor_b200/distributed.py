@@ -205,7 +205,9 @@ class DistributedSolver(Solver):
                     import torch.distributed._symmetric_memory as symm
                     grp = group if group is not None else dist.group.WORLD
                     if not symm.is_symm_mem_enabled_for_group(grp.group_name):
-                        symm.enable_symm_mem_for_group(grp.group_name)
+                        with warnings.catch_warnings():      # newer torch enables it implicitly and says so
+                            warnings.simplefilter("ignore", FutureWarning)
+                            symm.enable_symm_mem_for_group(grp.group_name)
                     bufs = [symm.empty(n, dtype=torch.float32, device=dev) for _ in range(2)]
                 except Exception as e:
                     err = repr(e)

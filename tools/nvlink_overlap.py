@@ -77,27 +77,55 @@ for overlap in (True, False):
         bnd = np.concatenate([x for x in (low, high) if len(x)]) if (len(low) or len(high)) else np.zeros((0, 2))
         # boundary work of pass n overlaps the interior kernel of pass n: intersection of the intervals
         ov = 0.0
-        per = max(len(bnd) // max(len(inter), 1), 1)
         for n in range(len(inter)):
-            for (s0, s1) in bnd[n * per:(n + 1) * per]:
-                ov += max(0.0, min(s1, inter[n, 1]) - max(s0, inter[n, 0]))
+            for part in (low, high):
+                if len(part) == len(inter):
+                    s0, s1 = part[n]
+                    ov += max(0.0, min(s1, inter[n, 1]) - max(s0, inter[n, 0]))
         r.update({"interior_kernel_us": float(np.mean(inter[:, 1] - inter[:, 0])) * 1e3,
                   "boundary_kernels_us_per_pass": float(np.sum(bnd[:, 1] - bnd[:, 0])) / len(inter) * 1e3,
                   "boundary_time_inside_interior_kernel_frac": float(ov / max(np.sum(bnd[:, 1] - bnd[:, 0]), 1e-9))})
     else:
         whole = np.array(iv["whole"])
         r.update({"whole_slab_kernel_us": float(np.mean(whole[:, 1] - whole[:, 0])) * 1e3})
-    if rank == 0 and tx0 is not None and tx1 is not None:
+    if rank == 0:
         n_nb = (1 if rank > 0 else 0) + (1 if rank < world - 1 else 0)
         expect = n_nb * 2 * g.plane_stride * 4 * g.bs * args.passes
-        r.update({"nvlink_tx_bytes_rank0": (tx1 - tx0) * 1024, "nvlink_rx_bytes_rank0": (rx1 - rx0) * 1024,
-                  "expected_tx_bytes_rank0": int(expect), "expected": "neighbours x 2 ghost planes x plane bytes x passes",
-                  "nvlink_tx_bytes_per_pass": (tx1 - tx0) * 1024 / args.passes})
+        r.update({"peer_store_bytes_rank0_protocol": int(expect), "peer_store_bytes_per_pass_per_neighbour": int(2 * g.plane_stride * 4 * g.bs),
+                  "protocol": "the boundary kernels store their first / last 2 output planes into the neighbour's ghost planes"})
+        counters = raw1 is not None and "KiB" in raw1
+        if counters:
+            r.update({"nvlink_tx_bytes_rank0": (tx1 - tx0) * 1024, "nvlink_rx_bytes_rank0": (rx1 - rx0) * 1024})
+        else:
+            r["nvlink_counters"] = "unavailable: `nvidia-smi nvlink -gt d` reports N/A for every link on this box"
         if overlap:
-            result["nvidia_smi_nvlink_raw_after"] = raw1[:4000] if raw1 else None
+            result["nvidia_smi_nvlink_raw_after"] = raw1[:600] if raw1 else None
     result[key] = r
     del S
     torch.cuda.empty_cache()
+# the same passes with NCCL send / recv of the ghost planes instead of one-sided peer stores
+S = DistributedSolver(host, device=dev, window=(w0, w1), shape=(side, side, side), overlap=True, p2p=False)
+S._advance(20); torch.cuda.synchronize(); dist.barrier()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); S._advance(2 * args.passes); e1.record(); torch.cuda.synchronize(); dist.barrier()
+t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+result["nccl_messages_overlap"] = {"ms_per_pass_max_over_ranks": float(t.item()) / args.passes, "p2p": bool(getattr(S, "p2p_active", False)),
+                                   "halo_bytes_sent_rank0": int(S.halo_bytes_sent)}
+del S
+torch.cuda.empty_cache()
+# raw peer-copy bandwidth between GPU 0 and GPU 1 (what the link delivers to a plain copy)
+if rank == 0 and torch.cuda.device_count() > 1:
+    a = torch.empty(1 << 28, dtype=torch.float32, device="cuda:0"); b = torch.empty(1 << 28, dtype=torch.float32, device="cuda:1")
+    b.copy_(a); torch.cuda.synchronize("cuda:0"); torch.cuda.synchronize("cuda:1")
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.device(0):
+        c0.record()
+        for _ in range(5):
+            b.copy_(a)
+        c1.record(); torch.cuda.synchronize()
+    result["peer_copy_gbs_gpu0_to_gpu1"] = 5 * a.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    del a, b
+dist.barrier()
 if rank == 0:
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", f"nvlink_overlap_{world}gpu.json"), "w") as fh:
