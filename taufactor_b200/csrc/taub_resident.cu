@@ -37,7 +37,9 @@ constexpr int R_MAX_BRICKS = 256;
 struct ResParams {
     taub_geom g;
     float *buf[2];           // [0]: the current field at launch, [1]: the other ping-pong buffer
-    const uint16_t *codes;   // binary kind: four 4-bit neighbour counts per float4 group
+    const uint16_t *codes;   // binary kind: four 4-bit neighbour counts per float4 group; class kind: one id per voxel
+    const float *table;      // class kind: [n_classes][8] weight rows (the last one inert)
+    int n_classes, tab_k;    // ... rows in all / staged in shared memory
     float omega;
     int colour0;             // colour (iter & 1) of the first iteration
     int n_pairs;
@@ -155,9 +157,26 @@ __device__ __forceinline__ void store_row(float *grow, const float *srow, int ZS
 
 // One colour step on the rows of a table (in place: an active voxel only reads voxels of the other colour).
 // Thread = (row slot, float4 group of the active half row).
+// Class kinds: the weight row of a class, from the shared copy of the first tab_k rows or -- rare classes -- global memory.
+struct ResClassTab {
+    const float4 *s, *g;    // shared copy / global table, two float4 per class
+    unsigned k;             // rows staged
+};
+__device__ __forceinline__ void res_class_row(unsigned cls, const ResClassTab &T, float4 &wa, float4 &wb)
+{
+    if (cls < T.k) {
+        wa = T.s[2 * cls];
+        wb = T.s[2 * cls + 1];
+    } else {
+        wa = __ldg(T.g + 2 * cls);
+        wb = __ldg(T.g + 2 * cls + 1);
+    }
+}
+
+template <int KIND>
 __device__ __forceinline__ void colour_step(const int2 *tab, int nrows, float *fld, const uint16_t *cod, const float2 *s_div,
-                                            int colour, int ZS, int row_stride, float omega, int my_r, int my_q,
-                                            int rows_per_round)
+                                            const ResClassTab &ctab, int colour, int ZS, int row_stride, float omega,
+                                            int my_r, int my_q, int rows_per_round)
 {
     const int ZH = ZS >> 1;
     if (my_r >= rows_per_round) return;
@@ -178,6 +197,28 @@ __device__ __forceinline__ void colour_step(const int2 *tab, int nrows, float *f
         // E active: z+ = O[m], z- = O[m-1];  O active: z- = E[m], z+ = E[m+1]
         const float4 zp = par ? make_float4(z4.y, z4.z, z4.w, ze) : z4;
         const float4 zm = par ? z4 : make_float4(ze, z4.x, z4.y, z4.z);
+        if (KIND == TAUB_MULTIPHASE_CLASS) {
+            // class ids of the row are stored colour-split like the field: four consecutive uint16 of the active half
+            const uint2 iw = *reinterpret_cast<const uint2 *>(cod + (d.y & 0x3fffffff) + (par ? ZH : 0) + 4 * my_q);
+            float4 wa0, wb0, wa1, wb1, wa2, wb2, wa3, wb3;
+            res_class_row(iw.x & 0xffffu, ctab, wa0, wb0);
+            res_class_row(iw.x >> 16, ctab, wa1, wb1);
+            res_class_row(iw.y & 0xffffu, ctab, wa2, wb2);
+            res_class_row(iw.y >> 16, ctab, wa3, wb3);
+            unsigned um = 0xffffffffu;
+            float n0 = sor_class_rows(c.x, xp.x, xm.x, yp.x, ym.x, zp.x, zm.x, wa0, wb0, omega, um);
+            float n1 = sor_class_rows(c.y, xp.y, xm.y, yp.y, ym.y, zp.y, zm.y, wa1, wb1, omega, um);
+            float n2 = sor_class_rows(c.z, xp.z, xm.z, yp.z, ym.z, zp.z, zm.z, wa2, wb2, omega, um);
+            float n3 = sor_class_rows(c.w, xp.w, xm.w, yp.w, ym.w, zp.w, zm.w, wa3, wb3, omega, um);
+            if (um < GUARD_T) {   // a non-zero sum below 2^-100: IEEE division, never the fast path
+                n0 = sor_class_rows<true>(c.x, xp.x, xm.x, yp.x, ym.x, zp.x, zm.x, wa0, wb0, omega, um);
+                n1 = sor_class_rows<true>(c.y, xp.y, xm.y, yp.y, ym.y, zp.y, zm.y, wa1, wb1, omega, um);
+                n2 = sor_class_rows<true>(c.z, xp.z, xm.z, yp.z, ym.z, zp.z, zm.z, wa2, wb2, omega, um);
+                n3 = sor_class_rows<true>(c.w, xp.w, xm.w, yp.w, ym.w, zp.w, zm.w, wa3, wb3, omega, um);
+            }
+            *reinterpret_cast<float4 *>(act) = make_float4(n0, n1, n2, n3);
+            continue;
+        }
         // neighbour counts: code words of storage groups 2q, 2q+1; E voxels are nibbles 0 and 2, O voxels 1 and 3
         const unsigned cw = *reinterpret_cast<const unsigned *>(cod + (d.y & 0x3fffffff) + 2 * my_q) >> (par ? 4 : 0);
         const float2 d0 = s_div[cw & 15u], d1 = s_div[(cw >> 8) & 15u], d2 = s_div[(cw >> 16) & 15u],
@@ -197,11 +238,12 @@ __device__ __forceinline__ void colour_step(const int2 *tab, int nrows, float *f
     }
 }
 
-template <int R_NT, int R_BATCH>
+template <int KIND, int R_NT, int R_BATCH>
 __global__ void __launch_bounds__(R_NT, 1)
 resident_kernel(const ResParams P)
 {
     constexpr int R_WARPS = R_NT / 32;
+    constexpr bool CLS = (KIND == TAUB_MULTIPHASE_CLASS);
     extern __shared__ __align__(16) unsigned char r_smem[];
     __shared__ __align__(128) float2 s_div[16];
     const taub_geom &g = P.g;
@@ -227,9 +269,12 @@ resident_kernel(const ResParams P)
     const int ZS = P.ZS, ZH = ZS >> 1, RY = P.BY + 4, CY = P.BY + 2, CG = ZS >> 2;
     const int LX = K.bx + 4, LY = K.by + 4;     // rows held: the brick and its 2-wide frame
     float *fld = reinterpret_cast<float *>(r_smem);                                 // [BX+4][BY+4][ZS]
-    uint16_t *cod = reinterpret_cast<uint16_t *>(fld + (size_t)(P.BX + 4) * RY * ZS);  // [BX+2][BY+2][ZS/4]
+    // binary: neighbour codes [BX+2][BY+2][ZS/4]; class kinds: ids [BX+2][BY+2][ZS] (colour-split rows)
+    uint16_t *cod = reinterpret_cast<uint16_t *>(fld + (size_t)(P.BX + 4) * RY * ZS);
+    const int CROW = CLS ? ZS : CG;             // uint16 per code / id row
+    float4 *s_tab = reinterpret_cast<float4 *>(cod + (((size_t)(P.BX + 2) * CY * CROW + 7) & ~(size_t)7));   // 16-byte aligned
     RowTab T;
-    T.frame = reinterpret_cast<int2 *>(cod + (((size_t)(P.BX + 2) * CY * CG + 3) & ~(size_t)3));   // 8-byte aligned
+    T.frame = reinterpret_cast<int2 *>(s_tab + 2 * (CLS ? P.tab_k : 0));
     T.pub = T.frame + 4 * (P.BY + 4) + 4 * P.BX;
     T.a_out = T.pub + P.BX * P.BY;
     T.b = T.a_out + (P.BX + 2) * (P.BY + 2);
@@ -272,10 +317,10 @@ resident_kernel(const ResParams P)
         const bool bnd = oi < 2 || oi >= K.bx - 2 || oj < 2 || oj >= K.by - 2;   // a neighbour's frame covers this row
         // .y: shared offset, bit 30 = interior row (published after the last pair only)
         T.pub[r] = make_int2(goff(oi + 2, oj + 2), soff(oi + 2, oj + 2) | (bnd ? 0 : 1 << 30));
-        T.b[r] = make_int2(soff(oi + 2, oj + 2), (((oi + 1) * CY + oj + 1) * CG) | (((K.x0 + oi + K.y0 + oj) & 1) << 30));
+        T.b[r] = make_int2(soff(oi + 2, oj + 2), (((oi + 1) * CY + oj + 1) * CROW) | (((K.x0 + oi + K.y0 + oj) & 1) << 30));
     }
     auto a_entry = [&](int li, int lj) {
-        return make_int2(soff(li, lj), (((li - 1) * CY + lj - 1) * CG) | (((K.x0 + li + K.y0 + lj) & 1) << 30));
+        return make_int2(soff(li, lj), (((li - 1) * CY + lj - 1) * CROW) | (((K.x0 + li + K.y0 + lj) & 1) << 30));
     };
     for (int r = tid; r < T.n_a_in; r += R_NT) T.a_in[r] = a_entry(3 + r / in_y, 3 + r % in_y);
     if (tid == 0) {          // the rest of the colour-A region, in order (a few hundred rows, once per launch)
@@ -301,6 +346,19 @@ resident_kernel(const ResParams P)
         const int gx = K.x0 - 1 + ci, gy = K.y0 - 1 + cj;
         const bool inside = gx >= 0 && gx < g.Nx && (per || (gy >= 0 && gy < g.Ny));
         const int sr = per ? G + wrap(gy, g.Ny) : G + gy;
+        if (CLS) {
+            // one uint16 class id per storage voxel; rows outside the volume: the inert class (the table's last row)
+            const uint16_t *irow = P.codes + (((int64_t)K.b * g.planes + (gx + G)) * g.rows + sr) * g.pitch;
+            uint16_t *srow = cod + (size_t)(ci * CY + cj) * ZS;
+            const unsigned inert = (unsigned)(P.n_classes - 1);
+            for (int g4 = lane; g4 < CG; g4 += 32) {
+                uint2 w = make_uint2(inert | (inert << 16), inert | (inert << 16));
+                if (inside) w = __ldg(reinterpret_cast<const uint2 *>(irow) + g4);      // ids of columns 4g4 .. 4g4+3
+                *reinterpret_cast<unsigned *>(srow + 2 * g4) = (w.x & 0xffffu) | (w.y << 16);            // even columns
+                *reinterpret_cast<unsigned *>(srow + ZH + 2 * g4) = (w.x >> 16) | (w.y & 0xffff0000u);   // odd columns
+            }
+            continue;
+        }
         const uint16_t *grow = P.codes + ((int64_t)K.b * g.planes + (gx + G)) * g.rows * (g.pitch >> 2) + (int64_t)sr * (g.pitch >> 2);
         for (int g4 = lane; g4 < CG; g4 += 32) {
             unsigned w = inside ? (unsigned)__ldg(grow + g4) : 0u;
@@ -312,6 +370,9 @@ resident_kernel(const ResParams P)
         }
     }
 
+    if (CLS)
+        for (int t = tid; t < 2 * P.tab_k; t += R_NT) s_tab[t] = __ldg(reinterpret_cast<const float4 *>(P.table) + t);
+    const ResClassTab ctab{s_tab, reinterpret_cast<const float4 *>(P.table), (unsigned)(CLS ? P.tab_k : 0)};
     const int QN = ZS >> 3;                         // float4 groups per half row
     const int rows_per_round = R_NT / QN;
     const int my_r = tid / QN, my_q = tid - my_r * QN;
@@ -357,7 +418,7 @@ resident_kernel(const ResParams P)
         float *wbuf = P.buf[(n & 1) ^ 1];            // pair n publishes into buf[1], buf[0], buf[1], ...
         if (prof) t_prev = clock64();
         // ---- colour A on the rows that do not need the frame (warps 1..), under the wait for the neighbours
-        colour_step(T.a_in, T.n_a_in, fld, cod, s_div, P.colour0, ZS, row_stride, P.omega, my_r_w, my_q_w, rows_per_round_w);
+        colour_step<KIND>(T.a_in, T.n_a_in, fld, cod, s_div, ctab, P.colour0, ZS, row_stride, P.omega, my_r_w, my_q_w, rows_per_round_w);
         if (n > 0) {
             // ---- wait for the neighbours' pair n-1, then re-read the frame from the buffer they wrote
             if (nb_flag >= 0) {
@@ -382,14 +443,14 @@ resident_kernel(const ResParams P)
             z_ghosts(T.a_out, T.n_a_out);      // ring rows just loaded (and, again, the brick's edge rows)
             __syncthreads();
         }
-        colour_step(T.a_out, T.n_a_out, fld, cod, s_div, P.colour0, ZS, row_stride, P.omega, my_r, my_q, rows_per_round);
+        colour_step<KIND>(T.a_out, T.n_a_out, fld, cod, s_div, ctab, P.colour0, ZS, row_stride, P.omega, my_r, my_q, rows_per_round);
         __syncthreads();
         PROF(2);
         if (per) {
             z_ghosts(T.b, T.n_b);
             __syncthreads();
         }
-        colour_step(T.b, T.n_b, fld, cod, s_div, P.colour0 ^ 1, ZS, row_stride, P.omega, my_r, my_q, rows_per_round);
+        colour_step<KIND>(T.b, T.n_b, fld, cod, s_div, ctab, P.colour0 ^ 1, ZS, row_stride, P.omega, my_r, my_q, rows_per_round);
         __syncthreads();
         if (per) z_ghosts(T.b, T.n_b);          // for the next pair's early colour-A rows (barriers below come first)
         PROF(3);
@@ -422,14 +483,17 @@ struct ResChoice {
     size_t smem;
 };
 
-static size_t resident_smem(int BX, int BY, int ZS)
+constexpr int R_TABK = 256;      // class kinds: weight rows staged in shared memory (most frequent classes first)
+
+static size_t resident_smem(int BX, int BY, int ZS, bool cls, int tab_k)
 {
     const size_t tables = (size_t)(4 * (BY + 4) + 4 * BX) + 3 * (size_t)BX * BY + (size_t)(BX + 2) * (BY + 2);   // int2 entries
-    return (size_t)(BX + 4) * (BY + 4) * ZS * 4 + (size_t)(BX + 2) * (BY + 2) * (ZS / 4) * 2 + tables * 8 + 16;
+    const size_t codes = (size_t)(BX + 2) * (BY + 2) * (cls ? ZS : ZS / 4) * 2;
+    return (size_t)(BX + 4) * (BY + 4) * ZS * 4 + codes + (cls ? (size_t)tab_k * 32 : 0) + tables * 8 + 32;
 }
 
 // Bricks: at most one per SM; smallest colour-A region ((BX + 2) x (BY + 2) rows per CTA), then the fewest frame rows.
-static ResChoice choose_bricks(const taub_geom &g, int sms)
+static ResChoice choose_bricks(const taub_geom &g, int sms, bool cls, int tab_k)
 {
     ResChoice best{};
     best.ok = false;
@@ -438,7 +502,7 @@ static ResChoice choose_bricks(const taub_geom &g, int sms)
     for (int nbx = 1; nbx <= g.Nx / 2 && nbx * g.bs <= sms; ++nbx) {
         for (int nby = 1; nby <= g.Ny / 2 && (int64_t)nbx * nby * g.bs <= sms; ++nby) {
             const int BX = ceil_div(g.Nx, nbx), BY = ceil_div(g.Ny, nby);
-            const size_t smem = resident_smem(BX, BY, ZS);
+            const size_t smem = resident_smem(BX, BY, ZS, cls, tab_k);
             if (smem > R_SMEM_MAX) continue;
             const long cost = (long)(BX + 2) * (BY + 2) * 64 + (BX + BY);
             if (best_cost < 0 || cost < best_cost) {
@@ -499,9 +563,15 @@ static int device_sms(int *sms, int *coop)
     return TAUB_OK;
 }
 
+static bool res_cls(const taub_problem *p) { return p->kind == TAUB_MULTIPHASE_CLASS; }
+static int res_tab_k(const taub_problem *p) { return res_cls(p) ? min(p->L, R_TABK) : 0; }
+
 int taub_can_reside(const taub_problem *p)
 {
-    if (!p || p->kind != TAUB_BINARY || !p->codes || !p->field[0] || !p->field[1] || !p->sync_ws) return 0;
+    if (!p || (p->kind != TAUB_BINARY && p->kind != TAUB_MULTIPHASE_CLASS) || !p->codes || !p->field[0] || !p->field[1] ||
+        !p->sync_ws)
+        return 0;
+    if (res_cls(p) && (!p->lut || p->L < 1)) return 0;
     if (!resident_env()) return 0;
     const taub_geom &g = p->g;
     if (g.i_offset != 0 || g.Nx != g.Nx_global) return 0;          // whole volumes only
@@ -511,7 +581,7 @@ int taub_can_reside(const taub_problem *p)
     int sms = 0, coop = 0;
     if (device_sms(&sms, &coop) != TAUB_OK || !coop) return 0;
     if ((int64_t)g.bs > sms) return 0;
-    return choose_bricks(g, sms).ok ? 1 : 0;
+    return choose_bricks(g, sms, res_cls(p), res_tab_k(p)).ok ? 1 : 0;
 }
 
 int taub_resident_pairs(taub_problem *p, int64_t iter, int n_pairs, void *stream)
@@ -524,7 +594,7 @@ int taub_resident_pairs(taub_problem *p, int64_t iter, int n_pairs, void *stream
     const taub_geom &g = p->g;
     int sms = 0, coop = 0;
     if (int rc = device_sms(&sms, &coop)) return rc;
-    const ResChoice c = choose_bricks(g, sms);
+    const ResChoice c = choose_bricks(g, sms, res_cls(p), res_tab_k(p));
     const int bricks = g.bs * c.nbx * c.nby;
     TAUB_REQUIRE(bricks <= R_MAX_BRICKS, "taub_resident_pairs: more bricks than counters");
     ResParams P;
@@ -532,6 +602,9 @@ int taub_resident_pairs(taub_problem *p, int64_t iter, int n_pairs, void *stream
     P.buf[0] = p->field[p->cur];
     P.buf[1] = p->field[p->cur ^ 1];
     P.codes = p->codes;
+    P.table = p->lut;
+    P.n_classes = p->L;
+    P.tab_k = res_tab_k(p);
     P.omega = p->omega;
     P.colour0 = (int)(iter & 1);
     P.n_pairs = n_pairs;
@@ -555,22 +628,23 @@ int taub_resident_pairs(taub_problem *p, int64_t iter, int n_pairs, void *stream
         return (e && atoi(e) == 1024) ? 1024 : 512;      // measured: 512 is 2-10 % faster at every size (32^3 .. 150^3)
     }();
     void *args[] = {(void *)&P};
-    static bool attr_set[2][64] = {};
-    if (nt == 512) {
-        if (!attr_set[0][dev & 63]) {
-            TAUB_CUDA(cudaFuncSetAttribute(resident_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM_MAX));
-            attr_set[0][dev & 63] = true;
-        }
-        TAUB_CUDA(cudaLaunchCooperativeKernel((const void *)resident_kernel<512, 8>, dim3(bricks), dim3(512), args, c.smem,
-                                              (cudaStream_t)stream));
+#define TAUB_LAUNCH_RESIDENT(KIND_, NT_, BATCH_, SLOT_)                                                                    \
+    do {                                                                                                                  \
+        static bool attr_set[64] = {};                                                                                    \
+        if (!attr_set[dev & 63]) {                                                                                        \
+            TAUB_CUDA(cudaFuncSetAttribute(resident_kernel<KIND_, NT_, BATCH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           (int)R_SMEM_MAX));                                                             \
+            attr_set[dev & 63] = true;                                                                                    \
+        }                                                                                                                 \
+        TAUB_CUDA(cudaLaunchCooperativeKernel((const void *)resident_kernel<KIND_, NT_, BATCH_>, dim3(bricks), dim3(NT_),  \
+                                              args, c.smem, (cudaStream_t)stream));                                       \
+    } while (0)
+    if (res_cls(p)) {
+        if (nt == 512) TAUB_LAUNCH_RESIDENT(TAUB_MULTIPHASE_CLASS, 512, 8, 0); else TAUB_LAUNCH_RESIDENT(TAUB_MULTIPHASE_CLASS, 1024, 4, 1);
     } else {
-        if (!attr_set[1][dev & 63]) {
-            TAUB_CUDA(cudaFuncSetAttribute(resident_kernel<1024, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM_MAX));
-            attr_set[1][dev & 63] = true;
-        }
-        TAUB_CUDA(cudaLaunchCooperativeKernel((const void *)resident_kernel<1024, 4>, dim3(bricks), dim3(1024), args, c.smem,
-                                              (cudaStream_t)stream));
+        if (nt == 512) TAUB_LAUNCH_RESIDENT(TAUB_BINARY, 512, 8, 2); else TAUB_LAUNCH_RESIDENT(TAUB_BINARY, 1024, 4, 3);
     }
+#undef TAUB_LAUNCH_RESIDENT
     count_launch();
     p->sync_epoch += n_pairs;
     // the last pair stored the whole field into its buffer: buf[1] after an odd number of pairs, buf[0] otherwise

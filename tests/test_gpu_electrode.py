@@ -74,8 +74,10 @@ def test_fused_kernel_redoes_chunks_with_ieee_division_when_a_sum_is_tiny():
     then redoes the affected chunks with IEEE division (taub_inexact_events counts them): the field stays bit-identical
     to the generic kernel (plain __fdiv_rn) all the way."""
     A, skw = make("el_labels_per")
-    B, _ = make("el_labels_per")
+    A.use_resident = False          # (the volume is small: by default it would run on the resident kernel, which
+    B, _ = make("el_labels_per")    #  falls back to IEEE division per work item and counts nothing)
     B.force_generic = True
+    assert A.sweep_kernel_name() == "fused_sweep2_kernel"
     e0 = A.inexact_events
     A.solve(verbose=False, **skw)
     B.solve(verbose=False, **skw)

@@ -495,8 +495,34 @@ def test_resident_kernel_is_not_taken_where_it_does_not_apply(tau):
                        ("Solver", (256, 256, 256))):
         S = getattr(tau, cls)(cases.random_img(shape, 0.6, seed=1), device="cuda")
         assert S.sweep_kernel_name() != "resident_kernel", (cls, shape)
-    S = tau.MultiPhaseSolver(cases.blobs3((32, 32, 32), seed=1), {0: 0.0, 1: 1.0, 2: 0.3}, device="cuda")
+    S = tau.AnisotropicSolver(cases.random_img((32, 32, 32), 0.6, seed=1), (1.0, 2.0, 0.5), device="cuda")
     assert S.sweep_kernel_name() != "resident_kernel"
+
+
+@pytest.mark.parametrize("cls,shape", [
+    ("MultiPhaseSolver", (64, 64, 64)), ("MultiPhaseSolver", (33, 17, 9)), ("MultiPhaseSolver", (100, 96, 104)),
+    ("MultiPhaseSolver", (3, 40, 36, 44)), ("PeriodicMultiPhaseSolver", (64, 64, 64)),
+    ("PeriodicMultiPhaseSolver", (20, 22, 30)), ("PeriodicMultiPhaseSolver", (2, 30, 16, 12))])
+def test_resident_kernel_multiphase_equals_the_marching_kernels(tau, cls, shape):
+    """The stencil-class kind on the resident kernel (class ids colour-split in shared memory, the most frequent
+    weight rows staged, per-item IEEE fallback) against the fused / generic class kernels, bit for bit."""
+    if len(shape) == 4:
+        img = np.stack([cases.blobs3(shape[1:], seed=sum(shape) + b) for b in range(shape[0])])
+    else:
+        img = cases.blobs3(shape, seed=sum(shape))
+    D = {0: 0.0, 1: 1.0, 2: 0.3}
+    A = getattr(tau, cls)(img, dict(D), device="cuda")
+    B = getattr(tau, cls)(img, dict(D), device="cuda")
+    B.use_resident = False
+    assert A.sweep_kernel_name() == "resident_kernel" and B.sweep_kernel_name() != "resident_kernel"
+    for n in (2, 3, 37, 100):
+        A._advance(n)
+        B._advance(n)
+        assert torch_equal(A.field, B.field), (cls, shape, n)
+    A.solve(verbose=False, iter_limit=600)
+    B.solve(verbose=False, iter_limit=600)
+    assert A.iter == B.iter and np.array_equal(A.tau, B.tau) and torch_equal(A.field, B.field)
+    assert A._lib.taub_resident_timeouts() == 0
 
 
 # ------------------------------------------------------------------ exact re-run of fused chunks (fused_redo_kernel)

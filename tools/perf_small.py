@@ -17,12 +17,13 @@ def timed(S, n):
     return e0.elapsed_time(e1)
 
 
-for cls in ("Solver", "PeriodicSolver"):
+for cls in ("Solver", "PeriodicSolver", "MultiPhaseSolver", "PeriodicMultiPhaseSolver"):
     for N in sizes:
-        img = cases.random_img((N, N, N), 0.5, 0)
+        multi = "MultiPhase" in cls
+        img = cases.blobs3((N, N, N), seed=N) if multi else cases.random_img((N, N, N), 0.5, 0)
         row, prof = [], ""
         for resident in (True, False):
-            S = getattr(tau, cls)(img, device="cuda")
+            S = getattr(tau, cls)(img, {0: 0.0, 1: 1.0, 2: 0.3}, device="cuda") if multi else getattr(tau, cls)(img, device="cuda")
             S.use_resident = resident
             n = 1000
             ms = min(timed(S, n) for _ in range(3))
