@@ -176,9 +176,9 @@ struct ClassTab {
 
 __device__ __forceinline__ void class_row(unsigned cls, const ClassTab &T, float4 &wa, float4 &wb)
 {
-    if (cls < T.k) {
-        wa = ld_sh<float4>(T.s + cls * 32u);
-        wb = ld_sh<float4>(T.s + cls * 32u + 16u);
+    if (cls < T.k) {   // staged as two arrays of half rows: consecutive classes sit in consecutive 16-byte bank groups
+        wa = ld_sh<float4>(T.s + cls * 16u);
+        wb = ld_sh<float4>(T.s + (T.k + cls) * 16u);
     } else {
         const float4 *row = T.g + 2 * cls;
         wa = __ldg(row);
@@ -616,7 +616,7 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
     if (ANI && tid < ANISO_CLASSES) s_div[tid] = reinterpret_cast<const float2 *>(P.table)[tid];
     if (MPC) {
         const float4 *tab4 = reinterpret_cast<const float4 *>(P.table);
-        for (int t = tid; t < 2 * P.tab_k; t += F_NT) s_tab[t] = __ldg(tab4 + t);
+        for (int t = tid; t < 2 * P.tab_k; t += F_NT) s_tab[(t & 1) * P.tab_k + (t >> 1)] = __ldg(tab4 + t);
     }
     const bool tiny = fused_march<OGT, PA0, KIND, OP, false>(P, &tmap, &cmap, smem_raw, s_div, blockIdx.x, blockIdx.y, blockIdx.z);
     // a value below 2^-100 went through the fast division: put this chunk on the list fused_redo_kernel works off
@@ -655,7 +655,7 @@ fused_redo_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tmap,
     if (ANI && tid < ANISO_CLASSES) s_div[tid] = reinterpret_cast<const float2 *>(P.table)[tid];
     if (MPC) {
         const float4 *tab4 = reinterpret_cast<const float4 *>(P.table);
-        for (int t = tid; t < 2 * P.tab_k; t += F_NT) s_tab[t] = __ldg(tab4 + t);
+        for (int t = tid; t < 2 * P.tab_k; t += F_NT) s_tab[(t & 1) * P.tab_k + (t >> 1)] = __ldg(tab4 + t);
     }
     const uint32_t mbar_u32 = smem_u32(mbar);
     const int n = listed <= REDO_CAP ? listed : grid_x * grid_y * grid_z;
@@ -838,8 +838,39 @@ static int make_code_map(CUtensorMap *map, const taub_geom &g, const uint16_t *b
     return TAUB_OK;
 }
 
-// Plane chunks per tile column: fewest "waves x (planes + prologue)" on the resident-CTA capacity.
-static void choose_chunks(int n_planes, int64_t tiles, int capacity, int *chunk_len, int *chunks)
+// Plane chunks per tile column.  A CTA that marches `len` output planes is busy for about len + 6 plane steps (two
+// more colour-A planes, the ring prologue, its launch; len + 4 where the prologue hides behind the SM's other CTA).  Two regimes, both measured (profiles/r2_chunks.md):
+//   * list    -- CTAs run at a pace of their own (the kernel is bound by its instruction / shared-memory rate: the
+//                class kinds, volumes that sit in L2): the cost is the makespan of handing the CTAs out in grid order
+//                to `capacity` resident slots; the last chunk of a column may be short, which is what lets 300 CTAs
+//                beat 260 on 296 slots;
+//   * elastic -- the pass is HBM-bound (binary kinds on volumes well beyond L2): resident CTAs share the memory
+//                system, so fewer of them run faster and the cost is the work per slot plus one CTA of tail; many
+//                short chunks win although they load more planes (the re-read planes of neighbouring chunks are
+//                still in L2).
+static double chunk_cost(int n_planes, int64_t tiles, int capacity, bool elastic, int cl, int ce)
+{
+    const double oh = elastic ? 4.0 : 6.0;                              // (elastic: the ring prologue overlaps the SM's
+    const double d = cl + oh, d2 = (n_planes - (ce - 1) * cl) + oh;     //  other CTA); full chunks, last chunk
+    if (elastic) return ((double)tiles * ((ce - 1) * d + d2)) / capacity + d;
+    const int64_t n1 = tiles * (ce - 1);                 // CTAs of full length come first in grid order
+    const int64_t R = n1 / capacity, r = n1 % capacity;
+    const double t_full = (double)(R + (r > 0)) * d;     // when the last full-length CTA ends
+    int64_t f = capacity - r;                            // slots free at R * d for the short CTAs
+    double t_last;
+    if (tiles <= f) {
+        t_last = R * d + d2;
+    } else {
+        const int64_t k = (int64_t)(d / d2);             // rounds of short CTAs on those slots before the rest free up
+        if (r > 0 && tiles > k * f)
+            t_last = (R + 1) * d + (double)ceil_div64(tiles - k * f, capacity) * d2;
+        else
+            t_last = R * d + (double)ceil_div64(tiles, f) * d2;
+    }
+    return t_full > t_last ? t_full : t_last;
+}
+
+static void choose_chunks(int n_planes, int64_t tiles, int capacity, bool elastic, int *chunk_len, int *chunks)
 {
     double best = 1e30;
     *chunk_len = n_planes + (n_planes & 1);
@@ -848,8 +879,7 @@ static void choose_chunks(int n_planes, int64_t tiles, int capacity, int *chunk_
         int cl = ceil_div(n_planes, c);
         cl += cl & 1;   // even: every CTA starts with the same row parity
         const int ce = ceil_div(n_planes, cl);
-        const int64_t waves = ceil_div64(tiles * ce, capacity);
-        const double cost = (double)waves * (cl + 5);
+        const double cost = chunk_cost(n_planes, tiles, capacity, elastic, cl, ce);
         if (cost < best - 1e-9) {
             best = cost;
             *chunk_len = cl;
@@ -953,7 +983,19 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     if (!sm_count[dev_ord & 63])
         TAUB_CUDA(cudaDeviceGetAttribute(&sm_count[dev_ord & 63], cudaDevAttrMultiProcessorCount, dev_ord));
     int chunk_len, chunks;
-    choose_chunks(n_planes, tiles, 2 * sm_count[dev_ord & 63], &chunk_len, &chunks);
+    // HBM-bound passes (binary kind, a field that does not sit in the 126 MB of L2: 320^3 and up) take the elastic
+    // chunk model; the anisotropic and class kinds measured faster with the list model at every size
+    const int chunk_model = env_int("TAUB_CHUNK_MODEL", -1);         // measurements: 0 = list, 1 = elastic
+    const bool elastic = chunk_model >= 0 ? chunk_model == 1
+                                          : (p->kind == TAUB_BINARY &&
+                                             (double)g.bs * n_planes * g.plane_stride * 4.0 > 100e6);
+    choose_chunks(n_planes, tiles, 2 * sm_count[dev_ord & 63], elastic, &chunk_len, &chunks);
+    const int chunks_env = env_int("TAUB_FUSED_CHUNKS", 0);          // measurements: plane chunks per tile column
+    if (chunks_env > 0 && chunks_env <= (n_planes + 1) / 2) {
+        chunk_len = ceil_div(n_planes, chunks_env);
+        chunk_len += chunk_len & 1;
+        chunks = ceil_div(n_planes, chunk_len);
+    }
     P.chunk_len = chunk_len;
     TAUB_REQUIRE(chunks <= 65535, "taub_fused_sweep2: too many plane chunks");
     P.slot_f4 = ((t.LR * t.LG + 7) / 8) * 8;
