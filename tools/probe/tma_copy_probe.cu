@@ -21,6 +21,7 @@ struct Prm {
     int tiles_k, tiles_j, chunk_len, NB;
     int slot_bytes;
     int do_store, do_load, order;
+    int store_cs, load_hint;      // stores as st.global.cs; TMA loads with an L2 evict_first (1) / evict_last (2) policy
     int n_out_planes;
 };
 
@@ -48,14 +49,23 @@ __global__ void __launch_bounds__(256, 2) probe_kernel(const Prm P, const __grid
     const int total = c1 - c0 + 4;                   // planes c0 .. c1+3 of storage (2 halo planes each side)
     const uint32_t tx = (uint32_t)P.LR * P.LGf * 4u;
     int issued = 0;
+    uint64_t pol = 0;
+    if (P.load_hint == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    if (P.load_hint == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     auto issue = [&]() {
         const uint32_t slot = issued % P.NB;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb + 8u * slot), "r"(tx) : "memory");
-        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-                         pl + slot * P.slot_bytes),
-                     "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(C0), "r"(R0), "r"(c0 + issued), "r"(mb + 8u * slot)
-                     : "memory");
+        if (P.load_hint)
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
+                             pl + slot * P.slot_bytes),
+                         "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(C0), "r"(R0), "r"(c0 + issued), "r"(mb + 8u * slot), "l"(pol)
+                         : "memory");
+        else
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                             pl + slot * P.slot_bytes),
+                         "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(C0), "r"(R0), "r"(c0 + issued), "r"(mb + 8u * slot)
+                         : "memory");
         ++issued;
     };
     if (tid == 0 && P.do_load)
@@ -82,7 +92,10 @@ __global__ void __launch_bounds__(256, 2) probe_kernel(const Prm P, const __grid
             const int gr = R0 + P.hr + r, gc = C0 + P.hc + 4 * q;
             float4 v = P.do_load ? splane[((P.hr + r) * P.LGf + P.hc) / 4 + q] : make_float4(1.f, 2.f, 3.f, 4.f);
             if (gr < P.rows && gc + 3 < P.pitch) {
-                if (P.do_store) *reinterpret_cast<float4 *>(dplane + (size_t)gr * P.pitch + gc) = v;
+                if (P.do_store) {
+                    if (P.store_cs) __stcs(reinterpret_cast<float4 *>(dplane + (size_t)gr * P.pitch + gc), v);
+                    else *reinterpret_cast<float4 *>(dplane + (size_t)gr * P.pitch + gc) = v;
+                }
                 else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
             }
         }
@@ -119,23 +132,28 @@ int main(int argc, char **argv)
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
         printf("plain copy                                              : %7.1f us  %6.0f GB/s (read + write)\n", ms * 100, 2.0 * n * 4 * 10 / ms / 1e6);
     }
-    struct Var { const char *name; int LR, LGq, OR_, OGq, hr, hcq, NB, promo, do_load, do_store, order, chunks; };
+    struct Var { const char *name; int LR, LGq, OR_, OGq, hr, hcq, NB, promo, do_load, do_store, order, chunks, store_cs, load_hint; };
     const Var vars[] = {
-        {"fused geometry: box 30x35g, out 26x32g, NB 6, 256B promo", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 7},
-        {"  same, 128B promotion", 30, 35, 26, 32, 2, 1, 6, 2, 1, 1, 0, 7},
-        {"  same, no promotion", 30, 35, 26, 32, 2, 1, 6, 0, 1, 1, 0, 7},
-        {"  same, loads only", 30, 35, 26, 32, 2, 1, 6, 3, 1, 0, 0, 7},
-        {"  same, stores only", 30, 35, 26, 32, 2, 1, 6, 3, 0, 1, 0, 7},
-        {"  same, chunk-fastest CTA order", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 1, 7},
-        {"  same, 4 chunks (1 wave, 320 CTAs > 296)", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 4},
-        {"  same, 11 chunks", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 11},
-        {"no halo: box 26x32g = out, NB 6", 26, 32, 26, 32, 0, 0, 6, 3, 1, 1, 0, 7},
-        {"box 30x36g (144 B pad), out 26x32g", 30, 36, 26, 32, 2, 1, 6, 3, 1, 1, 0, 7},
-        {"wide: box 14x67g, out 10x64g", 14, 67, 10, 64, 2, 1, 6, 3, 1, 1, 0, 7},
-        {"wide: box 12x130g (whole rows), out 8x128g", 12, 130, 8, 128, 2, 1, 6, 3, 1, 1, 0, 7},
-        {"tall: box 58x19g, out 54x16g", 58, 19, 54, 16, 2, 1, 6, 3, 1, 1, 0, 7},
-        {"fused geometry, NB 4", 30, 35, 26, 32, 2, 1, 4, 3, 1, 1, 0, 7},
-        {"fused geometry, NB 3", 30, 35, 26, 32, 2, 1, 3, 3, 1, 1, 0, 7},
+        {"fused geometry (box 30x35g, out 26x32g, NB 6), 7 chunks", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 7, 0, 0},
+        {"  11 chunks", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 11, 0, 0},
+        {"  16 chunks", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 16, 0, 0},
+        {"  22 chunks", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 22, 0, 0},
+        {"  32 chunks", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 32, 0, 0},
+        {"  43 chunks", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 43, 0, 0},
+        {"  22 chunks, stores .cs", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 22, 1, 0},
+        {"  22 chunks, loads evict_first", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 22, 0, 1},
+        {"  22 chunks, loads evict_last", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 22, 0, 2},
+        {"  22 chunks, stores .cs + loads evict_last", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 22, 1, 2},
+        {"  7 chunks, stores .cs + loads evict_last", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 7, 1, 2},
+        {"  22 chunks, loads only", 30, 35, 26, 32, 2, 1, 6, 3, 1, 0, 0, 22, 0, 0},
+        {"  22 chunks, loads only, evict_last", 30, 35, 26, 32, 2, 1, 6, 3, 1, 0, 0, 22, 0, 2},
+        {"  22 chunks, stores only", 30, 35, 26, 32, 2, 1, 6, 3, 0, 1, 0, 22, 0, 0},
+        {"  22 chunks, stores only .cs", 30, 35, 26, 32, 2, 1, 6, 3, 0, 1, 0, 22, 1, 0},
+        {"  22 chunks, chunk-fastest CTA order", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 1, 22, 0, 0},
+        {"no halo: box 26x32g = out, 22 chunks", 26, 32, 26, 32, 0, 0, 6, 3, 1, 1, 0, 22, 0, 0},
+        {"fused geometry, NB 4, 22 chunks", 30, 35, 26, 32, 2, 1, 4, 3, 1, 1, 0, 22, 0, 0},
+        {"NB 4, box 42x35g, out 38x32g, 22 chunks", 42, 35, 38, 32, 2, 1, 4, 3, 1, 1, 0, 22, 0, 0},
+        {"NB 4, box 30x51g, out 26x48g, 22 chunks", 30, 51, 26, 48, 2, 1, 4, 3, 1, 1, 0, 22, 0, 0},
     };
     for (const Var &v : vars) {
         Prm P; memset(&P, 0, sizeof(P));
@@ -146,7 +164,7 @@ int main(int argc, char **argv)
         P.chunk_len = (N + v.chunks - 1) / v.chunks; P.chunk_len += P.chunk_len & 1;
         const int chunks = (N + P.chunk_len - 1) / P.chunk_len;
         P.slot_bytes = ((v.LR * v.LGq * 16 + 127) / 128) * 128;
-        P.do_load = v.do_load; P.do_store = v.do_store; P.order = v.order;
+        P.do_load = v.do_load; P.do_store = v.do_store; P.order = v.order; P.store_cs = v.store_cs; P.load_hint = v.load_hint;
         const size_t smem = (size_t)P.NB * P.slot_bytes + 128 + 128;
         if (smem > 113 * 1024) { printf("%-56s: skipped (%zu B of shared memory)\n", v.name, smem); continue; }
         CUtensorMap tm;

@@ -10,7 +10,8 @@ size = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 mode = sys.argv[2] if len(sys.argv) > 2 else "fused"
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 8
 img = cases.blobs(size, 0.5, seed=size)
-S = tau.Solver(img, device="cuda")
+cls = sys.argv[4] if len(sys.argv) > 4 else "Solver"
+S = getattr(tau, cls)(img, device="cuda")
 S.force_generic = (mode == "generic")
 S._advance(n)
 S._check_only()
