@@ -1,0 +1,8 @@
+#!/usr/bin/env bash
+set -u
+mkdir -p gpurun_out
+SECONDS=0
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_electrode.py tests/test_gpu_benchmark.py -q -m gpu -p no:cacheprovider -x > gpurun_out/gpu_tests_ab.txt 2>&1; echo "tests rc=$? in ${SECONDS}s"; tail -7 gpurun_out/gpu_tests_ab.txt
+echo "--- in-tree"; timeout 300 python tools/perf_quick.py 2>&1 | tee -a gpurun_out/perf_quick_rcta.txt
+echo "--- in-tree, TAUB_PDL=1"; TAUB_PDL=1 timeout 300 python tools/perf_quick.py 2>&1 | grep -i "periodic" | tee -a gpurun_out/perf_quick_rcta.txt
+echo "--- in-tree, TAUB_FUSED_REFRESH=0"; TAUB_FUSED_REFRESH=0 timeout 300 python tools/perf_quick.py 2>&1 | grep -i "periodic" | tee -a gpurun_out/perf_quick_rcta.txt
