@@ -22,6 +22,7 @@ struct Prm {
     int slot_bytes;
     int do_store, do_load, order;
     int store_cs, load_hint;      // stores as st.global.cs; TMA loads with an L2 evict_first (1) / evict_last (2) policy
+    int cluster_sync;             // 1: the per-step barrier is a cluster barrier (launch with cluster dims)
     int n_out_planes;
 };
 
@@ -73,7 +74,11 @@ __global__ void __launch_bounds__(256, 2) probe_kernel(const Prm P, const __grid
     const int OGq = P.OGf / 4;                       // float4 groups per output row
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int s = 0; s < total; ++s) {
-        __syncthreads();
+        if (P.cluster_sync) {
+            asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+        } else {
+            __syncthreads();
+        }
         if (tid == 0 && P.do_load && s + P.NB - 1 < total) issue();
         const int slot = s % P.NB;
         if (P.do_load) {
@@ -132,28 +137,18 @@ int main(int argc, char **argv)
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
         printf("plain copy                                              : %7.1f us  %6.0f GB/s (read + write)\n", ms * 100, 2.0 * n * 4 * 10 / ms / 1e6);
     }
-    struct Var { const char *name; int LR, LGq, OR_, OGq, hr, hcq, NB, promo, do_load, do_store, order, chunks, store_cs, load_hint; };
+    struct Var { const char *name; int LR, LGq, OR_, OGq, hr, hcq, NB, promo, do_load, do_store, order, chunks, store_cs, load_hint, cx, cy, csync; };
     const Var vars[] = {
-        {"fused geometry (box 30x35g, out 26x32g, NB 6), 7 chunks", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 7, 0, 0},
-        {"  11 chunks", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 11, 0, 0},
-        {"  16 chunks", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 16, 0, 0},
-        {"  22 chunks", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 22, 0, 0},
-        {"  32 chunks", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 32, 0, 0},
-        {"  43 chunks", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 43, 0, 0},
-        {"  22 chunks, stores .cs", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 22, 1, 0},
-        {"  22 chunks, loads evict_first", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 22, 0, 1},
-        {"  22 chunks, loads evict_last", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 22, 0, 2},
-        {"  22 chunks, stores .cs + loads evict_last", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 22, 1, 2},
-        {"  7 chunks, stores .cs + loads evict_last", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 7, 1, 2},
-        {"  22 chunks, loads only", 30, 35, 26, 32, 2, 1, 6, 3, 1, 0, 0, 22, 0, 0},
-        {"  22 chunks, loads only, evict_last", 30, 35, 26, 32, 2, 1, 6, 3, 1, 0, 0, 22, 0, 2},
-        {"  22 chunks, stores only", 30, 35, 26, 32, 2, 1, 6, 3, 0, 1, 0, 22, 0, 0},
-        {"  22 chunks, stores only .cs", 30, 35, 26, 32, 2, 1, 6, 3, 0, 1, 0, 22, 1, 0},
-        {"  22 chunks, chunk-fastest CTA order", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 1, 22, 0, 0},
-        {"no halo: box 26x32g = out, 22 chunks", 26, 32, 26, 32, 0, 0, 6, 3, 1, 1, 0, 22, 0, 0},
-        {"fused geometry, NB 4, 22 chunks", 30, 35, 26, 32, 2, 1, 4, 3, 1, 1, 0, 22, 0, 0},
-        {"NB 4, box 42x35g, out 38x32g, 22 chunks", 42, 35, 38, 32, 2, 1, 4, 3, 1, 1, 0, 22, 0, 0},
-        {"NB 4, box 30x51g, out 26x48g, 22 chunks", 30, 51, 26, 48, 2, 1, 4, 3, 1, 1, 0, 22, 0, 0},
+        {"fused geometry (box 30x35g, out 26x32g, NB 6), 20 chunks", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 20, 0, 0, 1, 1, 0},
+        {"  cluster 4x1 (z neighbours), no cluster barrier", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 20, 0, 0, 4, 1, 0},
+        {"  cluster 4x1, cluster barrier every step", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 20, 0, 0, 4, 1, 1},
+        {"  cluster 2x1, cluster barrier every step", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 20, 0, 0, 2, 1, 1},
+        {"  cluster 8x1 (4 z x 2 y), cluster barrier every step", 30, 35, 26, 32, 2, 1, 6, 3, 1, 1, 0, 20, 0, 0, 8, 1, 1},
+        {"  loads only", 30, 35, 26, 32, 2, 1, 6, 3, 1, 0, 0, 20, 0, 0, 1, 1, 0},
+        {"  loads only, cluster 4x1 + barrier", 30, 35, 26, 32, 2, 1, 6, 3, 1, 0, 0, 20, 0, 0, 4, 1, 1},
+        {"  loads only, cluster 8x1 + barrier", 30, 35, 26, 32, 2, 1, 6, 3, 1, 0, 0, 20, 0, 0, 8, 1, 1},
+        {"no halo: box 26x32g = out, 20 chunks", 26, 32, 26, 32, 0, 0, 6, 3, 1, 1, 0, 20, 0, 0, 1, 1, 0},
+        {"no halo, loads only", 26, 32, 26, 32, 0, 0, 6, 3, 1, 0, 0, 20, 0, 0, 1, 1, 0},
     };
     for (const Var &v : vars) {
         Prm P; memset(&P, 0, sizeof(P));
@@ -164,7 +159,7 @@ int main(int argc, char **argv)
         P.chunk_len = (N + v.chunks - 1) / v.chunks; P.chunk_len += P.chunk_len & 1;
         const int chunks = (N + P.chunk_len - 1) / P.chunk_len;
         P.slot_bytes = ((v.LR * v.LGq * 16 + 127) / 128) * 128;
-        P.do_load = v.do_load; P.do_store = v.do_store; P.order = v.order; P.store_cs = v.store_cs; P.load_hint = v.load_hint;
+        P.do_load = v.do_load; P.do_store = v.do_store; P.order = v.order; P.store_cs = v.store_cs; P.load_hint = v.load_hint; P.cluster_sync = v.csync;
         const size_t smem = (size_t)P.NB * P.slot_bytes + 128 + 128;
         if (smem > 113 * 1024) { printf("%-56s: skipped (%zu B of shared memory)\n", v.name, smem); continue; }
         CUtensorMap tm;
@@ -177,11 +172,18 @@ int main(int argc, char **argv)
         if (r != CUDA_SUCCESS) { printf("%-56s: encode failed %d\n", v.name, (int)r); continue; }
         CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(P.tiles_j * P.tiles_k, chunks);
-        for (int w = 0; w < 3; ++w) probe_kernel<<<grid, 256, smem>>>(P, tm);
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = grid; cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = 0;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = v.cx; at[0].val.clusterDim.y = v.cy; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = (v.cx * v.cy > 1) ? 1 : 0;
+        if (grid.x % v.cx || grid.y % v.cy) { printf("%-56s: grid %dx%d not divisible by the cluster\n", v.name, grid.x, grid.y); continue; }
+        for (int w = 0; w < 3; ++w) CK(cudaLaunchKernelEx(&cfg, probe_kernel, P, tm));
         CK(cudaGetLastError());
         CK(cudaEventRecord(e0));
         const int reps = 20;
-        for (int w = 0; w < reps; ++w) probe_kernel<<<grid, 256, smem>>>(P, tm);
+        for (int w = 0; w < reps; ++w) CK(cudaLaunchKernelEx(&cfg, probe_kernel, P, tm));
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
         const double useful = (double)N * N * N * 4 * ((v.do_load ? 1 : 0) + (v.do_store ? 1 : 0));
