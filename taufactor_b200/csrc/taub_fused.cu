@@ -844,15 +844,19 @@ static int make_code_map(CUtensorMap *map, const taub_geom &g, const uint16_t *b
 //                class kinds, volumes that sit in L2): the cost is the makespan of handing the CTAs out in grid order
 //                to `capacity` resident slots; the last chunk of a column may be short, which is what lets 300 CTAs
 //                beat 260 on 296 slots;
-//   * elastic -- the pass is HBM-bound (binary kinds on volumes well beyond L2): resident CTAs share the memory
-//                system, so fewer of them run faster and the cost is the work per slot plus one CTA of tail; many
-//                short chunks win although they load more planes (the re-read planes of neighbouring chunks are
-//                still in L2).
+//   * elastic -- the pass is HBM-bound (binary kind on a field beyond L2): resident CTAs share the memory system, so
+//                fewer of them run faster and what counts is the work per slot plus a CTA of tail -- and the tiles of
+//                a plane drift apart while they march, so the halo rows / columns a tile shares with its neighbours
+//                miss L2 the more often the longer the chunk: on random voxels a plane step of a 22-plane chunk costs
+//                0.75 of one of an 86-plane chunk (1024^3, profiles/r2_chunks_1024.txt; blob structures, which store
+//                half as much, gain less).  Cost per plane step ~ 1 + len / 200, against 4 steps of overhead per chunk
+//                (the planes neighbouring chunks load twice are mostly still in L2): 24 .. 28 planes at every size
+//                from 384^3 to 2048^3.
 static double chunk_cost(int n_planes, int64_t tiles, int capacity, bool elastic, int cl, int ce)
 {
     const double oh = elastic ? 4.0 : 6.0;                              // (elastic: the ring prologue overlaps the SM's
     const double d = cl + oh, d2 = (n_planes - (ce - 1) * cl) + oh;     //  other CTA); full chunks, last chunk
-    if (elastic) return ((double)tiles * ((ce - 1) * d + d2)) / capacity + d;
+    if (elastic) return ((double)tiles * ((ce - 1) * d + d2)) / capacity * (1.0 + cl / 200.0) + 0.25 * d;
     const int64_t n1 = tiles * (ce - 1);                 // CTAs of full length come first in grid order
     const int64_t R = n1 / capacity, r = n1 % capacity;
     const double t_full = (double)(R + (r > 0)) * d;     // when the last full-length CTA ends
