@@ -18,6 +18,7 @@ constexpr int COL0 = TAUB_COL0;
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);   // bumps the counter behind taub_launch_count()
 extern thread_local bool g_fused_pdl;   // taub_fused.cu: launch the passes of taub_iterate as programmatic dependents
+extern thread_local unsigned g_launch_cluster_x;   // taub_fused.cu: cluster width of the next launch_maybe_pdl (0 / 1: none)
 
 // Launch with or without cudaLaunchAttributeProgrammaticStreamSerialization (g_fused_pdl).  A kernel launched
 // through this must execute pdl_wait() in EVERY thread before its first access to global memory that an
@@ -31,11 +32,22 @@ inline cudaError_t launch_maybe_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bl
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (g_fused_pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (g_launch_cluster_x > 1 && grid.x % g_launch_cluster_x == 0) {   // co-scheduled CTAs (no cluster barrier anywhere)
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = g_launch_cluster_x;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = g_fused_pdl ? 1 : 0;
+    cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #ifdef __CUDACC__

@@ -790,6 +790,7 @@ static thread_local MapCache g_maps;
 
 // taub_iterate flags bit 1 (per host thread): launch the fused passes as programmatic dependents
 thread_local bool g_fused_pdl = false;
+thread_local unsigned g_launch_cluster_x = 0;
 
 // 3-D view of one ping-pong buffer: (columns = pitch, rows, bs * planes), fp32, box = LG*4 x LR x 1.
 static int make_field_map(CUtensorMap *map, const taub_geom &g, const float *base, int LR, int LG, int dev)
@@ -1006,6 +1007,13 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     P.cslot_h = ((t.LR * t.LGc * cpg * 2 + 127) / 128) * 64;
     const size_t smem = fused_smem_bytes(t.LR, t.LG, t.LGc, cpg, ring_depth(cpg), code_ring_depth(cpg), tab_k);
     dim3 grid(t.tiles_j * t.tiles_k, chunks, g.bs);
+    // z-neighbour tiles are launched as clusters of two: co-scheduled CTAs start their march together, so the halo columns
+    // they share are requested at about the same time and hit L2 (no cluster barrier, no distributed shared memory: the
+    // kernel is unchanged).  512^3: blobs +0.6 %, random voxels +3 %, 256^3 +2 %; clusters of four: random +5 %, blobs
+    // -3 % (a cluster waits for four free slots in one GPC); the class kind loses 1.5 % at 512^3, hence binary only.
+    // TAUB_FUSED_CLUSTER=k overrides (0 / 1: none).
+    static const unsigned cluster_env = (unsigned)env_int("TAUB_FUSED_CLUSTER", 2);
+    const unsigned cluster_x = (p->kind == TAUB_BINARY && cluster_env > 1 && grid.x % cluster_env == 0) ? cluster_env : 0;
     cudaStream_t s = (cudaStream_t)stream;
     CUtensorMap tmap, cmap;
     if (int rc = make_field_map(&tmap, g, P.src, t.LR, t.LG, dev_ord)) return rc;
@@ -1024,8 +1032,15 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
             smem_set[dev_ord & 63].store(smem, std::memory_order_relaxed);                                        \
         }                                                                                                         \
-        TAUB_CUDA(launch_maybe_pdl(fused_sweep2_kernel<OG_, PA_, KIND_, OP_>, grid, dim3(F_NT), smem, s, P, tmap,  \
-                                   cmap));                                                                        \
+        g_launch_cluster_x = cluster_x;                                                                           \
+        cudaError_t le_ = launch_maybe_pdl(fused_sweep2_kernel<OG_, PA_, KIND_, OP_>, grid, dim3(F_NT), smem, s, P, tmap,  \
+                                           cmap);                                                                 \
+        g_launch_cluster_x = 0;                                                                                   \
+        if (le_ != cudaSuccess && cluster_x > 1) {   /* a device / partition that cannot place the cluster */       \
+            (void)cudaGetLastError();                                                                             \
+            le_ = launch_maybe_pdl(fused_sweep2_kernel<OG_, PA_, KIND_, OP_>, grid, dim3(F_NT), smem, s, P, tmap, cmap); \
+        }                                                                                                         \
+        TAUB_CUDA(le_);                                                                                           \
         if (P.redo) {                                                                                             \
             static std::atomic<size_t> smem_set_r[64];                                                            \
             if (smem > smem_set_r[dev_ord & 63].load(std::memory_order_relaxed)) {                                \
