@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
     cmd = [nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += os.environ.get("TAUB_NVCC_EXTRA", "").split()     # e.g. -DTAUB_EARLY_WAIT=1 for an A/B build
+    cmd += os.environ.get("TAUB_NVCC_EXTRA", "").split()     # extra nvcc flags (-D...) for an A/B build
     cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
     subprocess.check_call(cmd)
     return LIB
