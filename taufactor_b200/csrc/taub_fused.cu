@@ -72,6 +72,9 @@ struct FusedParams {
     int write_solid;   // binary kind: 1 = also store float4 groups whose four voxels are all non-conductive
     int *redo;         // optional: redo list of this launch (see fused_redo_kernel)
     int force_redo;    // testing (TAUB_FORCE_REDO=1): list every chunk, i.e. the whole pass is redone with IEEE division
+    int perm_R, perm_S;   // plane chunk of grid row y: (y % perm_R) * perm_S + y / perm_R (perm_R <= 1: y) -- the chunk rows
+                          // that are in flight together lie perm_S chunks apart, and a chunk starts when its lower
+                          // neighbour ends: the planes the two share are then still in L2
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -618,12 +621,14 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
         const float4 *tab4 = reinterpret_cast<const float4 *>(P.table);
         for (int t = tid; t < 2 * P.tab_k; t += F_NT) s_tab[(t & 1) * P.tab_k + (t >> 1)] = __ldg(tab4 + t);
     }
-    const bool tiny = fused_march<OGT, PA0, KIND, OP, false>(P, &tmap, &cmap, smem_raw, s_div, blockIdx.x, blockIdx.y, blockIdx.z);
+    const int cy = P.perm_R > 1 ? ((int)blockIdx.y % P.perm_R) * P.perm_S + (int)blockIdx.y / P.perm_R : (int)blockIdx.y;
+    if (P.i_lo + cy * P.chunk_len >= P.i_hi) return;   // (a grid row the permutation pads the chunks with)
+    const bool tiny = fused_march<OGT, PA0, KIND, OP, false>(P, &tmap, &cmap, smem_raw, s_div, blockIdx.x, cy, blockIdx.z);
     // a value below 2^-100 went through the fast division: put this chunk on the list fused_redo_kernel works off
     if (__syncthreads_or(tiny || P.force_redo) && tid == 0) {
         if (P.redo) {
             const int k = atomicAdd(P.redo, 1);
-            if (k < REDO_CAP) P.redo[2 + k] = (int)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+            if (k < REDO_CAP) P.redo[2 + k] = (int)((blockIdx.z * gridDim.y + cy) * gridDim.x + blockIdx.x);
         }
         atomicAdd(&g_inexact_events, 1ULL);
     }
@@ -662,6 +667,7 @@ fused_redo_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tmap,
     bool armed = false;
     for (int k = blockIdx.x; k < n; k += gridDim.x) {
         const int id = listed <= REDO_CAP ? P.redo[2 + k] : k;
+        if (P.i_lo + ((id / grid_x) % grid_y) * P.chunk_len >= P.i_hi) continue;   // (a padding row of the chunk permutation)
         __syncthreads();                          // every box of the previous chunk has been consumed
         if (tid == 0) {
             for (int m = 0; m < NB; ++m) {
@@ -1007,6 +1013,20 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     P.cslot_h = ((t.LR * t.LGc * cpg * 2 + 127) / 128) * 64;
     const size_t smem = fused_smem_bytes(t.LR, t.LG, t.LGc, cpg, ring_depth(cpg), code_ring_depth(cpg), tab_k);
     dim3 grid(t.tiles_j * t.tiles_k, chunks, g.bs);
+    // Elastic passes whose tiles do not fill the device by themselves run several chunk rows at a time.  Grid rows are
+    // handed out in order, so with the plain numbering rows y and y+1 start together and the planes they share are
+    // loaded a whole CTA lifetime apart (40 % L2 hits).  Numbered with a stride, the rows in flight lie perm_S chunks
+    // apart and chunk y+1 starts when chunk y ends.  TAUB_FUSED_PERM=0: plain numbering (measurements).
+    P.perm_R = 1;
+    P.perm_S = chunks;
+    if (elastic && env_int("TAUB_FUSED_PERM", 1)) {
+        const int R = min(chunks, ceil_div(2 * sm_count[dev_ord & 63], (int)grid.x));
+        if (R > 1) {
+            P.perm_R = R;
+            P.perm_S = ceil_div(chunks, R);
+            grid.y = R * P.perm_S;      // (rows whose chunk lies beyond the last one return at once)
+        }
+    }
     // z-neighbour tiles are launched as clusters of two: co-scheduled CTAs start their march together, so the halo columns
     // they share are requested at about the same time and hit L2 (no cluster barrier, no distributed shared memory: the
     // kernel is unchanged).  512^3: blobs +0.6 %, random voxels +3 %, 256^3 +2 %; clusters of four: random +5 %, blobs
