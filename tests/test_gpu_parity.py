@@ -525,6 +525,33 @@ def test_resident_kernel_multiphase_equals_the_marching_kernels(tau, cls, shape)
     assert A._lib.taub_resident_timeouts() == 0
 
 
+# ------------------------------------------------------------------ HBM-bound passes: short chunks, strided numbering, clusters
+@pytest.mark.parametrize("cls", ["Solver", "PeriodicSolver"])
+def test_elastic_chunking_permutation_and_clusters_change_nothing(tau, monkeypatch, cls):
+    """A field beyond L2 (320^3: 146 MB) takes the elastic chunk model: many short plane chunks, grid rows numbered
+    with a stride over the chunks (padding rows return at once), z-neighbour tiles launched as clusters of two.  None of
+    it may change a bit: against the plain numbering without clusters, against the list model, against the generic
+    kernel -- and the exact re-run (every chunk listed) has to find its chunks through the permutation."""
+    import torch
+    img = cases.random_img((320, 320, 320), 0.6, seed=11)
+    mk = lambda: getattr(tau, cls)(img, device="cuda")
+    A, B, C, D = mk(), mk(), mk(), mk()
+    C.force_generic = True
+    D.exact_redo = True
+    for n in (2, 5, 12):
+        A._advance(n)
+        monkeypatch.setenv("TAUB_FUSED_PERM", "0"); monkeypatch.setenv("TAUB_FUSED_CLUSTER", "0")
+        monkeypatch.setenv("TAUB_CHUNK_MODEL", "0" if n == 5 else "1")
+        B._advance(n)
+        monkeypatch.delenv("TAUB_FUSED_PERM"); monkeypatch.delenv("TAUB_FUSED_CLUSTER"); monkeypatch.delenv("TAUB_CHUNK_MODEL")
+        C._advance(n)
+        monkeypatch.setenv("TAUB_FORCE_REDO", "1")
+        D._advance(n)
+        monkeypatch.delenv("TAUB_FORCE_REDO")
+        assert torch.equal(A.field, B.field) and torch.equal(A.field, C.field) and torch.equal(A.field, D.field), (cls, n)
+    assert A.sweep_kernel_name() == "fused_sweep2_kernel" and D.inexact_events > 0
+
+
 # ------------------------------------------------------------------ exact re-run of fused chunks (fused_redo_kernel)
 @pytest.mark.parametrize("cls,shape,kw", [
     ("Solver", (48, 40, 36), {}), ("Solver", (5, 64, 130), {}), ("Solver", (70, 130, 260), {}),

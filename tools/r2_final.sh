@@ -11,4 +11,3 @@ SECONDS=0
 timeout 900 python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref bench rc=$? in ${SECONDS}s"; cat gpurun_out/bench_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_bench_512.csv python bench.py --steps 2 --warmup 3 --no-cpu --skip scale_base,config1,config3,config4 > gpurun_out/bench_under_ncu.log 2>&1; echo "ncu launch list rc=$?"
 timeout 400 python tools/perf_quick.py > gpurun_out/perf_quick_final.txt 2>&1; cat gpurun_out/perf_quick_final.txt
-timeout 400 python tools/perf_small.py 32 64 100 128 150 > gpurun_out/perf_small_final.txt 2>&1; grep -v phases gpurun_out/perf_small_final.txt
