@@ -551,7 +551,10 @@ def run_ours(args):
                 "launches": sweep_launches, "avg_launch_us": 1e3 * ms_sw / max(sweep_launches, 1),
                 "algorithmic_bytes_per_lup": BYTES_PER_LUP,
                 "note": "algorithmic bytes (8.125 B/LUP x LUPs) / CUDA-event time of 200 iterations; the fused "
-                        "kernel does two iterations per HBM pass so frac may exceed 1"}
+                        "kernel does two iterations per HBM pass so frac may exceed 1.  The 200-iteration sample "
+                        "(~20 ms) runs right behind the timed region and largely at boost clocks, like the burst "
+                        "figure it is divided by; the timed region of `value` (steps x 100 iterations + check) is "
+                        "long enough to sit at the power-capped clock reported under `clocks`"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
