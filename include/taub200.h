@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TAUB_ABI_VERSION 12
+#define TAUB_ABI_VERSION 13
 #define TAUB_GHOST 2            /* ghost width in x (planes), y (rows) and z (columns) */
 #define TAUB_COL0 4             /* column of interior voxel k = 0 */
 #define TAUB_MAX_LABELS 64      /* dense phase indices 0..L-1, L <= 64; index L = "outside" */
@@ -179,8 +179,14 @@ int taub_half_sweep(const taub_problem *p, int64_t iter, int i_lo, int i_hi, voi
  * blocked, TMA-bulk staged shared-memory tiles, register-rotating plane march.  Binary kind.
  * Returns TAUB_ERR_UNSUPPORTED when the problem does not qualify (see taub_can_fuse). */
 int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, void *stream);
-int taub_can_fuse(const taub_problem *p);   /* periodic problems with odd Ny / Nz: only with the experimental
-                                             * OP kernel variant, environment TAUB_FUSE_ODD_PERIODIC=1 */
+int taub_can_fuse(const taub_problem *p);   /* binary, stencil-class and anisotropic kinds with their side arrays bound;
+                                             * periodic problems with odd Ny / Nz run the OP kernel variant */
+/* Diagnostics, no CUDA call: the launch plan taub_fused_sweep2 uses for planes [i_lo, i_hi) on a device with
+ * `resident_ctas` CTA slots (2 x SM count).  out = { loaded tile rows, output tile rows, output float4 groups per tile
+ * row, tile rows, tile columns, planes per chunk, plane chunks, grid rows (>= chunks: the chunk numbering may pad),
+ * perm_R, perm_S (chunk of grid row y = (y % perm_R) * perm_S + y / perm_R; perm_R = 1: y), cluster width (0: none),
+ * elastic chunk model (0 / 1) }.  Only p->g, p->kind, p->L and the non-nullness of the pointers are looked at. */
+int taub_fused_plan(const taub_problem *p, int i_lo, int i_hi, int resident_ctas, int32_t out[12]);
 /* The fused kernel divides by the neighbour count / prefactor with an FMA-corrected reciprocal that equals the IEEE
  * quotient for s == 0 and every |s| >= 2^-100.  A CTA whose threads met a non-zero value below 2^-100 (where that
  * sequence may be one subnormal ulp off) puts its chunk on a list in p->redo_ws, and a second kernel launched behind

@@ -61,6 +61,7 @@ SIGNATURES = {
     "taub_can_fuse": (c_int, [ctypes.POINTER(Problem)]),
     "taub_iterate": (c_int, [ctypes.POINTER(Problem), c_i64, c_int, c_int, c_vp]),
     "taub_can_reside": (c_int, [ctypes.POINTER(Problem)]),
+    "taub_fused_plan": (c_int, [ctypes.POINTER(Problem), c_int, c_int, c_int, ctypes.POINTER(ctypes.c_int32)]),
     "taub_resident_pairs": (c_int, [ctypes.POINTER(Problem), c_i64, c_int, c_vp]),
     "taub_sync_ws_ints": (ctypes.c_size_t, []),
     "taub_resident_timeouts": (ctypes.c_ulonglong, []),
@@ -96,7 +97,7 @@ def load():
                 continue            # ... and it may lack the newest diagnostics
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.taub_abi_version() != 12 and not os.environ.get("TAUB200_LIB"):
+        if lib.taub_abi_version() != 13 and not os.environ.get("TAUB200_LIB"):
             raise ImportError("libtaub200.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib

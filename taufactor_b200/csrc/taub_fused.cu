@@ -621,8 +621,13 @@ fused_sweep2_kernel(const FusedParams P, const __grid_constant__ CUtensorMap tma
         const float4 *tab4 = reinterpret_cast<const float4 *>(P.table);
         for (int t = tid; t < 2 * P.tab_k; t += F_NT) s_tab[(t & 1) * P.tab_k + (t >> 1)] = __ldg(tab4 + t);
     }
-    const int cy = P.perm_R > 1 ? ((int)blockIdx.y % P.perm_R) * P.perm_S + (int)blockIdx.y / P.perm_R : (int)blockIdx.y;
-    if (P.i_lo + cy * P.chunk_len >= P.i_hi) return;   // (a grid row the permutation pads the chunks with)
+    // (only the binary kind takes the elastic chunk model and with it the strided numbering: the other kinds, which have
+    //  no register to spare, are compiled without it -- the class kind lost 4 % to these two lines)
+    int cy = (int)blockIdx.y;
+    if (KIND == TAUB_BINARY) {
+        if (P.perm_R > 1) cy = ((int)blockIdx.y % P.perm_R) * P.perm_S + (int)blockIdx.y / P.perm_R;
+        if (P.i_lo + cy * P.chunk_len >= P.i_hi) return;   // (a grid row the permutation pads the chunks with)
+    }
     const bool tiny = fused_march<OGT, PA0, KIND, OP, false>(P, &tmap, &cmap, smem_raw, s_div, blockIdx.x, cy, blockIdx.z);
     // a value below 2^-100 went through the fast division: put this chunk on the list fused_redo_kernel works off
     if (__syncthreads_or(tiny || P.force_redo) && tid == 0) {
@@ -918,6 +923,66 @@ static int class_rows_in_smem(const taub_problem *p)
     return p->kind == TAUB_MULTIPHASE_CLASS ? min(p->L, tabk) : 0;
 }
 
+// The launch plan of a fused pass over planes [i_lo, i_hi): tile shape, plane chunks, grid, chunk numbering, cluster
+// width.  Pure host arithmetic (no CUDA call): taub_fused_sweep2 launches what this returns, taub_fused_plan reports it.
+struct FusedPlan {
+    TileChoice t;
+    int cpg, tab_k;
+    bool op, elastic;
+    int chunk_len, chunks;
+    int grid_x, grid_y;
+    int perm_R, perm_S;
+    unsigned cluster_x;
+};
+
+static FusedPlan make_plan(const taub_problem *p, int i_lo, int i_hi, int resident_ctas)
+{
+    const taub_geom &g = p->g;
+    FusedPlan f;
+    f.cpg = (p->kind == TAUB_MULTIPHASE_CLASS || p->kind == TAUB_ANISOTROPIC) ? 4 : 1;
+    f.tab_k = class_rows_in_smem(p);
+    f.op = odd_periodic(g);   // the odd-periodic variant of the kernel is compiled for the narrow tile only
+    f.t = choose_tile(g, f.cpg, f.tab_k, f.op);
+    const int n_planes = i_hi - i_lo;
+    const int64_t tiles = (int64_t)f.t.tiles_j * f.t.tiles_k * g.bs;
+    // HBM-bound passes (binary kind, a field that does not sit in the 126 MB of L2: 320^3 and up) take the elastic
+    // chunk model; the anisotropic and class kinds measured faster with the list model at every size
+    const int chunk_model = env_int("TAUB_CHUNK_MODEL", -1);         // measurements: 0 = list, 1 = elastic
+    f.elastic = chunk_model >= 0 ? chunk_model == 1
+                                 : (p->kind == TAUB_BINARY && (double)g.bs * n_planes * g.plane_stride * 4.0 > 100e6);
+    choose_chunks(n_planes, tiles, resident_ctas, f.elastic, &f.chunk_len, &f.chunks);
+    const int chunks_env = env_int("TAUB_FUSED_CHUNKS", 0);          // measurements: plane chunks per tile column
+    if (chunks_env > 0 && chunks_env <= (n_planes + 1) / 2) {
+        f.chunk_len = ceil_div(n_planes, chunks_env);
+        f.chunk_len += f.chunk_len & 1;
+        f.chunks = ceil_div(n_planes, f.chunk_len);
+    }
+    f.grid_x = f.t.tiles_j * f.t.tiles_k;
+    f.grid_y = f.chunks;
+    // Elastic passes whose tiles do not fill the device by themselves run several chunk rows at a time.  Grid rows are
+    // handed out in order, so with the plain numbering rows y and y+1 start together and the planes they share are
+    // loaded a whole CTA lifetime apart (40 % L2 hits).  Numbered with a stride, the rows in flight lie perm_S chunks
+    // apart and chunk y+1 starts when chunk y ends.  TAUB_FUSED_PERM=0: plain numbering (measurements).
+    f.perm_R = 1;
+    f.perm_S = f.chunks;
+    if (f.elastic && p->kind == TAUB_BINARY && env_int("TAUB_FUSED_PERM", 1)) {
+        const int R = min(f.chunks, ceil_div(resident_ctas, f.grid_x));
+        if (R > 1) {
+            f.perm_R = R;
+            f.perm_S = ceil_div(f.chunks, R);
+            f.grid_y = R * f.perm_S;      // (rows whose chunk lies beyond the last one return at once)
+        }
+    }
+    // z-neighbour tiles are launched as clusters of two: co-scheduled CTAs start their march together, so the halo columns
+    // they share are requested at about the same time and hit L2 (no cluster barrier, no distributed shared memory: the
+    // kernel is unchanged).  512^3: blobs +0.6 %, random voxels +3 %, 256^3 +2 %; clusters of four: random +5 %, blobs
+    // -3 % (a cluster waits for four free slots in one GPC); the class kind loses 1.5 % at 512^3, hence binary only.
+    // TAUB_FUSED_CLUSTER=k overrides (0 / 1: none).
+    static const unsigned cluster_env = (unsigned)env_int("TAUB_FUSED_CLUSTER", 2);
+    f.cluster_x = (p->kind == TAUB_BINARY && cluster_env > 1 && f.grid_x % cluster_env == 0) ? cluster_env : 0;
+    return f;
+}
+
 extern "C" {
 
 unsigned long long taub_inexact_events(void)
@@ -943,6 +1008,21 @@ int taub_can_fuse(const taub_problem *p)
                : 0;
 }
 
+int taub_fused_plan(const taub_problem *p, int i_lo, int i_hi, int resident_ctas, int32_t out[12])
+{
+    TAUB_REQUIRE(p && out && resident_ctas >= 1, "taub_fused_plan: bad arguments");
+    if (taub_can_fuse(p) != 1) {
+        set_error("taub_fused_plan: problem does not qualify for the fused path");
+        return TAUB_ERR_UNSUPPORTED;
+    }
+    TAUB_REQUIRE(i_lo >= 0 && i_hi <= p->g.Nx && i_lo < i_hi, "taub_fused_plan: planes [%d, %d) outside the slab", i_lo, i_hi);
+    const FusedPlan f = make_plan(p, i_lo, i_hi, resident_ctas);
+    const int32_t v[12] = {f.t.LR, f.t.OR_, f.t.OG, f.t.tiles_j, f.t.tiles_k, f.chunk_len, f.chunks, f.grid_y,
+                           f.perm_R, f.perm_S, (int32_t)f.cluster_x, f.elastic ? 1 : 0};
+    for (int k = 0; k < 12; ++k) out[k] = v[k];
+    return TAUB_OK;
+}
+
 int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, void *stream)
 {
     if (taub_can_fuse(p) != 1) {
@@ -951,10 +1031,15 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     }
     const taub_geom &g = p->g;
     TAUB_REQUIRE(i_lo >= 0 && i_hi <= g.Nx && i_lo < i_hi, "taub_fused_sweep2: planes [%d, %d) outside the slab", i_lo, i_hi);
-    const int cpg = (p->kind == TAUB_MULTIPHASE_CLASS || p->kind == TAUB_ANISOTROPIC) ? 4 : 1;
-    const int tab_k = class_rows_in_smem(p);
-    const bool op = odd_periodic(g);   // the odd-periodic variant of the kernel is compiled for the narrow tile only
-    const TileChoice t = choose_tile(g, cpg, tab_k, op);
+    int dev_ord = 0;
+    TAUB_CUDA(cudaGetDevice(&dev_ord));
+    static int sm_count[64] = {0};   // per device
+    if (!sm_count[dev_ord & 63])
+        TAUB_CUDA(cudaDeviceGetAttribute(&sm_count[dev_ord & 63], cudaDevAttrMultiProcessorCount, dev_ord));
+    const FusedPlan plan = make_plan(p, i_lo, i_hi, 2 * sm_count[dev_ord & 63]);
+    const TileChoice &t = plan.t;
+    const int cpg = plan.cpg, tab_k = plan.tab_k;
+    const bool op = plan.op;
     FusedParams P;
     P.g = g;
     P.src = p->field[p->cur];
@@ -986,54 +1071,15 @@ int taub_fused_sweep2(const taub_problem *p, int64_t iter, int i_lo, int i_hi, v
     P.a_hi = min(i_hi + 1, g.Nx_global - g.i_offset);
     P.LR = t.LR; P.LG = t.LG; P.LGc = t.LGc; P.LGt = t.LGt; P.OR_ = t.OR_; P.OG = t.OG;   // OR_ even, OG % 8 == 0
     P.tiles_k = t.tiles_k;
-    const int n_planes = i_hi - i_lo;
-    const int64_t tiles = (int64_t)t.tiles_j * t.tiles_k * g.bs;
-    int dev_ord = 0;
-    TAUB_CUDA(cudaGetDevice(&dev_ord));
-    static int sm_count[64] = {0};   // per device
-    if (!sm_count[dev_ord & 63])
-        TAUB_CUDA(cudaDeviceGetAttribute(&sm_count[dev_ord & 63], cudaDevAttrMultiProcessorCount, dev_ord));
-    int chunk_len, chunks;
-    // HBM-bound passes (binary kind, a field that does not sit in the 126 MB of L2: 320^3 and up) take the elastic
-    // chunk model; the anisotropic and class kinds measured faster with the list model at every size
-    const int chunk_model = env_int("TAUB_CHUNK_MODEL", -1);         // measurements: 0 = list, 1 = elastic
-    const bool elastic = chunk_model >= 0 ? chunk_model == 1
-                                          : (p->kind == TAUB_BINARY &&
-                                             (double)g.bs * n_planes * g.plane_stride * 4.0 > 100e6);
-    choose_chunks(n_planes, tiles, 2 * sm_count[dev_ord & 63], elastic, &chunk_len, &chunks);
-    const int chunks_env = env_int("TAUB_FUSED_CHUNKS", 0);          // measurements: plane chunks per tile column
-    if (chunks_env > 0 && chunks_env <= (n_planes + 1) / 2) {
-        chunk_len = ceil_div(n_planes, chunks_env);
-        chunk_len += chunk_len & 1;
-        chunks = ceil_div(n_planes, chunk_len);
-    }
-    P.chunk_len = chunk_len;
-    TAUB_REQUIRE(chunks <= 65535, "taub_fused_sweep2: too many plane chunks");
+    P.chunk_len = plan.chunk_len;
+    TAUB_REQUIRE(plan.grid_y <= 65535, "taub_fused_sweep2: too many plane chunks");
     P.slot_f4 = ((t.LR * t.LG + 7) / 8) * 8;
     P.cslot_h = ((t.LR * t.LGc * cpg * 2 + 127) / 128) * 64;
     const size_t smem = fused_smem_bytes(t.LR, t.LG, t.LGc, cpg, ring_depth(cpg), code_ring_depth(cpg), tab_k);
-    dim3 grid(t.tiles_j * t.tiles_k, chunks, g.bs);
-    // Elastic passes whose tiles do not fill the device by themselves run several chunk rows at a time.  Grid rows are
-    // handed out in order, so with the plain numbering rows y and y+1 start together and the planes they share are
-    // loaded a whole CTA lifetime apart (40 % L2 hits).  Numbered with a stride, the rows in flight lie perm_S chunks
-    // apart and chunk y+1 starts when chunk y ends.  TAUB_FUSED_PERM=0: plain numbering (measurements).
-    P.perm_R = 1;
-    P.perm_S = chunks;
-    if (elastic && env_int("TAUB_FUSED_PERM", 1)) {
-        const int R = min(chunks, ceil_div(2 * sm_count[dev_ord & 63], (int)grid.x));
-        if (R > 1) {
-            P.perm_R = R;
-            P.perm_S = ceil_div(chunks, R);
-            grid.y = R * P.perm_S;      // (rows whose chunk lies beyond the last one return at once)
-        }
-    }
-    // z-neighbour tiles are launched as clusters of two: co-scheduled CTAs start their march together, so the halo columns
-    // they share are requested at about the same time and hit L2 (no cluster barrier, no distributed shared memory: the
-    // kernel is unchanged).  512^3: blobs +0.6 %, random voxels +3 %, 256^3 +2 %; clusters of four: random +5 %, blobs
-    // -3 % (a cluster waits for four free slots in one GPC); the class kind loses 1.5 % at 512^3, hence binary only.
-    // TAUB_FUSED_CLUSTER=k overrides (0 / 1: none).
-    static const unsigned cluster_env = (unsigned)env_int("TAUB_FUSED_CLUSTER", 2);
-    const unsigned cluster_x = (p->kind == TAUB_BINARY && cluster_env > 1 && grid.x % cluster_env == 0) ? cluster_env : 0;
+    dim3 grid(plan.grid_x, plan.grid_y, g.bs);
+    P.perm_R = plan.perm_R;
+    P.perm_S = plan.perm_S;
+    const unsigned cluster_x = plan.cluster_x;
     cudaStream_t s = (cudaStream_t)stream;
     CUtensorMap tmap, cmap;
     if (int rc = make_field_map(&tmap, g, P.src, t.LR, t.LG, dev_ord)) return rc;

@@ -24,7 +24,7 @@ def test_header_symbols_exported(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in taub200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes prototype"
-    assert lib.taub_abi_version() == 12
+    assert lib.taub_abi_version() == 13
 
 
 def test_struct_layout_matches_header(lib):
