@@ -297,3 +297,21 @@ def test_native_decoders_survive_damaged_streams():
             except TiffError:
                 want = None
             assert (got is None) == (want is None) and (got is None or bytes(got) == want), (compression, it)
+
+
+def test_deflate_strip_cannot_expand_beyond_its_declared_size():
+    """A crafted Deflate strip (1000 : 1) is cut off at the strip's declared size: TiffError, and the decoder never holds
+    more than that size -- not the 64 MB the stream would inflate to."""
+    import tracemalloc
+    import zlib
+    from taufactor_b200 import io as tio
+    bomb = zlib.compress(b"\0" * (64 << 20), 9)
+    assert len(bomb) < 100_000
+    tracemalloc.start()
+    with pytest.raises(tio.TiffError):
+        tio._decompress(bomb, 8, 4096)
+    peak = tracemalloc.get_traced_memory()[1]
+    tracemalloc.stop()
+    assert peak < (2 << 20), peak
+    good = zlib.compress(bytes(range(256)) * 16)
+    assert tio._decompress(good, 8, 4096) == bytes(range(256)) * 16
